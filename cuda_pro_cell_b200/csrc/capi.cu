@@ -1,0 +1,330 @@
+/* capi.cu - the thin host layer above the sm_100a kernels: resident engine + one-shot proliferate.
+ *
+ * Replaces the reference's host drivers simulation::create_cells_population
+ * (src/simulation/cells_population.cu:18-54) and simulation::proliferate / run_iteration
+ * (src/simulation/proliferation.cu:26-284): no per-level cudaMalloc, no host loop, no seed-cell round trip
+ * through host memory - one upload of kilobytes of tables, one persistent kernel, one download of the
+ * count tensor.  There is no CPU fallback: without a CUDA device every simulate call returns
+ * PROCELL_ERR_CUDA.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "host_plan.h"
+#include "procell_math_tables.inc"
+#include "sim_kernels.h"
+
+using namespace procell_b200;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        if (e == cudaSuccess) cap = bytes ? bytes : 16;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+const uint64_t kLogRows[1 << PCM_LOG_N_BITS][2] = { PCM_LOG_TABLE_ROWS };
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    return fail(PROCELL_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CU(call, what)                                   \
+    do {                                                 \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess) return cuda_fail(e__, what); \
+    } while (0)
+
+}  // namespace
+
+struct procell_engine {
+    int device = 0;
+    int sm_count = 0;
+    DevBuf bin_start, bin_keybase, bin_kdiv, type_cum, type_sel, type_musd, logtab;
+    DevBuf counts, divisions, ctl, q_seq, q_data, spill;
+    SimParams P{};
+    bool loaded = false;
+    int kernel = PROCELL_KERNEL_COOP;
+    int grid = 0, block = 0;
+    size_t smem = 0;
+    size_t counts_len = 0;
+    size_t n_sets = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int launches_last = 0;
+};
+
+extern "C" {
+
+int procell_engine_create(int device, procell_engine** out)
+{
+    if (!out) return fail(PROCELL_ERR_ARG, "procell_engine_create: null out");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(PROCELL_ERR_CUDA, std::string("no CUDA device available (this library has no CPU path): ") +
+                                          cudaGetErrorString(e));
+    if (device < 0 || device >= n_dev) return fail(PROCELL_ERR_ARG, "device index out of range");
+    CU(cudaSetDevice(device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(PROCELL_ERR_CUDA, "device is not compute capability 10.x: the kernels are built for sm_100a only");
+    procell_engine* en = new procell_engine();
+    en->device = device;
+    en->sm_count = prop.multiProcessorCount;
+    if (en->logtab.reserve(sizeof(kLogRows)) != cudaSuccess ||
+        cudaMemcpy(en->logtab.p, kLogRows, sizeof(kLogRows), cudaMemcpyHostToDevice) != cudaSuccess ||
+        en->ctl.reserve(sizeof(ControlBlock)) != cudaSuccess ||
+        en->q_seq.reserve(sizeof(unsigned long long) * kQueueCap) != cudaSuccess ||
+        en->q_data.reserve(sizeof(unsigned long long) * (size_t)kQueueCap * kChunkWords) != cudaSuccess ||
+        cudaEventCreate(&en->ev0) != cudaSuccess || cudaEventCreate(&en->ev1) != cudaSuccess) {
+        cudaError_t le = cudaGetLastError();
+        procell_engine_destroy(en);
+        return cuda_fail(le, "engine allocation");
+    }
+    *out = en;
+    return PROCELL_OK;
+}
+
+void procell_engine_destroy(procell_engine* en)
+{
+    if (!en) return;
+    cudaSetDevice(en->device);
+    DevBuf* bufs[] = { &en->bin_start, &en->bin_keybase, &en->bin_kdiv, &en->type_cum, &en->type_sel, &en->type_musd,
+                       &en->logtab, &en->counts, &en->divisions, &en->ctl, &en->q_seq, &en->q_data, &en->spill };
+    for (DevBuf* b : bufs) b->release();
+    if (en->ev0) cudaEventDestroy(en->ev0);
+    if (en->ev1) cudaEventDestroy(en->ev1);
+    delete en;
+}
+
+size_t procell_engine_counts_len(const procell_engine* en) { return en ? en->counts_len : 0; }
+
+int procell_engine_load(procell_engine* en, const procell_plan* plan, const procell_sim_params* sp)
+{
+    if (!en || !plan || !sp || !sp->types) return fail(PROCELL_ERR_ARG, "procell_engine_load: null argument");
+    const size_t T = sp->n_types, S = sp->n_sets, B = plan->bin_value.size(), K = plan->n_keys;
+    if (T == 0 || T > 64) return fail(PROCELL_ERR_ARG, "n_types must be 1..64");
+    if (S == 0 || S > 65536) return fail(PROCELL_ERR_ARG, "n_sets must be 1..65536");
+    if (!(sp->t_max >= 0.0)) return fail(PROCELL_ERR_ARG, "t_max must be >= 0");
+    if ((double)S * (double)K * (double)T >= 4294967296.0)
+        return fail(PROCELL_ERR_ARG, "n_sets * n_keys * n_types must be below 2^32");
+    if (sp->shard_world > 1 && sp->shard_rank >= sp->shard_world) return fail(PROCELL_ERR_ARG, "shard_rank >= shard_world");
+    for (size_t s = 0; s < S; ++s) {
+        int rc = procell_check_proportions(sp->types + s * T, T);
+        if (rc != PROCELL_OK) return rc;
+    }
+    CU(cudaSetDevice(en->device), "cudaSetDevice");
+
+    /* histogram plan -> HBM */
+    std::vector<uint32_t> h_start(B + 1);
+    for (size_t b = 0; b <= B; ++b) h_start[b] = (uint32_t)plan->bin_start[b];
+    std::vector<uint8_t> h_kdiv(B + 1, 0);
+    for (size_t b = 0; b < B; ++b) h_kdiv[b] = (uint8_t)(plan->bin_kdiv[b] | (plan->bin_count0[b] ? 0x80u : 0u));
+    CU(en->bin_start.reserve((B + 1) * 4), "alloc bin_start");
+    CU(en->bin_keybase.reserve((B + 1) * 4), "alloc bin_keybase");
+    CU(en->bin_kdiv.reserve(B + 1), "alloc bin_kdiv");
+    CU(cudaMemcpy(en->bin_start.p, h_start.data(), (B + 1) * 4, cudaMemcpyHostToDevice), "upload bin_start");
+    if (B) CU(cudaMemcpy(en->bin_keybase.p, plan->bin_keybase.data(), B * 4, cudaMemcpyHostToDevice), "upload bin_keybase");
+    CU(cudaMemcpy(en->bin_kdiv.p, h_kdiv.data(), B + 1, cudaMemcpyHostToDevice), "upload bin_kdiv");
+
+    /* type tables: selection order = descending proportion, stable (parser.cu:184; thrust::sort is not
+     * stable - ties keep file order here), cumulative sums accumulated in that order (cell.cu:88) */
+    std::vector<double> h_cum(S * T);
+    std::vector<uint8_t> h_sel(S * T);
+    std::vector<double2> h_musd(S * T);
+    for (size_t s = 0; s < S; ++s) {
+        const procell_cell_type* ty = sp->types + s * T;
+        std::vector<int> order(T);
+        for (size_t j = 0; j < T; ++j) order[j] = (int)j;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ty[a].proportion > ty[b].proportion; });
+        double acc = 0.0;
+        for (size_t j = 0; j < T; ++j) {
+            acc += ty[order[j]].proportion;
+            h_cum[s * T + j] = acc;
+            h_sel[s * T + j] = (uint8_t)order[j];
+            h_musd[s * T + j] = make_double2(ty[j].mean, ty[j].stddev);
+        }
+    }
+    CU(en->type_cum.reserve(S * T * 8), "alloc type_cum");
+    CU(en->type_sel.reserve(S * T), "alloc type_sel");
+    CU(en->type_musd.reserve(S * T * 16), "alloc type_musd");
+    CU(cudaMemcpy(en->type_cum.p, h_cum.data(), S * T * 8, cudaMemcpyHostToDevice), "upload type_cum");
+    CU(cudaMemcpy(en->type_sel.p, h_sel.data(), S * T, cudaMemcpyHostToDevice), "upload type_sel");
+    CU(cudaMemcpy(en->type_musd.p, h_musd.data(), S * T * 16, cudaMemcpyHostToDevice), "upload type_musd");
+
+    en->counts_len = S * K * T;
+    en->n_sets = S;
+    CU(en->counts.reserve(en->counts_len * 8), "alloc counts");
+    CU(en->divisions.reserve(S * 8), "alloc divisions");
+
+    SimParams& P = en->P;
+    P.bin_start = (const uint32_t*)en->bin_start.p;
+    P.bin_keybase = (const uint32_t*)en->bin_keybase.p;
+    P.bin_kdiv = (const uint8_t*)en->bin_kdiv.p;
+    P.type_cum = (const double*)en->type_cum.p;
+    P.type_sel = (const uint8_t*)en->type_sel.p;
+    P.type_musd = (const double2*)en->type_musd.p;
+    P.logtab = (const double*)en->logtab.p;
+    P.counts = (long long*)en->counts.p;
+    P.divisions = (long long*)en->divisions.p;
+    P.ctl = (ControlBlock*)en->ctl.p;
+    P.q_seq = (unsigned long long*)en->q_seq.p;
+    P.q_data = (unsigned long long*)en->q_data.p;
+    P.n_bins = (uint32_t)B; P.n_types = (uint32_t)T; P.n_sets = (uint32_t)S; P.n_keys = (uint32_t)K;
+    P.n_cells = (uint32_t)plan->n_cells;
+    P.shard_world = sp->shard_world > 1 ? sp->shard_world : 1;
+    P.shard_rank = sp->shard_world > 1 ? sp->shard_rank : 0;
+    P.refcompat = sp->seeding_mode == PROCELL_SEEDING_REFCOMPAT;
+    P.t_max = sp->t_max;
+    P.key0 = (uint32_t)sp->seed; P.key1 = (uint32_t)(sp->seed >> 32);
+
+    /* claim unit: 256 seed cells, smaller when there are too few cells to give every warp of every GPU work */
+    uint32_t unit = sp->shard_unit;
+    if (unit == 0) {
+        const double per_warp = (double)plan->n_cells * (double)S / (148.0 * kCoopWarps * 4.0 * P.shard_world);
+        unit = 256;
+        while (unit > 1 && (double)unit > per_warp) unit >>= 1;
+    }
+    P.unit = unit;
+    P.units_per_set = (uint32_t)((plan->n_cells + unit - 1) / unit);
+    P.local_units_per_set = P.units_per_set > P.shard_rank
+                                ? (P.units_per_set - P.shard_rank + P.shard_world - 1) / P.shard_world : 0;
+    P.total_local_units = (unsigned long long)P.local_units_per_set * S;
+
+    en->kernel = sp->kernel;
+    if (en->kernel == PROCELL_KERNEL_SIMPLE) {
+        en->block = kSimpleThreads;
+        en->grid = en->sm_count * 8;
+        en->smem = kLogTabDoubles * 8;
+        P.smem_hist_slots = 0;
+        P.spill = nullptr;
+    } else {
+        int max_smem = 0;
+        CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, en->device), "query smem");
+        const size_t fixed = coop_smem_bytes(0);
+        size_t slots = ((size_t)max_smem > fixed + 1024) ? ((size_t)max_smem - fixed - 1024) / 4 : 0;
+        if (slots > en->counts_len) slots = en->counts_len;
+        P.smem_hist_slots = (uint32_t)slots;
+        en->smem = coop_smem_bytes(P.smem_hist_slots);
+        int grid = 0;
+        CU(coop_max_grid(en->device, en->smem, &grid), "occupancy query");
+        if (grid <= 0) return fail(PROCELL_ERR_CUDA, "cooperative kernel does not fit on this device");
+        en->grid = grid;
+        en->block = kCoopThreads;
+        CU(en->spill.reserve((size_t)grid * kCoopWarps * kSpillCap * kChunkWords * 8), "alloc spill rings");
+        P.spill = (unsigned long long*)en->spill.p;
+    }
+    en->loaded = true;
+    return PROCELL_OK;
+}
+
+int procell_engine_run(procell_engine* en, uint64_t seed, void* stream_v, int64_t* d_counts, int64_t* d_divisions)
+{
+    if (!en || !en->loaded) return fail(PROCELL_ERR_ARG, "procell_engine_run: engine not loaded");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CU(cudaSetDevice(en->device), "cudaSetDevice");
+    SimParams P = en->P;
+    P.key0 = (uint32_t)seed; P.key1 = (uint32_t)(seed >> 32);
+    if (d_counts) P.counts = (long long*)d_counts;
+    if (d_divisions) P.divisions = (long long*)d_divisions;
+    en->timed = (d_counts == nullptr);
+    if (en->timed) CU(cudaEventRecord(en->ev0, stream), "event record");
+    CU(cudaMemsetAsync(P.counts, 0, en->counts_len * 8, stream), "zero counts");
+    CU(cudaMemsetAsync(P.divisions, 0, en->n_sets * 8, stream), "zero divisions");
+    CU(launch_queue_init(P.q_seq, P.ctl, stream), "launch k_queue_init");
+    if (en->kernel == PROCELL_KERNEL_SIMPLE) CU(launch_simple(P, en->grid, stream), "launch k_proliferate_simple");
+    else CU(launch_coop(P, en->grid, stream), "launch k_proliferate_coop");
+    en->launches_last = 2;
+    if (en->timed) CU(cudaEventRecord(en->ev1, stream), "event record");
+    return PROCELL_OK;
+}
+
+int procell_engine_finish(procell_engine* en, void* stream_v, int64_t* counts, int64_t* divisions, procell_run_stats* stats)
+{
+    if (!en || !en->loaded) return fail(PROCELL_ERR_ARG, "procell_engine_finish: engine not loaded");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CU(cudaSetDevice(en->device), "cudaSetDevice");
+    CU(cudaStreamSynchronize(stream), "kernel execution");
+    int status = 0;
+    CU(cudaMemcpy(&status, &((ControlBlock*)en->ctl.p)->status, sizeof(int), cudaMemcpyDeviceToHost), "read status");
+    if (status != kStatusOk)
+        return fail(PROCELL_ERR_OVERFLOW, "device work pool failure, status " + std::to_string(status));
+    if (counts) CU(cudaMemcpy(counts, en->counts.p, en->counts_len * 8, cudaMemcpyDeviceToHost), "download counts");
+    std::vector<int64_t> div(en->n_sets);
+    CU(cudaMemcpy(div.data(), en->divisions.p, en->n_sets * 8, cudaMemcpyDeviceToHost), "download divisions");
+    if (divisions) memcpy(divisions, div.data(), en->n_sets * 8);
+    if (stats) {
+        stats->divisions = 0;
+        for (int64_t d : div) stats->divisions += d;
+        float ms = 0.f;
+        if (en->timed) cudaEventElapsedTime(&ms, en->ev0, en->ev1);
+        stats->kernel_ms = ms;
+        stats->n_launches = en->launches_last;
+        stats->grid = en->grid; stats->block = en->block; stats->smem_bytes = (int)en->smem;
+    }
+    return PROCELL_OK;
+}
+
+int procell_proliferate(const procell_plan* plan, const procell_sim_params* params, int device, int64_t* counts,
+                        int64_t* divisions, procell_run_stats* stats)
+{
+    if (!plan || !params || !counts) return fail(PROCELL_ERR_ARG, "procell_proliferate: null argument");
+    procell_engine* en = nullptr;
+    int rc = procell_engine_create(device, &en);
+    if (rc != PROCELL_OK) return rc;
+    rc = procell_engine_load(en, plan, params);
+    if (rc == PROCELL_OK) rc = procell_engine_run(en, params->seed, nullptr, nullptr, nullptr);
+    if (rc == PROCELL_OK) rc = procell_engine_finish(en, nullptr, counts, divisions, stats);
+    procell_engine_destroy(en);
+    return rc;
+}
+
+int procell_rng_ceiling(int device, int iters, double* ms_out, double* pairs_out)
+{
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(PROCELL_ERR_CUDA, "no CUDA device available");
+    CU(cudaSetDevice(device), "cudaSetDevice");
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), "query SMs");
+    double* d_tab = nullptr;
+    unsigned long long* d_sink = nullptr;
+    CU(cudaMalloc(&d_tab, sizeof(kLogRows)), "alloc");
+    CU(cudaMalloc(&d_sink, 16), "alloc");
+    CU(cudaMemcpy(d_tab, kLogRows, sizeof(kLogRows), cudaMemcpyHostToDevice), "upload");
+    CU(cudaMemset(d_sink, 0, 16), "memset");
+    const int block = 256, grid = sms * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    CU(launch_rng_ceiling(grid, block, 16, d_tab, 48.33, 21.6, 168.0, 1u, 2u, d_sink, nullptr), "warm-up launch");
+    cudaEventRecord(e0);
+    CU(launch_rng_ceiling(grid, block, iters, d_tab, 48.33, 21.6, 168.0, 1u, 2u, d_sink, nullptr), "launch");
+    cudaEventRecord(e1);
+    CU(cudaEventSynchronize(e1), "rng ceiling kernel");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms_out) *ms_out = ms;
+    if (pairs_out) *pairs_out = (double)grid * block * (double)iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_tab); cudaFree(d_sink);
+    return PROCELL_OK;
+}
+
+}  // extern "C"

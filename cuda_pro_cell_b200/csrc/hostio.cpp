@@ -1,0 +1,225 @@
+/* hostio.cpp - text formats and the result-key plan (host only, no CUDA).
+ *
+ * Replaces the reference's src/io/parser.cu: load_fluorescences (:68-154), load_cell_types (:156-185),
+ * assert_proportion_sum (:46-66), save_fluorescences (:187-217).  File formats are kept byte for byte:
+ *   histogram : whitespace-separated "<double value> <uint64 frequency>" pairs, read until the first parse
+ *               failure; frequency-0 lines skipped; order preserved; duplicates allowed
+ *   types     : "<proportion> <mean> <stddev>" triples, type id = 0-based line index
+ *   output    : rows with frequency > 0, ascending value, value printed with precision 10 (== %.10g),
+ *               TAB, frequency, then with -r one TAB-separated count per type in file order
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "host_plan.h"
+
+namespace procell_b200 {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int fail(int code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+}  // namespace procell_b200
+
+using procell_b200::fail;
+
+extern "C" {
+
+const char* procell_last_error(void) { return procell_b200::g_last_error.c_str(); }
+
+const char* procell_version(void) { return "procell-b200 0.1 (sm_100a)"; }
+
+void procell_free(void* p) { free(p); }
+
+int procell_read_histogram(const char* path, double** value, uint64_t** freq, size_t* n_lines)
+{
+    if (!path || !value || !freq || !n_lines) return fail(PROCELL_ERR_ARG, "procell_read_histogram: null argument");
+    std::ifstream in(path);
+    if (!in.is_open()) return fail(PROCELL_ERR_IO, std::string("cannot open histogram file ") + path);
+    std::vector<double> v;
+    std::vector<uint64_t> f;
+    double x = 0.0;
+    uint64_t c = 0;
+    while (in >> x >> c) {   /* parser.cu:103-106 */
+        v.push_back(x);
+        f.push_back(c);
+    }
+    *n_lines = v.size();
+    *value = static_cast<double*>(malloc((v.size() + 1) * sizeof(double)));
+    *freq = static_cast<uint64_t*>(malloc((v.size() + 1) * sizeof(uint64_t)));
+    if (!*value || !*freq) return fail(PROCELL_ERR_ARG, "out of host memory");
+    if (!v.empty()) {
+        memcpy(*value, v.data(), v.size() * sizeof(double));
+        memcpy(*freq, f.data(), f.size() * sizeof(uint64_t));
+    }
+    return PROCELL_OK;
+}
+
+int procell_check_proportions(const procell_cell_type* types, size_t n_types)
+{
+    double sum = 0.0;    /* thrust::reduce from 0.0, left to right (parser.cu:52-58) */
+    for (size_t j = 0; j < n_types; ++j) sum = sum + types[j].proportion;
+    double err = 1 / pow(10.0, 8.0);
+    if (std::fabs(1.0 - sum) > err)
+        return fail(PROCELL_ERR_PROPORTION, "ERROR: proportion distribution of cell types does not sum to 1, aborting.");
+    return PROCELL_OK;
+}
+
+int procell_read_cell_types(const char* path, procell_cell_type** types, size_t* n_types)
+{
+    if (!path || !types || !n_types) return fail(PROCELL_ERR_ARG, "procell_read_cell_types: null argument");
+    std::ifstream in(path);
+    if (!in.is_open()) return fail(PROCELL_ERR_IO, std::string("cannot open cell types file ") + path);
+    std::vector<procell_cell_type> t;
+    procell_cell_type c;
+    while (in >> c.proportion >> c.mean >> c.stddev) t.push_back(c);   /* parser.cu:167-175 */
+    *n_types = t.size();
+    *types = static_cast<procell_cell_type*>(malloc((t.size() + 1) * sizeof(procell_cell_type)));
+    if (!*types) return fail(PROCELL_ERR_ARG, "out of host memory");
+    if (!t.empty()) memcpy(*types, t.data(), t.size() * sizeof(procell_cell_type));
+    return procell_check_proportions(*types, *n_types);
+}
+
+int procell_write_histogram(const char* path, int save_ratio, size_t n_types, size_t n_rows,
+                            const double* row_value, const int64_t* row_freq, const int64_t* row_ratio)
+{
+    if (n_rows && (!row_value || !row_freq)) return fail(PROCELL_ERR_ARG, "procell_write_histogram: null rows");
+    if (save_ratio && n_rows && !row_ratio) return fail(PROCELL_ERR_ARG, "procell_write_histogram: null ratios");
+    std::ofstream file;
+    if (path) {
+        file.open(path);
+        if (!file.is_open()) return fail(PROCELL_ERR_IO, std::string("cannot open output file ") + path);
+    }
+    std::ostream& out = path ? static_cast<std::ostream&>(file) : std::cout;
+    std::ostringstream buf;
+    buf.precision(10);   /* parser.cu:194-195 */
+    for (size_t i = 0; i < n_rows; ++i) {
+        if (row_freq[i] <= 0) continue;
+        buf << row_value[i] << "\t" << row_freq[i];
+        if (save_ratio)
+            for (size_t j = 0; j < n_types; ++j) buf << "\t" << row_ratio[i * n_types + j];
+        buf << "\n";
+        if (buf.tellp() > (1 << 20)) { out << buf.str(); buf.str(std::string()); }
+    }
+    out << buf.str();
+    out.flush();
+    if (!out.good()) return fail(PROCELL_ERR_IO, "write failed");
+    return PROCELL_OK;
+}
+
+int procell_plan_create(const double* value, const uint64_t* freq, size_t n_lines, double phi, procell_plan** out)
+{
+    if (!out || (n_lines && (!value || !freq))) return fail(PROCELL_ERR_ARG, "procell_plan_create: null argument");
+    if (!(phi >= 0.0)) return fail(PROCELL_ERR_ARG, "phi must be >= 0 (0 selects the default)");
+    procell_plan* p = new procell_plan();
+    if (phi == 0.0) {   /* parser.cu:80-96: smallest value whose frequency is > 0 */
+        for (size_t i = 0; i < n_lines; ++i)
+            if (freq[i] > 0 && (phi == 0.0 || value[i] < phi)) phi = value[i];
+    }
+    p->phi = phi;
+    uint64_t total = 0;
+    size_t n_keys = 0;
+    for (size_t i = 0; i < n_lines; ++i) {
+        if (freq[i] == 0) continue;   /* parser.cu:110-111 */
+        p->bin_value.push_back(value[i]);
+        p->bin_freq.push_back(freq[i]);
+        p->bin_start.push_back(total);
+        total += freq[i];
+        /* how often may a cell of this bin halve: node rule f/2 > phi (proliferation.cu:323), evaluated with
+         * the same repeated division by two the reference applies to the fluorescence itself */
+        unsigned k = 0;
+        double f = value[i];
+        while (k < 63 && f / 2 > phi) { f = f / 2; ++k; }
+        if (k == 63 && f / 2 > phi) p->depth_capped = true;
+        p->bin_kdiv.push_back(static_cast<uint8_t>(k));
+        p->bin_count0.push_back(static_cast<uint8_t>(value[i] >= phi));   /* parser.cu:127 */
+        p->bin_keybase.push_back(static_cast<uint32_t>(n_keys));
+        n_keys += k + 1;
+        if (n_keys > 0x7FFFFFFFu) { delete p; return fail(PROCELL_ERR_ARG, "key space too large"); }
+    }
+    p->bin_start.push_back(total);
+    p->n_cells = total;
+    p->n_keys = n_keys;
+    const size_t nb = p->bin_value.size();
+    if (nb > 65535) { delete p; return fail(PROCELL_ERR_ARG, "more than 65535 non-empty histogram lines"); }
+    if (total > 0xFFFFFFFFull) { delete p; return fail(PROCELL_ERR_ARG, "more than 2^32-1 seed cells"); }
+    /* value of every key by repeated halving (parser.cu:126-137), then the ordered set of them (:142-151) */
+    std::vector<double> key_value(n_keys);
+    std::vector<double> rows;
+    rows.reserve(n_keys);
+    for (size_t b = 0; b < nb; ++b) {
+        double f = p->bin_value[b];
+        for (unsigned k = 0; k <= p->bin_kdiv[b]; ++k) {
+            key_value[p->bin_keybase[b] + k] = f;
+            if (k > 0 || p->bin_count0[b]) rows.push_back(f);
+            f = f / 2;
+        }
+    }
+    std::sort(rows.begin(), rows.end());
+    rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+    p->row_value = rows;
+    p->key_row.assign(n_keys, 0xFFFFFFFFu);
+    for (size_t b = 0; b < nb; ++b)
+        for (unsigned k = 0; k <= p->bin_kdiv[b]; ++k) {
+            if (k == 0 && !p->bin_count0[b]) continue;
+            size_t key = p->bin_keybase[b] + k;
+            auto it = std::lower_bound(rows.begin(), rows.end(), key_value[key]);
+            p->key_row[key] = static_cast<uint32_t>(it - rows.begin());
+        }
+    *out = p;
+    return PROCELL_OK;
+}
+
+void procell_plan_destroy(procell_plan* plan) { delete plan; }
+size_t procell_plan_n_bins(const procell_plan* plan) { return plan ? plan->bin_value.size() : 0; }
+size_t procell_plan_n_keys(const procell_plan* plan) { return plan ? plan->n_keys : 0; }
+size_t procell_plan_n_rows(const procell_plan* plan) { return plan ? plan->row_value.size() : 0; }
+uint64_t procell_plan_n_cells(const procell_plan* plan) { return plan ? plan->n_cells : 0; }
+double procell_plan_phi(const procell_plan* plan) { return plan ? plan->phi : 0.0; }
+int procell_plan_depth_capped(const procell_plan* plan) { return plan && plan->depth_capped; }
+
+int procell_plan_export(const procell_plan* plan, double* row_value, uint32_t* key_row, uint32_t* bin_keybase,
+                        uint8_t* bin_kdiv)
+{
+    if (!plan) return fail(PROCELL_ERR_ARG, "procell_plan_export: null plan");
+    if (row_value && !plan->row_value.empty())
+        memcpy(row_value, plan->row_value.data(), plan->row_value.size() * sizeof(double));
+    if (key_row && plan->n_keys) memcpy(key_row, plan->key_row.data(), plan->n_keys * sizeof(uint32_t));
+    if (bin_keybase && !plan->bin_keybase.empty())
+        memcpy(bin_keybase, plan->bin_keybase.data(), plan->bin_keybase.size() * sizeof(uint32_t));
+    if (bin_kdiv && !plan->bin_kdiv.empty()) memcpy(bin_kdiv, plan->bin_kdiv.data(), plan->bin_kdiv.size());
+    return PROCELL_OK;
+}
+
+int procell_merge_rows(const procell_plan* plan, const int64_t* counts, size_t n_types, int64_t* row_freq,
+                       int64_t* row_ratio)
+{
+    if (!plan || !counts || !row_freq) return fail(PROCELL_ERR_ARG, "procell_merge_rows: null argument");
+    const size_t n_rows = plan->row_value.size();
+    std::fill(row_freq, row_freq + n_rows, int64_t(0));
+    if (row_ratio) std::fill(row_ratio, row_ratio + n_rows * n_types, int64_t(0));
+    for (size_t key = 0; key < plan->n_keys; ++key) {
+        const uint32_t row = plan->key_row[key];
+        if (row == 0xFFFFFFFFu) continue;
+        for (size_t j = 0; j < n_types; ++j) {
+            const int64_t c = counts[key * n_types + j];
+            row_freq[row] += c;
+            if (row_ratio) row_ratio[static_cast<size_t>(row) * n_types + j] += c;
+        }
+    }
+    return PROCELL_OK;
+}
+
+}  // extern "C"

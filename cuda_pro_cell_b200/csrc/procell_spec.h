@@ -1,0 +1,207 @@
+/* procell_spec.h - the arithmetic specification of the B200 proliferation simulator.
+ *
+ * Everything that decides WHICH histogram comes out lives here: the Philox4x32-10 stream
+ * layout, the bits->uniform maps, the fixed-operation-sequence FP64 log / sincos used by the
+ * Box-Muller transform, and the node rule.  The sm_100a kernels (sim_kernels.cu) include this
+ * header; the CPU oracle (oracle/procell_oracle.c) restates it independently in plain C.
+ *
+ * Replaces, in the reference (ericniso/cuda-pro-cell):
+ *   src/utils/util.cu:143-169     init_random / uniform_random / normal_random (cuRAND XORWOW,
+ *                                 a fresh curand_init per draw) -> counter-based Philox keyed by
+ *                                 (root cell, tree path), one block per DIVISION (both daughters).
+ *   src/simulation/cell.cu:106-143 determine_cell_timer / determine_cell_initial_t
+ *   src/simulation/proliferation.cu:321-350,404-410  node rule / out_of_time
+ *
+ * Bit-reproducibility: only IEEE-754 correctly-rounded primitives are used (add, mul, fma,
+ * sqrt) in a fixed order, through intrinsics the compiler may not contract or reassociate.
+ */
+#ifndef PROCELL_SPEC_H
+#define PROCELL_SPEC_H
+
+#include <stdint.h>
+#include <string.h>
+#include "procell_math_tables.inc"
+
+#if defined(__CUDACC__)
+#define PCS_HD __host__ __device__ __forceinline__
+#else
+#define PCS_HD static inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define PCS_ADD(a, b) __dadd_rn((a), (b))
+#define PCS_MUL(a, b) __dmul_rn((a), (b))
+#define PCS_FMA(a, b, c) __fma_rn((a), (b), (c))
+#define PCS_SQRT(a) __dsqrt_rn((a))
+#else
+/* host build: compile with -ffp-contract=off (the Makefile does) so a*b+c is never fused */
+#define PCS_ADD(a, b) ((a) + (b))
+#define PCS_MUL(a, b) ((a) * (b))
+#define PCS_FMA(a, b, c) __builtin_fma((a), (b), (c))
+#define PCS_SQRT(a) __builtin_sqrt((a))
+#endif
+
+PCS_HD double pcs_bits2d(uint64_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double d;
+    memcpy(&d, &u, 8);
+    return d;
+#endif
+}
+
+PCS_HD uint64_t pcs_d2bits(double d)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t u;
+    memcpy(&u, &d, 8);
+    return u;
+#endif
+}
+
+/* ------------------------------------------------------------------ limits of the key layout */
+#define PCS_MAX_LEVEL 63u        /* heap index of a node at level k lies in [2^k, 2^(k+1)) */
+#define PCS_MAX_RETRY 255u       /* retry field is 8 bits; at 255 the timer falls back to the mean */
+#define PCS_MAX_SETS 65536u      /* parameter-set id is 16 bits */
+#define PCS_MAX_TYPES 64u
+#define PCS_MAX_BINS 65535u
+#define PCS_TAG_DIVISION 0u      /* one block per division: both daughters' timers */
+#define PCS_TAG_SEED 1u          /* one block per seed cell: type uniform + initial-age uniform */
+
+/* ------------------------------------------------------------------ Philox4x32-10 (Salmon et al., SC'11) */
+#define PCS_PHILOX_M0 0xD2511F53u
+#define PCS_PHILOX_M1 0xCD9E8D57u
+#define PCS_PHILOX_W0 0x9E3779B9u
+#define PCS_PHILOX_W1 0xBB67AE85u
+
+struct pcs_u32x4 { uint32_t x, y, z, w; };
+
+PCS_HD pcs_u32x4 pcs_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                   uint32_t k0, uint32_t k1)
+{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)PCS_PHILOX_M0 * (uint64_t)c0;
+        uint64_t p1 = (uint64_t)PCS_PHILOX_M1 * (uint64_t)c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += PCS_PHILOX_W0;
+        k1 += PCS_PHILOX_W1;
+    }
+    pcs_u32x4 o;
+    o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+/* counter layout: c0 = root cell id, c1 = set | retry<<16 | tag<<24, (c3:c2) = heap index */
+PCS_HD pcs_u32x4 pcs_draw(uint32_t root, uint32_t set, uint32_t retry, uint32_t tag, uint64_t heap,
+                          uint32_t k0, uint32_t k1)
+{
+    return pcs_philox4x32_10(root, set | (retry << 16) | (tag << 24), (uint32_t)heap,
+                             (uint32_t)(heap >> 32), k0, k1);
+}
+
+/* ------------------------------------------------------------------ bits -> uniform in (0,1) */
+/* 52 random mantissa bits m -> (2m+1) * 2^-53, exact: never 0, never 1 */
+PCS_HD double pcs_unit_from_mant52(uint64_t mant52)
+{
+    double d = pcs_bits2d(0x3FF0000000000000ULL | mant52);      /* [1,2) */
+    return PCS_ADD(d, -pcs_bits2d(PCM_BITS_ONE_M));              /* exact */
+}
+
+PCS_HD double pcs_u53(uint32_t lo, uint32_t hi)
+{
+    return pcs_unit_from_mant52((((uint64_t)hi << 32) | (uint64_t)lo) >> 12);
+}
+
+/* ------------------------------------------------------------------ -2*ln(u), u in (0,1), normal double
+ * tab: 128 rows {invc, logc} as 256 doubles (a shared-memory copy on the device).
+ * log(u) = k*ln2 + logc_i + log1p(r),  r = z*invc_i - 1,  |r| <= 2^-8,  log1p by Taylor to r^6. */
+PCS_HD double pcs_neg2log(double u, const double* tab)
+{
+    uint64_t ix = pcs_d2bits(u);
+    uint64_t tmp = ix - PCM_LOG_OFF;
+    uint32_t i = (uint32_t)(tmp >> (52 - PCM_LOG_N_BITS)) & ((1u << PCM_LOG_N_BITS) - 1u);
+    int32_t k = (int32_t)((int64_t)tmp >> 52);
+    double z = pcs_bits2d(ix - (tmp & 0xFFF0000000000000ULL));
+    double invc = tab[2 * i];
+    double logc = tab[2 * i + 1];
+    double r = PCS_FMA(z, invc, -1.0);
+    double q = pcs_bits2d(PCM_BITS_LOG1P_B6);
+    q = PCS_FMA(q, r, pcs_bits2d(PCM_BITS_LOG1P_B5));
+    q = PCS_FMA(q, r, pcs_bits2d(PCM_BITS_LOG1P_B4));
+    q = PCS_FMA(q, r, pcs_bits2d(PCM_BITS_LOG1P_B3));
+    q = PCS_FMA(q, r, pcs_bits2d(PCM_BITS_LOG1P_B2));
+    double r2 = PCS_MUL(r, r);
+    double l = PCS_FMA(r2, q, r);
+    double base = PCS_FMA((double)k, pcs_bits2d(PCM_BITS_LN2), logc);
+    double lg = PCS_ADD(base, l);
+    return PCS_MUL(lg, -2.0);
+}
+
+/* ------------------------------------------------------------------ sin/cos(2*pi*V/2^64) from 64 random bits
+ * octant q = top 3 bits; next 52 bits y (complemented in odd octants) -> theta = (pi/4)*(2y+1)*2^-53 in
+ * (0, pi/4); Taylor sin to x^15, cos to x^16; octant symmetries by selects and sign flips (exact). */
+PCS_HD void pcs_sincos2pi(uint64_t v, double* s_out, double* c_out)
+{
+    uint32_t q = (uint32_t)(v >> 61);
+    uint64_t y = (v >> 9) & 0x000FFFFFFFFFFFFFULL;
+    if (q & 1u) y ^= 0x000FFFFFFFFFFFFFULL;
+    double th = PCS_MUL(pcs_unit_from_mant52(y), pcs_bits2d(PCM_BITS_PIO4));
+    double t2 = PCS_MUL(th, th);
+    double ps = pcs_bits2d(PCM_BITS_SIN_S7);
+    ps = PCS_FMA(ps, t2, pcs_bits2d(PCM_BITS_SIN_S6));
+    ps = PCS_FMA(ps, t2, pcs_bits2d(PCM_BITS_SIN_S5));
+    ps = PCS_FMA(ps, t2, pcs_bits2d(PCM_BITS_SIN_S4));
+    ps = PCS_FMA(ps, t2, pcs_bits2d(PCM_BITS_SIN_S3));
+    ps = PCS_FMA(ps, t2, pcs_bits2d(PCM_BITS_SIN_S2));
+    ps = PCS_FMA(ps, t2, pcs_bits2d(PCM_BITS_SIN_S1));
+    double t3 = PCS_MUL(th, t2);
+    double sn = PCS_FMA(t3, ps, th);
+    double pc = pcs_bits2d(PCM_BITS_COS_C8);
+    pc = PCS_FMA(pc, t2, pcs_bits2d(PCM_BITS_COS_C7));
+    pc = PCS_FMA(pc, t2, pcs_bits2d(PCM_BITS_COS_C6));
+    pc = PCS_FMA(pc, t2, pcs_bits2d(PCM_BITS_COS_C5));
+    pc = PCS_FMA(pc, t2, pcs_bits2d(PCM_BITS_COS_C4));
+    pc = PCS_FMA(pc, t2, pcs_bits2d(PCM_BITS_COS_C3));
+    pc = PCS_FMA(pc, t2, pcs_bits2d(PCM_BITS_COS_C2));
+    pc = PCS_FMA(pc, t2, pcs_bits2d(PCM_BITS_COS_C1));
+    double cs = PCS_FMA(t2, pc, 1.0);
+    /* q: 0 (s,c) 1 (c,s) 2 (c,-s) 3 (s,-c) 4 (-s,-c) 5 (-c,-s) 6 (-c,s) 7 (-s,c) */
+    bool swap = ((q + 1u) & 2u) != 0u;
+    double a = swap ? cs : sn;
+    double b = swap ? sn : cs;
+    uint64_t sa = (uint64_t)(q >> 2) << 63;                 /* sin negative in octants 4..7 */
+    uint64_t sb = (uint64_t)(((q + 2u) >> 2) & 1u) << 63;   /* cos negative in octants 2..5 */
+    *s_out = pcs_bits2d(pcs_d2bits(a) ^ sa);
+    *c_out = pcs_bits2d(pcs_d2bits(b) ^ sb);
+}
+
+/* ------------------------------------------------------------------ one Box-Muller pair from one Philox block
+ * z0 = rad*sin, z1 = rad*cos with rad = sqrt(-2 ln u); child c of a division uses z_c.
+ * u_override (refcompat seeding) replaces the radius uniform when > 0. */
+PCS_HD void pcs_normal_pair(pcs_u32x4 w, const double* tab, double u_override, double* z0, double* z1)
+{
+    double u = pcs_u53(w.x, w.y);
+    if (u_override > 0.0) u = u_override;
+    double rad = PCS_SQRT(pcs_neg2log(u, tab));
+    double s, c;
+    pcs_sincos2pi(((uint64_t)w.w << 32) | (uint64_t)w.z, &s, &c);
+    *z0 = PCS_MUL(rad, s);
+    *z1 = PCS_MUL(rad, c);
+}
+
+/* timer = mean + sd*z (one fma), accepted iff > 0 (cell.cu:106-122: redraw while rnd <= 0) */
+PCS_HD double pcs_timer(double mean, double sd, double z) { return PCS_FMA(sd, z, mean); }
+
+#endif /* PROCELL_SPEC_H */

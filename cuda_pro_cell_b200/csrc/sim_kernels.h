@@ -1,0 +1,79 @@
+/* sim_kernels.h - device-side parameter block and launchers of the sm_100a simulation kernels. */
+#ifndef PROCELL_SIM_KERNELS_H
+#define PROCELL_SIM_KERNELS_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace procell_b200 {
+
+/* ---- geometry of the warp-cooperative kernel ---- */
+constexpr int kCoopWarps = 16;                 /* warps per CTA, one CTA per SM */
+constexpr int kCoopThreads = kCoopWarps * 32;
+constexpr int kStackCap = 128;                 /* nodes per warp kept in shared memory (ring) */
+constexpr int kChunkNodes = 32;                /* spill / donation granule: one node per lane */
+constexpr int kChunkWords = 4 * kChunkNodes;   /* 4 x u64 fields per node, field-major */
+constexpr int kSpillCap = 128;                 /* private spill ring, chunks per warp */
+constexpr int kQueueCap = 8192;                /* shared donation queue, chunks (power of two) */
+constexpr int kLogTabDoubles = 256;
+constexpr int kSimpleThreads = 128;
+constexpr int kSimpleStack = 136;              /* >= 2*63 + slack entries per thread */
+
+/* device status word */
+constexpr int kStatusOk = 0;
+constexpr int kStatusSpillOverflow = 1;
+constexpr int kStatusQueueTimeout = 2;
+constexpr int kStatusIdleTimeout = 3;
+
+/* control block in global memory; every hot word on its own 128-byte line */
+struct alignas(128) ControlBlock {
+    unsigned long long cursor;      unsigned long long pad0[15];
+    unsigned long long q_head;      unsigned long long pad1[15];
+    unsigned long long q_tail;      unsigned long long pad2[15];
+    int active;                     int pad3[31];
+    int idle;                       int pad4[31];
+    int status;                     int pad5[31];
+};
+
+struct SimParams {
+    /* histogram plan, resident in HBM */
+    const uint32_t* bin_start;    /* [n_bins+1] first seed-cell id of each bin */
+    const uint32_t* bin_keybase;  /* [n_bins]   first key of the bin */
+    const uint8_t* bin_kdiv;      /* [n_bins]   halvings allowed (<=63) | 0x80 if level-0 leaves are countable */
+    /* type tables, [n_sets][n_types] */
+    const double* type_cum;       /* running proportion sums in selection order (descending proportion) */
+    const uint8_t* type_sel;      /* file id of the j-th type in selection order */
+    const double2* type_musd;     /* (mean, sd) by file id */
+    const double* logtab;         /* 128 x {invc, logc} */
+    /* outputs */
+    long long* counts;            /* [n_sets][n_keys][n_types] */
+    long long* divisions;         /* [n_sets] */
+    /* work distribution */
+    ControlBlock* ctl;
+    unsigned long long* q_seq;    /* [kQueueCap] slot sequence numbers (Vyukov bounded queue) */
+    unsigned long long* q_data;   /* [kQueueCap][kChunkWords] */
+    unsigned long long* spill;    /* [grid*kCoopWarps][kSpillCap][kChunkWords] */
+    uint32_t n_bins, n_types, n_sets, n_keys;
+    uint32_t n_cells;
+    uint32_t unit;                /* seed cells per claim unit */
+    uint32_t units_per_set;       /* ceil(n_cells / unit) */
+    uint32_t local_units_per_set; /* units with u % world == rank */
+    uint32_t shard_world, shard_rank;
+    unsigned long long total_local_units;   /* n_sets * local_units_per_set */
+    uint32_t key0, key1;          /* Philox key = seed */
+    uint32_t smem_hist_slots;     /* keys below this are privatised in shared memory */
+    int refcompat;
+    double t_max;
+};
+
+size_t coop_smem_bytes(uint32_t hist_slots);
+cudaError_t launch_coop(const SimParams& p, int grid, cudaStream_t stream);
+cudaError_t coop_max_grid(int device, size_t smem_bytes, int* grid_out);
+cudaError_t launch_simple(const SimParams& p, int grid, cudaStream_t stream);
+cudaError_t launch_queue_init(unsigned long long* q_seq, ControlBlock* ctl, cudaStream_t stream);
+cudaError_t launch_rng_ceiling(int grid, int block, int iters, const double* logtab, double mean, double sd,
+                               double t_max, uint32_t key0, uint32_t key1, unsigned long long* sink,
+                               cudaStream_t stream);
+
+}  // namespace procell_b200
+#endif

@@ -1,0 +1,135 @@
+/* procell_b200.h - C ABI of the B200-native ProCell proliferation simulator (libprocell_b200.so).
+ *
+ * The reference (ericniso/cuda-pro-cell) has no FFI: its hot path sits behind three C++ host functions
+ * that simulation::Simulator calls, plus the text parser/writer.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference root).  Plain pointers and sizes only;
+ * nothing throws or exit()s across this boundary; every function returns PROCELL_OK (0) or a negative
+ * PROCELL_ERR_* code and procell_last_error() gives the message of the calling thread's last failure.
+ * There is NO CPU fallback: anything that simulates needs a CUDA device of compute capability 10.x.
+ */
+#ifndef PROCELL_B200_H
+#define PROCELL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PROCELL_OK 0
+#define PROCELL_ERR_ARG (-1)         /* bad argument / limit of the key layout exceeded */
+#define PROCELL_ERR_CUDA (-2)        /* CUDA runtime error (no device, launch failure, ...) */
+#define PROCELL_ERR_PROPORTION (-3)  /* |1 - sum(proportion)| > 1e-8 (src/io/parser.cu:46-66) */
+#define PROCELL_ERR_IO (-4)          /* file could not be opened / written */
+#define PROCELL_ERR_OVERFLOW (-5)    /* device work pool overflow or watchdog abort; results invalid */
+
+#define PROCELL_SEEDING_IDEAL 0      /* all draws independent */
+#define PROCELL_SEEDING_REFCOMPAT 1  /* seed cell's type uniform doubles as the Box-Muller radius uniform of
+                                        its first timer, as the reference's one-seed-many-draws does
+                                        (src/simulation/cell.cu:38,55 + src/utils/util.cu:153-169) */
+
+#define PROCELL_KERNEL_COOP 0        /* warp-cooperative depth-first kernel (default) */
+#define PROCELL_KERNEL_SIMPLE 1      /* one thread per lineage, global atomics (bring-up / cross-check) */
+
+/* one subpopulation: src/simulation/data_types.h:21-27 (cell_type) minus `name` (= array index) */
+typedef struct procell_cell_type {
+    double proportion;
+    double mean;     /* < 0: quiescent (README "-1 -1") */
+    double stddev;
+} procell_cell_type;
+
+typedef struct procell_plan procell_plan;     /* host: bins, key space, merged output rows */
+typedef struct procell_engine procell_engine; /* one GPU: resident tables, work pool, count tensor */
+
+const char* procell_last_error(void);
+const char* procell_version(void);
+
+/* ---- text I/O ------------------------------------------------------------------------------- */
+/* replaces io::load_fluorescences' reading loop (src/io/parser.cu:103-106): "<double> <uint64>" pairs
+ * until the first parse failure; lines with frequency 0 are KEPT here (the plan skips them).
+ * Arrays are malloc'd; release with procell_free. */
+int procell_read_histogram(const char* path, double** value, uint64_t** freq, size_t* n_lines);
+/* replaces io::load_cell_types (src/io/parser.cu:156-185): "<proportion> <mean> <stddev>" triples, file
+ * order kept (type id = line index); checks the proportion sum. */
+int procell_read_cell_types(const char* path, procell_cell_type** types, size_t* n_types);
+/* replaces io::save_fluorescences (src/io/parser.cu:187-217): rows with frequency > 0, ascending value,
+ * "%.10g" TAB frequency [TAB per-type counts in file order]; path == NULL writes to stdout. */
+int procell_write_histogram(const char* path, int save_ratio, size_t n_types, size_t n_rows,
+                            const double* row_value, const int64_t* row_freq, const int64_t* row_ratio);
+void procell_free(void* p);
+int procell_check_proportions(const procell_cell_type* types, size_t n_types);
+
+/* ---- plan: the result-key precomputation of io::load_fluorescences (src/io/parser.cu:68-154) ---- */
+/* phi == 0 selects the default (smallest value with frequency > 0, parser.cu:80-96). */
+int procell_plan_create(const double* value, const uint64_t* freq, size_t n_lines, double phi,
+                        procell_plan** out);
+void procell_plan_destroy(procell_plan* plan);
+size_t procell_plan_n_bins(const procell_plan* plan);   /* lines with frequency > 0 */
+size_t procell_plan_n_keys(const procell_plan* plan);   /* (bin, k) pairs, k = 0..kdiv(bin) */
+size_t procell_plan_n_rows(const procell_plan* plan);   /* distinct values value/2^k >= phi, ascending */
+uint64_t procell_plan_n_cells(const procell_plan* plan);
+double procell_plan_phi(const procell_plan* plan);
+int procell_plan_depth_capped(const procell_plan* plan);
+/* any pointer may be NULL; sizes: row_value[n_rows], key_row[n_keys], bin_keybase[n_bins], bin_kdiv[n_bins] */
+int procell_plan_export(const procell_plan* plan, double* row_value, uint32_t* key_row,
+                        uint32_t* bin_keybase, uint8_t* bin_kdiv);
+/* counts of ONE parameter set [n_keys][n_types] -> rows: row_freq[n_rows], row_ratio[n_rows][n_types] */
+int procell_merge_rows(const procell_plan* plan, const int64_t* counts, size_t n_types,
+                       int64_t* row_freq, int64_t* row_ratio);
+
+/* ---- simulation ------------------------------------------------------------------------------- */
+typedef struct procell_sim_params {
+    const procell_cell_type* types; /* [n_sets][n_types], file order */
+    size_t n_types;                 /* 1..64 */
+    size_t n_sets;                  /* 1..65536 parameter sets simulated in ONE launch on the same histogram */
+    double t_max;
+    uint64_t seed;                  /* Philox key */
+    int seeding_mode;               /* PROCELL_SEEDING_* */
+    int kernel;                     /* PROCELL_KERNEL_* */
+    uint32_t shard_rank;            /* this GPU simulates the seed-cell units u with u % shard_world == rank */
+    uint32_t shard_world;           /* 0 or 1: everything */
+    uint32_t shard_unit;            /* seed cells per unit; 0: default (256) */
+} procell_sim_params;
+
+typedef struct procell_run_stats {
+    int64_t divisions;   /* total over sets, this shard */
+    double kernel_ms;    /* CUDA-event time of memsets + kernel on the engine's stream (host-API runs) */
+    int n_launches;      /* kernels launched by the run */
+    int grid, block;     /* launch shape of the simulation kernel */
+    int smem_bytes;
+} procell_run_stats;
+
+/* One-shot, host buffers in and out: replaces simulation::create_cells_population
+ * (src/simulation/cells_population.h:12-18) + simulation::proliferate (src/simulation/proliferation.h:12-19);
+ * seed cells are never materialised.  counts: [n_sets][n_keys][n_types] int64; divisions: [n_sets] or NULL. */
+int procell_proliferate(const procell_plan* plan, const procell_sim_params* params, int device,
+                        int64_t* counts, int64_t* divisions, procell_run_stats* stats);
+
+/* Resident engine: tables live in HBM across runs. */
+int procell_engine_create(int device, procell_engine** out);
+void procell_engine_destroy(procell_engine* engine);
+/* host -> device upload of the plan and type tables (the H2D leg of an end-to-end step) */
+int procell_engine_load(procell_engine* engine, const procell_plan* plan, const procell_sim_params* params);
+/* Enqueue one simulation on `stream` (a cudaStream_t, NULL = default stream): zero the count tensor, run the
+ * kernel.  d_counts / d_divisions are DEVICE pointers ([n_sets][n_keys][n_types] / [n_sets] int64) or NULL to
+ * use the engine's own tensors.  Asynchronous. */
+int procell_engine_run(procell_engine* engine, uint64_t seed, void* stream, int64_t* d_counts,
+                       int64_t* d_divisions);
+/* wait for the stream, check the device status word, copy the engine's own tensors to host buffers */
+int procell_engine_finish(procell_engine* engine, void* stream, int64_t* counts, int64_t* divisions,
+                          procell_run_stats* stats);
+size_t procell_engine_counts_len(const procell_engine* engine); /* n_sets*n_keys*n_types */
+
+/* RNG-only micro-kernel: per thread `iters` Philox blocks + Box-Muller pairs + timers into a register
+ * accumulator (the instruction-issue ceiling the roofline fraction is quoted against).  Returns ms. */
+int procell_rng_ceiling(int device, int iters, double* ms_out, double* pairs_out);
+
+/* ---- the `procell` command line (src/main.cu:18-34 + src/io/cmdargs.cpp:11-76) ---------------- */
+/* Returns the process exit code; prints errors to stdout as the reference does. */
+int procell_main(int argc, char** argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROCELL_B200_H */
