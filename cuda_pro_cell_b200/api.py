@@ -153,12 +153,13 @@ def proliferate(plan: Plan, types, t_max: float, seed: int = 0x5EED0000, seeding
     lib = _lib.load()
     t = _types_array(types)
     p = _make_params(t, t_max, seed, seeding_mode, kernel, shard)
-    counts = np.zeros((t.shape[0], plan.n_keys, t.shape[1]), dtype=np.int64)
+    shape = (t.shape[0], plan.n_keys, t.shape[1])
+    flat = np.zeros(max(int(np.prod(shape)), 1), dtype=np.int64)     # never a NULL pointer, even for 0 keys
     div = np.zeros(t.shape[0], dtype=np.int64)
     st = RunStats()
-    check(lib.procell_proliferate(plan.h, C.byref(p), int(device), counts.ctypes.data_as(_i64p),
+    check(lib.procell_proliferate(plan.h, C.byref(p), int(device), flat.ctypes.data_as(_i64p),
                                   div.ctypes.data_as(_i64p), C.byref(st)))
-    return Result(counts, div, _stats_dict(st))
+    return Result(flat[: int(np.prod(shape))].reshape(shape), div, _stats_dict(st))
 
 
 class Engine:
@@ -191,12 +192,13 @@ class Engine:
 
     def finish(self, stream: int = 0, fetch: bool = True) -> Result:
         st = RunStats()
-        counts = np.zeros(self.shape, dtype=np.int64) if fetch else None
+        n = int(np.prod(self.shape))
+        flat = np.zeros(max(n, 1), dtype=np.int64) if fetch else None
         div = np.zeros(self.shape[0], dtype=np.int64)
         check(_lib.load().procell_engine_finish(self.h, C.c_void_p(stream or None),
-                                                counts.ctypes.data_as(_i64p) if fetch else None,
+                                                flat.ctypes.data_as(_i64p) if fetch else None,
                                                 div.ctypes.data_as(_i64p), C.byref(st)))
-        return Result(counts, div, _stats_dict(st))
+        return Result(flat[:n].reshape(self.shape) if fetch else None, div, _stats_dict(st))
 
     def close(self):
         if getattr(self, "h", None):

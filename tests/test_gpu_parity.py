@@ -1,0 +1,178 @@
+"""GPU parity: the sm_100a kernels, called through the C ABI, must reproduce the CPU oracle BIT FOR BIT
+(int64 count tensor keyed (set, bin, k, type) and the division counter) on the same seeded inputs."""
+import subprocess
+
+import numpy as np
+import pytest
+
+from cuda_pro_cell_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = {"coop": 0, "simple": 1}
+
+
+def _run_both(gpu_api, oracle, values, freqs, phi, types, t_max, seed, kernel, refcompat=False, shard=(0, 1, 0)):
+    plan = gpu_api.Plan(values, freqs, phi)
+    oplan = oracle.OraclePlan(values, freqs, phi)
+    assert plan.n_keys == oplan.n_keys and plan.n_rows == oplan.n_rows
+    got = gpu_api.proliferate(plan, types, t_max, seed, seeding_mode=int(refcompat), kernel=kernel, shard=shard)
+    want = oracle.simulate(oplan, types, t_max, seed, refcompat=refcompat,
+                           shard=shard if shard[1] > 1 else (0, 1, 1))
+    return plan, got, want
+
+
+@pytest.mark.parametrize("kernel", list(KERNELS))
+@pytest.mark.parametrize("config,scale", [(1, 1.0), (2, 0.02), (3, 0.002), (4, 0.05)])
+def test_configs_bit_exact(gpu_api, oracle, kernel, config, scale):
+    w = synth.workload(config, scale)
+    if config == 4:
+        w.t_max = 456.0   # 19 generations of the fast type instead of 30: keeps the oracle within seconds
+    plan, got, want = _run_both(gpu_api, oracle, w.values, w.freqs, w.phi, w.types, w.t_max, w.seed, KERNELS[kernel])
+    assert np.array_equal(got.divisions, want["divisions"])
+    assert np.array_equal(got.counts, want["counts"])
+    rf, rr = plan.merge_rows(got.counts[0])
+    assert np.array_equal(rf, want["row_freq"][0]) and np.array_equal(rr, want["row_ratio"][0])
+
+
+@pytest.mark.parametrize("kernel", list(KERNELS))
+def test_sweep_sets_bit_exact(gpu_api, oracle, kernel):
+    """config 5 shape: many parameter sets on one histogram in one launch (32 sets x 3000 cells here)."""
+    values, freqs = synth.synthetic_histogram(3000)
+    types = synth.sweep_types(1024)[::32]
+    plan, got, want = _run_both(gpu_api, oracle, values, freqs, 0.5, types, 168.0, 0x5EED0005, KERNELS[kernel])
+    assert np.array_equal(got.divisions, want["divisions"])
+    assert np.array_equal(got.counts, want["counts"])
+
+
+def test_refcompat_seeding_bit_exact(gpu_api, oracle):
+    w = synth.workload(1)
+    _, got, want = _run_both(gpu_api, oracle, w.values, w.freqs, 1.0, w.types, w.t_max, 77, 0, refcompat=True)
+    assert np.array_equal(got.counts, want["counts"])
+    _, ideal, _ = _run_both(gpu_api, oracle, w.values, w.freqs, 1.0, w.types, w.t_max, 77, 0, refcompat=False)
+    assert not np.array_equal(got.counts, ideal.counts)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_shards_sum_to_whole(gpu_api, oracle, world):
+    """seed-cell units sharded over `world` GPUs: every shard equals the oracle's shard, and the int64 sum of the
+    shards equals the unsharded run (what the single NCCL reduce produces)."""
+    w = synth.workload(2, 0.01)
+    plan, whole, want = _run_both(gpu_api, oracle, w.values, w.freqs, w.phi, w.types, w.t_max, w.seed, 0)
+    total = np.zeros_like(whole.counts)
+    div = 0
+    for rank in range(world):
+        _, got, want_r = _run_both(gpu_api, oracle, w.values, w.freqs, w.phi, w.types, w.t_max, w.seed, 0,
+                                   shard=(rank, world, 64))
+        assert np.array_equal(got.counts, want_r["counts"])
+        total += got.counts
+        div += int(got.divisions[0])
+    assert np.array_equal(total, whole.counts) and div == int(whole.divisions[0])
+    assert np.array_equal(whole.counts, want["counts"])
+
+
+def test_result_independent_of_claim_unit(gpu_api, oracle):
+    w = synth.workload(2, 0.005)
+    plan = gpu_api.Plan(w.values, w.freqs, w.phi)
+    ref = gpu_api.proliferate(plan, w.types, w.t_max, w.seed)
+    for unit in (1, 7, 32, 100, 256):
+        got = gpu_api.proliferate(plan, w.types, w.t_max, w.seed, shard=(0, 1, unit))
+        assert np.array_equal(got.counts, ref.counts)
+
+
+def test_edge_cases(gpu_api, oracle):
+    # t_max = 0: output histogram == input histogram (every seed is out of time at level 0)
+    values, freqs = synth.synthetic_histogram(5000)
+    for kernel in (0, 1):
+        plan, got, want = _run_both(gpu_api, oracle, values, freqs, 1.0, np.array([synth.TYPES_CONFIG1]), 0.0, 5, kernel)
+        assert np.array_equal(got.counts, want["counts"]) and int(got.divisions[0]) == 0
+        rf, _ = plan.merge_rows(got.counts[0])
+        assert np.array_equal(rf, freqs[freqs > 0].astype(np.int64))
+    # all quiescent: identity for any t_max
+    plan, got, want = _run_both(gpu_api, oracle, values, freqs, 1.0, np.array([[(1.0, -1.0, -1.0)]]), 500.0, 5, 0)
+    rf, _ = plan.merge_rows(got.counts[0])
+    assert np.array_equal(rf, freqs[freqs > 0].astype(np.int64))
+    # a single cell, ragged tiny inputs, duplicate values, values below phi
+    for v, f, phi in (([100.0], [1], 1.0), ([3.0, 3.0, 0.5, 8.0], [2, 5, 9, 1], 1.0), ([5.0, 7.0], [0, 3], 0.0),
+                      ([1e-3, 2e-3], [4, 4], 1.0)):
+        for kernel in (0, 1):
+            plan, got, want = _run_both(gpu_api, oracle, np.array(v), np.array(f, dtype=np.uint64), phi,
+                                        np.array([synth.TYPES_CONFIG2]), 300.0, 9, kernel)
+            assert np.array_equal(got.counts, want["counts"])
+            assert np.array_equal(got.divisions, want["divisions"])
+    # empty histogram
+    plan = gpu_api.Plan(np.zeros(0), np.zeros(0, dtype=np.uint64), 1.0)
+    got = gpu_api.proliferate(plan, np.array([synth.TYPES_CONFIG1]), 100.0, 1)
+    assert got.counts.size == 0 and int(got.divisions[0]) == 0
+    # sigma = 0: deterministic timers; retry path with a high rejection rate (mean << sd)
+    for types in ([[(1.0, 30.0, 0.0)]], [[(0.6, 5.0, 40.0), (0.4, 1.0, 10.0)]]):
+        for kernel in (0, 1):
+            plan, got, want = _run_both(gpu_api, oracle, values[700:800], freqs[700:800], 50.0, np.array(types),
+                                        60.0, 11, kernel)
+            assert np.array_equal(got.counts, want["counts"]) and np.array_equal(got.divisions, want["divisions"])
+
+
+def test_deep_tree_imbalance(gpu_api, oracle):
+    """few fast lineages own all the work (config 4 shape): exercises spill ring + donation queue; the two kernels
+    and the oracle must still agree exactly, and fluorescence mass is conserved (phi never binds)."""
+    values = np.array([1000.0, 2000.0])
+    freqs = np.array([3, 2], dtype=np.uint64)
+    types = np.array([[(1.0, 24.0, 4.0)]])
+    plan, got, want = _run_both(gpu_api, oracle, values, freqs, 1e-7, types, 420.0, 4, 0)
+    assert np.array_equal(got.counts, want["counts"]) and np.array_equal(got.divisions, want["divisions"])
+    rf, _ = plan.merge_rows(got.counts[0])
+    assert int(rf.sum()) - 5 == int(got.divisions[0])
+    assert np.isclose(float((rf * plan.row_value).sum()), 3 * 1000.0 + 2 * 2000.0, rtol=1e-12)
+    simple = gpu_api.proliferate(plan, types, 420.0, 4, kernel=1)
+    assert np.array_equal(simple.counts, got.counts)
+
+
+def test_full_size_properties(gpu_api):
+    """BASELINE config 2 at FULL size (1e6 cells, ~1e8 divisions): size-independent properties."""
+    w = synth.workload(2)
+    plan = gpu_api.Plan(w.values, w.freqs, w.phi)
+    a = gpu_api.proliferate(plan, w.types, w.t_max, w.seed)
+    b = gpu_api.proliferate(plan, w.types, w.t_max, w.seed)
+    assert np.array_equal(a.counts, b.counts) and np.array_equal(a.divisions, b.divisions)   # run-to-run identical
+    rf, rr = plan.merge_rows(a.counts[0])
+    assert np.array_equal(rr.sum(axis=1), rf)                      # -r columns sum to the total column
+    assert (np.diff(plan.row_value) > 0).all()
+    # quiescent type (file index 3) never divides: all its cells are counted at k = 0 of their own bin
+    q = a.counts[0][:, 3]
+    assert int(q.sum()) == int(q[plan.bin_keybase].sum())
+    assert abs(int(q.sum()) - 0.18 * 1e6) < 5 * np.sqrt(1e6 * 0.18 * 0.82)
+    # without phi binding (tiny phi) leaves - seeds == divisions and mass is conserved
+    plan2 = gpu_api.Plan(w.values, w.freqs, 1e-9)
+    c = gpu_api.proliferate(plan2, w.types, 100.0, w.seed)
+    rf2, _ = plan2.merge_rows(c.counts[0])
+    assert int(rf2.sum()) - plan2.n_cells == int(c.divisions[0])
+    assert np.isclose(float((rf2 * plan2.row_value).sum()), float((w.values * w.freqs).sum()), rtol=1e-9)
+
+
+def test_cli_end_to_end(gpu_api, oracle, tmp_path):
+    """`procell -h .. -c .. -t .. -o .. -p .. -r` writes the same rows the oracle predicts, in the reference's format."""
+    from cuda_pro_cell_b200 import _lib
+    w = synth.workload(1)
+    h, c, o = tmp_path / "h.txt", tmp_path / "c.txt", tmp_path / "o.txt"
+    h.write_text(synth.histogram_text(w.values, w.freqs))
+    c.write_text(synth.types_text(w.types[0]))
+    r = subprocess.run([str(_lib.CLI_PATH), "-h", str(h), "-c", str(c), "-t", "168", "-o", str(o), "-p", "2.5", "-r",
+                        "--seed", "1234"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    oplan = oracle.OraclePlan(w.values, w.freqs, 2.5)
+    want = oracle.simulate(oplan, w.types, 168.0, 1234)
+    lines = [ln.split("\t") for ln in o.read_text().splitlines()]
+    nz = want["row_freq"][0] > 0
+    assert len(lines) == int(nz.sum())
+    assert [ln[0] for ln in lines] == ["%.10g" % v for v in oplan.row_value[nz]]
+    assert [int(ln[1]) for ln in lines] == want["row_freq"][0][nz].tolist()
+    assert [[int(x) for x in ln[2:]] for ln in lines] == want["row_ratio"][0][nz].tolist()
+    # default phi (no -p) and stdout output
+    r2 = subprocess.run([str(_lib.CLI_PATH), "-h", str(h), "-c", str(c), "-t", "168", "--seed", "1234"],
+                        capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0
+    oplan2 = oracle.OraclePlan(w.values, w.freqs, 0.0)
+    want2 = oracle.simulate(oplan2, w.types, 168.0, 1234)
+    out_rows = [ln.split("\t") for ln in r2.stdout.splitlines()]
+    nz2 = want2["row_freq"][0] > 0
+    assert [int(ln[1]) for ln in out_rows] == want2["row_freq"][0][nz2].tolist()
