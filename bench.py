@@ -1,0 +1,364 @@
+#!/usr/bin/env python3
+"""bench.py - simulated cell divisions per second of the proliferation hot path on N B200s of one node.
+
+A step = one full simulation of the workload (BASELINE.json configs[1] shape: 1e6 seed cells per GPU, 3
+proliferating types + quiescent, t_max = 240, -r per-type counts, phi = 0.5; ~1.1e8 divisions per GPU).
+N > 1 is weak scaling: the histogram holds N x 1e6 cells, seed-cell units are sharded rank-strided, and the step
+ends with ONE NCCL reduce (sum, int64) of the count tensor + division counters to rank 0.
+
+  value     whole-job divisions/s, tables resident in HBM, CUDA-event time per step summed over K steps (L2 flushed
+            between steps, outside the events), max over ranks
+  e2e       the same metric through the C ABI with HOST buffers: histogram arrays -> plan -> H2D tables -> kernel ->
+            D2H count tensor -> merged rows, wall-clock per step bracketed by synchronize
+  roofline  instruction-issue roofline (this path is FP64/INT-issue bound, not HBM/tensor bound - DESIGN.md):
+            achieved divisions/s over the RNG-only ceiling kernel measured in the same run; HBM figures for completeness
+  cpu_baseline  the CPU oracle (oracle/, a port with the same Philox streams) on this box's host cores
+
+--impl reference times the UNMODIFIED reference CUDA build (oracle/_ref/procell_ref, one B200, whole-process wall
+clock: it has no internal timers and no resident mode) on the largest BASELINE config it can run.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "simulated cell divisions/sec"
+UNIT = "divisions/s"
+CELLS_PER_GPU = 1_000_000
+FLUSH_BYTES = 256 << 20
+SHARD_UNIT = 256
+
+
+def workload_for(n_gpus: int):
+    from cuda_pro_cell_b200 import synth
+    w = synth.workload(2)
+    if n_gpus > 1:
+        w.values, w.freqs = synth.synthetic_histogram(CELLS_PER_GPU * n_gpus)
+        w.n_cells = CELLS_PER_GPU * n_gpus
+    return w
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(w, max_seconds=25.0):
+    """The oracle port on this box's host cores, on the same workload (full config-2 shard of one GPU, repeated
+    until ~10 s of CPU work or 3 runs)."""
+    import oracle_lib
+    from cuda_pro_cell_b200 import synth
+    values, freqs = synth.synthetic_histogram(CELLS_PER_GPU)
+    plan = oracle_lib.OraclePlan(values, freqs, w.phi)
+    cores = oracle_lib.n_host_threads()
+    t_total, div_total, runs = 0.0, 0, 0
+    while runs < 3 and t_total < 10.0:
+        t0 = time.perf_counter()
+        r = oracle_lib.simulate(plan, w.types, w.t_max, w.seed + runs, n_threads=cores)
+        t_total += time.perf_counter() - t0
+        div_total += int(r["divisions"].sum())
+        runs += 1
+        if t_total > max_seconds:
+            break
+    return {"value": div_total / t_total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d full run(s) of the 1e6-cell config-2 workload (%.3g divisions, %.2f s)" % (runs, div_total, t_total)}
+
+
+def run_reference(args):
+    """--impl reference: the unmodified reference CUDA binary, whole-process wall clock per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ref = ROOT / "oracle" / "_ref" / "procell_ref"
+    import oracle_lib
+    from cuda_pro_cell_b200 import synth
+    w = workload_for(1)
+    cfg = {"workload": "BASELINE configs[1]: 1e6 seed cells, types 0.40/48.33/21.6 0.25/86.3/26.8 0.17/24/6 + 0.18 quiescent, "
+                       "t_max=240, phi=0.5, -r", "n_cells": int(w.n_cells), "l2": "n/a (separate process per step)"}
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg}
+    if not ref.exists():
+        # no reference binary on this box: time the oracle port on all host cores instead
+        cb = cpu_baseline(w)
+        line.update({"value": cb["value"], "ms_per_step": None, "cpu_baseline": cb,
+                     "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "note": "oracle/_ref/procell_ref missing; oracle port timed instead"})
+        print(json.dumps(line))
+        return 0
+    # expected divisions of the workload (equal in law to the reference's): from the oracle, once
+    tmp = Path(tempfile.mkdtemp(prefix="procell_ref_"))
+    steps_total = max(1, args.warmup) + args.steps
+    attempts = [(w, "configs[1] full (1e6 cells)")]
+    w_small = synth.workload(2, 0.1)
+    attempts.append((w_small, "configs[1] at 1e5 cells (the full size failed on the reference build)"))
+    w1 = synth.workload(1)
+    attempts.append((w1, "configs[0] (1e4 cells, t_max=168; larger inputs failed on the reference build)"))
+    for wl, label in attempts:
+        (tmp / "h.txt").write_text(synth.histogram_text(wl.values, wl.freqs))
+        (tmp / "c.txt").write_text(synth.types_text(wl.types[0]))
+        cmd = [str(ref), "-h", str(tmp / "h.txt"), "-c", str(tmp / "c.txt"), "-t", repr(float(wl.t_max)),
+               "-p", repr(float(wl.phi)), "-o", str(tmp / "o.txt")] + (["-r"] if wl.track_ratio else [])
+        oplan = oracle_lib.OraclePlan(wl.values, wl.freqs, wl.phi)
+        expect = oracle_lib.simulate(oplan, wl.types, wl.t_max, wl.seed)
+        exp_div = int(expect["divisions"].sum())
+        exp_leaves = int(expect["row_freq"].sum())
+        times, ok, leaves = [], True, []
+        n_warm, n_steps, i = max(1, args.warmup), args.steps, 0
+        while i < n_warm + n_steps:
+            t0 = time.perf_counter()
+            try:
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=150)
+            except subprocess.TimeoutExpired:
+                ok = False
+                break
+            dt = time.perf_counter() - t0
+            if r.returncode != 0 or not (tmp / "o.txt").exists():
+                ok = False
+                break
+            got = sum(int(ln.split("\t")[1]) for ln in (tmp / "o.txt").read_text().splitlines() if ln.strip())
+            leaves.append(got)
+            if abs(got - exp_leaves) > 0.2 * exp_leaves:   # lost subtrees (CDP2 pending-launch pool) or truncation
+                ok = False
+                break
+            if i == 0:   # bound the whole arm to ~2.5 minutes: each step is a whole process (>= 1.05 s apart)
+                n_warm = 1
+                n_steps = max(3, min(args.steps, int(150.0 / max(dt, 1.05)) - 1))
+            else:
+                times.append(dt)
+            (tmp / "o.txt").unlink()
+            if dt < 1.05:
+                time.sleep(1.05 - dt)      # the reference seeds from time(NULL): keep runs in distinct seconds
+            i += 1
+        if ok and times:
+            total = sum(times)
+            value = exp_div * len(times) / total
+            cfg["workload_run"] = label
+            line.update({"value": value, "ms_per_step": 1e3 * total / len(times), "steps": len(times),
+                         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
+                                          "sample": "%s; unmodified reference CUDA build (sm_100, CDP2) on one B200, "
+                                                    "whole-process wall clock, %d runs; divisions = oracle expectation %d "
+                                                    "(reference leaves %s vs expected %d)"
+                                                    % (label, len(times), exp_div, leaves[-3:], exp_leaves)},
+                         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            print(json.dumps(line))
+            return 0
+    line.update({"unavailable": "reference binary failed on every attempted input"})
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from cuda_pro_cell_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K = args.steps
+
+    w = workload_for(world)
+    n_types = w.types.shape[1]
+    plan = api.Plan(w.values, w.freqs, w.phi)
+    eng = api.Engine(local_rank)
+    shard = (rank, world, SHARD_UNIT)
+    eng.load(plan, w.types, w.t_max, w.seed, shard=shard)
+    n_counts = plan.n_keys * n_types
+    buf = torch.zeros(n_counts + 1, dtype=torch.int64, device=dev)        # counts + division counter: one reduce
+    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step(seed):
+        eng.run(seed, stream.cuda_stream, buf.data_ptr(), buf.data_ptr() + 8 * n_counts)
+        if world > 1:
+            dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        flush.fill_(i)
+        step(w.seed + i)
+    barrier()
+    # status check once before timing (finish() synchronises and reads the device status word)
+    eng.finish(stream.cuda_stream, fetch=False)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    div_acc = torch.zeros(1, dtype=torch.int64, device=dev)
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(i & 0xFF)                      # L2 flush (256 MiB > 126 MB L2), outside the event pair
+        evs[i][0].record(stream)
+        step(w.seed + 1000 + i)
+        evs[i][1].record(stream)
+        div_acc += buf[n_counts:]                  # exact division total of the timed steps (after the end event)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    gpu_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t_ms = torch.tensor([gpu_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    gpu_ms = float(t_ms.item())
+    eng.finish(stream.cuda_stream, fetch=False)    # device status word: no pool overflow / watchdog abort
+    div_timed = int(div_acc.item())                # rank 0 holds the reduced totals
+    div_per_step = div_timed / K
+    value = div_timed / (gpu_ms * 1e-3) if rank == 0 else 0.0
+
+    # ---- end to end through the C ABI with host buffers
+    E = max(1, args.e2e_steps)
+    h2d = plan.n_bins * 4 * 2 + plan.n_bins + 4 + w.types.size // 3 * (8 + 1 + 16) + 256 * 8
+    d2h = (n_counts + 1) * 8
+    host_values, host_freqs = w.values.copy(), w.freqs.copy()
+    e2e_div = 0
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(E):
+        p = api.Plan(host_values, host_freqs, w.phi)                       # parser.cu:68-154 work, on the host
+        eng.load(p, w.types, w.t_max, w.seed + i, shard=shard)             # H2D tables
+        eng.run(w.seed + 2000 + i, stream.cuda_stream, buf.data_ptr(), buf.data_ptr() + 8 * n_counts)
+        if world > 1:
+            dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
+        host = buf.cpu()                                                   # D2H count tensor + division counter
+        eng.finish(stream.cuda_stream, fetch=False)
+        if rank == 0:
+            rf, rr = p.merge_rows(host[:n_counts].numpy().reshape(plan.n_keys, n_types))
+            e2e_div += int(host[n_counts])
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    t_e = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    t_e2e = float(t_e.item())
+
+    if rank == 0:
+        # ---- roofline: the RNG-only ceiling kernel, measured now on this GPU
+        ms_c, pairs = api.rng_ceiling(local_rank, 4096)
+        ceiling = pairs / (ms_c * 1e-3)
+        per_gpu = value / world
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        alg_bytes = float(h2d + d2h)          # tables read once + count tensor written once per launch
+        ms_step = gpu_ms / K
+        roofline = {"bound": "fp64+int instruction issue (not hbm/tensor; see DESIGN.md)",
+                    "achieved": per_gpu / 1e9, "peak": ceiling / 1e9, "unit": "Gdivisions/s per GPU",
+                    "frac": per_gpu / ceiling,
+                    "peak_source": "k_rng_ceiling measured live: one Philox4x32-10 block + Box-Muller pair + 2 timers per division, no tree/atomics",
+                    "traffic": None,
+                    "hbm": {"achieved": alg_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                            "algorithmic_bytes_per_launch": alg_bytes}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BASELINE configs[1]: 1e6 seed cells per GPU (synthetic 1024-channel histogram), types "
+                                       "0.40/48.33/21.6 0.25/86.3/26.8 0.17/24/6 + 0.18 quiescent, t_max=240, phi=0.5, -r",
+                           "n_cells": int(plan.n_cells), "divisions_per_step": div_per_step,
+                           "sharding": "seed-cell units of %d, rank-strided; one NCCL reduce(sum,int64) per step" % SHARD_UNIT,
+                           "l2": "flushed between steps (256 MiB write), outside the timed events"},
+                "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
+                "e2e": {"value": e2e_div / t_e2e if t_e2e > 0 else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "steps": E,
+                        "path": "api.Plan (host) -> procell_engine_load (H2D) -> procell_engine_run -> reduce -> D2H -> merge_rows"},
+                "gpu_launches": 2 * K, "kernels_per_step": ["k_queue_init", "k_proliferate_coop"],
+                "clocks": clocks, "roofline": roofline}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(w)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

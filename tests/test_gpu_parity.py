@@ -87,11 +87,12 @@ def test_edge_cases(gpu_api, oracle):
         plan, got, want = _run_both(gpu_api, oracle, values, freqs, 1.0, np.array([synth.TYPES_CONFIG1]), 0.0, 5, kernel)
         assert np.array_equal(got.counts, want["counts"]) and int(got.divisions[0]) == 0
         rf, _ = plan.merge_rows(got.counts[0])
-        assert np.array_equal(rf, freqs[freqs > 0].astype(np.int64))
+        assert np.array_equal(rf[rf > 0], freqs[freqs > 0].astype(np.int64))
+        assert np.array_equal(plan.row_value[rf > 0], values[freqs > 0])
     # all quiescent: identity for any t_max
     plan, got, want = _run_both(gpu_api, oracle, values, freqs, 1.0, np.array([[(1.0, -1.0, -1.0)]]), 500.0, 5, 0)
     rf, _ = plan.merge_rows(got.counts[0])
-    assert np.array_equal(rf, freqs[freqs > 0].astype(np.int64))
+    assert np.array_equal(rf[rf > 0], freqs[freqs > 0].astype(np.int64))
     # a single cell, ragged tiny inputs, duplicate values, values below phi
     for v, f, phi in (([100.0], [1], 1.0), ([3.0, 3.0, 0.5, 8.0], [2, 5, 9, 1], 1.0), ([5.0, 7.0], [0, 3], 0.0),
                       ([1e-3, 2e-3], [4, 4], 1.0)):
