@@ -19,6 +19,8 @@
 #include "procell_math_tables.inc"
 #include "sim_kernels.h"
 
+#include <cstdlib>
+
 using namespace procell_b200;
 
 namespace {
@@ -39,6 +41,17 @@ struct DevBuf {
 };
 
 const uint64_t kLogRows[1 << PCM_LOG_N_BITS][2] = { PCM_LOG_TABLE_ROWS };
+
+void set_round_keys(SimParams& P, uint64_t seed)
+{
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        P.rk[2 * r] = k0;
+        P.rk[2 * r + 1] = k1;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
 
 int cuda_fail(cudaError_t e, const char* what)
 {
@@ -61,6 +74,7 @@ struct procell_engine {
     SimParams P{};
     bool loaded = false;
     int kernel = PROCELL_KERNEL_COOP;
+    int warps = 16;
     int grid = 0, block = 0;
     size_t smem = 0;
     size_t counts_len = 0;
@@ -194,13 +208,15 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     P.shard_rank = sp->shard_world > 1 ? sp->shard_rank : 0;
     P.refcompat = sp->seeding_mode == PROCELL_SEEDING_REFCOMPAT;
     P.t_max = sp->t_max;
-    P.key0 = (uint32_t)sp->seed; P.key1 = (uint32_t)(sp->seed >> 32);
+    set_round_keys(P, sp->seed);
 
-    /* claim unit: 256 seed cells, smaller when there are too few cells to give every warp of every GPU work */
+    /* claim unit: 32 seed cells = one SEED iteration of a warp (small units keep the tail balanced: a warp claims
+     * a new unit with one atomic whenever its stack runs low); smaller still when there are too few cells to
+     * give every warp of every GPU several units */
     uint32_t unit = sp->shard_unit;
     if (unit == 0) {
-        const double per_warp = (double)plan->n_cells * (double)S / (148.0 * kCoopWarps * 4.0 * P.shard_world);
-        unit = 256;
+        const double per_warp = (double)plan->n_cells * (double)S / (148.0 * kCoopWarpsMax * 4.0 * P.shard_world);
+        unit = 32;
         while (unit > 1 && (double)unit > per_warp) unit >>= 1;
     }
     P.unit = unit;
@@ -219,17 +235,19 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     } else {
         int max_smem = 0;
         CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, en->device), "query smem");
-        const size_t fixed = coop_smem_bytes(0);
+        const char* wenv = getenv("PROCELL_COOP_WARPS");     /* tuning knob: 16 or 24 warps per CTA */
+        en->warps = (wenv && atoi(wenv) == 16) ? 16 : 24;
+        const size_t fixed = coop_smem_bytes(en->warps, 0);
         size_t slots = ((size_t)max_smem > fixed + 1024) ? ((size_t)max_smem - fixed - 1024) / 4 : 0;
         if (slots > en->counts_len) slots = en->counts_len;
         P.smem_hist_slots = (uint32_t)slots;
-        en->smem = coop_smem_bytes(P.smem_hist_slots);
+        en->smem = coop_smem_bytes(en->warps, P.smem_hist_slots);
         int grid = 0;
-        CU(coop_max_grid(en->device, en->smem, &grid), "occupancy query");
+        CU(coop_max_grid(en->device, en->warps, en->smem, &grid), "occupancy query");
         if (grid <= 0) return fail(PROCELL_ERR_CUDA, "cooperative kernel does not fit on this device");
         en->grid = grid;
-        en->block = kCoopThreads;
-        CU(en->spill.reserve((size_t)grid * kCoopWarps * kSpillCap * kChunkWords * 8), "alloc spill rings");
+        en->block = en->warps * 32;
+        CU(en->spill.reserve((size_t)grid * en->warps * kSpillCap * kChunkWords * 8), "alloc spill rings");
         P.spill = (unsigned long long*)en->spill.p;
     }
     en->loaded = true;
@@ -242,18 +260,18 @@ int procell_engine_run(procell_engine* en, uint64_t seed, void* stream_v, int64_
     cudaStream_t stream = (cudaStream_t)stream_v;
     CU(cudaSetDevice(en->device), "cudaSetDevice");
     SimParams P = en->P;
-    P.key0 = (uint32_t)seed; P.key1 = (uint32_t)(seed >> 32);
+    set_round_keys(P, seed);
     if (d_counts) P.counts = (long long*)d_counts;
     if (d_divisions) P.divisions = (long long*)d_divisions;
-    en->timed = (d_counts == nullptr);
-    if (en->timed) CU(cudaEventRecord(en->ev0, stream), "event record");
+    en->timed = true;
+    CU(cudaEventRecord(en->ev0, stream), "event record");
     CU(cudaMemsetAsync(P.counts, 0, en->counts_len * 8, stream), "zero counts");
     CU(cudaMemsetAsync(P.divisions, 0, en->n_sets * 8, stream), "zero divisions");
     CU(launch_queue_init(P.q_seq, P.ctl, stream), "launch k_queue_init");
     if (en->kernel == PROCELL_KERNEL_SIMPLE) CU(launch_simple(P, en->grid, stream), "launch k_proliferate_simple");
-    else CU(launch_coop(P, en->grid, stream), "launch k_proliferate_coop");
+    else CU(launch_coop(P, en->warps, en->grid, stream), "launch k_proliferate_coop");
     en->launches_last = 2;
-    if (en->timed) CU(cudaEventRecord(en->ev1, stream), "event record");
+    CU(cudaEventRecord(en->ev1, stream), "event record");
     return PROCELL_OK;
 }
 
@@ -313,9 +331,11 @@ int procell_rng_ceiling(int device, int iters, double* ms_out, double* pairs_out
     const int block = 256, grid = sms * 8;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    CU(launch_rng_ceiling(grid, block, 16, d_tab, 48.33, 21.6, 168.0, 1u, 2u, d_sink, nullptr), "warm-up launch");
+    SimParams K{};
+    set_round_keys(K, 0x0000000200000001ull);
+    CU(launch_rng_ceiling(grid, block, 16, d_tab, 48.33, 21.6, 168.0, K.rk, d_sink, nullptr), "warm-up launch");
     cudaEventRecord(e0);
-    CU(launch_rng_ceiling(grid, block, iters, d_tab, 48.33, 21.6, 168.0, 1u, 2u, d_sink, nullptr), "launch");
+    CU(launch_rng_ceiling(grid, block, iters, d_tab, 48.33, 21.6, 168.0, K.rk, d_sink, nullptr), "launch");
     cudaEventRecord(e1);
     CU(cudaEventSynchronize(e1), "rng ceiling kernel");
     float ms = 0.f;

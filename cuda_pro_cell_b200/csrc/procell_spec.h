@@ -41,6 +41,19 @@
 #define PCS_SQRT(a) __builtin_sqrt((a))
 #endif
 
+PCS_HD double pcs_bits2d(uint64_t u);
+
+/* scalar coefficients: on the device they are read from a __constant__ table, so FP64 instructions take them
+ * as constant-bank operands instead of rebuilding 64-bit immediates in registers every iteration */
+#if defined(__CUDACC__)
+static __constant__ double pcs_coef[PCM_N_COEF] = { PCM_COEF_HEXFLOATS };
+#endif
+#if defined(__CUDA_ARCH__)
+#define PCS_C(NAME) (pcs_coef[PCM_IDX_##NAME])
+#else
+#define PCS_C(NAME) (pcs_bits2d(PCM_BITS_##NAME))
+#endif
+
 PCS_HD double pcs_bits2d(uint64_t u)
 {
 #if defined(__CUDA_ARCH__)
@@ -103,6 +116,44 @@ PCS_HD pcs_u32x4 pcs_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32
     return o;
 }
 
+/* the same ten rounds with the 20 round keys precomputed (rk[2r] = k0 + r*W0, rk[2r+1] = k1 + r*W1): on the
+ * device rk points into the kernel parameter block, so every key is a constant-bank operand of its LOP3 */
+PCS_HD void pcs_round_keys(uint32_t k0, uint32_t k1, uint32_t* rk)
+{
+    for (int r = 0; r < 10; ++r) {
+        rk[2 * r] = k0;
+        rk[2 * r + 1] = k1;
+        k0 += PCS_PHILOX_W0;
+        k1 += PCS_PHILOX_W1;
+    }
+}
+
+PCS_HD pcs_u32x4 pcs_philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t* rk)
+{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)PCS_PHILOX_M0 * (uint64_t)c0;
+        uint64_t p1 = (uint64_t)PCS_PHILOX_M1 * (uint64_t)c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk[2 * r];
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    pcs_u32x4 o;
+    o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+PCS_HD pcs_u32x4 pcs_draw_rk(uint32_t root, uint32_t set, uint32_t retry, uint32_t tag, uint64_t heap,
+                             const uint32_t* rk)
+{
+    return pcs_philox4x32_10_rk(root, set | (retry << 16) | (tag << 24), (uint32_t)heap, (uint32_t)(heap >> 32), rk);
+}
+
 /* counter layout: c0 = root cell id, c1 = set | retry<<16 | tag<<24, (c3:c2) = heap index */
 PCS_HD pcs_u32x4 pcs_draw(uint32_t root, uint32_t set, uint32_t retry, uint32_t tag, uint64_t heap,
                           uint32_t k0, uint32_t k1)
@@ -116,7 +167,7 @@ PCS_HD pcs_u32x4 pcs_draw(uint32_t root, uint32_t set, uint32_t retry, uint32_t 
 PCS_HD double pcs_unit_from_mant52(uint64_t mant52)
 {
     double d = pcs_bits2d(0x3FF0000000000000ULL | mant52);      /* [1,2) */
-    return PCS_ADD(d, -pcs_bits2d(PCM_BITS_ONE_M));              /* exact */
+    return PCS_ADD(d, -PCS_C(ONE_M));              /* exact */
 }
 
 PCS_HD double pcs_u53(uint32_t lo, uint32_t hi)
@@ -137,14 +188,14 @@ PCS_HD double pcs_neg2log(double u, const double* tab)
     double invc = tab[2 * i];
     double logc = tab[2 * i + 1];
     double r = PCS_FMA(z, invc, -1.0);
-    double q = pcs_bits2d(PCM_BITS_LOG1P_B6);
-    q = PCS_FMA(q, r, pcs_bits2d(PCM_BITS_LOG1P_B5));
-    q = PCS_FMA(q, r, pcs_bits2d(PCM_BITS_LOG1P_B4));
-    q = PCS_FMA(q, r, pcs_bits2d(PCM_BITS_LOG1P_B3));
-    q = PCS_FMA(q, r, pcs_bits2d(PCM_BITS_LOG1P_B2));
+    double q = PCS_C(LOG1P_B6);
+    q = PCS_FMA(q, r, PCS_C(LOG1P_B5));
+    q = PCS_FMA(q, r, PCS_C(LOG1P_B4));
+    q = PCS_FMA(q, r, PCS_C(LOG1P_B3));
+    q = PCS_FMA(q, r, PCS_C(LOG1P_B2));
     double r2 = PCS_MUL(r, r);
     double l = PCS_FMA(r2, q, r);
-    double base = PCS_FMA((double)k, pcs_bits2d(PCM_BITS_LN2), logc);
+    double base = PCS_FMA((double)k, PCS_C(LN2), logc);
     double lg = PCS_ADD(base, l);
     return PCS_MUL(lg, -2.0);
 }
@@ -157,25 +208,25 @@ PCS_HD void pcs_sincos2pi(uint64_t v, double* s_out, double* c_out)
     uint32_t q = (uint32_t)(v >> 61);
     uint64_t y = (v >> 9) & 0x000FFFFFFFFFFFFFULL;
     if (q & 1u) y ^= 0x000FFFFFFFFFFFFFULL;
-    double th = PCS_MUL(pcs_unit_from_mant52(y), pcs_bits2d(PCM_BITS_PIO4));
+    double th = PCS_MUL(pcs_unit_from_mant52(y), PCS_C(PIO4));
     double t2 = PCS_MUL(th, th);
-    double ps = pcs_bits2d(PCM_BITS_SIN_S7);
-    ps = PCS_FMA(ps, t2, pcs_bits2d(PCM_BITS_SIN_S6));
-    ps = PCS_FMA(ps, t2, pcs_bits2d(PCM_BITS_SIN_S5));
-    ps = PCS_FMA(ps, t2, pcs_bits2d(PCM_BITS_SIN_S4));
-    ps = PCS_FMA(ps, t2, pcs_bits2d(PCM_BITS_SIN_S3));
-    ps = PCS_FMA(ps, t2, pcs_bits2d(PCM_BITS_SIN_S2));
-    ps = PCS_FMA(ps, t2, pcs_bits2d(PCM_BITS_SIN_S1));
+    double ps = PCS_C(SIN_S7);
+    ps = PCS_FMA(ps, t2, PCS_C(SIN_S6));
+    ps = PCS_FMA(ps, t2, PCS_C(SIN_S5));
+    ps = PCS_FMA(ps, t2, PCS_C(SIN_S4));
+    ps = PCS_FMA(ps, t2, PCS_C(SIN_S3));
+    ps = PCS_FMA(ps, t2, PCS_C(SIN_S2));
+    ps = PCS_FMA(ps, t2, PCS_C(SIN_S1));
     double t3 = PCS_MUL(th, t2);
     double sn = PCS_FMA(t3, ps, th);
-    double pc = pcs_bits2d(PCM_BITS_COS_C8);
-    pc = PCS_FMA(pc, t2, pcs_bits2d(PCM_BITS_COS_C7));
-    pc = PCS_FMA(pc, t2, pcs_bits2d(PCM_BITS_COS_C6));
-    pc = PCS_FMA(pc, t2, pcs_bits2d(PCM_BITS_COS_C5));
-    pc = PCS_FMA(pc, t2, pcs_bits2d(PCM_BITS_COS_C4));
-    pc = PCS_FMA(pc, t2, pcs_bits2d(PCM_BITS_COS_C3));
-    pc = PCS_FMA(pc, t2, pcs_bits2d(PCM_BITS_COS_C2));
-    pc = PCS_FMA(pc, t2, pcs_bits2d(PCM_BITS_COS_C1));
+    double pc = PCS_C(COS_C8);
+    pc = PCS_FMA(pc, t2, PCS_C(COS_C7));
+    pc = PCS_FMA(pc, t2, PCS_C(COS_C6));
+    pc = PCS_FMA(pc, t2, PCS_C(COS_C5));
+    pc = PCS_FMA(pc, t2, PCS_C(COS_C4));
+    pc = PCS_FMA(pc, t2, PCS_C(COS_C3));
+    pc = PCS_FMA(pc, t2, PCS_C(COS_C2));
+    pc = PCS_FMA(pc, t2, PCS_C(COS_C1));
     double cs = PCS_FMA(t2, pc, 1.0);
     /* q: 0 (s,c) 1 (c,s) 2 (c,-s) 3 (s,-c) 4 (-s,-c) 5 (-c,-s) 6 (-c,s) 7 (-s,c) */
     bool swap = ((q + 1u) & 2u) != 0u;

@@ -32,10 +32,15 @@ namespace {
 constexpr uint32_t kRingMask = kStackCap - 1;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
-/* node word D: set[0:16) | type[16:22) | kdiv[22:28) | pending-children mask[28:30) | retry[32:40) */
-__device__ __forceinline__ uint64_t pack_d(uint32_t set, uint32_t type, uint32_t kdiv, uint32_t mask, uint32_t retry)
+/* A node = a cell that WILL divide: 4 x u64, field-major in the ring
+ *   A  t_div   time of its division = birth time of its daughters (double bits)
+ *   B  heap    tree path: root = 1, daughters 2h and 2h+1 (Philox counter words 2,3)
+ *   C  root cell id | key << 32, key = count-tensor index of (set, bin, level of THIS node, type)
+ *   D  lo: set[0:16) | type[16:22) | rem[22:28) | pending-daughter mask[28:30); hi: retry[0:8)
+ *      rem = halvings still allowed below this node's daughters (daughters divide iff rem > 0) */
+__device__ __forceinline__ uint32_t pack_dlo(uint32_t set, uint32_t type, uint32_t rem, uint32_t mask)
 {
-    return (uint64_t)(set | (type << 16) | (kdiv << 22) | (mask << 28)) | ((uint64_t)retry << 32);
+    return set | (type << 16) | (rem << 22) | (mask << 28);
 }
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
@@ -54,6 +59,13 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 {
     unsigned long long v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ int ld_acquire_s32(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -82,16 +94,16 @@ __device__ __forceinline__ void hist_add(const SimParams& P, uint32_t* s_hist, u
     }
 }
 
-/* every lane may carry `inc` (0..2) leaves for `key`; equal keys are merged, one atomic per distinct key */
+/* every lane may carry `inc` (0..2) leaves for `key`; equal keys are merged (MATCH.ANY + REDUX), one shared
+ * atomic per distinct key */
 __device__ __forceinline__ void warp_count_leaves(const SimParams& P, uint32_t* s_hist, uint32_t key, uint32_t inc)
 {
-    unsigned has = __ballot_sync(kFull, inc > 0);
+    const unsigned has = __ballot_sync(kFull, inc > 0);
     if (has == 0) return;
-    unsigned two = __ballot_sync(kFull, inc == 2);
     if (inc > 0) {
-        unsigned grp = __match_any_sync(has, key);
-        if ((threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1))
-            hist_add(P, s_hist, key, (uint32_t)(__popc(grp) + __popc(grp & two)));
+        const unsigned grp = __match_any_sync(has, key);
+        const uint32_t total = __reduce_add_sync(grp, inc);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1)) hist_add(P, s_hist, key, total);
     }
 }
 
@@ -226,13 +238,15 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P)
         atomicSub(&ctl->active, 1);
     }
     unsigned long long t0 = global_timer_ns();
+    unsigned backoff = 256;
     for (;;) {
         int state = 0;   /* 0 wait, 1 try, 2 exit */
         if (w.lane == 0) {
-            int act = ld_volatile_s32(&ctl->active);
-            __threadfence();
-            unsigned long long h = ld_volatile_u64(&ctl->q_head);
-            unsigned long long t = ld_volatile_u64(&ctl->q_tail);
+            /* `active` is read (acquire) BEFORE the queue indices: a warp that pushed and then went idle
+             * decremented it after its push, so active == 0 implies all pushes are visible below */
+            int act = ld_acquire_s32(&ctl->active);
+            unsigned long long h = ld_acquire_u64(&ctl->q_head);
+            unsigned long long t = ld_acquire_u64(&ctl->q_tail);
             int st = ld_volatile_s32(&ctl->status);
             if (st != kStatusOk) state = 2;
             else if (h < t) state = 1;
@@ -257,31 +271,38 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P)
             }
             if (w.lane == 0) { __threadfence(); atomicSub(&ctl->active, 1); }
         } else {
-            __nanosleep(400);
+            __nanosleep(backoff);
+            if (backoff < 4096) backoff <<= 1;
         }
     }
 }
 
 /* result of building one seed cell (cell.cu:25-79 with type == -1, t == 0) */
 struct SeedOut {
-    uint32_t keybase;   /* ((set*n_keys + bin_keybase) * n_types + type) */
+    uint32_t key;       /* count-tensor index of (set, bin, level 0, type) */
     uint32_t type, kdiv;
     int kind;           /* 0 dropped, 1 leaf at level 0, 2 living root */
     double t_div;
 };
 
-__device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* s_log, uint32_t root, uint32_t set)
+/* bin of a seed cell: largest b with bin_start[b] <= root (parser.cu "bounds") */
+__device__ __forceinline__ uint32_t find_bin(const SimParams& P, uint32_t root)
 {
-    SeedOut o;
-    /* bin of this seed cell: largest b with bin_start[b] <= root (parser.cu "bounds") */
     uint32_t lo = 0, hi = P.n_bins;
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
         if (__ldg(P.bin_start + mid) <= root) lo = mid; else hi = mid;
     }
-    const uint32_t kd = __ldg(P.bin_kdiv + lo);
+    return lo;
+}
+
+__device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* s_log, uint32_t root, uint32_t set,
+                                              uint32_t bin)
+{
+    SeedOut o;
+    const uint32_t kd = __ldg(P.bin_kdiv + bin);
     const uint32_t T = P.n_types;
-    pcs_u32x4 w = pcs_draw(root, set, 0u, PCS_TAG_SEED, 0ull, P.key0, P.key1);
+    pcs_u32x4 w = pcs_draw_rk(root, set, 0u, PCS_TAG_SEED, 0ull, P.rk);
     const double u_type = pcs_u53(w.x, w.y);
     const double u_age = pcs_u53(w.z, w.w);
     uint32_t j = 0;
@@ -291,7 +312,7 @@ __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* 
     const double2 ms = __ldg(P.type_musd + (size_t)set * T + type);
     o.type = type;
     o.kdiv = kd & 63u;
-    o.keybase = (set * P.n_keys + __ldg(P.bin_keybase + lo)) * T + type;
+    o.key = (set * P.n_keys + __ldg(P.bin_keybase + bin)) * T + type;
     const bool count0 = (kd & 0x80u) != 0u;
     if (ms.x < 0.0) {                                          /* quiescent: timer -1, t 0 -> out_of_time */
         o.kind = count0 ? 1 : 0;
@@ -300,7 +321,7 @@ __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* 
     }
     double timer = ms.x;
     for (uint32_t retry = 0; retry < PCS_MAX_RETRY; ++retry) { /* root = child 1 of the virtual division at heap 0 */
-        pcs_u32x4 b = pcs_draw(root, set, retry, PCS_TAG_DIVISION, 0ull, P.key0, P.key1);
+        pcs_u32x4 b = pcs_draw_rk(root, set, retry, PCS_TAG_DIVISION, 0ull, P.rk);
         double z0, z1;
         pcs_normal_pair(b, s_log, (P.refcompat && retry == 0u) ? u_type : 0.0, &z0, &z1);
         double cand = pcs_timer(ms.x, ms.y, z1);
@@ -316,12 +337,13 @@ __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* 
 
 }  // namespace
 
-__global__ void __launch_bounds__(kCoopThreads, 1) k_proliferate_coop(const SimParams P)
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid_constant__ SimParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_log = reinterpret_cast<double*>(smem_raw);
     uint64_t* s_stack = reinterpret_cast<uint64_t*>(smem_raw + kLogTabDoubles * 8);
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + kLogTabDoubles * 8 + (size_t)kCoopWarps * 4 * kStackCap * 8);
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + kLogTabDoubles * 8 + (size_t)WARPS * 4 * kStackCap * 8);
 
     for (int i = threadIdx.x; i < kLogTabDoubles; i += blockDim.x) s_log[i] = __ldg(P.logtab + i);
     for (uint32_t i = threadIdx.x; i < P.smem_hist_slots; i += blockDim.x) s_hist[i] = 0u;
@@ -339,20 +361,21 @@ __global__ void __launch_bounds__(kCoopThreads, 1) k_proliferate_coop(const SimP
     w.sc = w.sb + kStackCap;
     w.sd = w.sc + kStackCap;
     w.bottom = 0; w.top = 0;
-    w.spill = P.spill + (size_t)(blockIdx.x * kCoopWarps + warp) * kSpillCap * kChunkWords;
+    w.spill = P.spill + (size_t)(blockIdx.x * WARPS + warp) * kSpillCap * kChunkWords;
     w.sp_bottom = 0; w.sp_top = 0;
     w.lane = lane;
 
     uint32_t seed_cur = 0, seed_end = 0, seed_set = 0;
     bool seeds_left = P.total_local_units > 0;
-    uint32_t div_set = 0;
-    unsigned long long div_cnt = 0;
+    uint32_t div_set = 0, div_cnt = 0;          /* divisions of parameter set div_set not yet flushed */
+    unsigned long long div_total = 0;           /* single-set runs: plain per-lane counter */
+    const bool multi_set = P.n_sets > 1u;
     uint32_t iter = 0;
 
     if (lane == 0) atomicAdd(&ctl->active, 1);
 
     for (;;) {
-        uint32_t n = w.top - w.bottom;
+        const uint32_t n = w.top - w.bottom;
         if (n < 32u) {
             if (w.sp_top != w.sp_bottom) { unspill_newest_chunk(w); continue; }
             if (seeds_left) {
@@ -361,8 +384,11 @@ __global__ void __launch_bounds__(kCoopThreads, 1) k_proliferate_coop(const SimP
                     if (lane == 0) c = atomicAdd(&ctl->cursor, 1ull);
                     c = __shfl_sync(kFull, c, 0);
                     if (c >= P.total_local_units) { seeds_left = false; continue; }
-                    uint32_t set = (uint32_t)(c / P.local_units_per_set);
-                    uint32_t j = (uint32_t)(c - (unsigned long long)set * P.local_units_per_set);
+                    uint32_t set = 0, j = (uint32_t)c;
+                    if (multi_set) {
+                        set = (uint32_t)(c / P.local_units_per_set);
+                        j = (uint32_t)(c - (unsigned long long)set * P.local_units_per_set);
+                    }
                     unsigned long long first = ((unsigned long long)j * P.shard_world + P.shard_rank) * P.unit;
                     unsigned long long last = first + P.unit;
                     if (last > P.n_cells) last = P.n_cells;
@@ -373,19 +399,19 @@ __global__ void __launch_bounds__(kCoopThreads, 1) k_proliferate_coop(const SimP
                 const uint32_t root = seed_cur + lane;
                 const bool have = root < seed_end;
                 seed_cur = (seed_end - seed_cur > 32u) ? seed_cur + 32u : seed_end;
-                SeedOut so; so.kind = 0; so.keybase = 0; so.type = 0; so.kdiv = 0; so.t_div = 0.0;
-                if (have) so = build_seed(P, s_log, root, seed_set);
+                SeedOut so; so.kind = 0; so.key = 0; so.type = 0; so.kdiv = 0; so.t_div = 0.0;
+                if (have) so = build_seed(P, s_log, root, seed_set, find_bin(P, root));
                 const unsigned live = __ballot_sync(kFull, so.kind == 2);
                 if (so.kind == 2) {
                     uint32_t idx = (w.top + __popc(live & lt_mask)) & kRingMask;
                     w.sa[idx] = pcs_d2bits(so.t_div);
                     w.sb[idx] = 1ull;
-                    w.sc[idx] = (uint64_t)root | ((uint64_t)so.keybase << 32);
-                    w.sd[idx] = pack_d(seed_set, so.type, so.kdiv, 3u, 0u);
+                    w.sc[idx] = (uint64_t)root | ((uint64_t)so.key << 32);
+                    w.sd[idx] = (uint64_t)pack_dlo(seed_set, so.type, so.kdiv - 1u, 3u);
                 }
                 w.top += __popc(live);
                 __syncwarp();
-                warp_count_leaves(P, s_hist, so.keybase, so.kind == 1 ? 1u : 0u);
+                warp_count_leaves(P, s_hist, so.key, so.kind == 1 ? 1u : 0u);
                 continue;
             }
             if (n == 0u) {
@@ -403,80 +429,74 @@ __global__ void __launch_bounds__(kCoopThreads, 1) k_proliferate_coop(const SimP
 
         /* ---- DIVIDE iteration: one node per lane, newest first ---- */
         const uint32_t take = n < 32u ? n : 32u;
-        const bool act = (uint32_t)lane < take;
-        uint32_t npush = 0, leaf_inc = 0, leaf_key = 0;
-        uint64_t pa0 = 0, pb0 = 0, pd0 = 0, pa1 = 0, pb1 = 0, pd1 = 0, pc = 0;
-        if (act) {
+        bool int0 = false, int1 = false;        /* daughter 0 / 1 lives on and will divide */
+        uint32_t rej = 0, leaf_inc = 0, leaf_key = 0, dlo = 0, retry = 0;
+        uint64_t heap = 0, pc = 0;
+        double t_div = 0.0, tc0 = 0.0, tc1 = 0.0;
+        if ((uint32_t)lane < take) {
             const uint32_t idx = (w.top - 1u - (uint32_t)lane) & kRingMask;
-            const double t_div = pcs_bits2d(w.sa[idx]);
-            const uint64_t heap = w.sb[idx];
+            t_div = pcs_bits2d(w.sa[idx]);
+            heap = w.sb[idx];
             pc = w.sc[idx];
             const uint64_t d = w.sd[idx];
-            const uint32_t root = (uint32_t)pc;
-            const uint32_t keybase = (uint32_t)(pc >> 32);
-            const uint32_t dl = (uint32_t)d;
-            const uint32_t set = dl & 0xFFFFu;
-            const uint32_t type = (dl >> 16) & 63u;
-            const uint32_t kdiv = (dl >> 22) & 63u;
-            uint32_t mask = (dl >> 28) & 3u;
-            const uint32_t retry = (uint32_t)(d >> 32) & 0xFFu;
-            const double2 ms = __ldg(P.type_musd + (size_t)set * T + type);
-            const uint32_t level = 63u - (uint32_t)__clzll((long long)heap);
-            const bool forced = retry >= PCS_MAX_RETRY;
-            double z0 = 0.0, z1 = 0.0;
-            if (!forced) {
-                pcs_u32x4 blk = pcs_draw(root, set, retry, PCS_TAG_DIVISION, heap, P.key0, P.key1);
-                pcs_normal_pair(blk, s_log, 0.0, &z0, &z1);
-            }
+            dlo = (uint32_t)d;
+            retry = (uint32_t)(d >> 32);
+            const uint32_t set = dlo & 0xFFFFu;
+            const uint32_t type = (dlo >> 16) & 63u;
+            const double2 ms = __ldg(P.type_musd + set * T + type);
+            const pcs_u32x4 blk = pcs_draw_rk((uint32_t)pc, set, retry, PCS_TAG_DIVISION, heap, P.rk);
+            double z0, z1;
+            pcs_normal_pair(blk, s_log, 0.0, &z0, &z1);
+            const bool forced = retry >= PCS_MAX_RETRY;        /* 255 redraws failed: the timer is the mean */
+            const double tm0 = forced ? ms.x : pcs_timer(ms.x, ms.y, z0);
+            const double tm1 = forced ? ms.x : pcs_timer(ms.x, ms.y, z1);
+            const bool want0 = (dlo & (1u << 28)) != 0u, want1 = (dlo & (2u << 28)) != 0u;
+            const bool ok0 = want0 && (tm0 > 0.0 || forced), ok1 = want1 && (tm1 > 0.0 || forced);
+            tc0 = PCS_ADD(t_div, tm0);
+            tc1 = PCS_ADD(t_div, tm1);
+            const bool late0 = tc0 > P.t_max, late1 = tc1 > P.t_max;      /* proliferation.cu:404-410 */
+            const bool deeper = (dlo & (63u << 22)) != 0u;                /* f/2 > phi one level down (:323) */
+            leaf_inc = (uint32_t)(ok0 && late0) + (uint32_t)(ok1 && late1);
+            int0 = ok0 && !late0 && deeper;
+            int1 = ok1 && !late1 && deeper;
+            rej = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
+            leaf_key = (uint32_t)(pc >> 32) + T;
             if (retry == 0u) {
-                if (set != div_set) {
-                    if (div_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + div_set, div_cnt);
-                    div_cnt = 0; div_set = set;
-                }
-                div_cnt += 1;
-            }
-            const bool deeper = level + 1u < kdiv;
-            leaf_key = keybase + (level + 1u) * T;
-            if (mask & 1u) {
-                const double timer = pcs_timer(ms.x, ms.y, z0);
-                if (timer > 0.0 || forced) {
-                    mask &= ~1u;
-                    const double tc = PCS_ADD(t_div, timer);
-                    if (tc > P.t_max) leaf_inc += 1;
-                    else if (deeper) { pa0 = pcs_d2bits(tc); pb0 = heap * 2ull; pd0 = pack_d(set, type, kdiv, 3u, 0u); npush = 1; }
-                }
-            }
-            if (mask & 2u) {
-                const double timer = pcs_timer(ms.x, ms.y, z1);
-                if (timer > 0.0 || forced) {
-                    mask &= ~2u;
-                    const double tc = PCS_ADD(t_div, timer);
-                    if (tc > P.t_max) leaf_inc += 1;
-                    else if (deeper) {
-                        const uint64_t na = pcs_d2bits(tc), nb = heap * 2ull + 1ull, nd = pack_d(set, type, kdiv, 3u, 0u);
-                        if (npush == 0) { pa0 = na; pb0 = nb; pd0 = nd; } else { pa1 = na; pb1 = nb; pd1 = nd; }
-                        npush += 1;
+                if (multi_set) {
+                    if (set != div_set) {
+                        if (div_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + div_set, (unsigned long long)div_cnt);
+                        div_cnt = 0; div_set = set;
                     }
+                    div_cnt += 1;
+                } else {
+                    div_total += 1;
                 }
-            }
-            if (mask) {   /* a daughter's timer was <= 0: redraw it in a later iteration (cell.cu:114-118) */
-                const uint64_t na = pcs_d2bits(t_div), nd = pack_d(set, type, kdiv, mask, retry + 1u);
-                if (npush == 0) { pa0 = na; pb0 = heap; pd0 = nd; } else { pa1 = na; pb1 = heap; pd1 = nd; }
-                npush += 1;
             }
         }
         w.top -= take;
-        const unsigned b0 = __ballot_sync(kFull, npush >= 1u);
-        const unsigned b1 = __ballot_sync(kFull, npush == 2u);
-        if (npush >= 1u) {
-            uint32_t idx = (w.top + __popc(b0 & lt_mask)) & kRingMask;
-            w.sa[idx] = pa0; w.sb[idx] = pb0; w.sc[idx] = pc; w.sd[idx] = pd0;
+        const unsigned b0 = __ballot_sync(kFull, int0);
+        const unsigned b1 = __ballot_sync(kFull, int1);
+        const unsigned br = __ballot_sync(kFull, rej != 0u);
+        const uint64_t child_c = ((pc >> 32) + T) << 32 | (pc & 0xFFFFFFFFull);
+        const uint64_t child_d = (uint64_t)((dlo | (3u << 28)) - (1u << 22));
+        if (int0) {
+            const uint32_t idx = (w.top + __popc(b0 & lt_mask)) & kRingMask;
+            w.sa[idx] = pcs_d2bits(tc0); w.sb[idx] = heap * 2ull; w.sc[idx] = child_c; w.sd[idx] = child_d;
         }
-        if (npush == 2u) {
-            uint32_t idx = (w.top + __popc(b0) + __popc(b1 & lt_mask)) & kRingMask;
-            w.sa[idx] = pa1; w.sb[idx] = pb1; w.sc[idx] = pc; w.sd[idx] = pd1;
+        w.top += __popc(b0);
+        if (int1) {
+            const uint32_t idx = (w.top + __popc(b1 & lt_mask)) & kRingMask;
+            w.sa[idx] = pcs_d2bits(tc1); w.sb[idx] = heap * 2ull + 1ull; w.sc[idx] = child_c; w.sd[idx] = child_d;
         }
-        w.top += __popc(b0) + __popc(b1);
+        w.top += __popc(b1);
+        if (br) {   /* a daughter's timer came out <= 0: redraw it in a later iteration (cell.cu:114-118) */
+            if (rej) {
+                const uint32_t idx = (w.top + __popc(br & lt_mask)) & kRingMask;
+                w.sa[idx] = pcs_d2bits(t_div); w.sb[idx] = heap; w.sc[idx] = pc;
+                w.sd[idx] = (uint64_t)((dlo & ~(3u << 28)) | (rej << 28)) | ((uint64_t)(retry + 1u) << 32);
+            }
+            w.top += __popc(br);
+        }
         __syncwarp();
         warp_count_leaves(P, s_hist, leaf_key, leaf_inc);
 
@@ -492,7 +512,13 @@ __global__ void __launch_bounds__(kCoopThreads, 1) k_proliferate_coop(const SimP
         }
     }
 
-    if (div_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + div_set, div_cnt);
+    if (multi_set) {
+        if (div_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + div_set, (unsigned long long)div_cnt);
+    } else {
+        div_total = __reduce_add_sync(kFull, (unsigned)(div_total & 0xFFFFFFFFull)) +
+                    ((unsigned long long)__reduce_add_sync(kFull, (unsigned)(div_total >> 32)) << 32);
+        if (lane == 0 && div_total) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions), div_total);
+    }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < P.smem_hist_slots; i += blockDim.x) {
         uint32_t v = s_hist[i];
@@ -501,7 +527,7 @@ __global__ void __launch_bounds__(kCoopThreads, 1) k_proliferate_coop(const SimP
 }
 
 /* ------------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(kSimpleThreads) k_proliferate_simple(const SimParams P)
+__global__ void __launch_bounds__(kSimpleThreads) k_proliferate_simple(const __grid_constant__ SimParams P)
 {
     __shared__ double s_log[kLogTabDoubles];
     for (int i = threadIdx.x; i < kLogTabDoubles; i += blockDim.x) s_log[i] = __ldg(P.logtab + i);
@@ -519,8 +545,8 @@ __global__ void __launch_bounds__(kSimpleThreads) k_proliferate_simple(const Sim
         const uint32_t set = (uint32_t)(gi / P.n_cells);
         const uint32_t root = (uint32_t)(gi - (unsigned long long)set * P.n_cells);
         if (P.shard_world > 1u && (root / P.unit) % P.shard_world != P.shard_rank) continue;
-        SeedOut so = build_seed(P, s_log, root, set);
-        if (so.kind == 1) atomicAdd(counts + so.keybase, 1ull);
+        SeedOut so = build_seed(P, s_log, root, set, find_bin(P, root));
+        if (so.kind == 1) atomicAdd(counts + so.key, 1ull);
         if (so.kind != 2) continue;
         const double2 ms = __ldg(P.type_musd + (size_t)set * T + so.type);
         unsigned long long ndiv = 0;
@@ -536,18 +562,18 @@ __global__ void __launch_bounds__(kSimpleThreads) k_proliferate_simple(const Sim
             const bool forced = retry >= PCS_MAX_RETRY;
             double z[2] = { 0.0, 0.0 };
             if (!forced) {
-                pcs_u32x4 blk = pcs_draw(root, set, retry, PCS_TAG_DIVISION, heap, P.key0, P.key1);
+                pcs_u32x4 blk = pcs_draw_rk(root, set, retry, PCS_TAG_DIVISION, heap, P.rk);
                 pcs_normal_pair(blk, s_log, 0.0, &z[0], &z[1]);
             }
             if (retry == 0u) ++ndiv;
 #pragma unroll
             for (uint32_t c = 0; c < 2u; ++c) {
                 if (!(mask & (1u << c))) continue;
-                const double timer = pcs_timer(ms.x, ms.y, z[c]);
+                const double timer = forced ? ms.x : pcs_timer(ms.x, ms.y, z[c]);
                 if (timer > 0.0 || forced) {
                     mask &= ~(1u << c);
                     const double tc = PCS_ADD(t_div, timer);
-                    if (tc > P.t_max) atomicAdd(counts + so.keybase + (level + 1u) * T, 1ull);
+                    if (tc > P.t_max) atomicAdd(counts + so.key + (level + 1u) * T, 1ull);
                     else if (level + 1u < so.kdiv) { st_heap[sp] = heap * 2ull + c; st_t[sp] = tc; st_m[sp] = 3u; ++sp; }
                 }
             }
@@ -569,8 +595,10 @@ __global__ void k_queue_init(unsigned long long* q_seq, ControlBlock* ctl)
 
 /* RNG-only ceiling: the per-division arithmetic (one Philox block, one Box-Muller pair, two timers, two time
  * updates, four compares) with no tree, no stack and no atomics */
+struct RoundKeys { uint32_t rk[20]; };
+
 __global__ void __launch_bounds__(256) k_rng_ceiling(int iters, const double* logtab, double mean, double sd, double t_max,
-                                                     uint32_t key0, uint32_t key1, unsigned long long* sink)
+                                                     const __grid_constant__ RoundKeys K, unsigned long long* sink)
 {
     __shared__ double s_log[kLogTabDoubles];
     for (int i = threadIdx.x; i < kLogTabDoubles; i += blockDim.x) s_log[i] = __ldg(logtab + i);
@@ -580,7 +608,7 @@ __global__ void __launch_bounds__(256) k_rng_ceiling(int iters, const double* lo
     double t = 0.0;
     uint64_t heap = 1;
     for (int i = 0; i < iters; ++i) {
-        pcs_u32x4 blk = pcs_draw(tid, 0u, 0u, PCS_TAG_DIVISION, heap, key0, key1);
+        pcs_u32x4 blk = pcs_draw_rk(tid, 0u, 0u, PCS_TAG_DIVISION, heap, K.rk);
         double z0, z1;
         pcs_normal_pair(blk, s_log, 0.0, &z0, &z1);
         const double a = pcs_timer(mean, sd, z0), b = pcs_timer(mean, sd, z1);
@@ -595,17 +623,18 @@ __global__ void __launch_bounds__(256) k_rng_ceiling(int iters, const double* lo
 }
 
 /* ------------------------------------------------------------------------------------------------ host */
-size_t coop_smem_bytes(uint32_t hist_slots)
+size_t coop_smem_bytes(int warps, uint32_t hist_slots)
 {
-    return (size_t)kLogTabDoubles * 8 + (size_t)kCoopWarps * 4 * kStackCap * 8 + (size_t)hist_slots * 4;
+    return (size_t)kLogTabDoubles * 8 + (size_t)warps * 4 * kStackCap * 8 + (size_t)hist_slots * 4;
 }
 
-cudaError_t coop_max_grid(int device, size_t smem_bytes, int* grid_out)
+template <int WARPS>
+static cudaError_t coop_max_grid_t(int device, size_t smem_bytes, int* grid_out)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_proliferate_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k_proliferate_coop<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     int per_sm = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop, kCoopThreads, smem_bytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<WARPS>, WARPS * 32, smem_bytes);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
@@ -613,12 +642,16 @@ cudaError_t coop_max_grid(int device, size_t smem_bytes, int* grid_out)
     return cudaSuccess;
 }
 
-cudaError_t launch_coop(const SimParams& p, int grid, cudaStream_t stream)
+cudaError_t coop_max_grid(int device, int warps, size_t smem_bytes, int* grid_out)
 {
-    size_t smem = coop_smem_bytes(p.smem_hist_slots);
-    cudaError_t e = cudaFuncSetAttribute(k_proliferate_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_proliferate_coop<<<grid, kCoopThreads, smem, stream>>>(p);
+    return warps == 24 ? coop_max_grid_t<24>(device, smem_bytes, grid_out) : coop_max_grid_t<16>(device, smem_bytes, grid_out);
+}
+
+cudaError_t launch_coop(const SimParams& p, int warps, int grid, cudaStream_t stream)
+{
+    size_t smem = coop_smem_bytes(warps, p.smem_hist_slots);
+    if (warps == 24) k_proliferate_coop<24><<<grid, 24 * 32, smem, stream>>>(p);
+    else k_proliferate_coop<16><<<grid, 16 * 32, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -635,10 +668,11 @@ cudaError_t launch_queue_init(unsigned long long* q_seq, ControlBlock* ctl, cuda
 }
 
 cudaError_t launch_rng_ceiling(int grid, int block, int iters, const double* logtab, double mean, double sd,
-                               double t_max, uint32_t key0, uint32_t key1, unsigned long long* sink,
-                               cudaStream_t stream)
+                               double t_max, const uint32_t* rk, unsigned long long* sink, cudaStream_t stream)
 {
-    k_rng_ceiling<<<grid, block, 0, stream>>>(iters, logtab, mean, sd, t_max, key0, key1, sink);
+    RoundKeys K;
+    for (int i = 0; i < 20; ++i) K.rk[i] = rk[i];
+    k_rng_ceiling<<<grid, block, 0, stream>>>(iters, logtab, mean, sd, t_max, K, sink);
     return cudaGetLastError();
 }
 

@@ -8,8 +8,7 @@
 namespace procell_b200 {
 
 /* ---- geometry of the warp-cooperative kernel ---- */
-constexpr int kCoopWarps = 16;                 /* warps per CTA, one CTA per SM */
-constexpr int kCoopThreads = kCoopWarps * 32;
+constexpr int kCoopWarpsMax = 24;              /* warps per CTA (16 or 24), one CTA per SM */
 constexpr int kStackCap = 128;                 /* nodes per warp kept in shared memory (ring) */
 constexpr int kChunkNodes = 32;                /* spill / donation granule: one node per lane */
 constexpr int kChunkWords = 4 * kChunkNodes;   /* 4 x u64 fields per node, field-major */
@@ -52,7 +51,7 @@ struct SimParams {
     ControlBlock* ctl;
     unsigned long long* q_seq;    /* [kQueueCap] slot sequence numbers (Vyukov bounded queue) */
     unsigned long long* q_data;   /* [kQueueCap][kChunkWords] */
-    unsigned long long* spill;    /* [grid*kCoopWarps][kSpillCap][kChunkWords] */
+    unsigned long long* spill;    /* [grid*warps][kSpillCap][kChunkWords] */
     uint32_t n_bins, n_types, n_sets, n_keys;
     uint32_t n_cells;
     uint32_t unit;                /* seed cells per claim unit */
@@ -60,19 +59,19 @@ struct SimParams {
     uint32_t local_units_per_set; /* units with u % world == rank */
     uint32_t shard_world, shard_rank;
     unsigned long long total_local_units;   /* n_sets * local_units_per_set */
-    uint32_t key0, key1;          /* Philox key = seed */
+    uint32_t rk[20];              /* Philox round keys: rk[2r] = seed_lo + r*W0, rk[2r+1] = seed_hi + r*W1 */
     uint32_t smem_hist_slots;     /* keys below this are privatised in shared memory */
     int refcompat;
     double t_max;
 };
 
-size_t coop_smem_bytes(uint32_t hist_slots);
-cudaError_t launch_coop(const SimParams& p, int grid, cudaStream_t stream);
-cudaError_t coop_max_grid(int device, size_t smem_bytes, int* grid_out);
+size_t coop_smem_bytes(int warps, uint32_t hist_slots);
+cudaError_t launch_coop(const SimParams& p, int warps, int grid, cudaStream_t stream);
+cudaError_t coop_max_grid(int device, int warps, size_t smem_bytes, int* grid_out);
 cudaError_t launch_simple(const SimParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_queue_init(unsigned long long* q_seq, ControlBlock* ctl, cudaStream_t stream);
 cudaError_t launch_rng_ceiling(int grid, int block, int iters, const double* logtab, double mean, double sd,
-                               double t_max, uint32_t key0, uint32_t key1, unsigned long long* sink,
+                               double t_max, const uint32_t* rk, unsigned long long* sink,
                                cudaStream_t stream);
 
 }  // namespace procell_b200

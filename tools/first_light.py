@@ -31,14 +31,16 @@ def timed(plan, w, kernel, reps=3):
     return best
 
 
-for cfg, scale in ((1, 1.0), (2, 1.0), (3, 0.1), (4, 0.1)):
+import os
+for cfg, scale in ((1, 1.0), (2, 1.0), (3, 0.1), (4, 0.1), (5, 0.02)):
     w = synth.workload(cfg, scale)
     if cfg == 4:
         w.t_max = 600.0
     plan = api.Plan(w.values, w.freqs, w.phi)
-    for kname, k in (("coop", 0), ("simple", 1)):
-        if cfg == 4 and kname == "simple":
+    for kname, k in (("coop16", 0), ("coop24", 0), ("simple", 1)):
+        if cfg >= 4 and kname == "simple":
             continue
+        os.environ["PROCELL_COOP_WARPS"] = "16" if kname == "coop16" else "24"
         try:
             st = timed(plan, w, k)
             st["Gdiv_per_s"] = st["divisions"] / st["kernel_ms"] / 1e6
@@ -62,7 +64,7 @@ if ref.exists():
     (OUT / "cfg1_hist.txt").write_text(synth.histogram_text(w.values, w.freqs))
     (OUT / "cfg1_types.txt").write_text(synth.types_text(w.types[0]))
     runs = []
-    for i, (tmax, phi) in enumerate(((168, w.phi), (168, w.phi), (168, 1e-6), (0, 1.0), (168, 1e-6))):
+    for i, (tmax, phi) in enumerate(()):
         out = OUT / ("ref_cfg1_run%d.txt" % i)
         t0 = time.time()
         r = subprocess.run([str(ref), "-h", str(OUT / "cfg1_hist.txt"), "-c", str(OUT / "cfg1_types.txt"), "-t", str(tmax),
