@@ -328,7 +328,7 @@ int procell_rng_ceiling(int device, int iters, double* ms_out, double* pairs_out
     CU(cudaMalloc(&d_sink, 16), "alloc");
     CU(cudaMemcpy(d_tab, kLogRows, sizeof(kLogRows), cudaMemcpyHostToDevice), "upload");
     CU(cudaMemset(d_sink, 0, 16), "memset");
-    const int block = 256, grid = sms * 8;
+    const int block = 256, grid = sms * 6;   /* 6 CTAs of 256 threads per SM fit at 34 registers: one full wave */
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     SimParams K{};

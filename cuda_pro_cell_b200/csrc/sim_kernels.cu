@@ -30,6 +30,7 @@ namespace procell_b200 {
 namespace {
 
 constexpr uint32_t kRingMask = kStackCap - 1;
+constexpr int kSmemCtlBytes = 64;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 /* A node = a cell that WILL divide: 4 x u64, field-major in the ring
@@ -228,8 +229,12 @@ __device__ __forceinline__ void donate_chunk(WarpCtx& w, const SimParams& P)
     queue_push(P, w.lane, a, b, c, d);
 }
 
-/* A warp with nothing left: wait for donated work or for global quiescence.  true = a chunk was loaded. */
-__device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P)
+/* A warp with nothing left: wait for donated work or for global quiescence.  true = a chunk was loaded.
+ * Only ONE idle warp per CTA polls the global control block at a time (shared-memory lock), so a chip full of
+ * idle warps costs the L2 at most 148 pollers instead of thousands hammering three cache lines that the busy
+ * warps also need.  Quiescence (no active warp and an empty queue) is stable, so the warp that observes it
+ * publishes it to its CTA through s_ctl[1]. */
+__device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volatile int* s_ctl)
 {
     ControlBlock* ctl = P.ctl;
     if (w.lane == 0) {
@@ -237,21 +242,27 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P)
         __threadfence();
         atomicSub(&ctl->active, 1);
     }
-    unsigned long long t0 = global_timer_ns();
-    unsigned backoff = 256;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned backoff = 128;
     for (;;) {
         int state = 0;   /* 0 wait, 1 try, 2 exit */
         if (w.lane == 0) {
-            /* `active` is read (acquire) BEFORE the queue indices: a warp that pushed and then went idle
-             * decremented it after its push, so active == 0 implies all pushes are visible below */
-            int act = ld_acquire_s32(&ctl->active);
-            unsigned long long h = ld_acquire_u64(&ctl->q_head);
-            unsigned long long t = ld_acquire_u64(&ctl->q_tail);
-            int st = ld_volatile_s32(&ctl->status);
-            if (st != kStatusOk) state = 2;
-            else if (h < t) state = 1;
-            else if (act == 0) state = 2;
-            else if (global_timer_ns() - t0 > 120000000000ull) { atomicExch(&ctl->status, kStatusIdleTimeout); state = 2; }
+            if (s_ctl[1]) state = 2;
+            else if (atomicCAS(const_cast<int*>(s_ctl), 0, 1) == 0) {
+                /* `active` is read (acquire) BEFORE the queue indices: a warp that pushed and then went idle
+                 * decremented it after its push, so active == 0 implies all pushes are visible below */
+                const int act = ld_acquire_s32(&ctl->active);
+                const unsigned long long h = ld_acquire_u64(&ctl->q_head);
+                const unsigned long long t = ld_acquire_u64(&ctl->q_tail);
+                const int st = ld_volatile_s32(&ctl->status);
+                if (st != kStatusOk) state = 2;
+                else if (h < t) state = 1;
+                else if (act == 0) state = 2;
+                else if (global_timer_ns() - t0 > 120000000000ull) { atomicExch(&ctl->status, kStatusIdleTimeout); state = 2; }
+                if (state == 2) s_ctl[1] = 1;
+                __threadfence_block();
+                atomicExch(const_cast<int*>(s_ctl), 0);
+            }
         }
         state = __shfl_sync(kFull, state, 0);
         if (state == 2) {
@@ -270,9 +281,10 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P)
                 return true;
             }
             if (w.lane == 0) { __threadfence(); atomicSub(&ctl->active, 1); }
+            backoff = 128;
         } else {
             __nanosleep(backoff);
-            if (backoff < 4096) backoff <<= 1;
+            if (backoff < 2048) backoff <<= 1;
         }
     }
 }
@@ -342,9 +354,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_log = reinterpret_cast<double*>(smem_raw);
-    uint64_t* s_stack = reinterpret_cast<uint64_t*>(smem_raw + kLogTabDoubles * 8);
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + kLogTabDoubles * 8 + (size_t)WARPS * 4 * kStackCap * 8);
+    volatile int* s_ctl = reinterpret_cast<volatile int*>(smem_raw + kLogTabDoubles * 8);   /* [0] poll lock, [1] quiescent */
+    uint64_t* s_stack = reinterpret_cast<uint64_t*>(smem_raw + kLogTabDoubles * 8 + kSmemCtlBytes);
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + kLogTabDoubles * 8 + kSmemCtlBytes + (size_t)WARPS * 4 * kStackCap * 8);
 
+    if (threadIdx.x < 2) s_ctl[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < kLogTabDoubles; i += blockDim.x) s_log[i] = __ldg(P.logtab + i);
     for (uint32_t i = threadIdx.x; i < P.smem_hist_slots; i += blockDim.x) s_hist[i] = 0u;
     __syncthreads();
@@ -371,6 +385,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     unsigned long long div_total = 0;           /* single-set runs: plain per-lane counter */
     const bool multi_set = P.n_sets > 1u;
     uint32_t iter = 0;
+    bool hungry = false;
 
     if (lane == 0) atomicAdd(&ctl->active, 1);
 
@@ -415,16 +430,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 continue;
             }
             if (n == 0u) {
-                if (!idle_wait(w, P)) break;
+                if (!idle_wait(w, P, s_ctl)) break;
                 continue;
             }
         }
         if (n > (uint32_t)(kStackCap - 32)) { spill_bottom_chunk(w, P); continue; }
 
-        /* hunger probe (load issued now, consumed after the math) */
+        /* hunger probe (load issued now, consumed after the math): every 8th iteration, every iteration while
+         * somebody is known to be starving */
         ++iter;
         int probe_idle = 0;
-        const bool probe = !seeds_left && (iter & 3u) == 0u && (n + 32u * (w.sp_top - w.sp_bottom)) >= 96u;
+        const bool probe = !seeds_left && (hungry || (iter & 7u) == 0u) && (n + 32u * (w.sp_top - w.sp_bottom)) >= 64u;
         if (probe && lane == 0) probe_idle = ld_volatile_s32(&ctl->idle);
 
         /* ---- DIVIDE iteration: one node per lane, newest first ---- */
@@ -505,10 +521,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
             if (lane == 0 && probe_idle > 0) {
                 unsigned long long h = ld_volatile_u64(&ctl->q_head);
                 unsigned long long t = ld_volatile_u64(&ctl->q_tail);
-                want = (t - h) < (unsigned long long)probe_idle && (t - h) < (unsigned long long)(kQueueCap / 2);
+                want = 1 + ((t - h) < (unsigned long long)probe_idle && (t - h) < (unsigned long long)(kQueueCap / 2));
             }
             want = __shfl_sync(kFull, want, 0);
-            if (want && (w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= 64u) donate_chunk(w, P);
+            hungry = want != 0;
+            if (want == 2 && (w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= 64u) donate_chunk(w, P);
         }
     }
 
@@ -625,7 +642,7 @@ __global__ void __launch_bounds__(256) k_rng_ceiling(int iters, const double* lo
 /* ------------------------------------------------------------------------------------------------ host */
 size_t coop_smem_bytes(int warps, uint32_t hist_slots)
 {
-    return (size_t)kLogTabDoubles * 8 + (size_t)warps * 4 * kStackCap * 8 + (size_t)hist_slots * 4;
+    return (size_t)kLogTabDoubles * 8 + kSmemCtlBytes + (size_t)warps * 4 * kStackCap * 8 + (size_t)hist_slots * 4;
 }
 
 template <int WARPS>
