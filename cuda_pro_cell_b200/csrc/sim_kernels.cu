@@ -436,12 +436,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         }
         if (n > (uint32_t)(kStackCap - 32)) { spill_bottom_chunk(w, P); continue; }
 
-        /* hunger probe (load issued now, consumed after the math): every 8th iteration, every iteration while
-         * somebody is known to be starving */
+        /* hunger probe (loads issued now, consumed after the math): every 8th iteration, every iteration while
+         * somebody is known to be starving.  A warp that never ran dry has not seen the seed cursor run out,
+         * so the probe also looks at the cursor. */
         ++iter;
         int probe_idle = 0;
-        const bool probe = !seeds_left && (hungry || (iter & 7u) == 0u) && (n + 32u * (w.sp_top - w.sp_bottom)) >= 64u;
-        if (probe && lane == 0) probe_idle = ld_volatile_s32(&ctl->idle);
+        unsigned long long probe_cursor = 0;
+        const bool probe = (hungry || (iter & 7u) == 0u) && (n + 32u * (w.sp_top - w.sp_bottom)) >= 64u;
+        if (probe && lane == 0) {
+            probe_idle = ld_volatile_s32(&ctl->idle);
+            if (seeds_left) probe_cursor = ld_volatile_u64(&ctl->cursor);
+        }
 
         /* ---- DIVIDE iteration: one node per lane, newest first ---- */
         const uint32_t take = n < 32u ? n : 32u;
@@ -518,7 +523,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 
         if (probe) {
             int want = 0;
-            if (lane == 0 && probe_idle > 0) {
+            if (seeds_left) seeds_left = __shfl_sync(kFull, probe_cursor, 0) < P.total_local_units;
+            if (lane == 0 && probe_idle > 0 && !seeds_left) {
                 unsigned long long h = ld_volatile_u64(&ctl->q_head);
                 unsigned long long t = ld_volatile_u64(&ctl->q_tail);
                 want = 1 + ((t - h) < (unsigned long long)probe_idle && (t - h) < (unsigned long long)(kQueueCap / 2));
