@@ -380,12 +380,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     w.lane = lane;
 
     uint32_t seed_cur = 0, seed_end = 0, seed_set = 0;
-    bool seeds_left = P.total_local_units > 0;
+    /* s_ctl[2]: snapshot of the global idle-warp count; s_ctl[3]: 1 once the seed-unit cursor has run out.  Both are
+     * refreshed from HBM by ONE warp of the CTA every few iterations and read from shared memory by all. */
+    if (threadIdx.x == 0) { s_ctl[2] = 0; s_ctl[3] = P.total_local_units == 0; }
+    __syncthreads();
     uint32_t div_set = 0, div_cnt = 0;          /* divisions of parameter set div_set not yet flushed */
     unsigned long long div_total = 0;           /* single-set runs: plain per-lane counter */
     const bool multi_set = P.n_sets > 1u;
     uint32_t iter = 0;
-    bool hungry = false;
 
     if (lane == 0) atomicAdd(&ctl->active, 1);
 
@@ -393,12 +395,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         const uint32_t n = w.top - w.bottom;
         if (n < 32u) {
             if (w.sp_top != w.sp_bottom) { unspill_newest_chunk(w); continue; }
-            if (seeds_left) {
+            if (seed_cur != seed_end || !s_ctl[3]) {
                 if (seed_cur == seed_end) {
                     unsigned long long c = 0;
                     if (lane == 0) c = atomicAdd(&ctl->cursor, 1ull);
                     c = __shfl_sync(kFull, c, 0);
-                    if (c >= P.total_local_units) { seeds_left = false; continue; }
+                    if (c >= P.total_local_units) { if (lane == 0) s_ctl[3] = 1; __syncwarp(); continue; }
                     uint32_t set = 0, j = (uint32_t)c;
                     if (multi_set) {
                         set = (uint32_t)(c / P.local_units_per_set);
@@ -436,17 +438,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         }
         if (n > (uint32_t)(kStackCap - 32)) { spill_bottom_chunk(w, P); continue; }
 
-        /* hunger probe (loads issued now, consumed after the math): every 8th iteration, every iteration while
-         * somebody is known to be starving.  A warp that never ran dry has not seen the seed cursor run out,
-         * so the probe also looks at the cursor. */
+        /* hunger probe.  Every 64th iteration (staggered by warp) this warp refreshes the CTA's shared snapshot of
+         * "how many warps are starving" and "is the seed cursor exhausted" from HBM; every iteration all warps
+         * read the snapshot from shared memory.  Loads are issued now and consumed after the math. */
         ++iter;
         int probe_idle = 0;
         unsigned long long probe_cursor = 0;
-        const bool probe = (hungry || (iter & 7u) == 0u) && (n + 32u * (w.sp_top - w.sp_bottom)) >= 64u;
-        if (probe && lane == 0) {
+        const bool refresh = ((iter + (uint32_t)warp * 3u) & 63u) == 0u;
+        if (refresh && lane == 0) {
             probe_idle = ld_volatile_s32(&ctl->idle);
-            if (seeds_left) probe_cursor = ld_volatile_u64(&ctl->cursor);
+            if (!s_ctl[3]) probe_cursor = ld_volatile_u64(&ctl->cursor);
         }
+        const bool hungry = s_ctl[2] > 0 && s_ctl[3] && (n + 32u * (w.sp_top - w.sp_bottom)) >= 64u;
 
         /* ---- DIVIDE iteration: one node per lane, newest first ---- */
         const uint32_t take = n < 32u ? n : 32u;
@@ -521,17 +524,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         __syncwarp();
         warp_count_leaves(P, s_hist, leaf_key, leaf_inc);
 
-        if (probe) {
+        if (refresh && lane == 0) {
+            s_ctl[2] = probe_idle;
+            if (!s_ctl[3] && probe_cursor >= P.total_local_units) s_ctl[3] = 1;
+        }
+        if (hungry) {   /* somebody starves and no seeds are left: give away the shallowest chunk */
             int want = 0;
-            if (seeds_left) seeds_left = __shfl_sync(kFull, probe_cursor, 0) < P.total_local_units;
-            if (lane == 0 && probe_idle > 0 && !seeds_left) {
-                unsigned long long h = ld_volatile_u64(&ctl->q_head);
-                unsigned long long t = ld_volatile_u64(&ctl->q_tail);
-                want = 1 + ((t - h) < (unsigned long long)probe_idle && (t - h) < (unsigned long long)(kQueueCap / 2));
+            if (lane == 0) {
+                const unsigned long long h = ld_volatile_u64(&ctl->q_head);
+                const unsigned long long t = ld_volatile_u64(&ctl->q_tail);
+                const int idle_now = s_ctl[2];
+                want = (t - h) < (unsigned long long)idle_now && (t - h) < (unsigned long long)(kQueueCap / 2);
             }
             want = __shfl_sync(kFull, want, 0);
-            hungry = want != 0;
-            if (want == 2 && (w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= 64u) donate_chunk(w, P);
+            if (want && (w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= 64u) donate_chunk(w, P);
         }
     }
 
