@@ -281,8 +281,9 @@ int procell_engine_finish(procell_engine* en, void* stream_v, int64_t* counts, i
     cudaStream_t stream = (cudaStream_t)stream_v;
     CU(cudaSetDevice(en->device), "cudaSetDevice");
     CU(cudaStreamSynchronize(stream), "kernel execution");
-    int status = 0;
-    CU(cudaMemcpy(&status, &((ControlBlock*)en->ctl.p)->status, sizeof(int), cudaMemcpyDeviceToHost), "read status");
+    ControlBlock cb;
+    CU(cudaMemcpy(&cb, en->ctl.p, sizeof(ControlBlock), cudaMemcpyDeviceToHost), "read status");
+    const int status = cb.status;
     if (status != kStatusOk)
         return fail(PROCELL_ERR_OVERFLOW, "device work pool failure, status " + std::to_string(status));
     if (counts) CU(cudaMemcpy(counts, en->counts.p, en->counts_len * 8, cudaMemcpyDeviceToHost), "download counts");
@@ -297,6 +298,7 @@ int procell_engine_finish(procell_engine* en, void* stream_v, int64_t* counts, i
         stats->kernel_ms = ms;
         stats->n_launches = en->launches_last;
         stats->grid = en->grid; stats->block = en->block; stats->smem_bytes = (int)en->smem;
+        stats->donations = (int64_t)cb.q_tail;
     }
     return PROCELL_OK;
 }

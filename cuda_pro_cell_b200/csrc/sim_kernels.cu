@@ -380,14 +380,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     w.lane = lane;
 
     uint32_t seed_cur = 0, seed_end = 0, seed_set = 0;
-    /* s_ctl[2]: snapshot of the global idle-warp count; s_ctl[3]: 1 once the seed-unit cursor has run out.  Both are
-     * refreshed from HBM by ONE warp of the CTA every few iterations and read from shared memory by all. */
-    if (threadIdx.x == 0) { s_ctl[2] = 0; s_ctl[3] = P.total_local_units == 0; }
+    /* s_ctl[2]: snapshot of the global idle-warp count; s_ctl[3]: 1 once the seed-unit cursor has run out;
+     * s_ctl[4]: snapshot of the donation-queue length; s_ctl[5]: snapshot epoch.  They are refreshed from HBM by ONE
+     * warp of the CTA every few iterations and read from shared memory by all: busy warps never poll HBM. */
+    if (threadIdx.x == 0) { s_ctl[2] = 0; s_ctl[3] = P.total_local_units == 0; s_ctl[4] = 0; s_ctl[5] = 0; }
     __syncthreads();
     uint32_t div_set = 0, div_cnt = 0;          /* divisions of parameter set div_set not yet flushed */
     unsigned long long div_total = 0;           /* single-set runs: plain per-lane counter */
     const bool multi_set = P.n_sets > 1u;
     uint32_t iter = 0;
+    int donate_epoch = -1;
 
     if (lane == 0) atomicAdd(&ctl->active, 1);
 
@@ -439,17 +441,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         if (n > (uint32_t)(kStackCap - 32)) { spill_bottom_chunk(w, P); continue; }
 
         /* hunger probe.  Every 64th iteration (staggered by warp) this warp refreshes the CTA's shared snapshot of
-         * "how many warps are starving" and "is the seed cursor exhausted" from HBM; every iteration all warps
-         * read the snapshot from shared memory.  Loads are issued now and consumed after the math. */
+         * "how many warps are starving", "how long is the donation queue" and "is the seed cursor exhausted" from
+         * HBM; every iteration all warps read the snapshot from shared memory.  Loads are issued now and consumed
+         * after the math. */
         ++iter;
         int probe_idle = 0;
-        unsigned long long probe_cursor = 0;
+        unsigned long long probe_cursor = 0, probe_head = 0, probe_tail = 0;
         const bool refresh = ((iter + (uint32_t)warp * 3u) & 63u) == 0u;
         if (refresh && lane == 0) {
             probe_idle = ld_volatile_s32(&ctl->idle);
+            probe_head = ld_volatile_u64(&ctl->q_head);
+            probe_tail = ld_volatile_u64(&ctl->q_tail);
             if (!s_ctl[3]) probe_cursor = ld_volatile_u64(&ctl->cursor);
         }
-        const bool hungry = s_ctl[2] > 0 && s_ctl[3] && (n + 32u * (w.sp_top - w.sp_bottom)) >= 64u;
+        /* donate at most once per snapshot epoch, and only while the queue is shorter than the line of starving warps */
+        const int epoch = s_ctl[5];
+        const bool hungry = s_ctl[3] && s_ctl[2] > s_ctl[4] && epoch != donate_epoch &&
+                            (n + 32u * (w.sp_top - w.sp_bottom)) >= 64u;
 
         /* ---- DIVIDE iteration: one node per lane, newest first ---- */
         const uint32_t take = n < 32u ? n : 32u;
@@ -525,19 +533,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         warp_count_leaves(P, s_hist, leaf_key, leaf_inc);
 
         if (refresh && lane == 0) {
+            const unsigned long long qlen = probe_tail - probe_head;
             s_ctl[2] = probe_idle;
+            s_ctl[4] = qlen < (unsigned long long)(kQueueCap / 2) ? (int)qlen : 0x7FFFFFFF;
             if (!s_ctl[3] && probe_cursor >= P.total_local_units) s_ctl[3] = 1;
+            s_ctl[5] = epoch + 1;
         }
         if (hungry) {   /* somebody starves and no seeds are left: give away the shallowest chunk */
-            int want = 0;
-            if (lane == 0) {
-                const unsigned long long h = ld_volatile_u64(&ctl->q_head);
-                const unsigned long long t = ld_volatile_u64(&ctl->q_tail);
-                const int idle_now = s_ctl[2];
-                want = (t - h) < (unsigned long long)idle_now && (t - h) < (unsigned long long)(kQueueCap / 2);
-            }
-            want = __shfl_sync(kFull, want, 0);
-            if (want && (w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= 64u) donate_chunk(w, P);
+            donate_epoch = epoch;
+            if ((w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= 64u) donate_chunk(w, P);
         }
     }
 

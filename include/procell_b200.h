@@ -98,6 +98,7 @@ typedef struct procell_run_stats {
     int n_launches;      /* kernels launched by the run */
     int grid, block;     /* launch shape of the simulation kernel */
     int smem_bytes;
+    int64_t donations;   /* 32-node chunks handed from busy to starving warps through the device queue */
 } procell_run_stats;
 
 /* One-shot, host buffers in and out: replaces simulation::create_cells_population
