@@ -225,6 +225,8 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
                                 ? (P.units_per_set - P.shard_rank + P.shard_world - 1) / P.shard_world : 0;
     P.total_local_units = (unsigned long long)P.local_units_per_set * S;
 
+    const char* denv = getenv("PROCELL_NO_DONATE");
+    P.donate = !(denv && atoi(denv) == 1);
     en->kernel = sp->kernel;
     if (en->kernel == PROCELL_KERNEL_SIMPLE) {
         en->block = kSimpleThreads;
@@ -299,6 +301,8 @@ int procell_engine_finish(procell_engine* en, void* stream_v, int64_t* counts, i
         stats->n_launches = en->launches_last;
         stats->grid = en->grid; stats->block = en->block; stats->smem_bytes = (int)en->smem;
         stats->donations = (int64_t)cb.q_tail;
+        stats->seed_phase_us = cb.t_exhausted == ~0ull ? -1.0 : (double)(cb.t_exhausted - cb.t_start) * 1e-3;
+        stats->total_us = cb.t_end ? (double)(cb.t_end - cb.t_start) * 1e-3 : -1.0;
     }
     return PROCELL_OK;
 }

@@ -391,7 +391,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     uint32_t iter = 0;
     int donate_epoch = -1;
 
-    if (lane == 0) atomicAdd(&ctl->active, 1);
+    if (lane == 0) {
+        atomicAdd(&ctl->active, 1);
+        atomicMin(&ctl->t_start, global_timer_ns());
+    }
 
     for (;;) {
         const uint32_t n = w.top - w.bottom;
@@ -402,7 +405,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                     unsigned long long c = 0;
                     if (lane == 0) c = atomicAdd(&ctl->cursor, 1ull);
                     c = __shfl_sync(kFull, c, 0);
-                    if (c >= P.total_local_units) { if (lane == 0) s_ctl[3] = 1; __syncwarp(); continue; }
+                    if (c >= P.total_local_units) {
+                        if (lane == 0) { s_ctl[3] = 1; atomicMin(&ctl->t_exhausted, global_timer_ns()); }
+                        __syncwarp();
+                        continue;
+                    }
                     uint32_t set = 0, j = (uint32_t)c;
                     if (multi_set) {
                         set = (uint32_t)(c / P.local_units_per_set);
@@ -456,7 +463,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         }
         /* donate at most once per snapshot epoch, and only while the queue is shorter than the line of starving warps */
         const int epoch = s_ctl[5];
-        const bool hungry = s_ctl[3] && s_ctl[2] > s_ctl[4] && epoch != donate_epoch &&
+        const bool hungry = P.donate && s_ctl[3] && s_ctl[2] > s_ctl[4] && epoch != donate_epoch &&
                             (n + 32u * (w.sp_top - w.sp_bottom)) >= 64u;
 
         /* ---- DIVIDE iteration: one node per lane, newest first ---- */
@@ -545,6 +552,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         }
     }
 
+    if (lane == 0) atomicMax(&ctl->t_end, global_timer_ns());
     if (multi_set) {
         if (div_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + div_set, (unsigned long long)div_cnt);
     } else {
@@ -623,6 +631,7 @@ __global__ void k_queue_init(unsigned long long* q_seq, ControlBlock* ctl)
     if (i < kQueueCap) q_seq[i] = (unsigned long long)i;
     if (i == 0) {
         ctl->cursor = 0; ctl->q_head = 0; ctl->q_tail = 0; ctl->active = 0; ctl->idle = 0; ctl->status = 0;
+        ctl->t_start = ~0ull; ctl->t_exhausted = ~0ull; ctl->t_end = 0;
     }
 }
 

@@ -32,6 +32,8 @@ struct alignas(128) ControlBlock {
     int active;                     int pad3[31];
     int idle;                       int pad4[31];
     int status;                     int pad5[31];
+    /* diagnostics (globaltimer ns): first warp start, seed cursor exhausted, last warp exit */
+    unsigned long long t_start, t_exhausted, t_end, pad6[13];
 };
 
 struct SimParams {
@@ -62,6 +64,7 @@ struct SimParams {
     uint32_t rk[20];              /* Philox round keys: rk[2r] = seed_lo + r*W0, rk[2r+1] = seed_hi + r*W1 */
     uint32_t smem_hist_slots;     /* keys below this are privatised in shared memory */
     int refcompat;
+    int donate;                   /* 0: never hand work to starving warps (diagnostic) */
     double t_max;
 };
 

@@ -99,6 +99,8 @@ typedef struct procell_run_stats {
     int grid, block;     /* launch shape of the simulation kernel */
     int smem_bytes;
     int64_t donations;   /* 32-node chunks handed from busy to starving warps through the device queue */
+    double seed_phase_us; /* device time from the first warp's start until the seed-unit cursor ran out (-1: n/a) */
+    double total_us;      /* device time from the first warp's start to the last warp's exit (-1: n/a) */
 } procell_run_stats;
 
 /* One-shot, host buffers in and out: replaces simulation::create_cells_population
