@@ -167,27 +167,19 @@ __device__ __forceinline__ bool queue_push(const SimParams& P, int lane, uint64_
     __stcg(dst + 96 + lane, d);
     __threadfence();
     __syncwarp();
-    if (lane == 0) st_release_u64(P.q_seq + slot, pos + 1);
+    if (lane == 0) {
+        st_release_u64(P.q_seq + slot, pos + 1);
+        __threadfence();
+        atomicAdd(&P.ctl->avail, 1);          /* one more permit, only after the chunk is published */
+    }
     return true;
 }
 
-/* returns true and the lane's node in (a,b,c,d) if a chunk was taken */
-__device__ __forceinline__ bool queue_try_pop(const SimParams& P, int lane, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d)
+/* read the chunk of head ticket h (the caller holds a permit, so the chunk is or will shortly be published) */
+__device__ __forceinline__ bool queue_read_ticket(const SimParams& P, int lane, unsigned long long h,
+                                                  uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d)
 {
-    unsigned long long h = 0;
-    int got = 0;
-    if (lane == 0) {
-        for (int attempt = 0; attempt < 8; ++attempt) {
-            h = ld_volatile_u64(&P.ctl->q_head);
-            unsigned long long t = ld_volatile_u64(&P.ctl->q_tail);
-            if (h >= t) break;
-            if (atomicCAS(&P.ctl->q_head, h, h + 1) == h) { got = 1; break; }
-        }
-    }
-    got = __shfl_sync(kFull, got, 0);
-    if (!got) return false;
-    h = __shfl_sync(kFull, h, 0);
-    uint32_t slot = (uint32_t)h & (kQueueCap - 1);
+    const uint32_t slot = (uint32_t)h & (kQueueCap - 1);
     int ok = 1;
     if (lane == 0) {
         unsigned long long t0 = global_timer_ns();
@@ -230,10 +222,10 @@ __device__ __forceinline__ void donate_chunk(WarpCtx& w, const SimParams& P)
 }
 
 /* A warp with nothing left: wait for donated work or for global quiescence.  true = a chunk was loaded.
- * Only ONE idle warp per CTA polls the global control block at a time (shared-memory lock), so a chip full of
- * idle warps costs the L2 at most 148 pollers instead of thousands hammering three cache lines that the busy
- * warps also need.  Quiescence (no active warp and an empty queue) is stable, so the warp that observes it
- * publishes it to its CTA through s_ctl[1]. */
+ * Only ONE idle warp per CTA touches the global control block at a time (shared-memory lock): it polls and, if a
+ * permit is available, claims a chunk with fetch-adds only (permit counter, then head ticket) - no CAS retry
+ * storms, at most 148 concurrent pollers.  Quiescence (no active warp, no permit) is stable, so the warp that
+ * observes it publishes it to its CTA through s_ctl[1]. */
 __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volatile int* s_ctl)
 {
     ControlBlock* ctl = P.ctl;
@@ -245,18 +237,28 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
     const unsigned long long t0 = global_timer_ns();
     unsigned backoff = 128;
     for (;;) {
-        int state = 0;   /* 0 wait, 1 try, 2 exit */
+        int state = 0;   /* 0 wait, 1 ticket taken, 2 exit */
+        unsigned long long ticket = 0;
         if (w.lane == 0) {
             if (s_ctl[1]) state = 2;
             else if (atomicCAS(const_cast<int*>(s_ctl), 0, 1) == 0) {
-                /* `active` is read (acquire) BEFORE the queue indices: a warp that pushed and then went idle
-                 * decremented it after its push, so active == 0 implies all pushes are visible below */
+                /* `active` is read (acquire) BEFORE the permit counter: a warp that pushed and then went idle
+                 * decremented `active` after its permit became visible, so active == 0 implies every permit is seen */
                 const int act = ld_acquire_s32(&ctl->active);
-                const unsigned long long h = ld_acquire_u64(&ctl->q_head);
-                const unsigned long long t = ld_acquire_u64(&ctl->q_tail);
+                const int av = ld_acquire_s32(&ctl->avail);
                 const int st = ld_volatile_s32(&ctl->status);
                 if (st != kStatusOk) state = 2;
-                else if (h < t) state = 1;
+                else if (av > 0) {
+                    atomicAdd(&ctl->active, 1);                    /* re-activate BEFORE taking work */
+                    if (atomicSub(&ctl->avail, 1) > 0) {
+                        ticket = atomicAdd(&ctl->q_head, 1ull);
+                        state = 1;
+                    } else {                                       /* lost the race for the last permit */
+                        atomicAdd(&ctl->avail, 1);
+                        __threadfence();
+                        atomicSub(&ctl->active, 1);
+                    }
+                }
                 else if (act == 0) state = 2;
                 else if (global_timer_ns() - t0 > 120000000000ull) { atomicExch(&ctl->status, kStatusIdleTimeout); state = 2; }
                 if (state == 2) s_ctl[1] = 1;
@@ -270,22 +272,18 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
             return false;
         }
         if (state == 1) {
-            if (w.lane == 0) atomicAdd(&ctl->active, 1);
+            ticket = __shfl_sync(kFull, ticket, 0);
             uint64_t a, b, c, d;
-            if (queue_try_pop(P, w.lane, a, b, c, d)) {
-                if (w.lane == 0) atomicSub(&ctl->idle, 1);
-                uint32_t idx = (w.top + w.lane) & kRingMask;
-                w.sa[idx] = a; w.sb[idx] = b; w.sc[idx] = c; w.sd[idx] = d;
-                w.top += kChunkNodes;
-                __syncwarp();
-                return true;
-            }
-            if (w.lane == 0) { __threadfence(); atomicSub(&ctl->active, 1); }
-            backoff = 128;
-        } else {
-            __nanosleep(backoff);
-            if (backoff < 2048) backoff <<= 1;
+            if (w.lane == 0) atomicSub(&ctl->idle, 1);
+            if (!queue_read_ticket(P, w.lane, ticket, a, b, c, d)) return false;     /* watchdog abort */
+            uint32_t idx = (w.top + w.lane) & kRingMask;
+            w.sa[idx] = a; w.sb[idx] = b; w.sc[idx] = c; w.sd[idx] = d;
+            w.top += kChunkNodes;
+            __syncwarp();
+            return true;
         }
+        __nanosleep(backoff);
+        if (backoff < 2048) backoff <<= 1;
     }
 }
 
@@ -453,12 +451,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
          * after the math. */
         ++iter;
         int probe_idle = 0;
-        unsigned long long probe_cursor = 0, probe_head = 0, probe_tail = 0;
+        unsigned long long probe_cursor = 0;
+        int probe_avail = 0;
         const bool refresh = ((iter + (uint32_t)warp * 3u) & 63u) == 0u;
         if (refresh && lane == 0) {
             probe_idle = ld_volatile_s32(&ctl->idle);
-            probe_head = ld_volatile_u64(&ctl->q_head);
-            probe_tail = ld_volatile_u64(&ctl->q_tail);
+            probe_avail = ld_volatile_s32(&ctl->avail);
             if (!s_ctl[3]) probe_cursor = ld_volatile_u64(&ctl->cursor);
         }
         /* donate at most once per snapshot epoch, and only while the queue is shorter than the line of starving warps */
@@ -540,9 +538,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         warp_count_leaves(P, s_hist, leaf_key, leaf_inc);
 
         if (refresh && lane == 0) {
-            const unsigned long long qlen = probe_tail - probe_head;
             s_ctl[2] = probe_idle;
-            s_ctl[4] = qlen < (unsigned long long)(kQueueCap / 2) ? (int)qlen : 0x7FFFFFFF;
+            s_ctl[4] = probe_avail < kQueueCap / 2 ? (probe_avail > 0 ? probe_avail : 0) : 0x7FFFFFFF;
             if (!s_ctl[3] && probe_cursor >= P.total_local_units) s_ctl[3] = 1;
             s_ctl[5] = epoch + 1;
         }
@@ -631,6 +628,7 @@ __global__ void k_queue_init(unsigned long long* q_seq, ControlBlock* ctl)
     if (i < kQueueCap) q_seq[i] = (unsigned long long)i;
     if (i == 0) {
         ctl->cursor = 0; ctl->q_head = 0; ctl->q_tail = 0; ctl->active = 0; ctl->idle = 0; ctl->status = 0;
+        ctl->avail = 0;
         ctl->t_start = ~0ull; ctl->t_exhausted = ~0ull; ctl->t_end = 0;
     }
 }

@@ -32,6 +32,7 @@ struct alignas(128) ControlBlock {
     int active;                     int pad3[31];
     int idle;                       int pad4[31];
     int status;                     int pad5[31];
+    int avail;                      int pad7[31];   /* published chunks not yet claimed (permits) */
     /* diagnostics (globaltimer ns): first warp start, seed cursor exhausted, last warp exit */
     unsigned long long t_start, t_exhausted, t_end, pad6[13];
 };
