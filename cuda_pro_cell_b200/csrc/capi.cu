@@ -233,17 +233,25 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         en->grid = en->sm_count * 8;
         en->smem = kLogTabDoubles * 8;
         P.smem_hist_slots = 0;
+        P.hist_hashed = 0;
         P.spill = nullptr;
     } else {
         int max_smem = 0;
         CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, en->device), "query smem");
         const char* wenv = getenv("PROCELL_COOP_WARPS");     /* tuning knob: 16 or 24 warps per CTA */
         en->warps = (wenv && atoi(wenv) == 16) ? 16 : 24;
-        const size_t fixed = coop_smem_bytes(en->warps, 0);
-        size_t slots = ((size_t)max_smem > fixed + 1024) ? ((size_t)max_smem - fixed - 1024) / 4 : 0;
-        if (slots > en->counts_len) slots = en->counts_len;
-        P.smem_hist_slots = (uint32_t)slots;
-        en->smem = coop_smem_bytes(en->warps, P.smem_hist_slots);
+        const size_t fixed = coop_smem_bytes(en->warps, 0, 0);
+        const size_t room = (size_t)max_smem > fixed ? (size_t)max_smem - fixed : 0;
+        if (en->counts_len * 4 <= room) {            /* the whole key space fits: direct u32 table */
+            P.hist_hashed = 0;
+            P.smem_hist_slots = (uint32_t)en->counts_len;
+        } else {                                     /* direct-mapped {key,count} cache, power-of-two slots */
+            uint32_t slots = 1;
+            while ((size_t)slots * 2 * 8 <= room) slots *= 2;
+            P.hist_hashed = 1;
+            P.smem_hist_slots = slots;
+        }
+        en->smem = coop_smem_bytes(en->warps, P.smem_hist_slots, P.hist_hashed);
         int grid = 0;
         CU(coop_max_grid(en->device, en->warps, en->smem, &grid), "occupancy query");
         if (grid <= 0) return fail(PROCELL_ERR_CUDA, "cooperative kernel does not fit on this device");

@@ -84,9 +84,28 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return t;
 }
 
-/* shared-memory privatised count; a u32 wrap carries 2^32 into the int64 tensor */
+/* shared-memory privatised count.
+ * direct mode: one u32 per key; a u32 wrap carries 2^32 into the int64 tensor.
+ * hashed mode (key space larger than shared memory: parameter sweeps, very deep histograms): a direct-mapped
+ *   cache of {key:32 | count:32} words indexed by the low key bits.  Keys of one parameter set are contiguous, so
+ *   they never collide with each other; a colliding key evicts the resident one, whose count goes to HBM. */
 __device__ __forceinline__ void hist_add(const SimParams& P, uint32_t* s_hist, uint32_t key, uint32_t v)
 {
+    if (P.hist_hashed) {
+        unsigned long long* slot = reinterpret_cast<unsigned long long*>(s_hist) + (key & (P.smem_hist_slots - 1u));
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(slot);
+        for (;;) {
+            const uint32_t tag = (uint32_t)(cur >> 32), cnt = (uint32_t)cur;
+            const bool same = tag == key && cnt < 0xF0000000u;
+            const unsigned long long want = same ? cur + v : (((unsigned long long)key << 32) | v);
+            const unsigned long long old = atomicCAS(slot, cur, want);
+            if (old == cur) {
+                if (!same && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + tag, (unsigned long long)cnt);
+                return;
+            }
+            cur = old;
+        }
+    }
     if (key < P.smem_hist_slots) {
         uint32_t old = atomicAdd(&s_hist[key], v);
         if (old + v < old) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + key, 1ull << 32);
@@ -358,7 +377,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 
     if (threadIdx.x < 2) s_ctl[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < kLogTabDoubles; i += blockDim.x) s_log[i] = __ldg(P.logtab + i);
-    for (uint32_t i = threadIdx.x; i < P.smem_hist_slots; i += blockDim.x) s_hist[i] = 0u;
+    if (P.hist_hashed) {
+        unsigned long long* tab = reinterpret_cast<unsigned long long*>(s_hist);
+        for (uint32_t i = threadIdx.x; i < P.smem_hist_slots; i += blockDim.x) tab[i] = 0xFFFFFFFF00000000ull;
+    } else {
+        for (uint32_t i = threadIdx.x; i < P.smem_hist_slots; i += blockDim.x) s_hist[i] = 0u;
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -558,9 +582,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         if (lane == 0 && div_total) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions), div_total);
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < P.smem_hist_slots; i += blockDim.x) {
-        uint32_t v = s_hist[i];
-        if (v) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + i, (unsigned long long)v);
+    if (P.hist_hashed) {
+        const unsigned long long* tab = reinterpret_cast<const unsigned long long*>(s_hist);
+        for (uint32_t i = threadIdx.x; i < P.smem_hist_slots; i += blockDim.x) {
+            const unsigned long long e = tab[i];
+            if ((uint32_t)e) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + (uint32_t)(e >> 32), (unsigned long long)(uint32_t)e);
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < P.smem_hist_slots; i += blockDim.x) {
+            uint32_t v = s_hist[i];
+            if (v) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + i, (unsigned long long)v);
+        }
     }
 }
 
@@ -663,9 +695,9 @@ __global__ void __launch_bounds__(256) k_rng_ceiling(int iters, const double* lo
 }
 
 /* ------------------------------------------------------------------------------------------------ host */
-size_t coop_smem_bytes(int warps, uint32_t hist_slots)
+size_t coop_smem_bytes(int warps, uint32_t hist_slots, int hashed)
 {
-    return (size_t)kLogTabDoubles * 8 + kSmemCtlBytes + (size_t)warps * 4 * kStackCap * 8 + (size_t)hist_slots * 4;
+    return (size_t)kLogTabDoubles * 8 + kSmemCtlBytes + (size_t)warps * 4 * kStackCap * 8 + (size_t)hist_slots * (hashed ? 8 : 4);
 }
 
 template <int WARPS>
@@ -689,7 +721,7 @@ cudaError_t coop_max_grid(int device, int warps, size_t smem_bytes, int* grid_ou
 
 cudaError_t launch_coop(const SimParams& p, int warps, int grid, cudaStream_t stream)
 {
-    size_t smem = coop_smem_bytes(warps, p.smem_hist_slots);
+    size_t smem = coop_smem_bytes(warps, p.smem_hist_slots, p.hist_hashed);
     if (warps == 24) k_proliferate_coop<24><<<grid, 24 * 32, smem, stream>>>(p);
     else k_proliferate_coop<16><<<grid, 16 * 32, smem, stream>>>(p);
     return cudaGetLastError();

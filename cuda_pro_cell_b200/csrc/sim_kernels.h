@@ -63,13 +63,15 @@ struct SimParams {
     uint32_t shard_world, shard_rank;
     unsigned long long total_local_units;   /* n_sets * local_units_per_set */
     uint32_t rk[20];              /* Philox round keys: rk[2r] = seed_lo + r*W0, rk[2r+1] = seed_hi + r*W1 */
-    uint32_t smem_hist_slots;     /* keys below this are privatised in shared memory */
+    uint32_t smem_hist_slots;     /* direct mode: keys below this are privatised in shared memory (u32 each);
+                                     hashed mode: number of {key,count} u64 slots, a power of two */
+    int hist_hashed;              /* 1: key space larger than shared memory -> direct-mapped {key,count} cache */
     int refcompat;
     int donate;                   /* 0: never hand work to starving warps (diagnostic) */
     double t_max;
 };
 
-size_t coop_smem_bytes(int warps, uint32_t hist_slots);
+size_t coop_smem_bytes(int warps, uint32_t hist_slots, int hashed);
 cudaError_t launch_coop(const SimParams& p, int warps, int grid, cudaStream_t stream);
 cudaError_t coop_max_grid(int device, int warps, size_t smem_bytes, int* grid_out);
 cudaError_t launch_simple(const SimParams& p, int grid, cudaStream_t stream);
