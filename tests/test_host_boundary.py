@@ -1,0 +1,130 @@
+"""The drop-in boundary on the host side (no GPU): C-ABI exports, text formats, plan, CLI argument handling."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from cuda_pro_cell_b200 import _lib, api, synth
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "procell_b200.h").read_text()
+    declared = set(re.findall(r"\b(procell_[a-z0-9_]+)\s*\(", header))
+    lib = C.CDLL(str(_lib.LIB_PATH))
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libprocell_b200.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), "python binding and header disagree"
+    assert b"sm_100a" in _lib.load().procell_version()
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    v, f = synth.synthetic_histogram(100)
+    plan = api.Plan(v, f, 1.0)
+    with pytest.raises(api.ProcellError) as e:
+        api.proliferate(plan, [synth.TYPES_CONFIG1], 10.0)
+    assert e.value.code == _lib.ERR_CUDA and "no CPU path" in str(e.value)
+
+
+def test_histogram_reader_follows_operator_semantics(tmp_path):
+    p = tmp_path / "h.txt"
+    p.write_text("1.0 0\n8.144 53\n  9823.85\t274\n1e3 7 garbage 5\n12 3\n")
+    v, f = api.read_histogram(p)
+    # pairs are read until the first parse failure (parser.cu:103-106); zero-frequency lines are kept here
+    assert v.tolist() == [1.0, 8.144, 9823.85, 1000.0] and f.tolist() == [0, 53, 274, 7]
+    with pytest.raises(api.ProcellError):
+        api.read_histogram(tmp_path / "missing.txt")
+
+
+def test_cell_types_reader_and_proportion_check(tmp_path):
+    p = tmp_path / "c.txt"
+    p.write_text("0.53 48.33 21.6\n0.29 86.3 26.8\n0.18 -1 -1\n")
+    t = api.read_cell_types(p)
+    assert t.tolist() == [[0.53, 48.33, 21.6], [0.29, 86.3, 26.8], [0.18, -1.0, -1.0]]
+    p.write_text("0.5 48.33 21.6\n0.3 86.3 26.8\n")
+    with pytest.raises(api.ProcellError) as e:
+        api.read_cell_types(p)
+    assert e.value.code == _lib.ERR_PROPORTION
+    assert "ERROR: proportion distribution of cell types does not sum to 1, aborting." in str(e.value)
+    p.write_text("0.5 1 1\n0.499999995 2 2\n")       # |1 - sum| <= 1e-8 is accepted (parser.cu:60-61)
+    assert len(api.read_cell_types(p)) == 2
+
+
+def test_writer_format(tmp_path):
+    out = tmp_path / "o.txt"
+    rv = np.array([0.8360867925, 1.5, 1234567.891234, 1e-7, 12.0])
+    rf = np.array([2, 0, 5, 1, 2**40], dtype=np.int64)
+    rr = np.array([[2, 0], [0, 0], [1, 4], [0, 1], [2**40 - 1, 1]], dtype=np.int64)
+    api.write_histogram(out, rv, rf, rr)
+    # precision(10) default float format == %.10g, TAB separated, zero rows skipped, int64 counts (parser.cu:187-217)
+    assert out.read_text() == ("0.8360867925\t2\t2\t0\n1234567.891\t5\t1\t4\n1e-07\t1\t0\t1\n"
+                               "12\t1099511627776\t1099511627775\t1\n")
+    api.write_histogram(out, rv, rf)
+    assert out.read_text().splitlines()[0] == "0.8360867925\t2"
+
+
+def test_plan_equals_oracle_plan(oracle):
+    rng = np.random.default_rng(0)
+    for n_lines, phi in ((1, 1.0), (50, 0.0), (300, 0.37), (1024, 1e-7), (40, 1e9)):
+        v = np.round(10 ** rng.uniform(-2, 4, n_lines), 6)
+        f = rng.integers(0, 50, n_lines).astype(np.uint64)
+        a, b = api.Plan(v, f, phi), oracle.OraclePlan(v, f, phi)
+        assert (a.n_bins, a.n_keys, a.n_rows, a.n_cells, a.phi) == (b.n_bins, b.n_keys, b.n_rows, b.n_cells, b.phi)
+        assert np.array_equal(a.row_value, b.row_value) and np.array_equal(a.key_row, b.key_row)
+        assert np.array_equal(a.bin_keybase, b.bin_keybase) and np.array_equal(a.bin_kdiv, b.bin_kdiv)
+    w = synth.workload(2)
+    a, b = api.Plan(w.values, w.freqs, w.phi), oracle.OraclePlan(w.values, w.freqs, w.phi)
+    assert np.array_equal(a.key_row, b.key_row) and a.n_keys == b.n_keys
+    counts = rng.integers(0, 9, (a.n_keys, 4)).astype(np.int64)
+    rf, rr = a.merge_rows(counts)
+    assert int(rf.sum()) == int(counts.sum()) and np.array_equal(rr.sum(axis=1), rf)
+
+
+def test_plan_limits():
+    with pytest.raises(api.ProcellError):
+        api.Plan(np.array([1.0]), np.array([2**33], dtype=np.uint64), 1.0)        # more than 2^32-1 seed cells
+    p = api.Plan(np.array([1.0]), np.array([3], dtype=np.uint64), 1e-300)           # halvings capped at 63
+    assert p.depth_capped and int(p.bin_kdiv[0]) == 63
+
+
+def _cli(*args):
+    return subprocess.run([str(_lib.CLI_PATH), *args], capture_output=True, text=True, timeout=60)
+
+
+def test_cli_messages_match_the_reference(tmp_path):
+    """stdout + exit status 1, same strings as cmdargs.cpp:41-45,48-75,97-106 (README spellings accepted too)"""
+    r = _cli("--bogus")
+    assert (r.returncode, r.stdout) == (1, "Invalid option --bogus\n")
+    r = _cli("-h", "a", "--histogram", "b")
+    assert (r.returncode, r.stdout) == (1, "Option --histogram (-h) already given\n")
+    r = _cli("-c")
+    assert (r.returncode, r.stdout) == (1, "Option --cell-types (-c) requires a filename\n")
+    r = _cli("-t", "-3")
+    assert (r.returncode, r.stdout) == (1, "Option --time-max (-t) requires an integer value >= 0\n")
+    r = _cli("-p", "0")
+    assert (r.returncode, r.stdout) == (1, "Option --phi-min (-p) requires a double value > 0\n")
+    r = _cli("-d", "24")
+    assert (r.returncode, r.stdout) == (1, "Option --tree-depth (-d) requires an integer value >= 1 && <= 23\n")
+    r = _cli("-r", "--track-ratio")
+    assert (r.returncode, r.stdout) == (1, "Option --track-ratio (-r) already given\n")
+    r = _cli("-o", "x")
+    assert r.returncode == 1 and r.stdout.splitlines() == ["The following missing arguments are required:",
+                                                           "--histogram (-h)", "--cell-types (-c)", "--t-max (-t)"]
+    r = _cli("--help")
+    assert r.returncode == 0 and "--histogram" in r.stdout
+    # -p is optional (README.md:98-102); both long spellings parse; bad proportions abort before any GPU work
+    h, c = tmp_path / "h.txt", tmp_path / "c.txt"
+    h.write_text("10 5\n")
+    c.write_text("0.5 10 1\n0.3 20 2\n")
+    r = _cli("--histogram", str(h), "--cell-types", str(c), "--time-max", "5", "--phi", "1", "--output", str(tmp_path / "o"),
+             "-d", "7", "-r")
+    assert (r.returncode, r.stdout) == (1, "ERROR: proportion distribution of cell types does not sum to 1, aborting.\n")
+    r = _cli("-h", str(tmp_path / "nope"), "-c", str(c), "-t", "5")
+    assert r.returncode == 1 and "cannot open histogram file" in r.stdout
