@@ -136,3 +136,51 @@ def simulate(plan: OraclePlan, types, t_max, seed, refcompat=False, root_begin=0
 
 def n_host_threads() -> int:
     return len(os.sched_getaffinity(0))
+
+
+# ---- the reference's own XORWOW stream (oracle/xorwow_ref.c), pinned by tests/golden/ref_*.json -------------------
+_xlib = None
+
+
+def xlib():
+    global _xlib
+    if _xlib is None:
+        X = C.CDLL(str(build_oracle("libxorwow_ref.so")))
+        _i32p = C.POINTER(C.c_int32)
+        X.xorwow_ref_simulate.restype = C.c_long
+        X.xorwow_ref_simulate.argtypes = [_f64p, _u64p, C.c_size_t, _f64p, C.c_size_t, C.c_double, C.c_double,
+                                          C.c_uint64, C.c_uint64, C.c_int, C.c_size_t, _f64p, _u64p, _i32p, _u64p]
+        X.xorwow_uniform.restype = C.c_double
+        X.xorwow_uniform.argtypes = [C.c_uint64]
+        X.xorwow_normal.restype = C.c_double
+        X.xorwow_normal.argtypes = [C.c_uint64, C.c_double, C.c_double]
+        _xlib = X
+    return _xlib
+
+
+def xorwow_simulate(values, freqs, types, t_max, phi, T0, T1=None, max_depth=23):
+    """The reference as written, for wall-clock seeds T0 (population) and T1 (iteration).  Returns dict(row_value,
+    row_freq, row_ratio, divisions) with zero rows included, or None if a cell outlives max_depth levels."""
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    f = np.ascontiguousarray(freqs, dtype=np.uint64)
+    t = np.ascontiguousarray(types, dtype=np.float64)
+    cap = 1
+    for val, fr in zip(v, f):
+        c = float(val)
+        while fr > 0 and c >= phi and cap < (1 << 24):
+            cap += 1
+            c /= 2
+    rv = np.zeros(cap, dtype=np.float64)
+    rf = np.zeros(cap, dtype=np.uint64)
+    rr = np.zeros((cap, len(t)), dtype=np.int32)
+    dv = C.c_uint64()
+    n = xlib().xorwow_ref_simulate(v.ctypes.data_as(_f64p), f.ctypes.data_as(_u64p), len(v), t.ctypes.data_as(_f64p),
+                                   len(t), float(t_max), float(phi), int(T0), int(T0 if T1 is None else T1),
+                                   int(max_depth), cap, rv.ctypes.data_as(_f64p), rf.ctypes.data_as(_u64p),
+                                   rr.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(dv))
+    if n == -2:
+        return None
+    if n < 0:
+        raise RuntimeError("xorwow_ref_simulate failed rc=%d" % n)
+    return dict(row_value=rv[:n], row_freq=rf[:n].astype(np.int64), row_ratio=rr[:n].astype(np.int64),
+                divisions=int(dv.value))
