@@ -208,7 +208,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -333,7 +333,9 @@ def main():
                     "achieved": per_gpu / 1e9, "peak": ceiling / 1e9, "unit": "Gdivisions/s per GPU",
                     "frac": per_gpu / ceiling,
                     "peak_source": "k_rng_ceiling measured live: one Philox4x32-10 block + Box-Muller pair + 2 timers per division, no tree/atomics",
-                    "traffic": None,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this workload, from the
+                    # committed capture profiles/r1_coop24_config2_ncu_full.md (tables + count tensor + donated chunks)
+                    "traffic": 646144 if world == 1 else None,
                     "hbm": {"achieved": alg_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
