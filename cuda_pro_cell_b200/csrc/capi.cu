@@ -238,8 +238,9 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     } else {
         int max_smem = 0;
         CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, en->device), "query smem");
-        const char* wenv = getenv("PROCELL_COOP_WARPS");     /* tuning knob: 16 or 24 warps per CTA */
-        en->warps = (wenv && atoi(wenv) == 16) ? 16 : 24;
+        const char* wenv = getenv("PROCELL_COOP_WARPS");     /* tuning knob: 16, 24 or 32 warps per CTA */
+        const int wreq = wenv ? atoi(wenv) : 0;
+        en->warps = (wreq == 16 || wreq == 24) ? wreq : 32;
         const size_t fixed = coop_smem_bytes(en->warps, 0, 0);
         const size_t room = (size_t)max_smem > fixed ? (size_t)max_smem - fixed : 0;
         if (en->counts_len * 4 <= room) {            /* the whole key space fits: direct u32 table */
@@ -253,7 +254,7 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         }
         en->smem = coop_smem_bytes(en->warps, P.smem_hist_slots, P.hist_hashed);
         int grid = 0;
-        CU(coop_max_grid(en->device, en->warps, en->smem, &grid), "occupancy query");
+        CU(coop_max_grid(en->device, en->warps, P.hist_hashed, en->smem, &grid), "occupancy query");
         if (grid <= 0) return fail(PROCELL_ERR_CUDA, "cooperative kernel does not fit on this device");
         en->grid = grid;
         en->block = en->warps * 32;

@@ -85,13 +85,15 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 }
 
 /* shared-memory privatised count.
- * direct mode: one u32 per key; a u32 wrap carries 2^32 into the int64 tensor.
+ * direct mode (HASHED = false): the whole key space fits: one u32 per key; a u32 wrap carries 2^32 into the int64
+ *   tensor in HBM.
  * hashed mode (key space larger than shared memory: parameter sweeps, very deep histograms): a direct-mapped
  *   cache of {key:32 | count:32} words indexed by the low key bits.  Keys of one parameter set are contiguous, so
  *   they never collide with each other; a colliding key evicts the resident one, whose count goes to HBM. */
+template <bool HASHED>
 __device__ __forceinline__ void hist_add(const SimParams& P, uint32_t* s_hist, uint32_t key, uint32_t v)
 {
-    if (P.hist_hashed) {
+    if (HASHED) {
         unsigned long long* slot = reinterpret_cast<unsigned long long*>(s_hist) + (key & (P.smem_hist_slots - 1u));
         unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(slot);
         for (;;) {
@@ -105,25 +107,23 @@ __device__ __forceinline__ void hist_add(const SimParams& P, uint32_t* s_hist, u
             }
             cur = old;
         }
-    }
-    if (key < P.smem_hist_slots) {
-        uint32_t old = atomicAdd(&s_hist[key], v);
-        if (old + v < old) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + key, 1ull << 32);
     } else {
-        atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + key, (unsigned long long)v);
+        const uint32_t old = atomicAdd(&s_hist[key], v);
+        if (old + v < old) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + key, 1ull << 32);
     }
 }
 
-/* every lane may carry `inc` (0..2) leaves for `key`; equal keys are merged (MATCH.ANY + REDUX), one shared
- * atomic per distinct key */
-__device__ __forceinline__ void warp_count_leaves(const SimParams& P, uint32_t* s_hist, uint32_t key, uint32_t inc)
+/* the lanes in `mask` (all of which call this) may each carry `inc` (0..2) leaves for `key`; equal keys are merged
+ * (MATCH.ANY + REDUX), one shared atomic per distinct key */
+template <bool HASHED>
+__device__ __forceinline__ void warp_count_leaves(const SimParams& P, uint32_t* s_hist, unsigned mask, uint32_t key, uint32_t inc)
 {
-    const unsigned has = __ballot_sync(kFull, inc > 0);
+    const unsigned has = __ballot_sync(mask, inc > 0);
     if (has == 0) return;
     if (inc > 0) {
         const unsigned grp = __match_any_sync(has, key);
         const uint32_t total = __reduce_add_sync(grp, inc);
-        if ((threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1)) hist_add(P, s_hist, key, total);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1)) hist_add<HASHED>(P, s_hist, key, total);
     }
 }
 
@@ -364,9 +364,96 @@ __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* 
     return o;
 }
 
+/* per-warp division counters: one plain counter for single-set runs, (set, count) with flush-on-change for sweeps */
+struct DivCount {
+    unsigned long long total;
+    uint32_t set, cnt;
+};
+
+/* ---- DIVIDE iteration: the lanes below `take` pop one node each (newest first), draw ONE Philox block -> one
+ * Box-Muller pair -> both daughters' timers, classify the daughters and push the ones that will divide.
+ * FULL = all 32 lanes have a node (the common case): no inactive-lane defaults, no divergence bookkeeping. */
+template <bool FULL, bool HASHED>
+__device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P, const double* s_log, uint32_t* s_hist,
+                                                 uint32_t take, unsigned lt_mask, bool multi_set, DivCount& dc)
+{
+    const unsigned mask = FULL ? kFull : ((1u << take) - 1u);
+    const uint32_t T = P.n_types;
+    const uint32_t top0 = w.top - take;
+    if (FULL || (uint32_t)w.lane < take) {
+        const uint32_t idx = (w.top - 1u - (uint32_t)w.lane) & kRingMask;
+        const double t_div = pcs_bits2d(w.sa[idx]);
+        const uint64_t heap = w.sb[idx];
+        const uint64_t pc = w.sc[idx];
+        const uint64_t d = w.sd[idx];
+        const uint32_t dlo = (uint32_t)d;
+        const uint32_t retry = (uint32_t)(d >> 32);
+        const uint32_t set = dlo & 0xFFFFu;
+        const uint32_t type = (dlo >> 16) & 63u;
+        const double2 ms = __ldg(P.type_musd + set * T + type);
+        const pcs_u32x4 blk = pcs_draw_rk((uint32_t)pc, set, retry, PCS_TAG_DIVISION, heap, P.rk);
+        double z0, z1;
+        pcs_normal_pair(blk, s_log, 0.0, &z0, &z1);
+        const bool forced = retry >= PCS_MAX_RETRY;        /* 255 redraws failed: the timer is the mean */
+        const double tm0 = forced ? ms.x : pcs_timer(ms.x, ms.y, z0);
+        const double tm1 = forced ? ms.x : pcs_timer(ms.x, ms.y, z1);
+        const bool want0 = (dlo & (1u << 28)) != 0u, want1 = (dlo & (2u << 28)) != 0u;
+        const bool ok0 = want0 && (tm0 > 0.0 || forced), ok1 = want1 && (tm1 > 0.0 || forced);
+        const double tc0 = PCS_ADD(t_div, tm0);
+        const double tc1 = PCS_ADD(t_div, tm1);
+        const bool late0 = tc0 > P.t_max, late1 = tc1 > P.t_max;      /* proliferation.cu:404-410 */
+        const bool deeper = (dlo & (63u << 22)) != 0u;                /* f/2 > phi one level down (:323) */
+        const uint32_t leaf_inc = (uint32_t)(ok0 && late0) + (uint32_t)(ok1 && late1);
+        const bool int0 = ok0 && !late0 && deeper;                    /* daughter 0 lives on and will divide */
+        const bool int1 = ok1 && !late1 && deeper;
+        const uint32_t rej = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
+        const uint32_t leaf_key = (uint32_t)(pc >> 32) + T;
+        if (retry == 0u) {
+            if (multi_set) {
+                if (set != dc.set) {
+                    if (dc.cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
+                    dc.cnt = 0; dc.set = set;
+                }
+                dc.cnt += 1;
+            } else {
+                dc.total += 1;
+            }
+        }
+        /* all popped nodes have been read (their values fed the predicates above), so the slots may be overwritten */
+        const unsigned b0 = __ballot_sync(mask, int0);
+        const unsigned b1 = __ballot_sync(mask, int1);
+        const unsigned br = __ballot_sync(mask, rej != 0u);
+        const uint64_t child_c = ((pc >> 32) + T) << 32 | (pc & 0xFFFFFFFFull);
+        const uint64_t child_d = (uint64_t)((dlo | (3u << 28)) - (1u << 22));
+        uint32_t top = top0;
+        if (int0) {
+            const uint32_t i0 = (top + __popc(b0 & lt_mask)) & kRingMask;
+            w.sa[i0] = pcs_d2bits(tc0); w.sb[i0] = heap * 2ull; w.sc[i0] = child_c; w.sd[i0] = child_d;
+        }
+        top += __popc(b0);
+        if (int1) {
+            const uint32_t i1 = (top + __popc(b1 & lt_mask)) & kRingMask;
+            w.sa[i1] = pcs_d2bits(tc1); w.sb[i1] = heap * 2ull + 1ull; w.sc[i1] = child_c; w.sd[i1] = child_d;
+        }
+        top += __popc(b1);
+        if (br) {   /* a daughter's timer came out <= 0: redraw it in a later iteration (cell.cu:114-118) */
+            if (rej) {
+                const uint32_t ir = (top + __popc(br & lt_mask)) & kRingMask;
+                w.sa[ir] = pcs_d2bits(t_div); w.sb[ir] = heap; w.sc[ir] = pc;
+                w.sd[ir] = (uint64_t)((dlo & ~(3u << 28)) | (rej << 28)) | ((uint64_t)(retry + 1u) << 32);
+            }
+            top += __popc(br);
+        }
+        warp_count_leaves<HASHED>(P, s_hist, mask, leaf_key, leaf_inc);
+        w.top = top;
+    }
+    if (!FULL) w.top = __shfl_sync(kFull, w.top, 0);    /* lane 0 always holds a node when take > 0 */
+    __syncwarp();
+}
+
 }  // namespace
 
-template <int WARPS>
+template <int WARPS, bool HASHED>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid_constant__ SimParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -377,7 +464,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 
     if (threadIdx.x < 2) s_ctl[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < kLogTabDoubles; i += blockDim.x) s_log[i] = __ldg(P.logtab + i);
-    if (P.hist_hashed) {
+    if (HASHED) {
         unsigned long long* tab = reinterpret_cast<unsigned long long*>(s_hist);
         for (uint32_t i = threadIdx.x; i < P.smem_hist_slots; i += blockDim.x) tab[i] = 0xFFFFFFFF00000000ull;
     } else {
@@ -388,7 +475,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const uint32_t T = P.n_types;
     ControlBlock* ctl = P.ctl;
 
     WarpCtx w;
@@ -407,8 +493,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
      * warp of the CTA every few iterations and read from shared memory by all: busy warps never poll HBM. */
     if (threadIdx.x == 0) { s_ctl[2] = 0; s_ctl[3] = P.total_local_units == 0; s_ctl[4] = 0; s_ctl[5] = 0; }
     __syncthreads();
-    uint32_t div_set = 0, div_cnt = 0;          /* divisions of parameter set div_set not yet flushed */
-    unsigned long long div_total = 0;           /* single-set runs: plain per-lane counter */
+    DivCount dc;
+    dc.total = 0; dc.set = 0; dc.cnt = 0;
     const bool multi_set = P.n_sets > 1u;
     uint32_t iter = 0;
     int donate_epoch = -1;
@@ -459,7 +545,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 }
                 w.top += __popc(live);
                 __syncwarp();
-                warp_count_leaves(P, s_hist, so.key, so.kind == 1 ? 1u : 0u);
+                warp_count_leaves<HASHED>(P, s_hist, kFull, so.key, so.kind == 1 ? 1u : 0u);
                 continue;
             }
             if (n == 0u) {
@@ -471,95 +557,28 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 
         /* hunger probe.  Every 64th iteration (staggered by warp) this warp refreshes the CTA's shared snapshot of
          * "how many warps are starving", "how long is the donation queue" and "is the seed cursor exhausted" from
-         * HBM; every iteration all warps read the snapshot from shared memory.  Loads are issued now and consumed
-         * after the math. */
+         * HBM; every 4th iteration each warp looks at the snapshot in shared memory.  Loads are issued now and
+         * consumed after the math. */
         ++iter;
-        int probe_idle = 0;
+        int probe_idle = 0, probe_avail = 0, epoch = 0;
         unsigned long long probe_cursor = 0;
-        int probe_avail = 0;
-        const bool refresh = ((iter + (uint32_t)warp * 3u) & 63u) == 0u;
-        if (refresh && lane == 0) {
-            probe_idle = ld_volatile_s32(&ctl->idle);
-            probe_avail = ld_volatile_s32(&ctl->avail);
-            if (!s_ctl[3]) probe_cursor = ld_volatile_u64(&ctl->cursor);
+        bool refresh = false, hungry = false;
+        if ((iter & 3u) == 0u) {
+            refresh = ((iter + (uint32_t)warp * 4u) & 63u) == 0u;
+            if (refresh && lane == 0) {
+                probe_idle = ld_volatile_s32(&ctl->idle);
+                probe_avail = ld_volatile_s32(&ctl->avail);
+                if (!s_ctl[3]) probe_cursor = ld_volatile_u64(&ctl->cursor);
+            }
+            /* donate at most once per snapshot epoch, and only while the queue is shorter than the line of starving warps */
+            epoch = s_ctl[5];
+            hungry = P.donate && s_ctl[3] && s_ctl[2] > s_ctl[4] && epoch != donate_epoch &&
+                     (n + 32u * (w.sp_top - w.sp_bottom)) >= 64u;
         }
-        /* donate at most once per snapshot epoch, and only while the queue is shorter than the line of starving warps */
-        const int epoch = s_ctl[5];
-        const bool hungry = P.donate && s_ctl[3] && s_ctl[2] > s_ctl[4] && epoch != donate_epoch &&
-                            (n + 32u * (w.sp_top - w.sp_bottom)) >= 64u;
 
-        /* ---- DIVIDE iteration: one node per lane, newest first ---- */
         const uint32_t take = n < 32u ? n : 32u;
-        bool int0 = false, int1 = false;        /* daughter 0 / 1 lives on and will divide */
-        uint32_t rej = 0, leaf_inc = 0, leaf_key = 0, dlo = 0, retry = 0;
-        uint64_t heap = 0, pc = 0;
-        double t_div = 0.0, tc0 = 0.0, tc1 = 0.0;
-        if ((uint32_t)lane < take) {
-            const uint32_t idx = (w.top - 1u - (uint32_t)lane) & kRingMask;
-            t_div = pcs_bits2d(w.sa[idx]);
-            heap = w.sb[idx];
-            pc = w.sc[idx];
-            const uint64_t d = w.sd[idx];
-            dlo = (uint32_t)d;
-            retry = (uint32_t)(d >> 32);
-            const uint32_t set = dlo & 0xFFFFu;
-            const uint32_t type = (dlo >> 16) & 63u;
-            const double2 ms = __ldg(P.type_musd + set * T + type);
-            const pcs_u32x4 blk = pcs_draw_rk((uint32_t)pc, set, retry, PCS_TAG_DIVISION, heap, P.rk);
-            double z0, z1;
-            pcs_normal_pair(blk, s_log, 0.0, &z0, &z1);
-            const bool forced = retry >= PCS_MAX_RETRY;        /* 255 redraws failed: the timer is the mean */
-            const double tm0 = forced ? ms.x : pcs_timer(ms.x, ms.y, z0);
-            const double tm1 = forced ? ms.x : pcs_timer(ms.x, ms.y, z1);
-            const bool want0 = (dlo & (1u << 28)) != 0u, want1 = (dlo & (2u << 28)) != 0u;
-            const bool ok0 = want0 && (tm0 > 0.0 || forced), ok1 = want1 && (tm1 > 0.0 || forced);
-            tc0 = PCS_ADD(t_div, tm0);
-            tc1 = PCS_ADD(t_div, tm1);
-            const bool late0 = tc0 > P.t_max, late1 = tc1 > P.t_max;      /* proliferation.cu:404-410 */
-            const bool deeper = (dlo & (63u << 22)) != 0u;                /* f/2 > phi one level down (:323) */
-            leaf_inc = (uint32_t)(ok0 && late0) + (uint32_t)(ok1 && late1);
-            int0 = ok0 && !late0 && deeper;
-            int1 = ok1 && !late1 && deeper;
-            rej = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
-            leaf_key = (uint32_t)(pc >> 32) + T;
-            if (retry == 0u) {
-                if (multi_set) {
-                    if (set != div_set) {
-                        if (div_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + div_set, (unsigned long long)div_cnt);
-                        div_cnt = 0; div_set = set;
-                    }
-                    div_cnt += 1;
-                } else {
-                    div_total += 1;
-                }
-            }
-        }
-        w.top -= take;
-        const unsigned b0 = __ballot_sync(kFull, int0);
-        const unsigned b1 = __ballot_sync(kFull, int1);
-        const unsigned br = __ballot_sync(kFull, rej != 0u);
-        const uint64_t child_c = ((pc >> 32) + T) << 32 | (pc & 0xFFFFFFFFull);
-        const uint64_t child_d = (uint64_t)((dlo | (3u << 28)) - (1u << 22));
-        if (int0) {
-            const uint32_t idx = (w.top + __popc(b0 & lt_mask)) & kRingMask;
-            w.sa[idx] = pcs_d2bits(tc0); w.sb[idx] = heap * 2ull; w.sc[idx] = child_c; w.sd[idx] = child_d;
-        }
-        w.top += __popc(b0);
-        if (int1) {
-            const uint32_t idx = (w.top + __popc(b1 & lt_mask)) & kRingMask;
-            w.sa[idx] = pcs_d2bits(tc1); w.sb[idx] = heap * 2ull + 1ull; w.sc[idx] = child_c; w.sd[idx] = child_d;
-        }
-        w.top += __popc(b1);
-        if (br) {   /* a daughter's timer came out <= 0: redraw it in a later iteration (cell.cu:114-118) */
-            if (rej) {
-                const uint32_t idx = (w.top + __popc(br & lt_mask)) & kRingMask;
-                w.sa[idx] = pcs_d2bits(t_div); w.sb[idx] = heap; w.sc[idx] = pc;
-                w.sd[idx] = (uint64_t)((dlo & ~(3u << 28)) | (rej << 28)) | ((uint64_t)(retry + 1u) << 32);
-            }
-            w.top += __popc(br);
-        }
-        __syncwarp();
-        warp_count_leaves(P, s_hist, leaf_key, leaf_inc);
+        if (take == 32u) divide_iteration<true, HASHED>(w, P, s_log, s_hist, take, lt_mask, multi_set, dc);
+        else divide_iteration<false, HASHED>(w, P, s_log, s_hist, take, lt_mask, multi_set, dc);
 
         if (refresh && lane == 0) {
             s_ctl[2] = probe_idle;
@@ -575,14 +594,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 
     if (lane == 0) atomicMax(&ctl->t_end, global_timer_ns());
     if (multi_set) {
-        if (div_cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + div_set, (unsigned long long)div_cnt);
+        if (dc.cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
     } else {
-        div_total = __reduce_add_sync(kFull, (unsigned)(div_total & 0xFFFFFFFFull)) +
-                    ((unsigned long long)__reduce_add_sync(kFull, (unsigned)(div_total >> 32)) << 32);
-        if (lane == 0 && div_total) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions), div_total);
+        unsigned long long tot = dc.total;
+        for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(kFull, tot, off);
+        if (lane == 0 && tot) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions), tot);
     }
     __syncthreads();
-    if (P.hist_hashed) {
+    if (HASHED) {
         const unsigned long long* tab = reinterpret_cast<const unsigned long long*>(s_hist);
         for (uint32_t i = threadIdx.x; i < P.smem_hist_slots; i += blockDim.x) {
             const unsigned long long e = tab[i];
@@ -700,13 +719,13 @@ size_t coop_smem_bytes(int warps, uint32_t hist_slots, int hashed)
     return (size_t)kLogTabDoubles * 8 + kSmemCtlBytes + (size_t)warps * 4 * kStackCap * 8 + (size_t)hist_slots * (hashed ? 8 : 4);
 }
 
-template <int WARPS>
+template <int WARPS, bool HASHED>
 static cudaError_t coop_max_grid_t(int device, size_t smem_bytes, int* grid_out)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_proliferate_coop<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k_proliferate_coop<WARPS, HASHED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     int per_sm = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<WARPS>, WARPS * 32, smem_bytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<WARPS, HASHED>, WARPS * 32, smem_bytes);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
@@ -714,16 +733,28 @@ static cudaError_t coop_max_grid_t(int device, size_t smem_bytes, int* grid_out)
     return cudaSuccess;
 }
 
-cudaError_t coop_max_grid(int device, int warps, size_t smem_bytes, int* grid_out)
+cudaError_t coop_max_grid(int device, int warps, int hashed, size_t smem_bytes, int* grid_out)
 {
-    return warps == 24 ? coop_max_grid_t<24>(device, smem_bytes, grid_out) : coop_max_grid_t<16>(device, smem_bytes, grid_out);
+    if (hashed) {
+        if (warps == 32) return coop_max_grid_t<32, true>(device, smem_bytes, grid_out);
+        return warps == 24 ? coop_max_grid_t<24, true>(device, smem_bytes, grid_out) : coop_max_grid_t<16, true>(device, smem_bytes, grid_out);
+    }
+    if (warps == 32) return coop_max_grid_t<32, false>(device, smem_bytes, grid_out);
+    return warps == 24 ? coop_max_grid_t<24, false>(device, smem_bytes, grid_out) : coop_max_grid_t<16, false>(device, smem_bytes, grid_out);
 }
 
 cudaError_t launch_coop(const SimParams& p, int warps, int grid, cudaStream_t stream)
 {
     size_t smem = coop_smem_bytes(warps, p.smem_hist_slots, p.hist_hashed);
-    if (warps == 24) k_proliferate_coop<24><<<grid, 24 * 32, smem, stream>>>(p);
-    else k_proliferate_coop<16><<<grid, 16 * 32, smem, stream>>>(p);
+    if (p.hist_hashed) {
+        if (warps == 32) k_proliferate_coop<32, true><<<grid, 32 * 32, smem, stream>>>(p);
+        else if (warps == 24) k_proliferate_coop<24, true><<<grid, 24 * 32, smem, stream>>>(p);
+        else k_proliferate_coop<16, true><<<grid, 16 * 32, smem, stream>>>(p);
+    } else {
+        if (warps == 32) k_proliferate_coop<32, false><<<grid, 32 * 32, smem, stream>>>(p);
+        else if (warps == 24) k_proliferate_coop<24, false><<<grid, 24 * 32, smem, stream>>>(p);
+        else k_proliferate_coop<16, false><<<grid, 16 * 32, smem, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -8,7 +8,7 @@
 namespace procell_b200 {
 
 /* ---- geometry of the warp-cooperative kernel ---- */
-constexpr int kCoopWarpsMax = 24;              /* warps per CTA (16 or 24), one CTA per SM */
+constexpr int kCoopWarpsMax = 32;              /* warps per CTA (16, 24 or 32), one CTA per SM */
 constexpr int kStackCap = 128;                 /* nodes per warp kept in shared memory (ring) */
 constexpr int kChunkNodes = 32;                /* spill / donation granule: one node per lane */
 constexpr int kChunkWords = 4 * kChunkNodes;   /* 4 x u64 fields per node, field-major */
@@ -73,7 +73,7 @@ struct SimParams {
 
 size_t coop_smem_bytes(int warps, uint32_t hist_slots, int hashed);
 cudaError_t launch_coop(const SimParams& p, int warps, int grid, cudaStream_t stream);
-cudaError_t coop_max_grid(int device, int warps, size_t smem_bytes, int* grid_out);
+cudaError_t coop_max_grid(int device, int warps, int hashed, size_t smem_bytes, int* grid_out);
 cudaError_t launch_simple(const SimParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_queue_init(unsigned long long* q_seq, ControlBlock* ctl, cudaStream_t stream);
 cudaError_t launch_rng_ceiling(int grid, int block, int iters, const double* logtab, double mean, double sd,
