@@ -354,7 +354,7 @@ def main():
                         "path": "api.Plan (host) -> procell_engine_load (H2D) -> procell_engine_run -> reduce -> D2H -> merge_rows"},
                 "gpu_launches": 2 * K, "kernels_per_step": ["k_queue_init", "k_proliferate_coop"],
                 "clocks": clocks, "roofline": roofline}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is timed on rank 0 at N = 1 only
             line["cpu_baseline"] = cpu_baseline(w)
         print(json.dumps(line))
     if world > 1:

@@ -53,6 +53,7 @@ SIGNATURES = {
     "procell_plan_export": (C.c_int, [C.c_void_p, _f64p, _u32p, _u32p, _u8p]),
     "procell_merge_rows": (C.c_int, [C.c_void_p, _i64p, C.c_size_t, _i64p, _i64p]),
     "procell_proliferate": (C.c_int, [C.c_void_p, C.POINTER(SimParams), C.c_int, _i64p, _i64p, C.POINTER(RunStats)]),
+    "procell_proliferate_multi": (C.c_int, [C.c_void_p, C.POINTER(SimParams), C.c_int, _i64p, _i64p, C.POINTER(RunStats)]),
     "procell_engine_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "procell_engine_destroy": (None, [C.c_void_p]),
     "procell_engine_load": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SimParams)]),

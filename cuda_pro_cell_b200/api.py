@@ -163,6 +163,21 @@ def proliferate(plan: Plan, types, t_max: float, seed: int = 0x5EED0000, seeding
     return Result(flat[: int(np.prod(shape))].reshape(shape), div, _stats_dict(st))
 
 
+def proliferate_multi(plan: Plan, types, t_max: float, seed: int = 0x5EED0000, n_gpus: int = 0,
+                      seeding_mode: int = SEEDING_IDEAL, kernel: int = KERNEL_COOP) -> Result:
+    """One process, n_gpus GPUs of this box (0 = all): sharded seed-cell units + one NCCL reduce onto GPU 0."""
+    lib = _lib.load()
+    t = _types_array(types)
+    p = _make_params(t, t_max, seed, seeding_mode, kernel, (0, 1, 0))
+    shape = (t.shape[0], plan.n_keys, t.shape[1])
+    flat = np.zeros(max(int(np.prod(shape)), 1), dtype=np.int64)
+    div = np.zeros(t.shape[0], dtype=np.int64)
+    st = RunStats()
+    check(lib.procell_proliferate_multi(plan.h, C.byref(p), int(n_gpus), flat.ctypes.data_as(_i64p),
+                                        div.ctypes.data_as(_i64p), C.byref(st)))
+    return Result(flat[: int(np.prod(shape))].reshape(shape), div, _stats_dict(st))
+
+
 class Engine:
     """Device-resident engine: tables stay in HBM between runs; run() is asynchronous on a CUDA stream."""
 

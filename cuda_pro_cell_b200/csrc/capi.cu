@@ -20,6 +20,7 @@
 #include "sim_kernels.h"
 
 #include <cstdlib>
+#include <dlfcn.h>
 
 using namespace procell_b200;
 
@@ -70,7 +71,7 @@ struct procell_engine {
     int device = 0;
     int sm_count = 0;
     DevBuf bin_start, bin_keybase, bin_kdiv, type_cum, type_sel, type_musd, logtab;
-    DevBuf counts, divisions, ctl, q_seq, q_data, spill;
+    DevBuf counts, ctl, q_seq, q_data, spill;   /* counts = count tensor followed by the division counters */
     SimParams P{};
     bool loaded = false;
     int kernel = PROCELL_KERNEL_COOP;
@@ -122,7 +123,7 @@ void procell_engine_destroy(procell_engine* en)
     if (!en) return;
     cudaSetDevice(en->device);
     DevBuf* bufs[] = { &en->bin_start, &en->bin_keybase, &en->bin_kdiv, &en->type_cum, &en->type_sel, &en->type_musd,
-                       &en->logtab, &en->counts, &en->divisions, &en->ctl, &en->q_seq, &en->q_data, &en->spill };
+                       &en->logtab, &en->counts, &en->ctl, &en->q_seq, &en->q_data, &en->spill };
     for (DevBuf* b : bufs) b->release();
     if (en->ev0) cudaEventDestroy(en->ev0);
     if (en->ev1) cudaEventDestroy(en->ev1);
@@ -186,8 +187,8 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
 
     en->counts_len = S * K * T;
     en->n_sets = S;
-    CU(en->counts.reserve(en->counts_len * 8), "alloc counts");
-    CU(en->divisions.reserve(S * 8), "alloc divisions");
+    /* one allocation: the count tensor followed by the division counters, so that a multi-GPU run needs ONE reduce */
+    CU(en->counts.reserve((en->counts_len + S) * 8), "alloc counts");
 
     SimParams& P = en->P;
     P.bin_start = (const uint32_t*)en->bin_start.p;
@@ -198,7 +199,7 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     P.type_musd = (const double2*)en->type_musd.p;
     P.logtab = (const double*)en->logtab.p;
     P.counts = (long long*)en->counts.p;
-    P.divisions = (long long*)en->divisions.p;
+    P.divisions = (long long*)en->counts.p + en->counts_len;
     P.ctl = (ControlBlock*)en->ctl.p;
     P.q_seq = (unsigned long long*)en->q_seq.p;
     P.q_data = (unsigned long long*)en->q_data.p;
@@ -299,7 +300,7 @@ int procell_engine_finish(procell_engine* en, void* stream_v, int64_t* counts, i
         return fail(PROCELL_ERR_OVERFLOW, "device work pool failure, status " + std::to_string(status));
     if (counts) CU(cudaMemcpy(counts, en->counts.p, en->counts_len * 8, cudaMemcpyDeviceToHost), "download counts");
     std::vector<int64_t> div(en->n_sets);
-    CU(cudaMemcpy(div.data(), en->divisions.p, en->n_sets * 8, cudaMemcpyDeviceToHost), "download divisions");
+    CU(cudaMemcpy(div.data(), (long long*)en->counts.p + en->counts_len, en->n_sets * 8, cudaMemcpyDeviceToHost), "download divisions");
     if (divisions) memcpy(divisions, div.data(), en->n_sets * 8);
     if (stats) {
         stats->divisions = 0;
@@ -327,6 +328,114 @@ int procell_proliferate(const procell_plan* plan, const procell_sim_params* para
     if (rc == PROCELL_OK) rc = procell_engine_run(en, params->seed, nullptr, nullptr, nullptr);
     if (rc == PROCELL_OK) rc = procell_engine_finish(en, nullptr, counts, divisions, stats);
     procell_engine_destroy(en);
+    return rc;
+}
+
+/* ---- single-process multi-GPU: seed-cell units sharded over the GPUs of one box, ONE ncclReduce(sum, int64) ---- */
+namespace {
+typedef struct ncclComm* ncclComm_t;
+struct NcclApi {
+    void* handle = nullptr;
+    int (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load()
+    {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) return false;
+        CommInitAll = (decltype(CommInitAll))dlsym(handle, "ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+        GroupStart = (decltype(GroupStart))dlsym(handle, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(handle, "ncclGroupEnd");
+        Reduce = (decltype(Reduce))dlsym(handle, "ncclReduce");
+        GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+        return CommInitAll && CommDestroy && GroupStart && GroupEnd && Reduce && GetErrorString;
+    }
+};
+NcclApi g_nccl;
+constexpr int kNcclInt64 = 4;   /* ncclInt64 */
+constexpr int kNcclSum = 0;     /* ncclSum */
+}  // namespace
+
+int procell_proliferate_multi(const procell_plan* plan, const procell_sim_params* params, int n_gpus, int64_t* counts,
+                              int64_t* divisions, procell_run_stats* stats)
+{
+    if (!plan || !params || !counts) return fail(PROCELL_ERR_ARG, "procell_proliferate_multi: null argument");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(PROCELL_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    if (n_gpus <= 0) n_gpus = n_dev;
+    if (n_gpus > n_dev) return fail(PROCELL_ERR_ARG, "more GPUs requested than present");
+    if (n_gpus == 1) return procell_proliferate(plan, params, 0, counts, divisions, stats);
+    if (!g_nccl.load()) return fail(PROCELL_ERR_CUDA, "libnccl.so.2 not found: multi-GPU runs need NCCL");
+
+    std::vector<procell_engine*> eng(n_gpus, nullptr);
+    std::vector<cudaStream_t> streams(n_gpus, nullptr);
+    std::vector<ncclComm_t> comms(n_gpus, nullptr);
+    std::vector<int> devs(n_gpus);
+    for (int i = 0; i < n_gpus; ++i) devs[i] = i;
+    int rc = PROCELL_OK;
+    auto cleanup = [&]() {
+        for (int i = 0; i < n_gpus; ++i) {
+            if (comms[i]) g_nccl.CommDestroy(comms[i]);
+            if (streams[i]) { cudaSetDevice(i); cudaStreamDestroy(streams[i]); }
+            procell_engine_destroy(eng[i]);
+        }
+    };
+    for (int i = 0; i < n_gpus && rc == PROCELL_OK; ++i) {
+        rc = procell_engine_create(i, &eng[i]);
+        if (rc != PROCELL_OK) break;
+        procell_sim_params sp = *params;
+        sp.shard_rank = (uint32_t)i;
+        sp.shard_world = (uint32_t)n_gpus;
+        if (sp.shard_unit == 0) sp.shard_unit = 256;
+        rc = procell_engine_load(eng[i], plan, &sp);
+        if (rc == PROCELL_OK && cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking) != cudaSuccess)
+            rc = fail(PROCELL_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    if (rc == PROCELL_OK) {
+        int nrc = g_nccl.CommInitAll(comms.data(), n_gpus, devs.data());
+        if (nrc != 0) rc = fail(PROCELL_ERR_CUDA, std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(nrc));
+    }
+    const size_t n_packed = eng[0] ? eng[0]->counts_len + eng[0]->n_sets : 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (rc == PROCELL_OK) {
+        cudaSetDevice(0);
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, streams[0]);
+        for (int i = 0; i < n_gpus && rc == PROCELL_OK; ++i)
+            rc = procell_engine_run(eng[i], params->seed, streams[i], nullptr, nullptr);
+    }
+    if (rc == PROCELL_OK) {     /* the single exchange step of the path: int64 sum onto GPU 0 over NVLink */
+        g_nccl.GroupStart();
+        for (int i = 0; i < n_gpus; ++i) {
+            int nrc = g_nccl.Reduce(eng[i]->counts.p, eng[i]->counts.p, n_packed, kNcclInt64, kNcclSum, 0, comms[i], streams[i]);
+            if (nrc != 0) rc = fail(PROCELL_ERR_CUDA, std::string("ncclReduce: ") + g_nccl.GetErrorString(nrc));
+        }
+        int nrc = g_nccl.GroupEnd();
+        if (nrc != 0 && rc == PROCELL_OK) rc = fail(PROCELL_ERR_CUDA, std::string("ncclGroupEnd: ") + g_nccl.GetErrorString(nrc));
+        cudaSetDevice(0);
+        cudaEventRecord(e1, streams[0]);
+    }
+    /* every GPU's status word is checked; GPU 0 then holds the reduced tensor */
+    procell_run_stats st0;
+    memset(&st0, 0, sizeof st0);
+    for (int i = n_gpus - 1; i >= 0 && rc == PROCELL_OK; --i)
+        rc = procell_engine_finish(eng[i], streams[i], i == 0 ? counts : nullptr, i == 0 ? divisions : nullptr, i == 0 ? &st0 : nullptr);
+    if (rc == PROCELL_OK && stats) {
+        *stats = st0;
+        float ms = 0.f;
+        cudaSetDevice(0);
+        cudaEventElapsedTime(&ms, e0, e1);
+        stats->kernel_ms = ms;
+    }
+    if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+    cleanup();
     return rc;
 }
 

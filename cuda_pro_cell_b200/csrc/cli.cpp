@@ -8,7 +8,7 @@
  * (README.md:98-102; the reference code wrongly requires it, cmdargs.cpp:48-49), default = smallest value
  * with a non-zero frequency (parser.cu:80-96).  -d/--tree-depth (1..23) is accepted and ignored: it only
  * sized the reference's dense level arrays.  Extensions (not in the reference): --seed, --seeding,
- * --kernel, --device, --stats.
+ * --kernel, --device, --gpus, --stats.
  */
 #include <cstdio>
 #include <cstdlib>
@@ -30,6 +30,7 @@ struct Args {
     int seeding = PROCELL_SEEDING_IDEAL;
     int kernel = PROCELL_KERNEL_COOP;
     int device = 0;
+    int gpus = 1;
 };
 
 void usage()
@@ -47,6 +48,7 @@ void usage()
         "      --seeding ideal|refcompat\n"
         "      --kernel coop|simple\n"
         "      --device N               CUDA device index\n"
+        "      --gpus N                 shard the seed cells over N GPUs of this box (0 = all), one NCCL reduce\n"
         "      --stats                  print run statistics as JSON on stderr\n";
 }
 
@@ -137,6 +139,9 @@ extern "C" int procell_main(int argc, char** argv)
         } else if (s == "--device" && i < argc - 1) {
             a.device = atoi(argv[++i]);
             r = 1;
+        } else if (s == "--gpus" && i < argc - 1) {
+            a.gpus = atoi(argv[++i]);
+            r = 1;
         } else if (s == "--stats") {
             a.stats = true;
             r = 1;
@@ -178,7 +183,8 @@ extern "C" int procell_main(int argc, char** argv)
         sp.types = types; sp.n_types = n_types; sp.n_sets = 1; sp.t_max = a.t_max; sp.seed = a.seed;
         sp.seeding_mode = a.seeding; sp.kernel = a.kernel;
         counts.assign(procell_plan_n_keys(plan) * n_types + 1, 0);
-        rc = procell_proliferate(plan, &sp, a.device, counts.data(), nullptr, &st);
+        if (a.gpus == 1) rc = procell_proliferate(plan, &sp, a.device, counts.data(), nullptr, &st);
+        else rc = procell_proliferate_multi(plan, &sp, a.gpus, counts.data(), nullptr, &st);
     }
     if (rc == PROCELL_OK) {
         /* Simulator::save_results (simulator.cu:40-56) */

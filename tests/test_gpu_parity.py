@@ -177,3 +177,39 @@ def test_cli_end_to_end(gpu_api, oracle, tmp_path):
     out_rows = [ln.split("\t") for ln in r2.stdout.splitlines()]
     nz2 = want2["row_freq"][0] > 0
     assert [int(ln[1]) for ln in out_rows] == want2["row_freq"][0][nz2].tolist()
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("n_gpus", [2, 4, 8])
+def test_single_process_multi_gpu_equals_oracle(gpu_api, oracle, n_gpus):
+    """procell_proliferate_multi: units sharded over n GPUs from one process, one ncclReduce(sum, int64) onto GPU 0;
+    the reduced tensor equals the unsharded oracle bit for bit"""
+    if _n_gpus() < n_gpus:
+        pytest.skip("needs %d GPUs" % n_gpus)
+    w = synth.workload(2, 0.02)
+    plan = gpu_api.Plan(w.values, w.freqs, w.phi)
+    oplan = oracle.OraclePlan(w.values, w.freqs, w.phi)
+    want = oracle.simulate(oplan, w.types, w.t_max, w.seed)
+    got = gpu_api.proliferate_multi(plan, w.types, w.t_max, w.seed, n_gpus=n_gpus)
+    assert np.array_equal(got.counts, want["counts"]) and np.array_equal(got.divisions, want["divisions"])
+
+
+def test_cli_multi_gpu(gpu_api, oracle, tmp_path):
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    from cuda_pro_cell_b200 import _lib
+    w = synth.workload(1)
+    h, c, o = tmp_path / "h.txt", tmp_path / "c.txt", tmp_path / "o.txt"
+    h.write_text(synth.histogram_text(w.values, w.freqs))
+    c.write_text(synth.types_text(w.types[0]))
+    r = subprocess.run([str(_lib.CLI_PATH), "-h", str(h), "-c", str(c), "-t", "168", "-o", str(o), "-p", "1.5",
+                        "--seed", "99", "--gpus", "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    oplan = oracle.OraclePlan(w.values, w.freqs, 1.5)
+    want = oracle.simulate(oplan, w.types, 168.0, 99)
+    nz = want["row_freq"][0] > 0
+    assert [int(ln.split("\t")[1]) for ln in o.read_text().splitlines()] == want["row_freq"][0][nz].tolist()
