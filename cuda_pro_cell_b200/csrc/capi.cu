@@ -225,6 +225,15 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     P.local_units_per_set = P.units_per_set > P.shard_rank
                                 ? (P.units_per_set - P.shard_rank + P.shard_world - 1) / P.shard_world : 0;
     P.total_local_units = (unsigned long long)P.local_units_per_set * S;
+    {   /* sweep batching: about four batches per set, so a CTA stays on one parameter set for a long stretch */
+        uint32_t per_set = P.local_units_per_set < 4u ? (P.local_units_per_set ? P.local_units_per_set : 1u) : 4u;
+        uint32_t bu = (P.local_units_per_set + per_set - 1) / per_set;
+        if (bu == 0) bu = 1;
+        if (bu > (1u << 22)) bu = 1u << 22;
+        P.batch_units = bu;
+        P.batches_per_set = P.local_units_per_set ? (P.local_units_per_set + bu - 1) / bu : 1;
+        P.total_batches = P.local_units_per_set ? (unsigned long long)P.batches_per_set * S : 0;
+    }
 
     const char* denv = getenv("PROCELL_NO_DONATE");
     P.donate = !(denv && atoi(denv) == 1);

@@ -491,7 +491,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     /* s_ctl[2]: snapshot of the global idle-warp count; s_ctl[3]: 1 once the seed-unit cursor has run out;
      * s_ctl[4]: snapshot of the donation-queue length; s_ctl[5]: snapshot epoch.  They are refreshed from HBM by ONE
      * warp of the CTA every few iterations and read from shared memory by all: busy warps never poll HBM. */
-    if (threadIdx.x == 0) { s_ctl[2] = 0; s_ctl[3] = P.total_local_units == 0; s_ctl[4] = 0; s_ctl[5] = 0; }
+    unsigned long long* s_batch = reinterpret_cast<unsigned long long*>(const_cast<int*>(s_ctl) + 8);
+    if (threadIdx.x == 0) {
+        s_ctl[2] = 0; s_ctl[3] = P.total_local_units == 0; s_ctl[4] = 0; s_ctl[5] = 0; s_ctl[6] = 0;
+        *s_batch = (0xFFFFFFFFFFull << 24) | 0x800000ull;   /* no batch yet (invalid id; offset bits leave room for increments) */
+    }
     __syncthreads();
     DivCount dc;
     dc.total = 0; dc.set = 0; dc.cnt = 0;
@@ -510,18 +514,50 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
             if (w.sp_top != w.sp_bottom) { unspill_newest_chunk(w); continue; }
             if (seed_cur != seed_end || !s_ctl[3]) {
                 if (seed_cur == seed_end) {
-                    unsigned long long c = 0;
-                    if (lane == 0) c = atomicAdd(&ctl->cursor, 1ull);
-                    c = __shfl_sync(kFull, c, 0);
-                    if (c >= P.total_local_units) {
+                    uint32_t set = 0, j = 0;
+                    bool got = false;
+                    if (!multi_set) {
+                        unsigned long long c = 0;
+                        if (lane == 0) c = atomicAdd(&ctl->cursor, 1ull);
+                        c = __shfl_sync(kFull, c, 0);
+                        got = c < P.total_local_units;
+                        j = (uint32_t)c;
+                    } else {
+                        /* s_batch = batch id << 24 | next unit offset; one 64-bit shared atomicAdd claims a unit */
+                        for (int spin = 0; spin < 1000000 && !got; ++spin) {
+                            unsigned long long old = 0;
+                            if (lane == 0) old = atomicAdd(s_batch, 1ull);
+                            old = __shfl_sync(kFull, old, 0);
+                            const uint32_t off = (uint32_t)old & 0xFFFFFFu;
+                            const unsigned long long gb = old >> 24;
+                            if (gb < P.total_batches) {
+                                set = (uint32_t)(gb / P.batches_per_set);
+                                const uint32_t first_unit = (uint32_t)(gb - (unsigned long long)set * P.batches_per_set) * P.batch_units;
+                                const uint32_t left = P.local_units_per_set - first_unit;      /* units in this batch */
+                                if (off < (left < P.batch_units ? left : P.batch_units)) { j = first_unit + off; got = true; continue; }
+                            }
+                            if (s_ctl[3]) break;
+                            if (lane == 0) {          /* batch used up: one warp of the CTA fetches the next one */
+                                if (atomicCAS(const_cast<int*>(s_ctl) + 6, 0, 1) == 0) {
+                                    const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(s_batch);
+                                    if ((cur >> 24) == gb) {      /* nobody has replaced it yet */
+                                        const unsigned long long g = atomicAdd(&ctl->cursor, 1ull);
+                                        if (g >= P.total_batches) s_ctl[3] = 1;
+                                        else atomicExch(s_batch, g << 24);
+                                    }
+                                    __threadfence_block();
+                                    atomicExch(const_cast<int*>(s_ctl) + 6, 0);
+                                } else {
+                                    __nanosleep(200);
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    if (!got) {
                         if (lane == 0) { s_ctl[3] = 1; atomicMin(&ctl->t_exhausted, global_timer_ns()); }
                         __syncwarp();
                         continue;
-                    }
-                    uint32_t set = 0, j = (uint32_t)c;
-                    if (multi_set) {
-                        set = (uint32_t)(c / P.local_units_per_set);
-                        j = (uint32_t)(c - (unsigned long long)set * P.local_units_per_set);
                     }
                     unsigned long long first = ((unsigned long long)j * P.shard_world + P.shard_rank) * P.unit;
                     unsigned long long last = first + P.unit;
@@ -583,7 +619,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         if (refresh && lane == 0) {
             s_ctl[2] = probe_idle;
             s_ctl[4] = probe_avail < kQueueCap / 2 ? (probe_avail > 0 ? probe_avail : 0) : 0x7FFFFFFF;
-            if (!s_ctl[3] && probe_cursor >= P.total_local_units) s_ctl[3] = 1;
+            if (!s_ctl[3] && !multi_set && probe_cursor >= P.total_local_units) s_ctl[3] = 1;
             s_ctl[5] = epoch + 1;
         }
         if (hungry) {   /* somebody starves and no seeds are left: give away the shallowest chunk */

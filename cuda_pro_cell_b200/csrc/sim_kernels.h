@@ -62,6 +62,11 @@ struct SimParams {
     uint32_t local_units_per_set; /* units with u % world == rank */
     uint32_t shard_world, shard_rank;
     unsigned long long total_local_units;   /* n_sets * local_units_per_set */
+    /* parameter sweeps (n_sets > 1): a CTA claims a BATCH of consecutive units of one set from the global cursor and
+     * its warps take units from it through shared memory, so that a CTA's histogram cache sees one set at a time */
+    uint32_t batch_units;         /* units per batch (< 2^24) */
+    uint32_t batches_per_set;
+    unsigned long long total_batches;
     uint32_t rk[20];              /* Philox round keys: rk[2r] = seed_lo + r*W0, rk[2r+1] = seed_hi + r*W1 */
     uint32_t smem_hist_slots;     /* direct mode: keys below this are privatised in shared memory (u32 each);
                                      hashed mode: number of {key,count} u64 slots, a power of two */

@@ -37,7 +37,7 @@ for cfg, scale in ((1, 1.0), (2, 1.0), (3, 0.1), (4, 0.1), (5, 0.02)):
     if cfg == 4:
         w.t_max = 600.0
     plan = api.Plan(w.values, w.freqs, w.phi)
-    for kname, k in (("coop24", 0), ("coop32", 0)):
+    for kname, k in (("coop32", 0),):
         os.environ["PROCELL_COOP_WARPS"] = kname[4:6]
         os.environ["PROCELL_NO_DONATE"] = "1" if kname.endswith("nodonate") else "0"
         try:
