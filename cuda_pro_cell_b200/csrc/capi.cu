@@ -19,8 +19,10 @@
 #include "procell_math_tables.inc"
 #include "sim_kernels.h"
 
+#include <chrono>
 #include <cstdlib>
 #include <dlfcn.h>
+#include <thread>
 
 using namespace procell_b200;
 
@@ -71,6 +73,7 @@ struct procell_engine {
     int device = 0;
     int sm_count = 0;
     DevBuf bin_start, bin_keybase, bin_kdiv, type_cum, type_sel, type_musd, logtab;
+    DevBuf dbg;
     DevBuf counts, ctl, q_seq, q_data, spill;   /* counts = count tensor followed by the division counters */
     SimParams P{};
     bool loaded = false;
@@ -123,7 +126,7 @@ void procell_engine_destroy(procell_engine* en)
     if (!en) return;
     cudaSetDevice(en->device);
     DevBuf* bufs[] = { &en->bin_start, &en->bin_keybase, &en->bin_kdiv, &en->type_cum, &en->type_sel, &en->type_musd,
-                       &en->logtab, &en->counts, &en->ctl, &en->q_seq, &en->q_data, &en->spill };
+                       &en->logtab, &en->counts, &en->dbg, &en->ctl, &en->q_seq, &en->q_data, &en->spill };
     for (DevBuf* b : bufs) b->release();
     if (en->ev0) cudaEventDestroy(en->ev0);
     if (en->ev1) cudaEventDestroy(en->ev1);
@@ -270,6 +273,12 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         en->block = en->warps * 32;
         CU(en->spill.reserve((size_t)grid * en->warps * kSpillCap * kChunkWords * 8), "alloc spill rings");
         P.spill = (unsigned long long*)en->spill.p;
+        CU(en->dbg.reserve((size_t)grid * en->warps * kDbgWords * 8), "alloc debug records");
+        CU(cudaMemset(en->dbg.p, 0, (size_t)grid * en->warps * kDbgWords * 8), "clear debug records");
+        P.dbg = (unsigned long long*)en->dbg.p;
+        const char* wd = getenv("PROCELL_WATCHDOG_S");       /* abort a launch whose warps run longer than this */
+        const double wd_s = wd && atof(wd) > 0 ? atof(wd) : 900.0;
+        P.watchdog_ns = (unsigned long long)(wd_s * 1e9);
     }
     en->loaded = true;
     return PROCELL_OK;
@@ -301,12 +310,67 @@ int procell_engine_finish(procell_engine* en, void* stream_v, int64_t* counts, i
     if (!en || !en->loaded) return fail(PROCELL_ERR_ARG, "procell_engine_finish: engine not loaded");
     cudaStream_t stream = (cudaStream_t)stream_v;
     CU(cudaSetDevice(en->device), "cudaSetDevice");
+    const char* hto = getenv("PROCELL_HOST_TIMEOUT_S");     /* debugging aid: give up on a launch that does not end */
+    if (hto && atof(hto) > 0) {
+        cudaEvent_t done;
+        CU(cudaEventCreateWithFlags(&done, cudaEventDisableTiming), "event create");
+        CU(cudaEventRecord(done, stream), "event record");
+        const double limit = atof(hto);
+        const auto t_begin = std::chrono::steady_clock::now();
+        while (cudaEventQuery(done) == cudaErrorNotReady) {
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count() > limit) {
+                std::string msg = "launch still running after host timeout;";
+                if (en->dbg.p) {
+                    cudaStream_t side;
+                    cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+                    const size_t nw = (size_t)en->grid * en->warps;
+                    std::vector<unsigned long long> rec(nw * kDbgWords);
+                    cudaMemcpyAsync(rec.data(), en->dbg.p, rec.size() * 8, cudaMemcpyDeviceToHost, side);
+                    cudaStreamSynchronize(side);
+                    std::vector<size_t> hist(100, 0);
+                    for (size_t i = 0; i < nw; ++i) hist[rec[i * kDbgWords + 1] % 100] += 1;
+                    msg += " warps by trace code:";
+                    for (size_t c = 0; c < 100; ++c)
+                        if (hist[c]) msg += " " + std::to_string(c) + ":" + std::to_string(hist[c]);
+                    ControlBlock cbs;
+                    cudaMemcpyAsync(&cbs, en->ctl.p, sizeof cbs, cudaMemcpyDeviceToHost, side);
+                    cudaStreamSynchronize(side);
+                    msg += " | active " + std::to_string(cbs.active) + " idle " + std::to_string(cbs.idle) + " avail " +
+                           std::to_string(cbs.avail) + " cursor " + std::to_string(cbs.cursor) + " head " +
+                           std::to_string(cbs.q_head) + " tail " + std::to_string(cbs.q_tail) + " status " + std::to_string(cbs.status);
+                }
+                return fail(PROCELL_ERR_OVERFLOW, msg);
+            }
+            std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        }
+        cudaEventDestroy(done);
+    }
     CU(cudaStreamSynchronize(stream), "kernel execution");
     ControlBlock cb;
     CU(cudaMemcpy(&cb, en->ctl.p, sizeof(ControlBlock), cudaMemcpyDeviceToHost), "read status");
     const int status = cb.status;
-    if (status != kStatusOk)
-        return fail(PROCELL_ERR_OVERFLOW, "device work pool failure, status " + std::to_string(status));
+    if (status != kStatusOk) {
+        std::string msg = "device work pool failure, status " + std::to_string(status);
+        if (status == kStatusWatchdog && en->dbg.p) {      /* where were the warps when the watchdog fired */
+            const size_t nw = (size_t)en->grid * en->warps;
+            std::vector<unsigned long long> rec(nw * kDbgWords);
+            if (cudaMemcpy(rec.data(), en->dbg.p, rec.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+                int shown = 0;
+                size_t fired = 0;
+                for (size_t i = 0; i < nw; ++i) fired += rec[i * kDbgWords] != 0;
+                msg += "; " + std::to_string(fired) + " of " + std::to_string(nw) + " warps reported:";
+                for (size_t i = 0; i < nw && shown < 12; ++i) {
+                    const unsigned long long* r = &rec[i * kDbgWords];
+                    if (!r[0]) continue;
+                    msg += " [w" + std::to_string(i) + " code " + std::to_string(r[0]);
+                    for (int k = 1; k < 7; ++k) msg += " " + std::to_string(r[k]);
+                    msg += "]";
+                    ++shown;
+                }
+            }
+        }
+        return fail(PROCELL_ERR_OVERFLOW, msg);
+    }
     if (counts) CU(cudaMemcpy(counts, en->counts.p, en->counts_len * 8, cudaMemcpyDeviceToHost), "download counts");
     std::vector<int64_t> div(en->n_sets);
     CU(cudaMemcpy(div.data(), (long long*)en->counts.p + en->counts_len, en->n_sets * 8, cudaMemcpyDeviceToHost), "download divisions");

@@ -29,6 +29,12 @@ namespace procell_b200 {
 
 namespace {
 
+#ifdef PROCELL_TRACE
+#define TRACE(P, gw, lane, code) do { if ((lane) == 0) __stcg((P).dbg + (size_t)(gw) * kDbgWords + 1, (unsigned long long)(code)); } while (0)
+#else
+#define TRACE(P, gw, lane, code) do { } while (0)
+#endif
+
 constexpr uint32_t kRingMask = kStackCap - 1;
 constexpr int kSmemCtlBytes = 64;
 constexpr unsigned kFull = 0xFFFFFFFFu;
@@ -113,17 +119,31 @@ __device__ __forceinline__ void hist_add(const SimParams& P, uint32_t* s_hist, u
     }
 }
 
-/* the lanes in `mask` (all of which call this) may each carry `inc` (0..2) leaves for `key`; equal keys are merged
- * (MATCH.ANY + REDUX), one shared atomic per distinct key */
+/* every lane of the warp calls this; each may carry `inc` (0..2) leaves for `key`; equal keys are merged
+ * (MATCH.ANY + REDUX among the lanes that have something), one shared atomic per distinct key */
 template <bool HASHED>
-__device__ __forceinline__ void warp_count_leaves(const SimParams& P, uint32_t* s_hist, unsigned mask, uint32_t key, uint32_t inc)
+__device__ __forceinline__ void warp_count_leaves(const SimParams& P, uint32_t* s_hist, uint32_t key, uint32_t inc)
 {
-    const unsigned has = __ballot_sync(mask, inc > 0);
+    const unsigned has = __ballot_sync(kFull, inc > 0);
     if (has == 0) return;
     if (inc > 0) {
         const unsigned grp = __match_any_sync(has, key);
         const uint32_t total = __reduce_add_sync(grp, inc);
         if ((threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1)) hist_add<HASHED>(P, s_hist, key, total);
+    }
+    __syncwarp();
+}
+
+/* watchdog: record where this warp is and abort the launch */
+__device__ __noinline__ void watchdog_fire(const SimParams& P, uint32_t gwarp, int lane, unsigned long long code,
+                                           unsigned long long a, unsigned long long b, unsigned long long c,
+                                           unsigned long long d, unsigned long long e, unsigned long long f)
+{
+    if (lane == 0) {
+        unsigned long long* r = P.dbg + (size_t)gwarp * kDbgWords;
+        r[0] = code; r[1] = a; r[2] = b; r[3] = c; r[4] = d; r[5] = e; r[6] = f; r[7] = global_timer_ns();
+        __threadfence();
+        atomicCAS(&P.ctl->status, kStatusOk, kStatusWatchdog);
     }
 }
 
@@ -245,7 +265,7 @@ __device__ __forceinline__ void donate_chunk(WarpCtx& w, const SimParams& P)
  * permit is available, claims a chunk with fetch-adds only (permit counter, then head ticket) - no CAS retry
  * storms, at most 148 concurrent pollers.  Quiescence (no active warp, no permit) is stable, so the warp that
  * observes it publishes it to its CTA through s_ctl[1]. */
-__device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volatile int* s_ctl)
+__device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volatile int* s_ctl, unsigned long long deadline, uint32_t gwarp)
 {
     ControlBlock* ctl = P.ctl;
     if (w.lane == 0) {
@@ -279,7 +299,10 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
                     }
                 }
                 else if (act == 0) state = 2;
-                else if (global_timer_ns() - t0 > 120000000000ull) { atomicExch(&ctl->status, kStatusIdleTimeout); state = 2; }
+                else if (global_timer_ns() > deadline) {
+                    watchdog_fire(P, gwarp, 0, 3, (unsigned long long)act, (unsigned long long)(long long)av, (unsigned long long)ld_volatile_s32(&ctl->idle), global_timer_ns() - t0, 0, 0);
+                    state = 2;
+                }
                 if (state == 2) s_ctl[1] = 1;
                 __threadfence_block();
                 atomicExch(const_cast<int*>(s_ctl), 0);
@@ -372,22 +395,25 @@ struct DivCount {
 
 /* ---- DIVIDE iteration: the lanes below `take` pop one node each (newest first), draw ONE Philox block -> one
  * Box-Muller pair -> both daughters' timers, classify the daughters and push the ones that will divide.
- * FULL = all 32 lanes have a node (the common case): no inactive-lane defaults, no divergence bookkeeping. */
+ * FULL = all 32 lanes have a node (the common case): straight-line code.  Otherwise the lanes without a node skip the
+ * arithmetic, and every warp collective below is still executed by all 32 lanes with the full mask. */
 template <bool FULL, bool HASHED>
 __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P, const double* s_log, uint32_t* s_hist,
                                                  uint32_t take, unsigned lt_mask, bool multi_set, DivCount& dc)
 {
-    const unsigned mask = FULL ? kFull : ((1u << take) - 1u);
     const uint32_t T = P.n_types;
-    const uint32_t top0 = w.top - take;
+    bool int0 = false, int1 = false;        /* daughter 0 / 1 lives on and will divide */
+    uint32_t rej = 0, leaf_inc = 0, leaf_key = 0, dlo = 0, retry = 0;
+    uint64_t heap = 0, pc = 0;
+    double t_div = 0.0, tc0 = 0.0, tc1 = 0.0;
     if (FULL || (uint32_t)w.lane < take) {
         const uint32_t idx = (w.top - 1u - (uint32_t)w.lane) & kRingMask;
-        const double t_div = pcs_bits2d(w.sa[idx]);
-        const uint64_t heap = w.sb[idx];
-        const uint64_t pc = w.sc[idx];
+        t_div = pcs_bits2d(w.sa[idx]);
+        heap = w.sb[idx];
+        pc = w.sc[idx];
         const uint64_t d = w.sd[idx];
-        const uint32_t dlo = (uint32_t)d;
-        const uint32_t retry = (uint32_t)(d >> 32);
+        dlo = (uint32_t)d;
+        retry = (uint32_t)(d >> 32);
         const uint32_t set = dlo & 0xFFFFu;
         const uint32_t type = (dlo >> 16) & 63u;
         const double2 ms = __ldg(P.type_musd + set * T + type);
@@ -399,15 +425,15 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
         const double tm1 = forced ? ms.x : pcs_timer(ms.x, ms.y, z1);
         const bool want0 = (dlo & (1u << 28)) != 0u, want1 = (dlo & (2u << 28)) != 0u;
         const bool ok0 = want0 && (tm0 > 0.0 || forced), ok1 = want1 && (tm1 > 0.0 || forced);
-        const double tc0 = PCS_ADD(t_div, tm0);
-        const double tc1 = PCS_ADD(t_div, tm1);
+        tc0 = PCS_ADD(t_div, tm0);
+        tc1 = PCS_ADD(t_div, tm1);
         const bool late0 = tc0 > P.t_max, late1 = tc1 > P.t_max;      /* proliferation.cu:404-410 */
         const bool deeper = (dlo & (63u << 22)) != 0u;                /* f/2 > phi one level down (:323) */
-        const uint32_t leaf_inc = (uint32_t)(ok0 && late0) + (uint32_t)(ok1 && late1);
-        const bool int0 = ok0 && !late0 && deeper;                    /* daughter 0 lives on and will divide */
-        const bool int1 = ok1 && !late1 && deeper;
-        const uint32_t rej = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
-        const uint32_t leaf_key = (uint32_t)(pc >> 32) + T;
+        leaf_inc = (uint32_t)(ok0 && late0) + (uint32_t)(ok1 && late1);
+        int0 = ok0 && !late0 && deeper;
+        int1 = ok1 && !late1 && deeper;
+        rej = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
+        leaf_key = (uint32_t)(pc >> 32) + T;
         if (retry == 0u) {
             if (multi_set) {
                 if (set != dc.set) {
@@ -419,36 +445,34 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
                 dc.total += 1;
             }
         }
-        /* all popped nodes have been read (their values fed the predicates above), so the slots may be overwritten */
-        const unsigned b0 = __ballot_sync(mask, int0);
-        const unsigned b1 = __ballot_sync(mask, int1);
-        const unsigned br = __ballot_sync(mask, rej != 0u);
-        const uint64_t child_c = ((pc >> 32) + T) << 32 | (pc & 0xFFFFFFFFull);
-        const uint64_t child_d = (uint64_t)((dlo | (3u << 28)) - (1u << 22));
-        uint32_t top = top0;
-        if (int0) {
-            const uint32_t i0 = (top + __popc(b0 & lt_mask)) & kRingMask;
-            w.sa[i0] = pcs_d2bits(tc0); w.sb[i0] = heap * 2ull; w.sc[i0] = child_c; w.sd[i0] = child_d;
-        }
-        top += __popc(b0);
-        if (int1) {
-            const uint32_t i1 = (top + __popc(b1 & lt_mask)) & kRingMask;
-            w.sa[i1] = pcs_d2bits(tc1); w.sb[i1] = heap * 2ull + 1ull; w.sc[i1] = child_c; w.sd[i1] = child_d;
-        }
-        top += __popc(b1);
-        if (br) {   /* a daughter's timer came out <= 0: redraw it in a later iteration (cell.cu:114-118) */
-            if (rej) {
-                const uint32_t ir = (top + __popc(br & lt_mask)) & kRingMask;
-                w.sa[ir] = pcs_d2bits(t_div); w.sb[ir] = heap; w.sc[ir] = pc;
-                w.sd[ir] = (uint64_t)((dlo & ~(3u << 28)) | (rej << 28)) | ((uint64_t)(retry + 1u) << 32);
-            }
-            top += __popc(br);
-        }
-        warp_count_leaves<HASHED>(P, s_hist, mask, leaf_key, leaf_inc);
-        w.top = top;
     }
-    if (!FULL) w.top = __shfl_sync(kFull, w.top, 0);    /* lane 0 always holds a node when take > 0 */
+    /* all popped nodes have been read (their values fed the predicates above), so the slots may be overwritten */
+    w.top -= take;
+    const unsigned b0 = __ballot_sync(kFull, int0);
+    const unsigned b1 = __ballot_sync(kFull, int1);
+    const unsigned br = __ballot_sync(kFull, rej != 0u);
+    const uint64_t child_c = ((pc >> 32) + T) << 32 | (pc & 0xFFFFFFFFull);
+    const uint64_t child_d = (uint64_t)((dlo | (3u << 28)) - (1u << 22));
+    if (int0) {
+        const uint32_t i0 = (w.top + __popc(b0 & lt_mask)) & kRingMask;
+        w.sa[i0] = pcs_d2bits(tc0); w.sb[i0] = heap * 2ull; w.sc[i0] = child_c; w.sd[i0] = child_d;
+    }
+    w.top += __popc(b0);
+    if (int1) {
+        const uint32_t i1 = (w.top + __popc(b1 & lt_mask)) & kRingMask;
+        w.sa[i1] = pcs_d2bits(tc1); w.sb[i1] = heap * 2ull + 1ull; w.sc[i1] = child_c; w.sd[i1] = child_d;
+    }
+    w.top += __popc(b1);
+    if (br) {   /* a daughter's timer came out <= 0: redraw it in a later iteration (cell.cu:114-118) */
+        if (rej) {
+            const uint32_t ir = (w.top + __popc(br & lt_mask)) & kRingMask;
+            w.sa[ir] = pcs_d2bits(t_div); w.sb[ir] = heap; w.sc[ir] = pc;
+            w.sd[ir] = (uint64_t)((dlo & ~(3u << 28)) | (rej << 28)) | ((uint64_t)(retry + 1u) << 32);
+        }
+        w.top += __popc(br);
+    }
     __syncwarp();
+    warp_count_leaves<HASHED>(P, s_hist, leaf_key, leaf_inc);
 }
 
 }  // namespace
@@ -507,13 +531,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         atomicAdd(&ctl->active, 1);
         atomicMin(&ctl->t_start, global_timer_ns());
     }
+    const uint32_t gwarp = blockIdx.x * WARPS + warp;
+    const unsigned long long deadline = global_timer_ns() + P.watchdog_ns;
+    uint32_t loops = 0;
 
     for (;;) {
         const uint32_t n = w.top - w.bottom;
+        if ((++loops & 255u) == 0u) {
+            unsigned long long now = global_timer_ns();
+            now = __shfl_sync(kFull, now, 0);
+            if (now > deadline) {
+                watchdog_fire(P, gwarp, lane, 1, n, w.sp_top - w.sp_bottom, seed_cur, seed_end, (unsigned long long)s_ctl[3], loops);
+                break;
+            }
+        }
         if (n < 32u) {
-            if (w.sp_top != w.sp_bottom) { unspill_newest_chunk(w); continue; }
-            if (seed_cur != seed_end || !s_ctl[3]) {
+            if (w.sp_top != w.sp_bottom) { TRACE(P, gwarp, lane, 41); unspill_newest_chunk(w); continue; }
+            /* RULE: every decision that depends on mutable shared/global state is taken by lane 0 and broadcast.
+             * Lanes of a warp are not guaranteed to be converged when they read a volatile flag, so a per-lane read
+             * can see two different values inside one warp and split it for good. */
+            int exhausted = 0;
+            if (seed_cur == seed_end) {
+                if (lane == 0) exhausted = s_ctl[3];
+                exhausted = __shfl_sync(kFull, exhausted, 0);
+            }
+            if (seed_cur != seed_end || !exhausted) {
                 if (seed_cur == seed_end) {
+                    TRACE(P, gwarp, lane, 10);
                     uint32_t set = 0, j = 0;
                     bool got = false;
                     if (!multi_set) {
@@ -523,35 +567,49 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                         got = c < P.total_local_units;
                         j = (uint32_t)c;
                     } else {
-                        /* s_batch = batch id << 24 | next unit offset; one 64-bit shared atomicAdd claims a unit */
+                        /* s_batch = batch id << 24 | next unit offset; one 64-bit shared atomicAdd claims a unit.
+                         * Lane 0 runs the whole protocol and broadcasts (status, set, unit). */
                         for (int spin = 0; spin < 1000000 && !got; ++spin) {
-                            unsigned long long old = 0;
-                            if (lane == 0) old = atomicAdd(s_batch, 1ull);
-                            old = __shfl_sync(kFull, old, 0);
-                            const uint32_t off = (uint32_t)old & 0xFFFFFFu;
-                            const unsigned long long gb = old >> 24;
-                            if (gb < P.total_batches) {
-                                set = (uint32_t)(gb / P.batches_per_set);
-                                const uint32_t first_unit = (uint32_t)(gb - (unsigned long long)set * P.batches_per_set) * P.batch_units;
-                                const uint32_t left = P.local_units_per_set - first_unit;      /* units in this batch */
-                                if (off < (left < P.batch_units ? left : P.batch_units)) { j = first_unit + off; got = true; continue; }
-                            }
-                            if (s_ctl[3]) break;
-                            if (lane == 0) {          /* batch used up: one warp of the CTA fetches the next one */
-                                if (atomicCAS(const_cast<int*>(s_ctl) + 6, 0, 1) == 0) {
-                                    const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(s_batch);
-                                    if ((cur >> 24) == gb) {      /* nobody has replaced it yet */
-                                        const unsigned long long g = atomicAdd(&ctl->cursor, 1ull);
-                                        if (g >= P.total_batches) s_ctl[3] = 1;
-                                        else atomicExch(s_batch, g << 24);
+                            int status = 0;      /* 0 retry, 1 got a unit, 2 no seed units left, 3 watchdog */
+                            if (lane == 0) {
+                                const unsigned long long old = atomicAdd(s_batch, 1ull);
+                                const uint32_t off = (uint32_t)old & 0xFFFFFFu;
+                                const unsigned long long gb = old >> 24;
+                                if (gb < P.total_batches) {
+                                    set = (uint32_t)(gb / P.batches_per_set);
+                                    const uint32_t first_unit = (uint32_t)(gb - (unsigned long long)set * P.batches_per_set) * P.batch_units;
+                                    const uint32_t left = P.local_units_per_set - first_unit;      /* units in this batch */
+                                    if (off < (left < P.batch_units ? left : P.batch_units)) { j = first_unit + off; status = 1; }
+                                }
+                                if (status == 0) {
+                                    if (s_ctl[3]) status = 2;
+                                    else if ((spin & 1023) == 1023 && global_timer_ns() > deadline) status = 3;
+                                    else if (atomicCAS(const_cast<int*>(s_ctl) + 6, 0, 1) == 0) {
+                                        /* batch used up: one warp of the CTA fetches the next one */
+                                        const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(s_batch);
+                                        if ((cur >> 24) == gb) {      /* nobody has replaced it yet */
+                                            const unsigned long long g = atomicAdd(&ctl->cursor, 1ull);
+                                            if (g >= P.total_batches) { s_ctl[3] = 1; status = 2; }
+                                            else atomicExch(s_batch, g << 24);
+                                        }
+                                        __threadfence_block();
+                                        atomicExch(const_cast<int*>(s_ctl) + 6, 0);
+                                    } else {
+                                        __nanosleep(200);
                                     }
-                                    __threadfence_block();
-                                    atomicExch(const_cast<int*>(s_ctl) + 6, 0);
-                                } else {
-                                    __nanosleep(200);
                                 }
                             }
-                            __syncwarp();
+                            status = __shfl_sync(kFull, status, 0);
+                            if (status == 1) {
+                                set = __shfl_sync(kFull, set, 0);
+                                j = __shfl_sync(kFull, j, 0);
+                                got = true;
+                            } else if (status == 3) {
+                                watchdog_fire(P, gwarp, lane, 2, spin, 0, 0, 0, 0, 0);
+                                break;
+                            } else if (status == 2) {
+                                break;
+                            }
                         }
                     }
                     if (!got) {
@@ -566,6 +624,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                     if (seed_cur >= seed_end) { seed_cur = seed_end; continue; }
                 }
                 /* ---- SEED iteration: one seed cell per lane ---- */
+                TRACE(P, gwarp, lane, 12);
                 const uint32_t root = seed_cur + lane;
                 const bool have = root < seed_end;
                 seed_cur = (seed_end - seed_cur > 32u) ? seed_cur + 32u : seed_end;
@@ -581,15 +640,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 }
                 w.top += __popc(live);
                 __syncwarp();
-                warp_count_leaves<HASHED>(P, s_hist, kFull, so.key, so.kind == 1 ? 1u : 0u);
+                warp_count_leaves<HASHED>(P, s_hist, so.key, so.kind == 1 ? 1u : 0u);
                 continue;
             }
             if (n == 0u) {
-                if (!idle_wait(w, P, s_ctl)) break;
+                TRACE(P, gwarp, lane, 30);
+                if (!idle_wait(w, P, s_ctl, deadline, gwarp)) break;
                 continue;
             }
         }
-        if (n > (uint32_t)(kStackCap - 32)) { spill_bottom_chunk(w, P); continue; }
+        if (n > (uint32_t)(kStackCap - 32)) { TRACE(P, gwarp, lane, 40); spill_bottom_chunk(w, P); continue; }
 
         /* hunger probe.  Every 64th iteration (staggered by warp) this warp refreshes the CTA's shared snapshot of
          * "how many warps are starving", "how long is the donation queue" and "is the seed cursor exhausted" from
@@ -601,17 +661,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         bool refresh = false, hungry = false;
         if ((iter & 3u) == 0u) {
             refresh = ((iter + (uint32_t)warp * 4u) & 63u) == 0u;
-            if (refresh && lane == 0) {
-                probe_idle = ld_volatile_s32(&ctl->idle);
-                probe_avail = ld_volatile_s32(&ctl->avail);
-                if (!s_ctl[3]) probe_cursor = ld_volatile_u64(&ctl->cursor);
+            int packed = 0;
+            if (lane == 0) {     /* lane 0 decides, the warp follows (see RULE above) */
+                if (refresh) {
+                    probe_idle = ld_volatile_s32(&ctl->idle);
+                    probe_avail = ld_volatile_s32(&ctl->avail);
+                    if (!s_ctl[3]) probe_cursor = ld_volatile_u64(&ctl->cursor);
+                }
+                /* donate at most once per snapshot epoch, and only while the queue is shorter than the line of starving warps */
+                const int ep = s_ctl[5];
+                const int hg = P.donate && s_ctl[3] && s_ctl[2] > s_ctl[4] && ep != donate_epoch;
+                packed = (ep << 1) | hg;
             }
-            /* donate at most once per snapshot epoch, and only while the queue is shorter than the line of starving warps */
-            epoch = s_ctl[5];
-            hungry = P.donate && s_ctl[3] && s_ctl[2] > s_ctl[4] && epoch != donate_epoch &&
-                     (n + 32u * (w.sp_top - w.sp_bottom)) >= 64u;
+            packed = __shfl_sync(kFull, packed, 0);
+            epoch = packed >> 1;
+            hungry = (packed & 1) && (n + 32u * (w.sp_top - w.sp_bottom)) >= 64u;
         }
 
+        TRACE(P, gwarp, lane, 20);
         const uint32_t take = n < 32u ? n : 32u;
         if (take == 32u) divide_iteration<true, HASHED>(w, P, s_log, s_hist, take, lt_mask, multi_set, dc);
         else divide_iteration<false, HASHED>(w, P, s_log, s_hist, take, lt_mask, multi_set, dc);
@@ -622,12 +689,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
             if (!s_ctl[3] && !multi_set && probe_cursor >= P.total_local_units) s_ctl[3] = 1;
             s_ctl[5] = epoch + 1;
         }
+        TRACE(P, gwarp, lane, 25);
         if (hungry) {   /* somebody starves and no seeds are left: give away the shallowest chunk */
+            TRACE(P, gwarp, lane, 50);
             donate_epoch = epoch;
             if ((w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= 64u) donate_chunk(w, P);
         }
     }
 
+    TRACE(P, gwarp, lane, 60);
     if (lane == 0) atomicMax(&ctl->t_end, global_timer_ns());
     if (multi_set) {
         if (dc.cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);

@@ -23,6 +23,8 @@ constexpr int kStatusOk = 0;
 constexpr int kStatusSpillOverflow = 1;
 constexpr int kStatusQueueTimeout = 2;
 constexpr int kStatusIdleTimeout = 3;
+constexpr int kStatusWatchdog = 4;
+constexpr int kDbgWords = 8;                   /* per-warp debug record written when the watchdog fires */
 
 /* control block in global memory; every hot word on its own 128-byte line */
 struct alignas(128) ControlBlock {
@@ -73,6 +75,8 @@ struct SimParams {
     int hist_hashed;              /* 1: key space larger than shared memory -> direct-mapped {key,count} cache */
     int refcompat;
     int donate;                   /* 0: never hand work to starving warps (diagnostic) */
+    unsigned long long watchdog_ns;   /* a warp that runs longer than this aborts the launch (status 4) */
+    unsigned long long* dbg;      /* [grid*warps][kDbgWords] */
     double t_max;
 };
 
