@@ -3,7 +3,10 @@ import ctypes as C
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libprocell_b200.so"
+import os as _os
+
+# PROCELL_LIB selects an alternative in-tree build of the same library (A/B experiments); default: the product build
+LIB_PATH = PKG_DIR / _os.environ.get("PROCELL_LIB", "libprocell_b200.so")
 CLI_PATH = PKG_DIR / "procell"
 
 OK, ERR_ARG, ERR_CUDA, ERR_PROPORTION, ERR_IO, ERR_OVERFLOW = 0, -1, -2, -3, -4, -5

@@ -36,7 +36,7 @@ namespace {
 #endif
 
 constexpr uint32_t kRingMask = kStackCap - 1;
-constexpr int kSmemCtlBytes = 64;
+constexpr int kSmemCtlBytes = 128;    /* control words (64 B) + three 16-byte snapshots of the control block */
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 /* A node = a cell that WILL divide: 4 x u64, field-major in the ring
@@ -62,13 +62,6 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
 __device__ __forceinline__ int ld_acquire_s32(const int* p)
 {
     int v;
@@ -81,6 +74,13 @@ __device__ __forceinline__ int ld_volatile_s32(const int* p)
     int v;
     asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+/* 16-byte asynchronous copy global -> shared that bypasses L1 (the source is written by other SMs) */
+__device__ __forceinline__ void cp_async16(volatile int* smem_dst, const void* gmem_src)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(const_cast<int*>(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
 }
 
 __device__ __forceinline__ unsigned long long global_timer_ns()
@@ -131,7 +131,9 @@ __device__ __forceinline__ void warp_count_leaves(const SimParams& P, uint32_t* 
         const uint32_t total = __reduce_add_sync(grp, inc);
         if ((threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1)) hist_add<HASHED>(P, s_hist, key, total);
     }
+#ifdef PROCELL_SYNC_AFTER_LEAVES
     __syncwarp();
+#endif
 }
 
 /* watchdog: record where this warp is and abort the launch */
@@ -389,8 +391,7 @@ __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* 
 
 /* per-warp division counters: one plain counter for single-set runs, (set, count) with flush-on-change for sweeps */
 struct DivCount {
-    unsigned long long total;
-    uint32_t set, cnt;
+    uint32_t set, cnt;      /* divisions of parameter set `set` counted by this lane and not yet flushed */
 };
 
 /* ---- DIVIDE iteration: the lanes below `take` pop one node each (newest first), draw ONE Philox block -> one
@@ -435,15 +436,11 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
         rej = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
         leaf_key = (uint32_t)(pc >> 32) + T;
         if (retry == 0u) {
-            if (multi_set) {
-                if (set != dc.set) {
-                    if (dc.cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
-                    dc.cnt = 0; dc.set = set;
-                }
-                dc.cnt += 1;
-            } else {
-                dc.total += 1;
+            if (multi_set && set != dc.set) {
+                if (dc.cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
+                dc.cnt = 0; dc.set = set;
             }
+            dc.cnt += 1;
         }
     }
     /* all popped nodes have been read (their values fed the predicates above), so the slots may be overwritten */
@@ -512,17 +509,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     w.lane = lane;
 
     uint32_t seed_cur = 0, seed_end = 0, seed_set = 0;
-    /* s_ctl[2]: snapshot of the global idle-warp count; s_ctl[3]: 1 once the seed-unit cursor has run out;
-     * s_ctl[4]: snapshot of the donation-queue length; s_ctl[5]: snapshot epoch.  They are refreshed from HBM by ONE
-     * warp of the CTA every few iterations and read from shared memory by all: busy warps never poll HBM. */
+    /* s_ctl[3]: 1 once the seed-unit cursor has run out; s_ctl[5]: snapshot epoch; s_ctl[6]: batch-refill lock;
+     * s_snap: copies of the control block's idle count, permit count and seed cursor, refreshed by one lane of the
+     * CTA every few iterations with cp.async and read from shared memory: busy warps never poll HBM. */
     unsigned long long* s_batch = reinterpret_cast<unsigned long long*>(const_cast<int*>(s_ctl) + 8);
+    volatile int* s_snap = s_ctl + 16;      /* [0] idle  [4] avail  [8..9] seed cursor: cp.async targets, 16 B each */
     if (threadIdx.x == 0) {
+        *reinterpret_cast<volatile unsigned long long*>(const_cast<int*>(s_ctl) + 10) = global_timer_ns() + P.watchdog_ns;
         s_ctl[2] = 0; s_ctl[3] = P.total_local_units == 0; s_ctl[4] = 0; s_ctl[5] = 0; s_ctl[6] = 0;
+        for (int i = 0; i < 12; ++i) s_snap[i] = 0;
         *s_batch = (0xFFFFFFFFFFull << 24) | 0x800000ull;   /* no batch yet (invalid id; offset bits leave room for increments) */
     }
     __syncthreads();
     DivCount dc;
-    dc.total = 0; dc.set = 0; dc.cnt = 0;
+    dc.set = 0; dc.cnt = 0;
     const bool multi_set = P.n_sets > 1u;
     uint32_t iter = 0;
     int donate_epoch = -1;
@@ -531,22 +531,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         atomicAdd(&ctl->active, 1);
         atomicMin(&ctl->t_start, global_timer_ns());
     }
-    const uint32_t gwarp = blockIdx.x * WARPS + warp;
-    const unsigned long long deadline = global_timer_ns() + P.watchdog_ns;
-    uint32_t loops = 0;
+#define GWARP (blockIdx.x * WARPS + warp)
+    /* watchdog deadline of this CTA, kept in shared memory (registers are scarce at 32 warps per SM) */
+    volatile unsigned long long* s_deadline = reinterpret_cast<volatile unsigned long long*>(const_cast<int*>(s_ctl) + 10);
 
     for (;;) {
         const uint32_t n = w.top - w.bottom;
-        if ((++loops & 255u) == 0u) {
-            unsigned long long now = global_timer_ns();
-            now = __shfl_sync(kFull, now, 0);
-            if (now > deadline) {
-                watchdog_fire(P, gwarp, lane, 1, n, w.sp_top - w.sp_bottom, seed_cur, seed_end, (unsigned long long)s_ctl[3], loops);
-                break;
-            }
-        }
         if (n < 32u) {
-            if (w.sp_top != w.sp_bottom) { TRACE(P, gwarp, lane, 41); unspill_newest_chunk(w); continue; }
+            if (w.sp_top != w.sp_bottom) { TRACE(P, GWARP, lane, 41); unspill_newest_chunk(w); continue; }
             /* RULE: every decision that depends on mutable shared/global state is taken by lane 0 and broadcast.
              * Lanes of a warp are not guaranteed to be converged when they read a volatile flag, so a per-lane read
              * can see two different values inside one warp and split it for good. */
@@ -557,7 +549,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
             }
             if (seed_cur != seed_end || !exhausted) {
                 if (seed_cur == seed_end) {
-                    TRACE(P, gwarp, lane, 10);
+                    TRACE(P, GWARP, lane, 10);
                     uint32_t set = 0, j = 0;
                     bool got = false;
                     if (!multi_set) {
@@ -583,7 +575,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                                 }
                                 if (status == 0) {
                                     if (s_ctl[3]) status = 2;
-                                    else if ((spin & 1023) == 1023 && global_timer_ns() > deadline) status = 3;
+                                    else if ((spin & 1023) == 1023 && global_timer_ns() > *s_deadline) status = 3;
                                     else if (atomicCAS(const_cast<int*>(s_ctl) + 6, 0, 1) == 0) {
                                         /* batch used up: one warp of the CTA fetches the next one */
                                         const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(s_batch);
@@ -605,7 +597,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                                 j = __shfl_sync(kFull, j, 0);
                                 got = true;
                             } else if (status == 3) {
-                                watchdog_fire(P, gwarp, lane, 2, spin, 0, 0, 0, 0, 0);
+                                watchdog_fire(P, GWARP, lane, 2, spin, 0, 0, 0, 0, 0);
                                 break;
                             } else if (status == 2) {
                                 break;
@@ -624,7 +616,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                     if (seed_cur >= seed_end) { seed_cur = seed_end; continue; }
                 }
                 /* ---- SEED iteration: one seed cell per lane ---- */
-                TRACE(P, gwarp, lane, 12);
+                TRACE(P, GWARP, lane, 12);
                 const uint32_t root = seed_cur + lane;
                 const bool have = root < seed_end;
                 seed_cur = (seed_end - seed_cur > 32u) ? seed_cur + 32u : seed_end;
@@ -644,67 +636,79 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 continue;
             }
             if (n == 0u) {
-                TRACE(P, gwarp, lane, 30);
-                if (!idle_wait(w, P, s_ctl, deadline, gwarp)) break;
+                TRACE(P, GWARP, lane, 30);
+                if (!idle_wait(w, P, s_ctl, *s_deadline, GWARP)) break;
                 continue;
             }
         }
-        if (n > (uint32_t)(kStackCap - 32)) { TRACE(P, gwarp, lane, 40); spill_bottom_chunk(w, P); continue; }
+        if (n > (uint32_t)(kStackCap - 32)) { TRACE(P, GWARP, lane, 40); spill_bottom_chunk(w, P); continue; }
 
-        /* hunger probe.  Every 64th iteration (staggered by warp) this warp refreshes the CTA's shared snapshot of
-         * "how many warps are starving", "how long is the donation queue" and "is the seed cursor exhausted" from
-         * HBM; every 4th iteration each warp looks at the snapshot in shared memory.  Loads are issued now and
-         * consumed after the math. */
         ++iter;
-        int probe_idle = 0, probe_avail = 0, epoch = 0;
-        unsigned long long probe_cursor = 0;
-        bool refresh = false, hungry = false;
-        if ((iter & 3u) == 0u) {
-            refresh = ((iter + (uint32_t)warp * 4u) & 63u) == 0u;
-            int packed = 0;
-            if (lane == 0) {     /* lane 0 decides, the warp follows (see RULE above) */
-                if (refresh) {
-                    probe_idle = ld_volatile_s32(&ctl->idle);
-                    probe_avail = ld_volatile_s32(&ctl->avail);
-                    if (!s_ctl[3]) probe_cursor = ld_volatile_u64(&ctl->cursor);
-                }
-                /* donate at most once per snapshot epoch, and only while the queue is shorter than the line of starving warps */
-                const int ep = s_ctl[5];
-                const int hg = P.donate && s_ctl[3] && s_ctl[2] > s_ctl[4] && ep != donate_epoch;
-                packed = (ep << 1) | hg;
+        if ((iter & 255u) == 0u) {       /* every 256 iterations: flush the 32-bit division counters, check the watchdog */
+            if (!multi_set) {
+                const uint32_t tot = __reduce_add_sync(kFull, dc.cnt);
+                if (lane == 0 && tot) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions), (unsigned long long)tot);
+                dc.cnt = 0;
+            } else if (dc.cnt > (1u << 30)) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
+                dc.cnt = 0;
             }
-            packed = __shfl_sync(kFull, packed, 0);
-            epoch = packed >> 1;
-            hungry = (packed & 1) && (n + 32u * (w.sp_top - w.sp_bottom)) >= 64u;
+            int late = 0;
+            if (lane == 0) late = global_timer_ns() > *s_deadline;
+            if (__shfl_sync(kFull, late, 0)) {
+                watchdog_fire(P, GWARP, lane, 1, n, w.sp_top - w.sp_bottom, seed_cur, seed_end, iter, 0);
+                break;
+            }
         }
 
-        TRACE(P, gwarp, lane, 20);
+        TRACE(P, GWARP, lane, 20);
         const uint32_t take = n < 32u ? n : 32u;
         if (take == 32u) divide_iteration<true, HASHED>(w, P, s_log, s_hist, take, lt_mask, multi_set, dc);
         else divide_iteration<false, HASHED>(w, P, s_log, s_hist, take, lt_mask, multi_set, dc);
 
-        if (refresh && lane == 0) {
-            s_ctl[2] = probe_idle;
-            s_ctl[4] = probe_avail < kQueueCap / 2 ? (probe_avail > 0 ? probe_avail : 0) : 0x7FFFFFFF;
-            if (!s_ctl[3] && !multi_set && probe_cursor >= P.total_local_units) s_ctl[3] = 1;
-            s_ctl[5] = epoch + 1;
-        }
-        TRACE(P, gwarp, lane, 25);
-        if (hungry) {   /* somebody starves and no seeds are left: give away the shallowest chunk */
-            TRACE(P, gwarp, lane, 50);
-            donate_epoch = epoch;
-            if ((w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= 64u) donate_chunk(w, P);
+        /* hunger probe, every 4th iteration.  The CTA keeps a snapshot of "how many warps are starving", "how many
+         * donated chunks are waiting" and "where is the seed cursor" in shared memory.  Every 64th iteration
+         * (staggered by warp) one lane refreshes it with three 16-byte cp.async.cg copies straight from the control
+         * block in HBM/L2 into shared memory: no registers, no waiting, the values simply turn up a little later.
+         * Lane 0 reads the snapshot and decides, the warp follows (see RULE above). */
+        if ((iter & 3u) == 0u) {
+            int packed = 0;
+            if (lane == 0) {
+                if (((iter + (uint32_t)warp * 4u) & 63u) == 0u) {
+                    cp_async16(s_snap, &ctl->idle);
+                    cp_async16(s_snap + 4, &ctl->avail);
+                    if (!multi_set && !s_ctl[3]) cp_async16(s_snap + 8, &ctl->cursor);
+                    s_ctl[5] = s_ctl[5] + 1;
+                }
+                const int idle_snap = s_snap[0], avail_snap = s_snap[4];
+                if (!multi_set && !s_ctl[3]) {
+                    const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(s_snap + 8);
+                    if (cur >= P.total_local_units) s_ctl[3] = 1;
+                }
+                /* donate at most once per snapshot epoch, and only while fewer chunks wait than warps starve */
+                const int ep = s_ctl[5];
+                const int hg = P.donate && s_ctl[3] && idle_snap > (avail_snap > 0 ? avail_snap : 0) &&
+                               avail_snap < kQueueCap / 2 && ep != donate_epoch;
+                packed = (ep << 1) | hg;
+            }
+            packed = __shfl_sync(kFull, packed, 0);
+            if ((packed & 1) && (w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= 64u) {
+                /* somebody starves and no seeds are left: give away the shallowest chunk */
+                TRACE(P, GWARP, lane, 50);
+                donate_epoch = packed >> 1;
+                donate_chunk(w, P);
+            }
         }
     }
 
-    TRACE(P, gwarp, lane, 60);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    TRACE(P, GWARP, lane, 60);
     if (lane == 0) atomicMax(&ctl->t_end, global_timer_ns());
     if (multi_set) {
         if (dc.cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
     } else {
-        unsigned long long tot = dc.total;
-        for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(kFull, tot, off);
-        if (lane == 0 && tot) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions), tot);
+        const uint32_t tot = __reduce_add_sync(kFull, dc.cnt);     /* < 32 * 256 since the last periodic flush */
+        if (lane == 0 && tot) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions), (unsigned long long)tot);
     }
     __syncthreads();
     if (HASHED) {

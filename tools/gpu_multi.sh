@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_n$N.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu_n$N.log
+timeout 400 python -m pytest tests -m gpu -x -q --timeout 90 > gpurun_out/pytest_gpu_n$N.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu_n$N.log
 for n in $(seq 1 $N); do
   if [ $n -eq 1 ] || [ $n -eq 2 ] || [ $n -eq 4 ] || [ $n -eq 8 ]; then
     if [ $n -eq 1 ]; then
