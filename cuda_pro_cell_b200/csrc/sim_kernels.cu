@@ -36,7 +36,8 @@ namespace {
 #endif
 
 constexpr uint32_t kRingMask = kStackCap - 1;
-constexpr int kSmemCtlBytes = 128;    /* control words (64 B) + three 16-byte snapshots of the control block */
+constexpr int kSmemMusdEntries = 64;  /* (mean, sd) table cached in shared memory when n_sets * n_types fits */
+constexpr int kSmemCtlBytes = 128 + kSmemMusdEntries * 16;    /* control words (64 B) + three 16-byte snapshots of the control block */
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 /* A node = a cell that WILL divide: 4 x u64, field-major in the ring
@@ -400,7 +401,8 @@ struct DivCount {
  * arithmetic, and every warp collective below is still executed by all 32 lanes with the full mask. */
 template <bool FULL, bool HASHED>
 __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P, const double* s_log, uint32_t* s_hist,
-                                                 uint32_t take, unsigned lt_mask, bool multi_set, DivCount& dc)
+                                                 const double2* s_musd, uint32_t take, unsigned lt_mask, bool multi_set,
+                                                 DivCount& dc)
 {
     const uint32_t T = P.n_types;
     bool int0 = false, int1 = false;        /* daughter 0 / 1 lives on and will divide */
@@ -417,7 +419,7 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
         retry = (uint32_t)(d >> 32);
         const uint32_t set = dlo & 0xFFFFu;
         const uint32_t type = (dlo >> 16) & 63u;
-        const double2 ms = __ldg(P.type_musd + set * T + type);
+        const double2 ms = s_musd ? s_musd[set * T + type] : __ldg(P.type_musd + set * T + type);
         const pcs_u32x4 blk = pcs_draw_rk((uint32_t)pc, set, retry, PCS_TAG_DIVISION, heap, P.rk);
         double z0, z1;
         pcs_normal_pair(blk, s_log, 0.0, &z0, &z1);
@@ -483,6 +485,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     uint64_t* s_stack = reinterpret_cast<uint64_t*>(smem_raw + kLogTabDoubles * 8 + kSmemCtlBytes);
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + kLogTabDoubles * 8 + kSmemCtlBytes + (size_t)WARPS * 4 * kStackCap * 8);
 
+    double2* s_musd_buf = reinterpret_cast<double2*>(smem_raw + kLogTabDoubles * 8 + 128);
+    const bool musd_cached = P.n_sets * P.n_types <= (uint32_t)kSmemMusdEntries;
+    if (musd_cached && threadIdx.x < P.n_sets * P.n_types) s_musd_buf[threadIdx.x] = __ldg(P.type_musd + threadIdx.x);
+    const double2* s_musd = musd_cached ? s_musd_buf : nullptr;
     if (threadIdx.x < 2) s_ctl[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < kLogTabDoubles; i += blockDim.x) s_log[i] = __ldg(P.logtab + i);
     if (HASHED) {
@@ -663,8 +669,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 
         TRACE(P, GWARP, lane, 20);
         const uint32_t take = n < 32u ? n : 32u;
-        if (take == 32u) divide_iteration<true, HASHED>(w, P, s_log, s_hist, take, lt_mask, multi_set, dc);
-        else divide_iteration<false, HASHED>(w, P, s_log, s_hist, take, lt_mask, multi_set, dc);
+        if (take == 32u) divide_iteration<true, HASHED>(w, P, s_log, s_hist, s_musd, take, lt_mask, multi_set, dc);
+        else divide_iteration<false, HASHED>(w, P, s_log, s_hist, s_musd, take, lt_mask, multi_set, dc);
 
         /* hunger probe, every 4th iteration.  The CTA keeps a snapshot of "how many warps are starving", "how many
          * donated chunks are waiting" and "where is the seed cursor" in shared memory.  Every 64th iteration
