@@ -247,7 +247,6 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         en->smem = kLogTabDoubles * 8;
         P.smem_hist_slots = 0;
         P.hist_hashed = 0;
-        P.plan_in_smem = 0;
         P.spill = nullptr;
     } else {
         int max_smem = 0;
@@ -255,8 +254,7 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         const char* wenv = getenv("PROCELL_COOP_WARPS");     /* tuning knob: 16, 24 or 32 warps per CTA */
         const int wreq = wenv ? atoi(wenv) : 0;
         en->warps = (wreq == 16 || wreq == 24) ? wreq : 32;
-        P.plan_in_smem = (B <= 1024 && S * T <= 64) ? 1 : 0;
-        const size_t fixed = coop_smem_bytes(en->warps, 0, 0, P.plan_in_smem);
+        const size_t fixed = coop_smem_bytes(en->warps, 0, 0);
         const size_t room = (size_t)max_smem > fixed ? (size_t)max_smem - fixed : 0;
         if (en->counts_len * 4 <= room) {            /* the whole key space fits: direct u32 table */
             P.hist_hashed = 0;
@@ -267,7 +265,7 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
             P.hist_hashed = 1;
             P.smem_hist_slots = slots;
         }
-        en->smem = coop_smem_bytes(en->warps, P.smem_hist_slots, P.hist_hashed, P.plan_in_smem);
+        en->smem = coop_smem_bytes(en->warps, P.smem_hist_slots, P.hist_hashed);
         int grid = 0;
         CU(coop_max_grid(en->device, en->warps, P.hist_hashed, en->smem, &grid), "occupancy query");
         if (grid <= 0) return fail(PROCELL_ERR_CUDA, "cooperative kernel does not fit on this device");

@@ -36,7 +36,6 @@ namespace {
 #endif
 
 constexpr uint32_t kRingMask = kStackCap - 1;
-constexpr int kSmemPlanBytes = 1028 * 4 + 1024 * 4 + 1024 + 64 * 8 + 64;   /* bin + type tables of the SEED path */
 constexpr int kSmemMusdEntries = 64;  /* (mean, sd) table cached in shared memory when n_sets * n_types fits */
 constexpr int kSmemCtlBytes = 128 + kSmemMusdEntries * 16;    /* control words (64 B) + three 16-byte snapshots of the control block */
 constexpr unsigned kFull = 0xFFFFFFFFu;
@@ -341,45 +340,34 @@ struct SeedOut {
     double t_div;
 };
 
-/* the read-only tables a seed cell needs; they point into shared memory when the histogram has <= 1024 non-empty
- * lines and n_sets * n_types <= 64 (the usual case), else into HBM (L1/L2-cached) */
-struct SeedTables {
-    const uint32_t* bin_start;
-    const uint32_t* bin_keybase;
-    const uint8_t* bin_kdiv;
-    const double* type_cum;
-    const uint8_t* type_sel;
-    const double2* type_musd;
-};
-
 /* bin of a seed cell: largest b with bin_start[b] <= root (parser.cu "bounds") */
-__device__ __forceinline__ uint32_t find_bin(const SimParams& P, const SeedTables& tb, uint32_t root)
+__device__ __forceinline__ uint32_t find_bin(const SimParams& P, uint32_t root)
 {
     uint32_t lo = 0, hi = P.n_bins;
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
-        if (tb.bin_start[mid] <= root) lo = mid; else hi = mid;
+        if (__ldg(P.bin_start + mid) <= root) lo = mid; else hi = mid;
     }
     return lo;
 }
 
-__device__ __forceinline__ SeedOut build_seed(const SimParams& P, const SeedTables& tb, const double* s_log, uint32_t root,
-                                              uint32_t set, uint32_t bin)
+__device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* s_log, uint32_t root, uint32_t set,
+                                              uint32_t bin)
 {
     SeedOut o;
-    const uint32_t kd = tb.bin_kdiv[bin];
+    const uint32_t kd = __ldg(P.bin_kdiv + bin);
     const uint32_t T = P.n_types;
     pcs_u32x4 w = pcs_draw_rk(root, set, 0u, PCS_TAG_SEED, 0ull, P.rk);
     const double u_type = pcs_u53(w.x, w.y);
     const double u_age = pcs_u53(w.z, w.w);
     uint32_t j = 0;
     for (; j + 1 < T; ++j)                                     /* cell.cu:81-104; Q17: none -> last */
-        if (u_type < tb.type_cum[(size_t)set * T + j]) break;
-    const uint32_t type = tb.type_sel[(size_t)set * T + j];
-    const double2 ms = tb.type_musd[(size_t)set * T + type];
+        if (u_type < __ldg(P.type_cum + (size_t)set * T + j)) break;
+    const uint32_t type = __ldg(P.type_sel + (size_t)set * T + j);
+    const double2 ms = __ldg(P.type_musd + (size_t)set * T + type);
     o.type = type;
     o.kdiv = kd & 63u;
-    o.key = (set * P.n_keys + tb.bin_keybase[bin]) * T + type;
+    o.key = (set * P.n_keys + __ldg(P.bin_keybase + bin)) * T + type;
     const bool count0 = (kd & 0x80u) != 0u;
     if (ms.x < 0.0) {                                          /* quiescent: timer -1, t 0 -> out_of_time */
         o.kind = count0 ? 1 : 0;
@@ -494,36 +482,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_log = reinterpret_cast<double*>(smem_raw);
     volatile int* s_ctl = reinterpret_cast<volatile int*>(smem_raw + kLogTabDoubles * 8);   /* [0] poll lock, [1] quiescent */
-    const size_t plan_bytes = P.plan_in_smem ? (size_t)kSmemPlanBytes : 0;
-    unsigned char* s_plan = smem_raw + kLogTabDoubles * 8 + kSmemCtlBytes;
-    uint64_t* s_stack = reinterpret_cast<uint64_t*>(s_plan + plan_bytes);
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_plan + plan_bytes + (size_t)WARPS * 4 * kStackCap * 8);
+    uint64_t* s_stack = reinterpret_cast<uint64_t*>(smem_raw + kLogTabDoubles * 8 + kSmemCtlBytes);
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + kLogTabDoubles * 8 + kSmemCtlBytes + (size_t)WARPS * 4 * kStackCap * 8);
 
     double2* s_musd_buf = reinterpret_cast<double2*>(smem_raw + kLogTabDoubles * 8 + 128);
     const bool musd_cached = P.n_sets * P.n_types <= (uint32_t)kSmemMusdEntries;
     if (musd_cached && threadIdx.x < P.n_sets * P.n_types) s_musd_buf[threadIdx.x] = __ldg(P.type_musd + threadIdx.x);
     const double2* s_musd = musd_cached ? s_musd_buf : nullptr;
-    SeedTables tb;
-    tb.bin_start = P.bin_start; tb.bin_keybase = P.bin_keybase; tb.bin_kdiv = P.bin_kdiv;
-    tb.type_cum = P.type_cum; tb.type_sel = P.type_sel; tb.type_musd = P.type_musd;
-    if (P.plan_in_smem) {       /* <= 1024 bins and <= 64 (set, type) pairs: ~10 KB */
-        uint32_t* sb_start = reinterpret_cast<uint32_t*>(s_plan);
-        uint32_t* sb_keybase = sb_start + 1028;
-        uint8_t* sb_kdiv = reinterpret_cast<uint8_t*>(sb_keybase + 1024);
-        double* st_cum = reinterpret_cast<double*>(sb_kdiv + 1024);
-        uint8_t* st_sel = reinterpret_cast<uint8_t*>(st_cum + 64);
-        for (uint32_t i = threadIdx.x; i <= P.n_bins; i += blockDim.x) sb_start[i] = __ldg(P.bin_start + i);
-        for (uint32_t i = threadIdx.x; i < P.n_bins; i += blockDim.x) {
-            sb_keybase[i] = __ldg(P.bin_keybase + i);
-            sb_kdiv[i] = __ldg(P.bin_kdiv + i);
-        }
-        for (uint32_t i = threadIdx.x; i < P.n_sets * P.n_types; i += blockDim.x) {
-            st_cum[i] = __ldg(P.type_cum + i);
-            st_sel[i] = __ldg(P.type_sel + i);
-        }
-        tb.bin_start = sb_start; tb.bin_keybase = sb_keybase; tb.bin_kdiv = sb_kdiv;
-        tb.type_cum = st_cum; tb.type_sel = st_sel; tb.type_musd = s_musd_buf;
-    }
     if (threadIdx.x < 2) s_ctl[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < kLogTabDoubles; i += blockDim.x) s_log[i] = __ldg(P.logtab + i);
     if (HASHED) {
@@ -662,7 +627,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 const bool have = root < seed_end;
                 seed_cur = (seed_end - seed_cur > 32u) ? seed_cur + 32u : seed_end;
                 SeedOut so; so.kind = 0; so.key = 0; so.type = 0; so.kdiv = 0; so.t_div = 0.0;
-                if (have) so = build_seed(P, tb, s_log, root, seed_set, find_bin(P, tb, root));
+                if (have) so = build_seed(P, s_log, root, seed_set, find_bin(P, root));
                 const unsigned live = __ballot_sync(kFull, so.kind == 2);
                 if (so.kind == 2) {
                     uint32_t idx = (w.top + __popc(live & lt_mask)) & kRingMask;
@@ -773,9 +738,6 @@ __global__ void __launch_bounds__(kSimpleThreads) k_proliferate_simple(const __g
     for (int i = threadIdx.x; i < kLogTabDoubles; i += blockDim.x) s_log[i] = __ldg(P.logtab + i);
     __syncthreads();
 
-    SeedTables tb;
-    tb.bin_start = P.bin_start; tb.bin_keybase = P.bin_keybase; tb.bin_kdiv = P.bin_kdiv;
-    tb.type_cum = P.type_cum; tb.type_sel = P.type_sel; tb.type_musd = P.type_musd;
     uint64_t st_heap[kSimpleStack];
     double st_t[kSimpleStack];
     uint32_t st_m[kSimpleStack];     /* mask | retry<<8 */
@@ -788,7 +750,7 @@ __global__ void __launch_bounds__(kSimpleThreads) k_proliferate_simple(const __g
         const uint32_t set = (uint32_t)(gi / P.n_cells);
         const uint32_t root = (uint32_t)(gi - (unsigned long long)set * P.n_cells);
         if (P.shard_world > 1u && (root / P.unit) % P.shard_world != P.shard_rank) continue;
-        SeedOut so = build_seed(P, tb, s_log, root, set, find_bin(P, tb, root));
+        SeedOut so = build_seed(P, s_log, root, set, find_bin(P, root));
         if (so.kind == 1) atomicAdd(counts + so.key, 1ull);
         if (so.kind != 2) continue;
         const double2 ms = __ldg(P.type_musd + (size_t)set * T + so.type);
@@ -868,10 +830,9 @@ __global__ void __launch_bounds__(256) k_rng_ceiling(int iters, const double* lo
 }
 
 /* ------------------------------------------------------------------------------------------------ host */
-size_t coop_smem_bytes(int warps, uint32_t hist_slots, int hashed, int plan_in_smem)
+size_t coop_smem_bytes(int warps, uint32_t hist_slots, int hashed)
 {
-    return (size_t)kLogTabDoubles * 8 + kSmemCtlBytes + (plan_in_smem ? kSmemPlanBytes : 0) +
-           (size_t)warps * 4 * kStackCap * 8 + (size_t)hist_slots * (hashed ? 8 : 4);
+    return (size_t)kLogTabDoubles * 8 + kSmemCtlBytes + (size_t)warps * 4 * kStackCap * 8 + (size_t)hist_slots * (hashed ? 8 : 4);
 }
 
 template <int WARPS, bool HASHED>
@@ -900,7 +861,7 @@ cudaError_t coop_max_grid(int device, int warps, int hashed, size_t smem_bytes, 
 
 cudaError_t launch_coop(const SimParams& p, int warps, int grid, cudaStream_t stream)
 {
-    size_t smem = coop_smem_bytes(warps, p.smem_hist_slots, p.hist_hashed, p.plan_in_smem);
+    size_t smem = coop_smem_bytes(warps, p.smem_hist_slots, p.hist_hashed);
     if (p.hist_hashed) {
         if (warps == 32) k_proliferate_coop<32, true><<<grid, 32 * 32, smem, stream>>>(p);
         else if (warps == 24) k_proliferate_coop<24, true><<<grid, 24 * 32, smem, stream>>>(p);

@@ -73,7 +73,6 @@ struct SimParams {
     uint32_t smem_hist_slots;     /* direct mode: keys below this are privatised in shared memory (u32 each);
                                      hashed mode: number of {key,count} u64 slots, a power of two */
     int hist_hashed;              /* 1: key space larger than shared memory -> direct-mapped {key,count} cache */
-    int plan_in_smem;             /* 1: bin and type tables of the SEED path are copied into shared memory */
     int refcompat;
     int donate;                   /* 0: never hand work to starving warps (diagnostic) */
     unsigned long long watchdog_ns;   /* a warp that runs longer than this aborts the launch (status 4) */
@@ -81,7 +80,7 @@ struct SimParams {
     double t_max;
 };
 
-size_t coop_smem_bytes(int warps, uint32_t hist_slots, int hashed, int plan_in_smem);
+size_t coop_smem_bytes(int warps, uint32_t hist_slots, int hashed);
 cudaError_t launch_coop(const SimParams& p, int warps, int grid, cudaStream_t stream);
 cudaError_t coop_max_grid(int device, int warps, int hashed, size_t smem_bytes, int* grid_out);
 cudaError_t launch_simple(const SimParams& p, int grid, cudaStream_t stream);
