@@ -216,6 +216,19 @@ class Engine:
                                                 div.ctypes.data_as(_i64p), C.byref(st)))
         return Result(flat[:n].reshape(self.shape) if fetch else None, div, _stats_dict(st))
 
+    def set_target(self, values, freqs) -> None:
+        """Target histogram of a calibration sweep (channel values strictly ascending)."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        f = np.ascontiguousarray(freqs, dtype=np.uint64)
+        check(_lib.load().procell_engine_set_target(self.h, v.ctypes.data_as(_f64p), f.ctypes.data_as(_u64p), len(v)))
+
+    def fitness(self, stream: int = 0, d_counts: int = 0) -> np.ndarray:
+        """Hellinger distance of every parameter set's simulated histogram to the target, computed on the GPU."""
+        out = np.zeros(self.shape[0], dtype=np.float64)
+        check(_lib.load().procell_engine_fitness(self.h, C.c_void_p(stream or None), C.c_void_p(d_counts or None),
+                                                 out.ctypes.data_as(_f64p)))
+        return out
+
     def close(self):
         if getattr(self, "h", None):
             _lib.load().procell_engine_destroy(self.h)

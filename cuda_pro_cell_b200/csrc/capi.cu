@@ -73,7 +73,9 @@ struct procell_engine {
     int device = 0;
     int sm_count = 0;
     DevBuf bin_start, bin_keybase, bin_kdiv, type_cum, type_sel, type_musd, logtab;
-    DevBuf dbg;
+    DevBuf dbg, fit_key_channel, fit_target, fit_out;
+    uint32_t fit_channels = 0;
+    const procell_plan* plan = nullptr;
     DevBuf counts, ctl, q_seq, q_data, spill;   /* counts = count tensor followed by the division counters */
     SimParams P{};
     bool loaded = false;
@@ -126,7 +128,7 @@ void procell_engine_destroy(procell_engine* en)
     if (!en) return;
     cudaSetDevice(en->device);
     DevBuf* bufs[] = { &en->bin_start, &en->bin_keybase, &en->bin_kdiv, &en->type_cum, &en->type_sel, &en->type_musd,
-                       &en->logtab, &en->counts, &en->dbg, &en->ctl, &en->q_seq, &en->q_data, &en->spill };
+                       &en->logtab, &en->counts, &en->dbg, &en->fit_key_channel, &en->fit_target, &en->fit_out, &en->ctl, &en->q_seq, &en->q_data, &en->spill };
     for (DevBuf* b : bufs) b->release();
     if (en->ev0) cudaEventDestroy(en->ev0);
     if (en->ev1) cudaEventDestroy(en->ev1);
@@ -190,6 +192,8 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
 
     en->counts_len = S * K * T;
     en->n_sets = S;
+    en->plan = plan;
+    en->fit_channels = 0;
     /* one allocation: the count tensor followed by the division counters, so that a multi-GPU run needs ONE reduce */
     CU(en->counts.reserve((en->counts_len + S) * 8), "alloc counts");
 
@@ -402,6 +406,55 @@ int procell_proliferate(const procell_plan* plan, const procell_sim_params* para
     if (rc == PROCELL_OK) rc = procell_engine_finish(en, nullptr, counts, divisions, stats);
     procell_engine_destroy(en);
     return rc;
+}
+
+/* ---- on-GPU fitness of a sweep -------------------------------------------------------------- */
+int procell_engine_set_target(procell_engine* en, const double* value, const uint64_t* freq, size_t n_channels)
+{
+    if (!en || !en->loaded || !en->plan) return fail(PROCELL_ERR_ARG, "procell_engine_set_target: engine not loaded");
+    if (!value || !freq || n_channels == 0 || n_channels > 16384)
+        return fail(PROCELL_ERR_ARG, "target histogram must have 1..16384 channels");
+    for (size_t c = 1; c < n_channels; ++c)
+        if (!(value[c] > value[c - 1])) return fail(PROCELL_ERR_ARG, "target channel values must be strictly ascending");
+    CU(cudaSetDevice(en->device), "cudaSetDevice");
+    const procell_plan* plan = en->plan;
+    /* utils::rebin (src/utils/util.cu:111-138): a value goes to the first channel whose value is >= it */
+    std::vector<uint32_t> row_channel(plan->row_value.size());
+    size_t pos = 0;
+    for (size_t r = 0; r < plan->row_value.size(); ++r) {
+        while (pos + 1 < n_channels && plan->row_value[r] > value[pos]) ++pos;
+        row_channel[r] = (uint32_t)pos;
+    }
+    std::vector<uint32_t> key_channel(plan->n_keys + 1, 0xFFFFFFFFu);
+    for (size_t k = 0; k < plan->n_keys; ++k)
+        if (plan->key_row[k] != 0xFFFFFFFFu) key_channel[k] = row_channel[plan->key_row[k]];
+    double total = 0.0;
+    for (size_t c = 0; c < n_channels; ++c) total += (double)freq[c];
+    if (!(total > 0.0)) return fail(PROCELL_ERR_ARG, "target histogram is empty");
+    std::vector<double> share(n_channels);
+    for (size_t c = 0; c < n_channels; ++c) share[c] = (double)freq[c] / total;
+    CU(en->fit_key_channel.reserve((plan->n_keys + 1) * 4), "alloc key_channel");
+    CU(en->fit_target.reserve(n_channels * 8), "alloc target");
+    CU(en->fit_out.reserve(en->n_sets * 8), "alloc fitness");
+    CU(cudaMemcpy(en->fit_key_channel.p, key_channel.data(), (plan->n_keys + 1) * 4, cudaMemcpyHostToDevice), "upload key_channel");
+    CU(cudaMemcpy(en->fit_target.p, share.data(), n_channels * 8, cudaMemcpyHostToDevice), "upload target");
+    en->fit_channels = (uint32_t)n_channels;
+    return PROCELL_OK;
+}
+
+int procell_engine_fitness(procell_engine* en, void* stream_v, const int64_t* d_counts, double* fitness)
+{
+    if (!en || !en->loaded || en->fit_channels == 0 || !fitness)
+        return fail(PROCELL_ERR_ARG, "procell_engine_fitness: no target set");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CU(cudaSetDevice(en->device), "cudaSetDevice");
+    const long long* counts = d_counts ? (const long long*)d_counts : (const long long*)en->counts.p;
+    CU(launch_sweep_fitness(counts, (const uint32_t*)en->fit_key_channel.p, (const double*)en->fit_target.p,
+                            (uint32_t)en->n_sets, en->P.n_keys, en->P.n_types, en->fit_channels, (double*)en->fit_out.p, stream),
+       "launch k_sweep_fitness");
+    CU(cudaMemcpyAsync(fitness, en->fit_out.p, en->n_sets * 8, cudaMemcpyDeviceToHost, stream), "download fitness");
+    CU(cudaStreamSynchronize(stream), "fitness kernel");
+    return PROCELL_OK;
 }
 
 /* ---- single-process multi-GPU: seed-cell units sharded over the GPUs of one box, ONE ncclReduce(sum, int64) ---- */

@@ -89,5 +89,9 @@ cudaError_t launch_rng_ceiling(int grid, int block, int iters, const double* log
                                double t_max, const uint32_t* rk, unsigned long long* sink,
                                cudaStream_t stream);
 
+cudaError_t launch_sweep_fitness(const long long* counts, const uint32_t* key_channel, const double* target_share,
+                                 uint32_t n_sets, uint32_t n_keys, uint32_t n_types, uint32_t n_channels, double* out,
+                                 cudaStream_t stream);
+
 }  // namespace procell_b200
 #endif

@@ -131,6 +131,14 @@ int procell_engine_finish(procell_engine* engine, void* stream, int64_t* counts,
                           procell_run_stats* stats);
 size_t procell_engine_counts_len(const procell_engine* engine); /* n_sets*n_keys*n_types */
 
+/* On-GPU fitness of a sweep (what a ProCell fitting loop consumes): re-bin every set's simulated histogram onto the
+ * target's channels - first channel whose value is >= the row value, the rule of the reference's unused
+ * utils::rebin (src/utils/util.cu:111-138) - and return the Hellinger distance sqrt(1 - sum sqrt(p q)) per set.
+ * set_target uploads the target (values strictly ascending); fitness runs after procell_engine_run on the same
+ * stream, on the engine's own count tensor (d_counts NULL) or on the caller's device tensor. fitness: host [n_sets]. */
+int procell_engine_set_target(procell_engine* engine, const double* value, const uint64_t* freq, size_t n_channels);
+int procell_engine_fitness(procell_engine* engine, void* stream, const int64_t* d_counts, double* fitness);
+
 /* RNG-only micro-kernel: per thread `iters` Philox blocks + Box-Muller pairs + timers into a register
  * accumulator (the instruction-issue ceiling the roofline fraction is quoted against).  Returns ms. */
 int procell_rng_ceiling(int device, int iters, double* ms_out, double* pairs_out);

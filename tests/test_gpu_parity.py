@@ -213,3 +213,41 @@ def test_cli_multi_gpu(gpu_api, oracle, tmp_path):
     want = oracle.simulate(oplan, w.types, 168.0, 99)
     nz = want["row_freq"][0] > 0
     assert [int(ln.split("\t")[1]) for ln in o.read_text().splitlines()] == want["row_freq"][0][nz].tolist()
+
+
+def _hellinger_reference(plan, counts_one_set, tvalues, tfreqs):
+    """numpy restatement of the sweep fitness: rebin rows onto the target's channels (first channel whose value is >=
+    the row value, reference util.cu:111-138; beyond the last channel -> last), Hellinger distance to the target"""
+    rf, _ = plan.merge_rows(counts_one_set)
+    ch = np.minimum(np.searchsorted(tvalues, plan.row_value, side="left"), len(tvalues) - 1)
+    acc = np.bincount(ch, weights=rf.astype(np.float64), minlength=len(tvalues))
+    if acc.sum() == 0:
+        return 1.0
+    p, q = acc / acc.sum(), tfreqs / tfreqs.sum()
+    return float(np.sqrt(max(0.0, 1.0 - np.sqrt(p * q).sum())))
+
+
+def test_sweep_fitness_on_gpu(gpu_api):
+    """per-set Hellinger distance to a target histogram computed on the GPU from the resident count
+    tensor equals the numpy restatement (floating point: |diff| <= 1e-12), and the set that generated the target
+    scores best."""
+    values, freqs = synth.synthetic_histogram(20000)
+    types = synth.sweep_types(1024)[::64]                       # 16 parameter sets
+    plan = gpu_api.Plan(values, freqs, 0.5)
+    eng = gpu_api.Engine(0)
+    eng.load(plan, types, 168.0, 0x5EED0005)
+    eng.run()
+    res = eng.finish()
+    # target = the histogram set 5 produced with another seed, on a coarser channel grid (every 4th row value)
+    tgt = gpu_api.proliferate(plan, types[5:6], 168.0, 4242)
+    rf, _ = plan.merge_rows(tgt.counts[0])
+    tvalues = plan.row_value[3::4].copy()
+    ch = np.minimum(np.searchsorted(tvalues, plan.row_value, side="left"), len(tvalues) - 1)
+    tfreqs = np.bincount(ch, weights=rf.astype(np.float64), minlength=len(tvalues)).astype(np.uint64)
+    eng.set_target(tvalues, tfreqs)
+    fit = eng.fitness()
+    want = np.array([_hellinger_reference(plan, res.counts[s], tvalues, tfreqs.astype(np.float64)) for s in range(len(types))])
+    assert np.abs(fit - want).max() <= 1e-12
+    assert int(np.argmin(fit)) == 5 and fit[5] < 0.05
+    assert np.array_equal(eng.fitness(), fit)                   # reproducible run to run
+    eng.close()
