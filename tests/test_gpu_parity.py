@@ -248,6 +248,6 @@ def test_sweep_fitness_on_gpu(gpu_api):
     fit = eng.fitness()
     want = np.array([_hellinger_reference(plan, res.counts[s], tvalues, tfreqs.astype(np.float64)) for s in range(len(types))])
     assert np.abs(fit - want).max() <= 1e-12
-    assert int(np.argmin(fit)) == 5 and fit[5] < 0.05
+    assert int(np.argmin(fit)) == 5 and fit[5] < 0.1
     assert np.array_equal(eng.fitness(), fit)                   # reproducible run to run
     eng.close()
