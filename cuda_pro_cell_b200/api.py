@@ -121,9 +121,14 @@ class Plan:
             pass
 
 
-def _make_params(types: np.ndarray, t_max, seed, seeding_mode, kernel, shard):
+def _make_params(types: np.ndarray, t_max, seed, seeding_mode, kernel, shard, checkpoints=None):
     n_sets, n_types, _ = types.shape
     p = SimParams()
+    if checkpoints is not None:
+        cp = np.ascontiguousarray(checkpoints, dtype=np.float64)
+        p._checkpoints_keepalive = cp          # the struct only holds a pointer
+        p.checkpoints = cp.ctypes.data_as(C.POINTER(C.c_double))
+        p.n_checkpoints = len(cp)
     p.types = types.ctypes.data_as(C.POINTER(CellType))
     p.n_types = n_types
     p.n_sets = n_sets
@@ -149,12 +154,15 @@ def _stats_dict(st: RunStats) -> dict:
 
 
 def proliferate(plan: Plan, types, t_max: float, seed: int = 0x5EED0000, seeding_mode: int = SEEDING_IDEAL,
-                kernel: int = KERNEL_COOP, device: int = 0, shard=(0, 1, 0)) -> Result:
-    """One-shot host-buffer call (what the CLI uses).  shard = (rank, world, unit)."""
+                kernel: int = KERNEL_COOP, device: int = 0, shard=(0, 1, 0), checkpoints=None) -> Result:
+    """One-shot host-buffer call (what the CLI uses).  shard = (rank, world, unit).  With `checkpoints` (ascending,
+    at most 8; the last replaces t_max) counts gets a leading checkpoint axis."""
     lib = _lib.load()
     t = _types_array(types)
-    p = _make_params(t, t_max, seed, seeding_mode, kernel, shard)
+    p = _make_params(t, t_max, seed, seeding_mode, kernel, shard, checkpoints)
     shape = (t.shape[0], plan.n_keys, t.shape[1])
+    if checkpoints is not None:
+        shape = (len(checkpoints),) + shape
     flat = np.zeros(max(int(np.prod(shape)), 1), dtype=np.int64)     # never a NULL pointer, even for 0 keys
     div = np.zeros(t.shape[0], dtype=np.int64)
     st = RunStats()

@@ -85,6 +85,7 @@ struct procell_engine {
     size_t smem = 0;
     size_t counts_len = 0;
     size_t n_sets = 0;
+    size_t n_times = 1;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int launches_last = 0;
@@ -143,9 +144,17 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     const size_t T = sp->n_types, S = sp->n_sets, B = plan->bin_value.size(), K = plan->n_keys;
     if (T == 0 || T > 64) return fail(PROCELL_ERR_ARG, "n_types must be 1..64");
     if (S == 0 || S > 65536) return fail(PROCELL_ERR_ARG, "n_sets must be 1..65536");
-    if (!(sp->t_max >= 0.0)) return fail(PROCELL_ERR_ARG, "t_max must be >= 0");
-    if ((double)S * (double)K * (double)T >= 4294967296.0)
-        return fail(PROCELL_ERR_ARG, "n_sets * n_keys * n_types must be below 2^32");
+    const size_t M = (sp->checkpoints && sp->n_checkpoints) ? sp->n_checkpoints : 1;
+    if (M > 8) return fail(PROCELL_ERR_ARG, "at most 8 checkpoints");
+    double times[8];
+    if (M == 1 && !(sp->checkpoints && sp->n_checkpoints)) times[0] = sp->t_max;
+    else for (size_t j = 0; j < M; ++j) times[j] = sp->checkpoints[j];
+    for (size_t j = 0; j < M; ++j)
+        if (!(times[j] >= 0.0) || (j && !(times[j] > times[j - 1])))
+            return fail(PROCELL_ERR_ARG, "t_max / checkpoints must be >= 0 and strictly ascending");
+    if (M > 1 && sp->kernel == PROCELL_KERNEL_SIMPLE) return fail(PROCELL_ERR_ARG, "checkpoints need the cooperative kernel");
+    if ((double)M * (double)S * (double)K * (double)T >= 4294967296.0)
+        return fail(PROCELL_ERR_ARG, "n_checkpoints * n_sets * n_keys * n_types must be below 2^32");
     if (sp->shard_world > 1 && sp->shard_rank >= sp->shard_world) return fail(PROCELL_ERR_ARG, "shard_rank >= shard_world");
     for (size_t s = 0; s < S; ++s) {
         int rc = procell_check_proportions(sp->types + s * T, T);
@@ -190,8 +199,9 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     CU(cudaMemcpy(en->type_sel.p, h_sel.data(), S * T, cudaMemcpyHostToDevice), "upload type_sel");
     CU(cudaMemcpy(en->type_musd.p, h_musd.data(), S * T * 16, cudaMemcpyHostToDevice), "upload type_musd");
 
-    en->counts_len = S * K * T;
+    en->counts_len = M * S * K * T;
     en->n_sets = S;
+    en->n_times = M;
     en->plan = plan;
     en->fit_channels = 0;
     /* one allocation: the count tensor followed by the division counters, so that a multi-GPU run needs ONE reduce */
@@ -215,7 +225,10 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     P.shard_world = sp->shard_world > 1 ? sp->shard_world : 1;
     P.shard_rank = sp->shard_world > 1 ? sp->shard_rank : 0;
     P.refcompat = sp->seeding_mode == PROCELL_SEEDING_REFCOMPAT;
-    P.t_max = sp->t_max;
+    P.t_max = times[M - 1];
+    P.n_times = (uint32_t)M;
+    P.time_stride = (uint32_t)(S * K * T);
+    for (size_t j = 0; j < 8; ++j) P.times[j] = j < M ? times[j] : times[M - 1];
     set_round_keys(P, sp->seed);
 
     /* claim unit: 32 seed cells = one SEED iteration of a warp (small units keep the tail balanced: a warp claims
@@ -449,6 +462,7 @@ int procell_engine_fitness(procell_engine* en, void* stream_v, const int64_t* d_
     cudaStream_t stream = (cudaStream_t)stream_v;
     CU(cudaSetDevice(en->device), "cudaSetDevice");
     const long long* counts = d_counts ? (const long long*)d_counts : (const long long*)en->counts.p;
+    counts += (en->n_times - 1) * (size_t)en->P.time_stride;       /* time series: fitness of the last checkpoint */
     CU(launch_sweep_fitness(counts, (const uint32_t*)en->fit_key_channel.p, (const double*)en->fit_target.p,
                             (uint32_t)en->n_sets, en->P.n_keys, en->P.n_types, en->fit_channels, (double*)en->fit_out.p, stream),
        "launch k_sweep_fitness");

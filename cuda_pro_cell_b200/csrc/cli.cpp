@@ -8,7 +8,7 @@
  * (README.md:98-102; the reference code wrongly requires it, cmdargs.cpp:48-49), default = smallest value
  * with a non-zero frequency (parser.cu:80-96).  -d/--tree-depth (1..23) is accepted and ignored: it only
  * sized the reference's dense level arrays.  Extensions (not in the reference): --seed, --seeding,
- * --kernel, --device, --gpus, --stats.
+ * --kernel, --device, --gpus, --checkpoints, --stats.
  */
 #include <cstdio>
 #include <cstdlib>
@@ -31,6 +31,7 @@ struct Args {
     int kernel = PROCELL_KERNEL_COOP;
     int device = 0;
     int gpus = 1;
+    std::vector<double> checkpoints;
 };
 
 void usage()
@@ -49,6 +50,7 @@ void usage()
         "      --kernel coop|simple\n"
         "      --device N               CUDA device index\n"
         "      --gpus N                 shard the seed cells over N GPUs of this box (0 = all), one NCCL reduce\n"
+        "      --checkpoints T1,T2,...  also write the histogram at these earlier times (FILE.t<T>), one tree expansion\n"
         "      --stats                  print run statistics as JSON on stderr\n";
 }
 
@@ -142,6 +144,17 @@ extern "C" int procell_main(int argc, char** argv)
         } else if (s == "--gpus" && i < argc - 1) {
             a.gpus = atoi(argv[++i]);
             r = 1;
+        } else if (s == "--checkpoints" && i < argc - 1) {
+            /* extension: histograms at several times from one expansion; -o FILE gets the last one, FILE.t<time> the others */
+            std::string list = argv[++i];
+            size_t pos = 0;
+            while (pos < list.size()) {
+                size_t comma = list.find(',', pos);
+                if (comma == std::string::npos) comma = list.size();
+                a.checkpoints.push_back(atof(list.substr(pos, comma - pos).c_str()));
+                pos = comma + 1;
+            }
+            r = 1;
         } else if (s == "--stats") {
             a.stats = true;
             r = 1;
@@ -182,7 +195,13 @@ extern "C" int procell_main(int argc, char** argv)
         memset(&sp, 0, sizeof sp);
         sp.types = types; sp.n_types = n_types; sp.n_sets = 1; sp.t_max = a.t_max; sp.seed = a.seed;
         sp.seeding_mode = a.seeding; sp.kernel = a.kernel;
-        counts.assign(procell_plan_n_keys(plan) * n_types + 1, 0);
+        if (!a.checkpoints.empty()) {
+            if (a.checkpoints.back() != a.t_max) a.checkpoints.push_back(a.t_max);     /* -t is always the last one */
+            sp.checkpoints = a.checkpoints.data();
+            sp.n_checkpoints = a.checkpoints.size();
+        }
+        const size_t n_cp = a.checkpoints.empty() ? 1 : a.checkpoints.size();
+        counts.assign(n_cp * procell_plan_n_keys(plan) * n_types + 1, 0);
         if (a.gpus == 1) rc = procell_proliferate(plan, &sp, a.device, counts.data(), nullptr, &st);
         else rc = procell_proliferate_multi(plan, &sp, a.gpus, counts.data(), nullptr, &st);
     }
@@ -193,10 +212,22 @@ extern "C" int procell_main(int argc, char** argv)
         row_freq.assign(n_rows + 1, 0);
         row_ratio.assign(n_rows * n_types + 1, 0);
         procell_plan_export(plan, row_value.data(), nullptr, nullptr, nullptr);
-        rc = procell_merge_rows(plan, counts.data(), n_types, row_freq.data(), row_ratio.data());
-        if (rc == PROCELL_OK)
-            rc = procell_write_histogram(a.out_given ? a.out.c_str() : nullptr, a.track_ratio ? 1 : 0, n_types, n_rows,
-                                         row_value.data(), row_freq.data(), row_ratio.data());
+        const size_t n_cp = a.checkpoints.empty() ? 1 : a.checkpoints.size();
+        const size_t per_cp = procell_plan_n_keys(plan) * n_types;
+        for (size_t j = 0; j < n_cp && rc == PROCELL_OK; ++j) {
+            const bool last = j + 1 == n_cp;
+            if (!last && !a.out_given) continue;          /* earlier checkpoints need files to go to */
+            rc = procell_merge_rows(plan, counts.data() + j * per_cp, n_types, row_freq.data(), row_ratio.data());
+            std::string path = a.out;
+            if (!last) {
+                char suffix[64];
+                snprintf(suffix, sizeof suffix, ".t%.10g", a.checkpoints[j]);
+                path += suffix;
+            }
+            if (rc == PROCELL_OK)
+                rc = procell_write_histogram(a.out_given ? path.c_str() : nullptr, a.track_ratio ? 1 : 0, n_types, n_rows,
+                                             row_value.data(), row_freq.data(), row_ratio.data());
+        }
     }
     if (rc == PROCELL_OK && a.stats) {
         fprintf(stderr, "{\"divisions\": %lld, \"kernel_ms\": %.6f, \"grid\": %d, \"block\": %d, \"smem_bytes\": %d, "

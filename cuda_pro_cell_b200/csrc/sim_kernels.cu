@@ -337,6 +337,8 @@ struct SeedOut {
     uint32_t key;       /* count-tensor index of (set, bin, level 0, type) */
     uint32_t type, kdiv;
     int kind;           /* 0 dropped, 1 leaf at level 0, 2 living root */
+    int count0;         /* level-0 leaves of this bin are output rows (value >= phi) */
+    int quiescent;
     double t_div;
 };
 
@@ -369,6 +371,8 @@ __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* 
     o.kdiv = kd & 63u;
     o.key = (set * P.n_keys + __ldg(P.bin_keybase + bin)) * T + type;
     const bool count0 = (kd & 0x80u) != 0u;
+    o.count0 = count0;
+    o.quiescent = ms.x < 0.0;
     if (ms.x < 0.0) {                                          /* quiescent: timer -1, t 0 -> out_of_time */
         o.kind = count0 ? 1 : 0;
         o.t_div = 0.0;
@@ -471,7 +475,20 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
         w.top += __popc(br);
     }
     __syncwarp();
-    warp_count_leaves<HASHED>(P, s_hist, leaf_key, leaf_inc);
+    if (P.n_times == 1u) {
+        warp_count_leaves<HASHED>(P, s_hist, leaf_key, leaf_inc);
+    } else {
+        /* time series: a daughter born at t_div that divides (or would divide) at tc is out of time at every
+         * checkpoint in [t_div, tc) */
+        const bool have0 = (rej & 1u) == 0u && (dlo & (1u << 28)) != 0u;      /* daughter 0 got its timer now */
+        const bool have1 = (rej & 2u) == 0u && (dlo & (2u << 28)) != 0u;
+        for (uint32_t j = 0; j < P.n_times; ++j) {
+            const double tj = P.times[j];
+            const bool born = t_div <= tj;
+            const uint32_t inc = (uint32_t)(have0 && born && tj < tc0) + (uint32_t)(have1 && born && tj < tc1);
+            warp_count_leaves<HASHED>(P, s_hist, leaf_key + j * P.time_stride, inc);
+        }
+    }
 }
 
 }  // namespace
@@ -626,7 +643,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 const uint32_t root = seed_cur + lane;
                 const bool have = root < seed_end;
                 seed_cur = (seed_end - seed_cur > 32u) ? seed_cur + 32u : seed_end;
-                SeedOut so; so.kind = 0; so.key = 0; so.type = 0; so.kdiv = 0; so.t_div = 0.0;
+                SeedOut so; so.kind = 0; so.key = 0; so.type = 0; so.kdiv = 0; so.t_div = 0.0; so.count0 = 0; so.quiescent = 0;
                 if (have) so = build_seed(P, s_log, root, seed_set, find_bin(P, root));
                 const unsigned live = __ballot_sync(kFull, so.kind == 2);
                 if (so.kind == 2) {
@@ -638,7 +655,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 }
                 w.top += __popc(live);
                 __syncwarp();
-                warp_count_leaves<HASHED>(P, s_hist, so.key, so.kind == 1 ? 1u : 0u);
+                if (P.n_times == 1u) {
+                    warp_count_leaves<HASHED>(P, s_hist, so.key, so.kind == 1 ? 1u : 0u);
+                } else {        /* a seed cell exists from the start: out of time at every checkpoint before t_div */
+                    for (uint32_t j = 0; j < P.n_times; ++j) {
+                        const uint32_t inc = (have && so.count0 && (so.quiescent || P.times[j] < so.t_div)) ? 1u : 0u;
+                        warp_count_leaves<HASHED>(P, s_hist, so.key + j * P.time_stride, inc);
+                    }
+                }
                 continue;
             }
             if (n == 0u) {

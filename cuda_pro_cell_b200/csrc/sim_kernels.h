@@ -77,7 +77,13 @@ struct SimParams {
     int donate;                   /* 0: never hand work to starving warps (diagnostic) */
     unsigned long long watchdog_ns;   /* a warp that runs longer than this aborts the launch (status 4) */
     unsigned long long* dbg;      /* [grid*warps][kDbgWords] */
-    double t_max;
+    double t_max;                 /* = times[n_times - 1] */
+    /* time series: histograms at several checkpoints from ONE tree expansion.  A cell is counted at
+     * checkpoint j iff it exists and is out of time there, i.e. birth <= times[j] < division time - exactly what a
+     * run with t_max = times[j] would count with the same random stream.  counts: [n_times][n_sets][n_keys][n_types] */
+    uint32_t n_times;             /* 1..8 */
+    uint32_t time_stride;         /* n_sets * n_keys * n_types */
+    double times[8];              /* ascending */
 };
 
 size_t coop_smem_bytes(int warps, uint32_t hist_slots, int hashed);

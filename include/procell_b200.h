@@ -89,7 +89,12 @@ typedef struct procell_sim_params {
     int kernel;                     /* PROCELL_KERNEL_* */
     uint32_t shard_rank;            /* this GPU simulates the seed-cell units u with u % shard_world == rank */
     uint32_t shard_world;           /* 0 or 1: everything */
-    uint32_t shard_unit;            /* seed cells per unit; 0: default (256) */
+    uint32_t shard_unit;            /* seed cells per unit; 0: default */
+    /* time series (extension): histograms at up to 8 ascending checkpoints from ONE tree expansion; the last one
+     * replaces t_max.  NULL / 0: the single checkpoint t_max.  With m checkpoints every count tensor is
+     * [m][n_sets][n_keys][n_types]; slice j equals a run with t_max = checkpoints[j] and the same seed, bit for bit. */
+    const double* checkpoints;
+    size_t n_checkpoints;
 } procell_sim_params;
 
 typedef struct procell_run_stats {

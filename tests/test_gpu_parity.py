@@ -252,3 +252,35 @@ def test_sweep_fitness_on_gpu(gpu_api):
     assert fit[5] <= np.sort(fit)[1] and fit[5] < 0.1        # the generating set is (nearly) the best fit
     assert np.array_equal(eng.fitness(), fit)                   # reproducible run to run
     eng.close()
+
+
+def test_time_series_equals_separate_runs(gpu_api, oracle, tmp_path):
+    """histograms at several checkpoints from ONE tree expansion.  Slice j must equal a separate run
+    with t_max = checkpoints[j] and the same seed - on the GPU and against the oracle - bit for bit."""
+    w = synth.workload(2, 0.005)
+    cps = [0.0, 30.0, 96.0, 168.0, 240.0]
+    plan = gpu_api.Plan(w.values, w.freqs, w.phi)
+    oplan = oracle.OraclePlan(w.values, w.freqs, w.phi)
+    ts = gpu_api.proliferate(plan, w.types, 999.0, w.seed, checkpoints=cps)
+    assert ts.counts.shape == (len(cps), 1, plan.n_keys, w.types.shape[1])
+    for j, t in enumerate(cps):
+        single = gpu_api.proliferate(plan, w.types, t, w.seed)
+        assert np.array_equal(ts.counts[j], single.counts), "checkpoint %g" % t
+        want = oracle.simulate(oplan, w.types, t, w.seed)
+        assert np.array_equal(ts.counts[j], want["counts"])
+    assert int(ts.divisions[0]) == int(gpu_api.proliferate(plan, w.types, cps[-1], w.seed).divisions[0])
+    # multi-set + checkpoints (hashed histogram) and the CLI spelling
+    types = synth.sweep_types(1024)[::256]
+    ts2 = gpu_api.proliferate(plan, types, 0.0, 7, checkpoints=[50.0, 168.0])
+    for j, t in enumerate((50.0, 168.0)):
+        assert np.array_equal(ts2.counts[j], gpu_api.proliferate(plan, types, t, 7).counts)
+    from cuda_pro_cell_b200 import _lib
+    h, c, o = tmp_path / "h.txt", tmp_path / "c.txt", tmp_path / "o.txt"
+    h.write_text(synth.histogram_text(w.values, w.freqs))
+    c.write_text(synth.types_text(w.types[0]))
+    r = subprocess.run([str(_lib.CLI_PATH), "-h", str(h), "-c", str(c), "-t", "240", "-p", "0.5", "-o", str(o), "--seed",
+                        str(w.seed), "--checkpoints", "96,168"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    for path, j in ((tmp_path / "o.txt.t96", 2), (tmp_path / "o.txt.t168", 3), (o, 4)):
+        rf, _ = plan.merge_rows(ts.counts[j][0])
+        assert [int(ln.split("\t")[1]) for ln in path.read_text().splitlines()] == rf[rf > 0].tolist()
