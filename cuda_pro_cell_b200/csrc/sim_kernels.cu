@@ -23,6 +23,8 @@
  */
 #include "sim_kernels.h"
 
+#include <cstddef>
+
 #include "procell_spec.h"
 
 namespace procell_b200 {
@@ -815,12 +817,13 @@ __global__ void __launch_bounds__(kSimpleThreads) k_proliferate_simple(const __g
 /* ------------------------------------------------------------------------------------------------ */
 __global__ void k_queue_init(unsigned long long* q_seq, ControlBlock* ctl)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < kQueueCap) q_seq[i] = (unsigned long long)i;
-    if (i == 0) {
-        ctl->cursor = 0; ctl->q_head = 0; ctl->q_tail = 0; ctl->active = 0; ctl->idle = 0; ctl->status = 0;
-        ctl->avail = 0;
-        ctl->t_start = ~0ull; ctl->t_exhausted = ~0ull; ctl->t_end = 0;
+    /* the whole control block, padding included (it is copied in 16-byte pieces and read back by the host) */
+    constexpr int kWords = (int)(sizeof(ControlBlock) / 8);
+    if (i < kWords) {
+        const bool ones = i == (int)(offsetof(ControlBlock, t_start) / 8) || i == (int)(offsetof(ControlBlock, t_exhausted) / 8);
+        reinterpret_cast<unsigned long long*>(ctl)[i] = ones ? ~0ull : 0ull;
     }
 }
 
