@@ -329,7 +329,8 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         alg_bytes = float(h2d + d2h)          # tables read once + count tensor written once per launch
         ms_step = gpu_ms / K
-        roofline = {"bound": "fp64+int instruction issue (not hbm/tensor; see DESIGN.md)",
+        roofline = {"bound": "issue",
+                    "bound_detail": "FP64 + INT instruction issue; neither HBM nor tensor bound (DESIGN.md section 5)",
                     "achieved": per_gpu / 1e9, "peak": ceiling / 1e9, "unit": "Gdivisions/s per GPU",
                     "frac": per_gpu / ceiling,
                     "peak_source": "k_rng_ceiling measured live: one Philox4x32-10 block + Box-Muller pair + 2 timers per division, no tree/atomics",
