@@ -199,13 +199,15 @@ class Engine:
         self.shape = None
 
     def load(self, plan: Plan, types, t_max: float, seed: int = 0x5EED0000, seeding_mode: int = SEEDING_IDEAL,
-             kernel: int = KERNEL_COOP, shard=(0, 1, 0)) -> None:
+             kernel: int = KERNEL_COOP, shard=(0, 1, 0), checkpoints=None) -> None:
         t = _types_array(types)
-        p = _make_params(t, t_max, seed, seeding_mode, kernel, shard)
+        p = _make_params(t, t_max, seed, seeding_mode, kernel, shard, checkpoints)
         check(_lib.load().procell_engine_load(self.h, plan.h, C.byref(p)))
         self.plan = plan
         self.seed = seed
         self.shape = (t.shape[0], plan.n_keys, t.shape[1])
+        if checkpoints is not None:
+            self.shape = (len(checkpoints),) + self.shape
 
     def run(self, seed: Optional[int] = None, stream: int = 0, d_counts: int = 0, d_divisions: int = 0) -> None:
         """stream: cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream); d_counts / d_divisions:
@@ -218,7 +220,7 @@ class Engine:
         st = RunStats()
         n = int(np.prod(self.shape))
         flat = np.zeros(max(n, 1), dtype=np.int64) if fetch else None
-        div = np.zeros(self.shape[0], dtype=np.int64)
+        div = np.zeros(self.shape[-3], dtype=np.int64)
         check(_lib.load().procell_engine_finish(self.h, C.c_void_p(stream or None),
                                                 flat.ctypes.data_as(_i64p) if fetch else None,
                                                 div.ctypes.data_as(_i64p), C.byref(st)))
@@ -232,7 +234,7 @@ class Engine:
 
     def fitness(self, stream: int = 0, d_counts: int = 0) -> np.ndarray:
         """Hellinger distance of every parameter set's simulated histogram to the target, computed on the GPU."""
-        out = np.zeros(self.shape[0], dtype=np.float64)
+        out = np.zeros(self.shape[-3], dtype=np.float64)
         check(_lib.load().procell_engine_fitness(self.h, C.c_void_p(stream or None), C.c_void_p(d_counts or None),
                                                  out.ctypes.data_as(_f64p)))
         return out

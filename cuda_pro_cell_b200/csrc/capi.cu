@@ -75,7 +75,8 @@ struct procell_engine {
     DevBuf bin_start, bin_keybase, bin_kdiv, type_cum, type_sel, type_musd, logtab;
     DevBuf dbg, fit_key_channel, fit_target, fit_out;
     uint32_t fit_channels = 0;
-    const procell_plan* plan = nullptr;
+    std::vector<double> plan_row_value;     /* copies of what fitness needs, so the plan may be destroyed after load */
+    std::vector<uint32_t> plan_key_row;
     DevBuf counts, ctl, q_seq, q_data, spill;   /* counts = count tensor followed by the division counters */
     SimParams P{};
     bool loaded = false;
@@ -202,7 +203,8 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     en->counts_len = M * S * K * T;
     en->n_sets = S;
     en->n_times = M;
-    en->plan = plan;
+    en->plan_row_value = plan->row_value;
+    en->plan_key_row = plan->key_row;
     en->fit_channels = 0;
     /* one allocation: the count tensor followed by the division counters, so that a multi-GPU run needs ONE reduce */
     CU(en->counts.reserve((en->counts_len + S) * 8), "alloc counts");
@@ -294,7 +296,7 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         CU(cudaMemset(en->dbg.p, 0, (size_t)grid * en->warps * kDbgWords * 8), "clear debug records");
         P.dbg = (unsigned long long*)en->dbg.p;
         const char* wd = getenv("PROCELL_WATCHDOG_S");       /* abort a launch whose warps run longer than this */
-        const double wd_s = wd && atof(wd) > 0 ? atof(wd) : 900.0;
+        const double wd_s = wd && atof(wd) > 0 ? atof(wd) : 3600.0;
         P.watchdog_ns = (unsigned long long)(wd_s * 1e9);
     }
     en->loaded = true;
@@ -424,32 +426,34 @@ int procell_proliferate(const procell_plan* plan, const procell_sim_params* para
 /* ---- on-GPU fitness of a sweep -------------------------------------------------------------- */
 int procell_engine_set_target(procell_engine* en, const double* value, const uint64_t* freq, size_t n_channels)
 {
-    if (!en || !en->loaded || !en->plan) return fail(PROCELL_ERR_ARG, "procell_engine_set_target: engine not loaded");
+    if (!en || !en->loaded) return fail(PROCELL_ERR_ARG, "procell_engine_set_target: engine not loaded");
     if (!value || !freq || n_channels == 0 || n_channels > 16384)
         return fail(PROCELL_ERR_ARG, "target histogram must have 1..16384 channels");
     for (size_t c = 1; c < n_channels; ++c)
         if (!(value[c] > value[c - 1])) return fail(PROCELL_ERR_ARG, "target channel values must be strictly ascending");
     CU(cudaSetDevice(en->device), "cudaSetDevice");
-    const procell_plan* plan = en->plan;
+    const std::vector<double>& row_value = en->plan_row_value;
+    const std::vector<uint32_t>& key_row = en->plan_key_row;
+    const size_t n_keys = key_row.size();
     /* utils::rebin (src/utils/util.cu:111-138): a value goes to the first channel whose value is >= it */
-    std::vector<uint32_t> row_channel(plan->row_value.size());
+    std::vector<uint32_t> row_channel(row_value.size());
     size_t pos = 0;
-    for (size_t r = 0; r < plan->row_value.size(); ++r) {
-        while (pos + 1 < n_channels && plan->row_value[r] > value[pos]) ++pos;
+    for (size_t r = 0; r < row_value.size(); ++r) {
+        while (pos + 1 < n_channels && row_value[r] > value[pos]) ++pos;
         row_channel[r] = (uint32_t)pos;
     }
-    std::vector<uint32_t> key_channel(plan->n_keys + 1, 0xFFFFFFFFu);
-    for (size_t k = 0; k < plan->n_keys; ++k)
-        if (plan->key_row[k] != 0xFFFFFFFFu) key_channel[k] = row_channel[plan->key_row[k]];
+    std::vector<uint32_t> key_channel(n_keys + 1, 0xFFFFFFFFu);
+    for (size_t k = 0; k < n_keys; ++k)
+        if (key_row[k] != 0xFFFFFFFFu) key_channel[k] = row_channel[key_row[k]];
     double total = 0.0;
     for (size_t c = 0; c < n_channels; ++c) total += (double)freq[c];
     if (!(total > 0.0)) return fail(PROCELL_ERR_ARG, "target histogram is empty");
     std::vector<double> share(n_channels);
     for (size_t c = 0; c < n_channels; ++c) share[c] = (double)freq[c] / total;
-    CU(en->fit_key_channel.reserve((plan->n_keys + 1) * 4), "alloc key_channel");
+    CU(en->fit_key_channel.reserve((n_keys + 1) * 4), "alloc key_channel");
     CU(en->fit_target.reserve(n_channels * 8), "alloc target");
     CU(en->fit_out.reserve(en->n_sets * 8), "alloc fitness");
-    CU(cudaMemcpy(en->fit_key_channel.p, key_channel.data(), (plan->n_keys + 1) * 4, cudaMemcpyHostToDevice), "upload key_channel");
+    CU(cudaMemcpy(en->fit_key_channel.p, key_channel.data(), (n_keys + 1) * 4, cudaMemcpyHostToDevice), "upload key_channel");
     CU(cudaMemcpy(en->fit_target.p, share.data(), n_channels * 8, cudaMemcpyHostToDevice), "upload target");
     en->fit_channels = (uint32_t)n_channels;
     return PROCELL_OK;
