@@ -334,3 +334,16 @@ def test_gpu_agrees_in_law_with_the_reference_binary(gpu_api, oracle):
     f_id, r_id = ours(gpu_api.SEEDING_IDEAL)
     assert T._chi2(T._type_k_table(values, freqs, phi, plan.row_value, r_id), t_ref) > 100.0
     assert T._ks(f_id, f_ref) > 0.04
+
+
+@pytest.mark.parametrize("config,scale", [(2, 1.0), (3, 0.1), (5, 0.01)])
+def test_large_configs_bit_exact(gpu_api, oracle, config, scale):
+    """BASELINE configs at (or near) full size against the oracle on all host cores: config 2 at FULL size (1e6 cells,
+    1.1e8 divisions), config 3 at 1e7 cells, config 5 with all 1024 parameter sets on 1e4 cells."""
+    w = synth.workload(config, scale)
+    plan = gpu_api.Plan(w.values, w.freqs, w.phi)
+    oplan = oracle.OraclePlan(w.values, w.freqs, w.phi)
+    got = gpu_api.proliferate(plan, w.types, w.t_max, w.seed)
+    want = oracle.simulate(oplan, w.types, w.t_max, w.seed)
+    assert np.array_equal(got.divisions, want["divisions"])
+    assert np.array_equal(got.counts, want["counts"])
