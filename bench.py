@@ -101,14 +101,14 @@ class ClockSampler:
 
 def cpu_baseline(w, max_seconds=25.0):
     """The oracle port on this box's host cores, on the same workload (full config-2 shard of one GPU, repeated
-    until ~10 s of CPU work or 3 runs)."""
+    with fresh seeds until ~10 s of CPU work)."""
     import oracle_lib
     from cuda_pro_cell_b200 import synth
     values, freqs = synth.synthetic_histogram(CELLS_PER_GPU)
     plan = oracle_lib.OraclePlan(values, freqs, w.phi)
     cores = oracle_lib.n_host_threads()
     t_total, div_total, runs = 0.0, 0, 0
-    while runs < 3 and t_total < 10.0:
+    while t_total < 10.0 and runs < 200:       # about 10 s of CPU work on all host cores
         t0 = time.perf_counter()
         r = oracle_lib.simulate(plan, w.types, w.t_max, w.seed + runs, n_threads=cores)
         t_total += time.perf_counter() - t0

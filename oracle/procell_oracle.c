@@ -23,7 +23,7 @@
  * deterministic invariants derivable from the reference source (t_max=0 identity, all-quiescent identity,
  * fluorescence-mass conservation, ratio-row sums, sigma=0 closed form), and (c) distributional agreement
  * with outputs of the reference binary itself run on a B200 (tests/golden/ref_*.json, made by
- * tools/make_ref_fixtures.sh).  See DESIGN.md "Oracle and pinning".
+ * tests/golden/make_ref_fixtures.py).  See DESIGN.md "Oracle and pinning".
  *
  * Build: gcc -O2 -ffp-contract=off -mfma -fopenmp -shared -fPIC (oracle/Makefile).  -ffp-contract=off matters:
  * no a*b+c may be fused except where fma() is written.

@@ -3,7 +3,7 @@
  * procell_oracle.c restates the reference's simulation semantics with the north-star Philox streams.  This file
  * restates the reference exactly as written - cuRAND XORWOW re-initialised from an integer seed for every draw,
  * the wall-clock-derived seed schedule, the level-synchronous dense ids - so that it can be checked against the
- * OUTPUT OF THE REFERENCE BINARY ITSELF run on a B200 (tests/golden/ref_*.json; see tools/make_ref_fixtures.py).
+ * OUTPUT OF THE REFERENCE BINARY ITSELF run on a B200 (tests/golden/ref_*.json; see tests/golden/make_ref_fixtures.py).
  * That pins the restatement of everything except the random stream; the Philox oracle then shares those
  * semantics and is compared with this one distributionally.
  *

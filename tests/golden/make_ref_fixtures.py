@@ -2,7 +2,7 @@
 """Generate tests/golden/ref_*.json: outputs of the UNMODIFIED reference binary (oracle/_ref/procell_ref, built by
 `make -C oracle ref` from /root/reference) run on a B200, together with the wall-clock window of each run (the
 reference seeds its RNG from time(NULL), proliferation.cu:242 / cells_population.cu:34).  Run on the GPU box:
-    gpurun -- python tools/make_ref_fixtures.py        (writes gpurun_out/golden/*.json; copy into tests/golden/)
+    gpurun -- python tests/golden/make_ref_fixtures.py   (writes gpurun_out/golden/*.json; copy into tests/golden/)
 """
 import json
 import subprocess
@@ -10,7 +10,7 @@ import sys
 import time
 from pathlib import Path
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from cuda_pro_cell_b200 import synth  # noqa: E402
 

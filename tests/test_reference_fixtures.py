@@ -1,5 +1,5 @@
 """Pinning against the reference itself.  tests/golden/ref_*.json are outputs of the UNMODIFIED reference binary run on
-a B200 (tools/make_ref_fixtures.py).  The reference seeds cuRAND from time(NULL), so each fixture records the
+a B200 (tests/golden/make_ref_fixtures.py).  The reference seeds cuRAND from time(NULL), so each fixture records the
 wall-clock window of its run; oracle/xorwow_ref.c - the restatement of the reference AS WRITTEN - must reproduce every
 fixture bit for bit for one (T0, T1) in that window.  The Philox oracle shares those semantics and is then compared with
 the reference distributionally (chi-square and KS on the output histogram, thresholds calibrated on reference-vs-

@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 2400 python tools/make_ref_fixtures.py 2>&1 | tail -30
+timeout 2400 python tests/golden/make_ref_fixtures.py 2>&1 | tail -30
 timeout 600 python - <<'PY'
 import sys; sys.path.insert(0,'.')
 from cuda_pro_cell_b200 import api, synth
