@@ -18,12 +18,14 @@
  * transform built from a fixed sequence of correctly-rounded IEEE-754 operations so that GPU and CPU
  * agree bit for bit.  oracle/xorwow_ref.c restates the reference's own stream for the distributional check.
  *
- * PARITY PINNING: the reference ships no tests, golden vectors or fixtures for this path.
- * This oracle is pinned by (a) Random123's published Philox4x32-10 known-answer vectors, (b) the
- * deterministic invariants derivable from the reference source (t_max=0 identity, all-quiescent identity,
- * fluorescence-mass conservation, ratio-row sums, sigma=0 closed form), and (c) distributional agreement
- * with outputs of the reference binary itself run on a B200 (tests/golden/ref_*.json, made by
- * tests/golden/make_ref_fixtures.py).  See DESIGN.md "Oracle and pinning".
+ * PARITY PINNING: the reference ships no tests, golden vectors or fixtures for this path, so the
+ * pin is the reference itself: tests/golden/ref_*.json hold outputs of the UNMODIFIED reference binary run on a
+ * B200 (tests/golden/make_ref_fixtures.py).  oracle/xorwow_ref.c - the restatement of the reference as written,
+ * sharing this file's semantics but the reference's XORWOW stream - reproduces every fixture bit for bit, and
+ * this Philox oracle agrees with it in law (chi-square / KS, tests/test_reference_fixtures.py).  Further pins:
+ * Random123's published Philox4x32-10 known-answer vectors and the deterministic invariants derivable from the
+ * reference source (t_max=0 identity, all-quiescent identity, fluorescence-mass conservation, ratio-row sums,
+ * sigma=0 closed form).  See DESIGN.md "Oracle and pinning".
  *
  * Build: gcc -O2 -ffp-contract=off -mfma -fopenmp -shared -fPIC (oracle/Makefile).  -ffp-contract=off matters:
  * no a*b+c may be fused except where fma() is written.
