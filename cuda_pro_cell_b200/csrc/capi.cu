@@ -72,7 +72,9 @@ int cuda_fail(cudaError_t e, const char* what)
 struct procell_engine {
     int device = 0;
     int sm_count = 0;
-    DevBuf bin_start, bin_keybase, bin_kdiv, type_cum, type_sel, type_musd, logtab;
+    DevBuf tables, logtab;                  /* tables: plan + type tables, one packed allocation */
+    void* stage = nullptr;                  /* pinned host staging for the packed tables */
+    size_t stage_cap = 0;
     DevBuf dbg, fit_key_channel, fit_target, fit_out;
     uint32_t fit_channels = 0;
     std::vector<double> plan_row_value;     /* copies of what fitness needs, so the plan may be destroyed after load */
@@ -129,9 +131,9 @@ void procell_engine_destroy(procell_engine* en)
 {
     if (!en) return;
     cudaSetDevice(en->device);
-    DevBuf* bufs[] = { &en->bin_start, &en->bin_keybase, &en->bin_kdiv, &en->type_cum, &en->type_sel, &en->type_musd,
-                       &en->logtab, &en->counts, &en->dbg, &en->fit_key_channel, &en->fit_target, &en->fit_out, &en->ctl, &en->q_seq, &en->q_data, &en->spill };
+    DevBuf* bufs[] = { &en->tables, &en->logtab, &en->counts, &en->dbg, &en->fit_key_channel, &en->fit_target, &en->fit_out, &en->ctl, &en->q_seq, &en->q_data, &en->spill };
     for (DevBuf* b : bufs) b->release();
+    if (en->stage) cudaFreeHost(en->stage);
     if (en->ev0) cudaEventDestroy(en->ev0);
     if (en->ev1) cudaEventDestroy(en->ev1);
     delete en;
@@ -163,28 +165,43 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     }
     CU(cudaSetDevice(en->device), "cudaSetDevice");
 
-    /* histogram plan -> HBM */
-    std::vector<uint32_t> h_start(B + 1);
+    /* histogram plan + type tables -> HBM: packed into ONE pinned staging buffer and uploaded with one copy.
+     * layout (16-byte aligned pieces): bin_start[B+1] u32 | bin_keybase[B] u32 | bin_kdiv[B+1] u8 |
+     *                                  type_cum[S*T] f64 | type_musd[S*T] double2 | type_sel[S*T] u8 */
+    auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t off_start = 0;
+    const size_t off_keybase = off_start + align16((B + 1) * 4);
+    const size_t off_kdiv = off_keybase + align16((B + 1) * 4);
+    const size_t off_cum = off_kdiv + align16(B + 1);
+    const size_t off_musd = off_cum + align16(S * T * 8);
+    const size_t off_sel = off_musd + align16(S * T * 16);
+    const size_t table_bytes = off_sel + align16(S * T);
+    if (table_bytes > en->stage_cap) {
+        if (en->stage) cudaFreeHost(en->stage);
+        en->stage = nullptr; en->stage_cap = 0;
+        CU(cudaMallocHost(&en->stage, table_bytes), "alloc pinned staging");
+        en->stage_cap = table_bytes;
+    }
+    unsigned char* st = static_cast<unsigned char*>(en->stage);
+    uint32_t* h_start = reinterpret_cast<uint32_t*>(st + off_start);
+    uint32_t* h_keybase = reinterpret_cast<uint32_t*>(st + off_keybase);
+    uint8_t* h_kdiv = st + off_kdiv;
+    double* h_cum = reinterpret_cast<double*>(st + off_cum);
+    double2* h_musd = reinterpret_cast<double2*>(st + off_musd);
+    uint8_t* h_sel = st + off_sel;
     for (size_t b = 0; b <= B; ++b) h_start[b] = (uint32_t)plan->bin_start[b];
-    std::vector<uint8_t> h_kdiv(B + 1, 0);
-    for (size_t b = 0; b < B; ++b) h_kdiv[b] = (uint8_t)(plan->bin_kdiv[b] | (plan->bin_count0[b] ? 0x80u : 0u));
-    CU(en->bin_start.reserve((B + 1) * 4), "alloc bin_start");
-    CU(en->bin_keybase.reserve((B + 1) * 4), "alloc bin_keybase");
-    CU(en->bin_kdiv.reserve(B + 1), "alloc bin_kdiv");
-    CU(cudaMemcpy(en->bin_start.p, h_start.data(), (B + 1) * 4, cudaMemcpyHostToDevice), "upload bin_start");
-    if (B) CU(cudaMemcpy(en->bin_keybase.p, plan->bin_keybase.data(), B * 4, cudaMemcpyHostToDevice), "upload bin_keybase");
-    CU(cudaMemcpy(en->bin_kdiv.p, h_kdiv.data(), B + 1, cudaMemcpyHostToDevice), "upload bin_kdiv");
-
+    for (size_t b = 0; b < B; ++b) {
+        h_keybase[b] = plan->bin_keybase[b];
+        h_kdiv[b] = (uint8_t)(plan->bin_kdiv[b] | (plan->bin_count0[b] ? 0x80u : 0u));
+    }
+    h_kdiv[B] = 0;
     /* type tables: selection order = descending proportion, stable (parser.cu:184; thrust::sort is not
      * stable - ties keep file order here), cumulative sums accumulated in that order (cell.cu:88) */
-    std::vector<double> h_cum(S * T);
-    std::vector<uint8_t> h_sel(S * T);
-    std::vector<double2> h_musd(S * T);
     for (size_t s = 0; s < S; ++s) {
         const procell_cell_type* ty = sp->types + s * T;
-        std::vector<int> order(T);
+        int order[64];
         for (size_t j = 0; j < T; ++j) order[j] = (int)j;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ty[a].proportion > ty[b].proportion; });
+        std::stable_sort(order, order + T, [&](int a, int b) { return ty[a].proportion > ty[b].proportion; });
         double acc = 0.0;
         for (size_t j = 0; j < T; ++j) {
             acc += ty[order[j]].proportion;
@@ -193,29 +210,20 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
             h_musd[s * T + j] = make_double2(ty[j].mean, ty[j].stddev);
         }
     }
-    CU(en->type_cum.reserve(S * T * 8), "alloc type_cum");
-    CU(en->type_sel.reserve(S * T), "alloc type_sel");
-    CU(en->type_musd.reserve(S * T * 16), "alloc type_musd");
-    CU(cudaMemcpy(en->type_cum.p, h_cum.data(), S * T * 8, cudaMemcpyHostToDevice), "upload type_cum");
-    CU(cudaMemcpy(en->type_sel.p, h_sel.data(), S * T, cudaMemcpyHostToDevice), "upload type_sel");
-    CU(cudaMemcpy(en->type_musd.p, h_musd.data(), S * T * 16, cudaMemcpyHostToDevice), "upload type_musd");
+    CU(en->tables.reserve(table_bytes), "alloc tables");
+    CU(cudaMemcpy(en->tables.p, st, table_bytes, cudaMemcpyHostToDevice), "upload tables");
+    unsigned char* dt = static_cast<unsigned char*>(en->tables.p);
 
-    en->counts_len = M * S * K * T;
-    en->n_sets = S;
-    en->n_times = M;
-    en->plan_row_value = plan->row_value;
-    en->plan_key_row = plan->key_row;
-    en->fit_channels = 0;
     /* one allocation: the count tensor followed by the division counters, so that a multi-GPU run needs ONE reduce */
     CU(en->counts.reserve((en->counts_len + S) * 8), "alloc counts");
 
     SimParams& P = en->P;
-    P.bin_start = (const uint32_t*)en->bin_start.p;
-    P.bin_keybase = (const uint32_t*)en->bin_keybase.p;
-    P.bin_kdiv = (const uint8_t*)en->bin_kdiv.p;
-    P.type_cum = (const double*)en->type_cum.p;
-    P.type_sel = (const uint8_t*)en->type_sel.p;
-    P.type_musd = (const double2*)en->type_musd.p;
+    P.bin_start = (const uint32_t*)(dt + off_start);
+    P.bin_keybase = (const uint32_t*)(dt + off_keybase);
+    P.bin_kdiv = (const uint8_t*)(dt + off_kdiv);
+    P.type_cum = (const double*)(dt + off_cum);
+    P.type_sel = (const uint8_t*)(dt + off_sel);
+    P.type_musd = (const double2*)(dt + off_musd);
     P.logtab = (const double*)en->logtab.p;
     P.counts = (long long*)en->counts.p;
     P.divisions = (long long*)en->counts.p + en->counts_len;
@@ -292,8 +300,11 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         en->block = en->warps * 32;
         CU(en->spill.reserve((size_t)grid * en->warps * kSpillCap * kChunkWords * 8), "alloc spill rings");
         P.spill = (unsigned long long*)en->spill.p;
-        CU(en->dbg.reserve((size_t)grid * en->warps * kDbgWords * 8), "alloc debug records");
-        CU(cudaMemset(en->dbg.p, 0, (size_t)grid * en->warps * kDbgWords * 8), "clear debug records");
+        const size_t dbg_bytes = (size_t)grid * en->warps * kDbgWords * 8;
+        if (dbg_bytes > en->dbg.cap || !en->dbg.p) {
+            CU(en->dbg.reserve(dbg_bytes), "alloc debug records");
+            CU(cudaMemset(en->dbg.p, 0, dbg_bytes), "clear debug records");
+        }
         P.dbg = (unsigned long long*)en->dbg.p;
         const char* wd = getenv("PROCELL_WATCHDOG_S");       /* abort a launch whose warps run longer than this */
         const double wd_s = wd && atof(wd) > 0 ? atof(wd) : 3600.0;
