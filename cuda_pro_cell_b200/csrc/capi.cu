@@ -214,6 +214,12 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     CU(cudaMemcpy(en->tables.p, st, table_bytes, cudaMemcpyHostToDevice), "upload tables");
     unsigned char* dt = static_cast<unsigned char*>(en->tables.p);
 
+    en->counts_len = M * S * K * T;
+    en->n_sets = S;
+    en->n_times = M;
+    en->plan_row_value = plan->row_value;
+    en->plan_key_row = plan->key_row;
+    en->fit_channels = 0;
     /* one allocation: the count tensor followed by the division counters, so that a multi-GPU run needs ONE reduce */
     CU(en->counts.reserve((en->counts_len + S) * 8), "alloc counts");
 
