@@ -16,6 +16,7 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <utility>
 
 #include "host_plan.h"
 
@@ -155,29 +156,27 @@ int procell_plan_create(const double* value, const uint64_t* freq, size_t n_line
     const size_t nb = p->bin_value.size();
     if (nb > 65535) { delete p; return fail(PROCELL_ERR_ARG, "more than 65535 non-empty histogram lines"); }
     if (total > 0xFFFFFFFFull) { delete p; return fail(PROCELL_ERR_ARG, "more than 2^32-1 seed cells"); }
-    /* value of every key by repeated halving (parser.cu:126-137), then the ordered set of them (:142-151) */
-    std::vector<double> key_value(n_keys);
-    std::vector<double> rows;
-    rows.reserve(n_keys);
+    /* value of every key by repeated halving (parser.cu:126-137), then the ordered set of them (:142-151):
+     * one sort of (value, key) pairs, rows and the key -> row map fall out of a single linear pass */
+    std::vector<std::pair<double, uint32_t>> kv;
+    kv.reserve(n_keys);
     for (size_t b = 0; b < nb; ++b) {
         double f = p->bin_value[b];
         for (unsigned k = 0; k <= p->bin_kdiv[b]; ++k) {
-            key_value[p->bin_keybase[b] + k] = f;
-            if (k > 0 || p->bin_count0[b]) rows.push_back(f);
+            if (k > 0 || p->bin_count0[b]) kv.emplace_back(f, (uint32_t)(p->bin_keybase[b] + k));
             f = f / 2;
         }
     }
-    std::sort(rows.begin(), rows.end());
-    rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
-    p->row_value = rows;
+    std::sort(kv.begin(), kv.end(), [](const std::pair<double, uint32_t>& x, const std::pair<double, uint32_t>& y) {
+        return x.first < y.first;
+    });
     p->key_row.assign(n_keys, 0xFFFFFFFFu);
-    for (size_t b = 0; b < nb; ++b)
-        for (unsigned k = 0; k <= p->bin_kdiv[b]; ++k) {
-            if (k == 0 && !p->bin_count0[b]) continue;
-            size_t key = p->bin_keybase[b] + k;
-            auto it = std::lower_bound(rows.begin(), rows.end(), key_value[key]);
-            p->key_row[key] = static_cast<uint32_t>(it - rows.begin());
-        }
+    p->row_value.clear();
+    p->row_value.reserve(kv.size());
+    for (size_t i = 0; i < kv.size(); ++i) {
+        if (p->row_value.empty() || kv[i].first != p->row_value.back()) p->row_value.push_back(kv[i].first);
+        p->key_row[kv[i].second] = (uint32_t)(p->row_value.size() - 1);
+    }
     *out = p;
     return PROCELL_OK;
 }
