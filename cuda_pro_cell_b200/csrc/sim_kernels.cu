@@ -16,7 +16,8 @@
  *   32-node chunks into a private spill ring in HBM.  Starving warps are fed through a bounded MPMC queue of
  *   chunks that busy warps fill from the BOTTOM of their stacks (the shallowest nodes = the largest subtrees).
  *   Leaves are counted in a shared-memory u32 histogram keyed (bin, k, type) with __match_any_sync aggregation;
- *   a wrap of a u32 slot carries 2^32 straight into the int64 tensor in HBM, the rest is flushed at the end.
+ *   u32 slots cannot wrap: every warp drains the CTA's table into the int64 tensor in HBM every 2^20 of its own
+ *   DIVIDE iterations (see kHistFlushIters), the rest is flushed at the end.
  *
  * k_proliferate_simple - one thread per lineage with a local-memory stack and global atomics: the bring-up
  *   kernel, kept as an independent device-side cross-check of the cooperative one.
@@ -94,8 +95,8 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 }
 
 /* shared-memory privatised count.
- * direct mode (HASHED = false): the whole key space fits: one u32 per key; a u32 wrap carries 2^32 into the int64
- *   tensor in HBM.
+ * direct mode (HASHED = false): the whole key space fits: one u32 per key, updated with a fire-and-forget shared
+ *   atomic (no return value, so no scoreboard wait).  The slots cannot wrap because of hist_drain below.
  * hashed mode (key space larger than shared memory: parameter sweeps, very deep histograms): a direct-mapped
  *   cache of {key:32 | count:32} words indexed by the low key bits.  Keys of one parameter set are contiguous, so
  *   they never collide with each other; a colliding key evicts the resident one, whose count goes to HBM. */
@@ -117,8 +118,27 @@ __device__ __forceinline__ void hist_add(const SimParams& P, uint32_t* s_hist, u
             cur = old;
         }
     } else {
-        const uint32_t old = atomicAdd(&s_hist[key], v);
-        if (old + v < old) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + key, 1ull << 32);
+        atomicAdd(&s_hist[key], v);
+    }
+}
+
+/* Wrap protection of the direct-mode u32 slots.  A lane adds at most 2 leaves per key and DIVIDE iteration, and a key
+ * of tree level 0 (the only kind SEED iterations touch) receives at most freq[bin] < 2^32 seed leaves in a whole run.
+ * Every warp drains ALL slots of its CTA (atomicExch -> int64 atomicAdd in HBM) each kHistFlushIters of its own
+ * DIVIDE iterations.  Between two consecutive drains of a slot no warp can have run more than kHistFlushIters
+ * iterations (its own drain would have been one of them), so the slot received < 1024 lanes * 2 * 2^20 = 2^31. */
+#ifndef PROCELL_HIST_FLUSH_ITERS
+#define PROCELL_HIST_FLUSH_ITERS (1u << 20)
+#endif
+constexpr uint32_t kHistFlushIters = PROCELL_HIST_FLUSH_ITERS;     /* power of two, multiple of 256 */
+static_assert((kHistFlushIters & (kHistFlushIters - 1u)) == 0u && kHistFlushIters >= 256u && kHistFlushIters <= (1u << 20), "");
+
+__device__ __noinline__ void hist_drain(const SimParams& P, uint32_t* s_hist, int lane)
+{
+    for (uint32_t i = (uint32_t)lane; i < P.smem_hist_slots; i += 32u) {
+        if (*reinterpret_cast<volatile uint32_t*>(s_hist + i) == 0u) continue;
+        const uint32_t v = atomicExch(s_hist + i, 0u);
+        if (v) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + i, (unsigned long long)v);
     }
 }
 
@@ -416,7 +436,7 @@ struct DivCount {
  * arithmetic, and every warp collective below is still executed by all 32 lanes with the full mask. */
 template <bool FULL, bool HASHED>
 __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P, const double* s_log, uint32_t* s_hist,
-                                                 const double2* s_musd, uint32_t take, unsigned lt_mask, bool multi_set,
+                                                 const double2* musd, uint32_t take, unsigned lt_mask, bool multi_set,
                                                  DivCount& dc)
 {
     const uint32_t T = P.n_types;
@@ -434,7 +454,7 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
         retry = (uint32_t)(d >> 32);
         const uint32_t set = dlo & 0xFFFFu;
         const uint32_t type = (dlo >> 16) & 63u;
-        const double2 ms = s_musd ? s_musd[set * T + type] : __ldg(P.type_musd + set * T + type);
+        const double2 ms = musd[set * T + type];          /* generic pointer: shared-memory copy or the HBM table */
         const pcs_u32x4 blk = pcs_draw_rk((uint32_t)pc, set, retry, PCS_TAG_DIVISION, heap, P.rk);
         double z0, z1;
         pcs_normal_pair(blk, s_log, 0.0, &z0, &z1);
@@ -452,13 +472,12 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
         int1 = ok1 && !late1 && deeper;
         rej = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
         leaf_key = (uint32_t)(pc >> 32) + T;
-        if (retry == 0u) {
-            if (multi_set && set != dc.set) {
-                if (dc.cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
-                dc.cnt = 0; dc.set = set;
-            }
-            dc.cnt += 1;
+        const uint32_t first = retry == 0u ? 1u : 0u;      /* a redraw is not another division */
+        if (multi_set && first && set != dc.set) {
+            if (dc.cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
+            dc.cnt = 0; dc.set = set;
         }
+        dc.cnt += first;
     }
     /* all popped nodes have been read (their values fed the predicates above), so the slots may be overwritten */
     w.top -= take;
@@ -516,7 +535,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     double2* s_musd_buf = reinterpret_cast<double2*>(smem_raw + kLogTabDoubles * 8 + 128);
     const bool musd_cached = P.n_sets * P.n_types <= (uint32_t)kSmemMusdEntries;
     if (musd_cached && threadIdx.x < P.n_sets * P.n_types) s_musd_buf[threadIdx.x] = __ldg(P.type_musd + threadIdx.x);
-    const double2* s_musd = musd_cached ? s_musd_buf : nullptr;
+    const double2* s_musd = musd_cached ? s_musd_buf : P.type_musd;
     if (threadIdx.x < 2) s_ctl[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < kLogTabDoubles; i += blockDim.x) s_log[i] = __ldg(P.logtab + i);
     if (HASHED) {
@@ -694,6 +713,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
                 dc.cnt = 0;
             }
+            if (!HASHED && (iter & (kHistFlushIters - 1u)) == 0u) hist_drain(P, s_hist, lane);
             int late = 0;
             if (lane == 0) late = global_timer_ns() > *s_deadline;
             if (__shfl_sync(kFull, late, 0)) {

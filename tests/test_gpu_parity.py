@@ -347,3 +347,32 @@ def test_large_configs_bit_exact(gpu_api, oracle, config, scale):
     want = oracle.simulate(oplan, w.types, w.t_max, w.seed)
     assert np.array_equal(got.divisions, want["divisions"])
     assert np.array_equal(got.counts, want["counts"])
+
+
+def test_periodic_drain_bit_exact(gpu_api, oracle, tmp_path):
+    """The direct-mode u32 count table is drained into the int64 tensor every 2^20 iterations of a warp (wrap
+    protection, sim_kernels.cu hist_drain).  libprocell_b200_drain256.so is the same library with the period set to
+    256, so config 2 at full size (about 730 iterations per warp) drains several times per warp, concurrently with
+    the other warps' atomics; the result must still be the oracle's, bit for bit."""
+    import os
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    lib = root / "cuda_pro_cell_b200" / "libprocell_b200_drain256.so"
+    assert lib.exists(), "build the test variant: make -C cuda_pro_cell_b200/csrc"
+    out = tmp_path / "drain.npz"
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from cuda_pro_cell_b200 import api, synth\n"
+        "w = synth.workload(2, 1.0)\n"
+        "plan = api.Plan(w.values, w.freqs, w.phi)\n"
+        "r = api.proliferate(plan, w.types, w.t_max, w.seed)\n"
+        "np.savez(%r, counts=r.counts, divisions=r.divisions)\n" % (str(root), str(out)))
+    env = dict(os.environ, PROCELL_LIB=lib.name)
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=150)
+    got = np.load(out)
+    w = synth.workload(2, 1.0)
+    want = oracle.simulate(oracle.OraclePlan(w.values, w.freqs, w.phi), w.types, w.t_max, w.seed)
+    assert np.array_equal(got["divisions"], want["divisions"])
+    assert np.array_equal(got["counts"], want["counts"])

@@ -5,8 +5,8 @@ for lib in "$@"; do
   for rep in 1 2 3; do
     a=$(PROCELL_LIB=$lib python tools/prof_one.py 2 1.0 | tail -1 | grep -o "'kernel_ms': [0-9.]*")
     b=$(PROCELL_LIB=$lib python tools/prof_one.py 4 0.1 600 | tail -1 | grep -o "'kernel_ms': [0-9.]*")
-    c=$(PROCELL_LIB=$lib python tools/prof_one.py 5 1.0 | tail -1 | grep -o "'kernel_ms': [0-9.]*")
-    d=$(PROCELL_LIB=$lib python tools/prof_one.py 3 0.05 | tail -1 | grep -o "'kernel_ms': [0-9.]*")
-    echo "$lib rep$rep cfg2 $a cfg4 $b cfg5 $c cfg3 $d"
+
+
+    echo "$lib rep$rep cfg2 $a cfg4 $b"
   done
 done
