@@ -142,16 +142,17 @@ __device__ __noinline__ void hist_drain(const SimParams& P, uint32_t* s_hist, in
     }
 }
 
-/* every lane of the warp calls this; each may carry `inc` (0..2) leaves for `key`.
+/* every lane of the warp calls this; each may carry `inc` (0, 1 or 2) leaves for `key`.
  * direct mode: every lane issues its own shared atomic; the shared-memory atomic unit serialises equal addresses
- *   faster than MATCH.ANY + REDUX + a leader's atomic can merge them (measured: config 2 1.64 -> 1.46 ms).
- * hashed mode: a slot update is a CAS loop, so equal keys are merged in registers first (MATCH.ANY + REDUX among
- *   the lanes that have something) and one lane per distinct key updates the cache. */
+ *   faster than any merging in registers (measured: config 2 1.64 -> 1.46 ms).
+ * hashed mode: a slot update is a CAS loop, so equal keys are merged first: MATCH.ANY groups the lanes by key and the
+ *   group's total is two population counts over the ballots of "has 1" and "has 2" - no REDUX, which the hardware
+ *   executes once per distinct group - and one lane per distinct key updates the cache. */
 template <bool HASHED>
 __device__ __forceinline__ void warp_count_leaves(const SimParams& P, uint32_t* s_hist, uint32_t key, uint32_t inc)
 {
-#ifdef PROCELL_HASHED_DIRECT
-    const bool direct = true;
+#ifdef PROCELL_DIRECT_MATCH
+    const bool direct = false;
 #else
     const bool direct = !HASHED;
 #endif
@@ -159,11 +160,13 @@ __device__ __forceinline__ void warp_count_leaves(const SimParams& P, uint32_t* 
         if (inc > 0) hist_add<HASHED>(P, s_hist, key, inc);
         return;
     }
-    const unsigned has = __ballot_sync(kFull, inc > 0);
+    const unsigned b1 = __ballot_sync(kFull, inc == 1u);
+    const unsigned b2 = __ballot_sync(kFull, inc >= 2u);
+    const unsigned has = b1 | b2;
     if (has == 0) return;
     if (inc > 0) {
         const unsigned grp = __match_any_sync(has, key);
-        const uint32_t total = __reduce_add_sync(grp, inc);
+        const uint32_t total = (uint32_t)__popc(grp & b1) + 2u * (uint32_t)__popc(grp & b2);
         if ((threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1)) hist_add<HASHED>(P, s_hist, key, total);
     }
 }
