@@ -376,14 +376,33 @@ struct SeedOut {
     double t_div;
 };
 
-/* bin of a seed cell: largest b with bin_start[b] <= root (parser.cu "bounds") */
-__device__ __forceinline__ uint32_t find_bin(const SimParams& P, uint32_t root)
+/* bin of a seed cell: largest b with bin_start[b] <= root (parser.cu "bounds"), searched in [lo, n_bins) */
+__device__ __forceinline__ uint32_t find_bin(const SimParams& P, uint32_t root, uint32_t lo = 0)
 {
-    uint32_t lo = 0, hi = P.n_bins;
+    uint32_t hi = P.n_bins;
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
         if (__ldg(P.bin_start + mid) <= root) lo = mid; else hi = mid;
     }
+    return lo;
+}
+
+/* the same for the 32 consecutive seed cells root0 .. root0+31 of one SEED iteration, called by the whole warp.
+ * The warp first finds root0's bin with a 32-ary search (every lane probes one boundary, a ballot counts the ones at
+ * or below root0: two dependent loads for 1024 bins instead of ten); the lanes whose root lies beyond that bin's end
+ * (sparse histograms) finish with a binary search above it. */
+__device__ __forceinline__ uint32_t find_bin_warp(const SimParams& P, uint32_t root0, int lane)
+{
+    uint32_t lo = 0, end = P.n_bins;                /* answer for root0 is in [lo, end) */
+    while (end - lo > 1u) {
+        const uint32_t step = (end - lo + 31u) >> 5;
+        const uint32_t probe = lo + ((uint32_t)lane + 1u) * step;
+        const bool le = probe < end && __ldg(P.bin_start + probe) <= root0;
+        lo += (uint32_t)__popc(__ballot_sync(kFull, le)) * step;      /* bin_start ascends: the hits are a prefix */
+        end = end - lo < step ? end : lo + step;
+    }
+    const uint32_t root = root0 + (uint32_t)lane;
+    if (root >= __ldg(P.bin_start + lo + 1u) && lo + 1u < P.n_bins) return find_bin(P, root, lo + 1u);
     return lo;
 }
 
@@ -677,7 +696,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 const bool have = root < seed_end;
                 seed_cur = (seed_end - seed_cur > 32u) ? seed_cur + 32u : seed_end;
                 SeedOut so; so.kind = 0; so.key = 0; so.type = 0; so.kdiv = 0; so.t_div = 0.0; so.count0 = 0; so.quiescent = 0;
-                if (have) so = build_seed(P, s_log, root, seed_set, find_bin(P, root));
+#ifdef PROCELL_LANE_BINSEARCH
+                const uint32_t bin = find_bin(P, root);
+#else
+                const uint32_t bin = find_bin_warp(P, root - (uint32_t)lane, lane);
+#endif
+                if (have) so = build_seed(P, s_log, root, seed_set, bin);
                 const unsigned live = __ballot_sync(kFull, so.kind == 2);
                 if (so.kind == 2) {
                     uint32_t idx = (w.top + __popc(live & lt_mask)) & kRingMask;

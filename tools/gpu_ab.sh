@@ -6,6 +6,7 @@ for lib in "$@"; do
     a=$(PROCELL_LIB=$lib python tools/prof_one.py 2 1.0 | tail -1 | grep -o "'kernel_ms': [0-9.]*")
     b=$(PROCELL_LIB=$lib python tools/prof_one.py 4 0.1 600 | tail -1 | grep -o "'kernel_ms': [0-9.]*")
     c=$(PROCELL_LIB=$lib python tools/prof_one.py 5 0.1 | tail -1 | grep -o "'kernel_ms': [0-9.]*")
-    echo "$lib rep$rep cfg2 $a cfg4 $b cfg5/10 $c"
+    d=$(PROCELL_LIB=$lib python tools/prof_one.py 3 0.1 | tail -1 | grep -o "'kernel_ms': [0-9.]*")
+    echo "$lib rep$rep cfg2 $a cfg4 $b cfg5/10 $c cfg3/10 $d"
   done
 done
