@@ -31,6 +31,18 @@ class RunStats(C.Structure):
                 ("seed_phase_us", C.c_double), ("total_us", C.c_double)]
 
 
+class SimInput(C.Structure):
+    _fields_ = [("bin_value", C.POINTER(C.c_double)), ("bin_freq", C.POINTER(C.c_uint64)), ("n_bins", C.c_size_t),
+                ("types", C.POINTER(CellType)), ("n_types", C.c_size_t), ("n_param_sets", C.c_size_t),
+                ("t_max", C.c_double), ("phi", C.c_double), ("track_ratio", C.c_int), ("seed", C.c_uint64),
+                ("n_gpus", C.c_int), ("seeding_mode", C.c_int)]
+
+
+class SimOutput(C.Structure):
+    _fields_ = [("value", C.POINTER(C.c_double)), ("freq", C.POINTER(C.c_int64)), ("ratio", C.POINTER(C.c_int64)),
+                ("n_rows", C.c_size_t), ("divisions", C.c_int64), ("kernel_ms", C.c_double)]
+
+
 _f64p = C.POINTER(C.c_double)
 _u64p = C.POINTER(C.c_uint64)
 _i64p = C.POINTER(C.c_int64)
@@ -58,6 +70,8 @@ SIGNATURES = {
     "procell_merge_rows": (C.c_int, [C.c_void_p, _i64p, C.c_size_t, _i64p, _i64p]),
     "procell_proliferate": (C.c_int, [C.c_void_p, C.POINTER(SimParams), C.c_int, _i64p, _i64p, C.POINTER(RunStats)]),
     "procell_proliferate_multi": (C.c_int, [C.c_void_p, C.POINTER(SimParams), C.c_int, _i64p, _i64p, C.POINTER(RunStats)]),
+    "procell_simulate": (C.c_int, [C.POINTER(SimInput), C.POINTER(SimOutput)]),
+    "procell_output_free": (None, [C.POINTER(SimOutput)]),
     "procell_engine_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "procell_engine_destroy": (None, [C.c_void_p]),
     "procell_engine_load": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SimParams)]),

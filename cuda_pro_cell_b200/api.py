@@ -251,6 +251,35 @@ class Engine:
             pass
 
 
+def simulate(values, freqs, types, t_max, phi=0.0, seed=0x5EED0000, track_ratio=True, n_gpus=1,
+             seeding_mode=SEEDING_IDEAL):
+    """procell_simulate: histogram arrays in, result rows out, one C call (plan + simulation + merge).
+    Returns (row_value[n_rows], freq[n_sets][n_rows], ratio[n_sets][n_rows][n_types] or None, divisions, kernel_ms)."""
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    f = np.ascontiguousarray(freqs, dtype=np.uint64)
+    t = np.ascontiguousarray(types, dtype=np.float64)
+    if t.ndim == 2:
+        t = t[None]
+    n_sets, n_types = t.shape[0], t.shape[1]
+    inp = _lib.SimInput(v.ctypes.data_as(_f64p), f.ctypes.data_as(_u64p), len(v),
+                        t.ctypes.data_as(C.POINTER(_lib.CellType)), n_types, n_sets, float(t_max), float(phi),
+                        int(bool(track_ratio)), int(seed), int(n_gpus), int(seeding_mode))
+    out = _lib.SimOutput()
+    lib = _lib.load()
+    check(lib.procell_simulate(C.byref(inp), C.byref(out)))
+    try:
+        n = out.n_rows
+        rows = np.ctypeslib.as_array(out.value, shape=(n,)).copy() if n else np.zeros(0)
+        freq = np.ctypeslib.as_array(out.freq, shape=(n_sets, n)).copy() if n else np.zeros((n_sets, 0), np.int64)
+        ratio = None
+        if track_ratio:
+            ratio = (np.ctypeslib.as_array(out.ratio, shape=(n_sets, n, n_types)).copy() if n
+                     else np.zeros((n_sets, 0, n_types), np.int64))
+        return rows, freq, ratio, int(out.divisions), float(out.kernel_ms)
+    finally:
+        lib.procell_output_free(C.byref(out))
+
+
 def rng_ceiling(device: int = 0, iters: int = 2048):
     """(ms, pairs): time of the RNG-only micro-kernel and the number of Philox+Box-Muller pairs it drew."""
     ms, pairs = C.c_double(), C.c_double()

@@ -600,6 +600,67 @@ int procell_proliferate_multi(const procell_plan* plan, const procell_sim_params
     return rc;
 }
 
+int procell_simulate(const procell_input* in, procell_output* out)
+{
+    if (!in || !out) return fail(PROCELL_ERR_ARG, "procell_simulate: null argument");
+    memset(out, 0, sizeof(*out));
+    if (!in->types || in->n_types == 0) return fail(PROCELL_ERR_ARG, "procell_simulate: no cell types");
+    const size_t n_sets = in->n_param_sets ? in->n_param_sets : 1;
+    for (size_t s = 0; s < n_sets; ++s) {
+        const int rc = procell_check_proportions(in->types + s * in->n_types, in->n_types);
+        if (rc != PROCELL_OK) return rc;
+    }
+    procell_plan* plan = nullptr;
+    int rc = procell_plan_create(in->bin_value, in->bin_freq, in->n_bins, in->phi, &plan);
+    if (rc != PROCELL_OK) return rc;
+    const size_t n_keys = procell_plan_n_keys(plan), n_rows = procell_plan_n_rows(plan), T = in->n_types;
+    procell_sim_params sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.types = in->types;
+    sp.n_types = T;
+    sp.n_sets = n_sets;
+    sp.t_max = in->t_max;
+    sp.seed = in->seed;
+    sp.seeding_mode = in->seeding_mode;
+    std::vector<int64_t> counts(n_sets * n_keys * T + 1, 0), divisions(n_sets, 0);
+    procell_run_stats st;
+    memset(&st, 0, sizeof(st));
+    if (in->n_gpus == 0 || in->n_gpus == 1) rc = procell_proliferate(plan, &sp, 0, counts.data(), divisions.data(), &st);
+    else rc = procell_proliferate_multi(plan, &sp, in->n_gpus, counts.data(), divisions.data(), &st);
+    if (rc == PROCELL_OK) {
+        out->n_rows = n_rows;
+        out->value = static_cast<double*>(malloc((n_rows + 1) * sizeof(double)));
+        out->freq = static_cast<int64_t*>(malloc((n_sets * n_rows + 1) * sizeof(int64_t)));
+        if (in->track_ratio) out->ratio = static_cast<int64_t*>(malloc((n_sets * n_rows * T + 1) * sizeof(int64_t)));
+        if (!out->value || !out->freq || (in->track_ratio && !out->ratio)) {
+            procell_output_free(out);
+            rc = fail(PROCELL_ERR_ARG, "out of host memory");
+        }
+    }
+    if (rc == PROCELL_OK) {
+        procell_plan_export(plan, out->value, nullptr, nullptr, nullptr);
+        for (size_t s = 0; s < n_sets && rc == PROCELL_OK; ++s)
+            rc = procell_merge_rows(plan, counts.data() + s * n_keys * T, T, out->freq + s * n_rows,
+                                    out->ratio ? out->ratio + s * n_rows * T : nullptr);
+        for (size_t s = 0; s < n_sets; ++s) out->divisions += divisions[s];
+        out->kernel_ms = st.kernel_ms;
+    }
+    procell_plan_destroy(plan);
+    return rc;
+}
+
+void procell_output_free(procell_output* out)
+{
+    if (!out) return;
+    free(out->value);
+    free(out->freq);
+    free(out->ratio);
+    out->value = nullptr;
+    out->freq = nullptr;
+    out->ratio = nullptr;
+    out->n_rows = 0;
+}
+
 int procell_rng_ceiling(int device, int iters, double* ms_out, double* pairs_out)
 {
     int n_dev = 0;

@@ -121,6 +121,37 @@ int procell_proliferate(const procell_plan* plan, const procell_sim_params* para
 int procell_proliferate_multi(const procell_plan* plan, const procell_sim_params* params, int n_gpus,
                               int64_t* counts, int64_t* divisions, procell_run_stats* stats);
 
+/* One call from histogram arrays to result rows (the entry point SURVEY section 8b proposes): plan + simulation on
+ * n_gpus GPUs + merge.  Replaces Simulator::load_params .. save_results minus the file I/O
+ * (src/simulation/simulator.cu:10-56).  The library allocates the output arrays; release them with
+ * procell_output_free.  Never exits, no exceptions cross the ABI; no global state besides the thread-local error. */
+typedef struct procell_input {
+    const double* bin_value;        /* histogram lines, file order (zero frequencies allowed) */
+    const uint64_t* bin_freq;
+    size_t n_bins;
+    const procell_cell_type* types; /* [n_param_sets][n_types] */
+    size_t n_types;
+    size_t n_param_sets;            /* 0 is read as 1 */
+    double t_max;
+    double phi;                     /* 0: default (smallest value with a non-zero frequency) */
+    int track_ratio;                /* fill `ratio` */
+    uint64_t seed;
+    int n_gpus;                     /* 0 or 1: device 0; > 1: the first n_gpus GPUs, one ncclReduce; < 0: all */
+    int seeding_mode;               /* PROCELL_SEEDING_* */
+} procell_input;
+
+typedef struct procell_output {
+    double* value;                  /* [n_rows] ascending */
+    int64_t* freq;                  /* [n_param_sets][n_rows] (rows with 0 are not printed by the writer) */
+    int64_t* ratio;                 /* [n_param_sets][n_rows][n_types], NULL unless track_ratio */
+    size_t n_rows;
+    int64_t divisions;              /* total over the parameter sets */
+    double kernel_ms;
+} procell_output;
+
+int procell_simulate(const procell_input* in, procell_output* out);
+void procell_output_free(procell_output* out);
+
 /* Resident engine: tables live in HBM across runs. */
 int procell_engine_create(int device, procell_engine** out);
 void procell_engine_destroy(procell_engine* engine);

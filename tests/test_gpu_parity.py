@@ -376,3 +376,17 @@ def test_periodic_drain_bit_exact(gpu_api, oracle, tmp_path):
     want = oracle.simulate(oracle.OraclePlan(w.values, w.freqs, w.phi), w.types, w.t_max, w.seed)
     assert np.array_equal(got["divisions"], want["divisions"])
     assert np.array_equal(got["counts"], want["counts"])
+
+
+@pytest.mark.parametrize("n_sets", [1, 3])
+def test_simulate_one_call_equals_oracle_rows(gpu_api, oracle, n_sets):
+    """procell_simulate: histogram arrays -> result rows in one C call; rows, frequencies, per-type columns and the
+    division total must equal the oracle's merged rows for every parameter set."""
+    w = synth.workload(2, 0.01)
+    types = synth.sweep_types(1024)[:: 1024 // n_sets][:n_sets] if n_sets > 1 else w.types
+    rows, freq, ratio, divisions, _ = gpu_api.simulate(w.values, w.freqs, types, w.t_max, w.phi, w.seed)
+    oplan = oracle.OraclePlan(w.values, w.freqs, w.phi)
+    want = oracle.simulate(oplan, np.asarray(types), w.t_max, w.seed)
+    assert np.array_equal(rows, oplan.row_value)
+    assert np.array_equal(freq, want["row_freq"]) and np.array_equal(ratio, want["row_ratio"])
+    assert divisions == int(want["divisions"].sum())

@@ -33,6 +33,20 @@ def test_no_cpu_fallback_without_a_device():
     assert e.value.code == _lib.ERR_CUDA and "no CPU path" in str(e.value)
 
 
+def test_simulate_entry_point_checks_before_touching_a_device():
+    """procell_simulate (SURVEY 8b's one-call entry): argument and proportion errors come back as codes, and on a box
+    without a GPU a valid request fails loudly instead of falling back to a CPU path."""
+    import torch
+    v, f = synth.synthetic_histogram(100)
+    with pytest.raises(api.ProcellError) as e:
+        api.simulate(v, f, [(0.5, 10.0, 2.0), (0.4, -1.0, -1.0)], 10.0)
+    assert e.value.code == _lib.ERR_PROPORTION and "does not sum to 1" in str(e.value)
+    if not torch.cuda.is_available():
+        with pytest.raises(api.ProcellError) as e:
+            api.simulate(v, f, synth.TYPES_CONFIG1, 10.0)
+        assert e.value.code == _lib.ERR_CUDA and "no CPU path" in str(e.value)
+
+
 def test_histogram_reader_follows_operator_semantics(tmp_path):
     p = tmp_path / "h.txt"
     p.write_text("1.0 0\n8.144 53\n  9823.85\t274\n1e3 7 garbage 5\n12 3\n")
