@@ -49,6 +49,33 @@ for cfg in (1, 2, 3, 4, 5):
     res["leaves_minus_seeds_minus_divisions_set0"] = int(rf.sum()) - int(plan.n_cells) - int(a.divisions[0])
     mass_in = float((w.values * w.freqs).sum())
     res["mass_out_over_in_set0"] = float((rf * plan.row_value).sum()) / mass_in
+    if cfg == 1:     # start-up bound: also the per-run time of 100 back-to-back in-process runs
+        os.environ["PROCELL_COOP_WARPS"] = "32"
+        eng = api.Engine(0)
+        eng.load(plan, w.types, w.t_max, w.seed)
+        eng.run(); eng.finish(fetch=False)
+        t0 = time.perf_counter()
+        for i in range(100):
+            eng.run(w.seed + i)
+        eng.finish(fetch=False)
+        res["in_process_loop_us_per_run"] = (time.perf_counter() - t0) * 1e4
+        res["in_process_loop_Gdiv_per_s"] = res["divisions"] / (res["in_process_loop_us_per_run"] * 1e-6) / 1e9
+        eng.close()
+    if cfg in (1, 2, 3):     # end-to-end wall time of the `procell` command line (process start, CUDA context, text I/O)
+        import subprocess
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            Path(d, "h.txt").write_text(synth.histogram_text(w.values, w.freqs))
+            Path(d, "c.txt").write_text(synth.types_text(w.types[0]))
+            cmd = [str(ROOT / "cuda_pro_cell_b200" / "procell"), "-h", d + "/h.txt", "-c", d + "/c.txt", "-t", repr(w.t_max), "-o", d + "/o.txt",
+                   "-p", repr(plan.phi)] + (["-r"] if w.track_ratio else [])
+            walls = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+                walls.append(time.perf_counter() - t0)
+            res["cli_wall_s"] = walls
+            res["cli_output_rows"] = len(Path(d, "o.txt").read_text().splitlines())
     out["config%d" % cfg] = res
     print(cfg, json.dumps(res), flush=True)
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
