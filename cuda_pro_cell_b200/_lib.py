@@ -28,7 +28,8 @@ class SimParams(C.Structure):
 class RunStats(C.Structure):
     _fields_ = [("divisions", C.c_int64), ("kernel_ms", C.c_double), ("n_launches", C.c_int),
                 ("grid", C.c_int), ("block", C.c_int), ("smem_bytes", C.c_int), ("donations", C.c_int64),
-                ("seed_phase_us", C.c_double), ("total_us", C.c_double)]
+                ("seed_phase_us", C.c_double), ("total_us", C.c_double), ("idle_warp_us", C.c_double),
+                ("idle_waits", C.c_int64)]
 
 
 class SimInput(C.Structure):

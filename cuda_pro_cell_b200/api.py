@@ -150,7 +150,8 @@ class Result:
 def _stats_dict(st: RunStats) -> dict:
     return dict(divisions=int(st.divisions), kernel_ms=float(st.kernel_ms), n_launches=int(st.n_launches),
                 grid=int(st.grid), block=int(st.block), smem_bytes=int(st.smem_bytes), donations=int(st.donations),
-                seed_phase_us=float(st.seed_phase_us), total_us=float(st.total_us))
+                seed_phase_us=float(st.seed_phase_us), total_us=float(st.total_us),
+                idle_warp_us=float(st.idle_warp_us), idle_waits=int(st.idle_waits))
 
 
 def proliferate(plan: Plan, types, t_max: float, seed: int = 0x5EED0000, seeding_mode: int = SEEDING_IDEAL,

@@ -422,6 +422,8 @@ int procell_engine_finish(procell_engine* en, void* stream_v, int64_t* counts, i
         stats->donations = (int64_t)cb.q_tail;
         stats->seed_phase_us = cb.t_exhausted == ~0ull ? -1.0 : (double)(cb.t_exhausted - cb.t_start) * 1e-3;
         stats->total_us = cb.t_end ? (double)(cb.t_end - cb.t_start) * 1e-3 : -1.0;
+        stats->idle_warp_us = (double)cb.idle_ns * 1e-3;
+        stats->idle_waits = (int64_t)cb.idle_waits;
     }
     return PROCELL_OK;
 }
@@ -554,7 +556,7 @@ int procell_proliferate_multi(const procell_plan* plan, const procell_sim_params
         procell_sim_params sp = *params;
         sp.shard_rank = (uint32_t)i;
         sp.shard_world = (uint32_t)n_gpus;
-        if (sp.shard_unit == 0) sp.shard_unit = 256;
+        if (sp.shard_unit == 0) sp.shard_unit = 32;
         rc = procell_engine_load(eng[i], plan, &sp);
         if (rc == PROCELL_OK && cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking) != cudaSuccess)
             rc = fail(PROCELL_ERR_CUDA, "cudaStreamCreate failed");

@@ -131,6 +131,16 @@ __device__ __forceinline__ void hist_add(const SimParams& P, uint32_t* s_hist, u
 #define PROCELL_HIST_FLUSH_ITERS (1u << 20)
 #endif
 constexpr uint32_t kHistFlushIters = PROCELL_HIST_FLUSH_ITERS;     /* power of two, multiple of 256 */
+
+/* work-donation policy knobs (A/B'd on the GPU) */
+#ifndef PROCELL_IDLE_BACKOFF_MAX_NS
+#define PROCELL_IDLE_BACKOFF_MAX_NS 512u
+#endif
+#ifndef PROCELL_DONATE_MIN_NODES
+#define PROCELL_DONATE_MIN_NODES 96u
+#endif
+constexpr unsigned kIdleBackoffMaxNs = PROCELL_IDLE_BACKOFF_MAX_NS;   /* idle warps poll with exponential back-off up to this */
+constexpr uint32_t kDonateMinNodes = PROCELL_DONATE_MIN_NODES;        /* a warp gives a chunk away only when its ring is about to spill anyway */
 static_assert((kHistFlushIters & (kHistFlushIters - 1u)) == 0u && kHistFlushIters >= 256u && kHistFlushIters <= (1u << 20), "");
 
 __device__ __noinline__ void hist_drain(const SimParams& P, uint32_t* s_hist, int lane)
@@ -346,14 +356,15 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
             }
         }
         state = __shfl_sync(kFull, state, 0);
-        if (state == 2) {
-            if (w.lane == 0) atomicSub(&ctl->idle, 1);
-            return false;
+        if (state != 0 && w.lane == 0) {
+            atomicSub(&ctl->idle, 1);
+            atomicAdd(&ctl->idle_ns, global_timer_ns() - t0);
+            atomicAdd(&ctl->idle_waits, 1ull);
         }
+        if (state == 2) return false;
         if (state == 1) {
             ticket = __shfl_sync(kFull, ticket, 0);
             uint64_t a, b, c, d;
-            if (w.lane == 0) atomicSub(&ctl->idle, 1);
             if (!queue_read_ticket(P, w.lane, ticket, a, b, c, d)) return false;     /* watchdog abort */
             uint32_t idx = (w.top + w.lane) & kRingMask;
             w.sa[idx] = a; w.sb[idx] = b; w.sc[idx] = c; w.sd[idx] = d;
@@ -362,7 +373,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
             return true;
         }
         __nanosleep(backoff);
-        if (backoff < 2048) backoff <<= 1;
+        if (backoff < kIdleBackoffMaxNs) backoff <<= 1;
     }
 }
 
@@ -684,6 +695,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                         __syncwarp();
                         continue;
                     }
+                    /* units are handed out from the LAST one down: histograms are written in ascending value, high
+                     * values may halve more often before reaching phi, so the biggest lineage trees start first and
+                     * the run ends on the small ones (longest-processing-time-first; shortens the tail) */
+#ifndef PROCELL_SEED_ORDER_ASC
+                    j = P.local_units_per_set - 1u - j;
+#endif
                     unsigned long long first = ((unsigned long long)j * P.shard_world + P.shard_rank) * P.unit;
                     unsigned long long last = first + P.unit;
                     if (last > P.n_cells) last = P.n_cells;
@@ -780,7 +797,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 packed = (ep << 1) | hg;
             }
             packed = __shfl_sync(kFull, packed, 0);
-            if ((packed & 1) && (w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= 64u) {
+            if ((packed & 1) && (w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= kDonateMinNodes) {
                 /* somebody starves and no seeds are left: give away the shallowest chunk */
                 TRACE(P, GWARP, lane, 50);
                 donate_epoch = packed >> 1;

@@ -35,8 +35,9 @@ struct alignas(128) ControlBlock {
     int idle;                       int pad4[31];
     int status;                     int pad5[31];
     int avail;                      int pad7[31];   /* published chunks not yet claimed (permits) */
-    /* diagnostics (globaltimer ns): first warp start, seed cursor exhausted, last warp exit */
-    unsigned long long t_start, t_exhausted, t_end, pad6[13];
+    /* diagnostics (globaltimer ns): first warp start, seed cursor exhausted, last warp exit; warp-ns spent waiting
+     * for donated work (summed over warps) and the number of such waits */
+    unsigned long long t_start, t_exhausted, t_end, idle_ns, idle_waits, pad6[11];
 };
 
 struct SimParams {

@@ -6,7 +6,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-DEFAULT_SHARD_UNIT = 256
+DEFAULT_SHARD_UNIT = 32
 
 
 def shard_spec(rank: int | None = None, world: int | None = None, unit: int = DEFAULT_SHARD_UNIT):

@@ -106,6 +106,8 @@ typedef struct procell_run_stats {
     int64_t donations;   /* 32-node chunks handed from busy to starving warps through the device queue */
     double seed_phase_us; /* device time from the first warp's start until the seed-unit cursor ran out (-1: n/a) */
     double total_us;      /* device time from the first warp's start to the last warp's exit (-1: n/a) */
+    double idle_warp_us;  /* time warps spent waiting for donated work, summed over all warps of the launch */
+    int64_t idle_waits;   /* how often a warp ran dry and waited */
 } procell_run_stats;
 
 /* One-shot, host buffers in and out: replaces simulation::create_cells_population
@@ -114,7 +116,7 @@ typedef struct procell_run_stats {
 int procell_proliferate(const procell_plan* plan, const procell_sim_params* params, int device,
                         int64_t* counts, int64_t* divisions, procell_run_stats* stats);
 
-/* Same, on the first n_gpus GPUs of this box from ONE process (n_gpus <= 0: all): seed-cell units of 256 cells are
+/* Same, on the first n_gpus GPUs of this box from ONE process (n_gpus <= 0: all): seed-cell units of 32 cells are
  * sharded GPU-strided, every GPU runs the same kernel on its units, and one ncclReduce(sum, int64) over NVLink
  * combines the count tensors on GPU 0.  The result equals the single-GPU result bit for bit.  The reference is
  * single-GPU (device 0 hard-coded, src/simulation/proliferation.cu:38).  NCCL is loaded with dlopen. */
