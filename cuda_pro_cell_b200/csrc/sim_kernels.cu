@@ -139,6 +139,14 @@ constexpr uint32_t kHistFlushIters = PROCELL_HIST_FLUSH_ITERS;     /* power of t
 #ifndef PROCELL_DONATE_MIN_NODES
 #define PROCELL_DONATE_MIN_NODES 96u
 #endif
+#ifndef PROCELL_DONATE_RESERVE
+#define PROCELL_DONATE_RESERVE 64
+#endif
+constexpr int kDonateReserve = PROCELL_DONATE_RESERVE;   /* chunks kept waiting in the queue even when nobody starves yet */
+#ifndef PROCELL_ENDGAME_IDLE
+#define PROCELL_ENDGAME_IDLE 512
+#endif
+constexpr int kEndgameIdle = PROCELL_ENDGAME_IDLE;
 constexpr unsigned kIdleBackoffMaxNs = PROCELL_IDLE_BACKOFF_MAX_NS;   /* idle warps poll with exponential back-off up to this */
 constexpr uint32_t kDonateMinNodes = PROCELL_DONATE_MIN_NODES;        /* a warp gives a chunk away only when its ring is about to spill anyway */
 static_assert((kHistFlushIters & (kHistFlushIters - 1u)) == 0u && kHistFlushIters >= 256u && kHistFlushIters <= (1u << 20), "");
@@ -315,6 +323,28 @@ __device__ __forceinline__ void donate_chunk(WarpCtx& w, const SimParams& P)
 __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volatile int* s_ctl, unsigned long long deadline, uint32_t gwarp)
 {
     ControlBlock* ctl = P.ctl;
+#ifndef PROCELL_NO_FAST_TAKE
+    {   /* fast path: a published chunk is already waiting - take it with two fetch-adds and stay "active" (no idle /
+         * active bookkeeping, no CTA poll lock); the chunk is then read exactly as on the slow path */
+        int fast = 0;
+        unsigned long long ticket = 0;
+        if (w.lane == 0 && ld_acquire_s32(&ctl->avail) > 0) {
+            if (atomicSub(&ctl->avail, 1) > 0) { ticket = atomicAdd(&ctl->q_head, 1ull); fast = 1; }
+            else atomicAdd(&ctl->avail, 1);                       /* lost the race for the last permit */
+        }
+        fast = __shfl_sync(kFull, fast, 0);
+        if (fast) {
+            ticket = __shfl_sync(kFull, ticket, 0);
+            uint64_t a, b, c, d;
+            if (!queue_read_ticket(P, w.lane, ticket, a, b, c, d)) return false;     /* watchdog abort */
+            uint32_t idx = (w.top + w.lane) & kRingMask;
+            w.sa[idx] = a; w.sb[idx] = b; w.sc[idx] = c; w.sd[idx] = d;
+            w.top += kChunkNodes;
+            __syncwarp();
+            return true;
+        }
+    }
+#endif
     if (w.lane == 0) {
         atomicAdd(&ctl->idle, 1);
         __threadfence();
@@ -792,15 +822,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 }
                 /* donate at most once per snapshot epoch, and only while fewer chunks wait than warps starve */
                 const int ep = s_ctl[5];
-                const int hg = P.donate && s_ctl[3] && idle_snap > (avail_snap > 0 ? avail_snap : 0) &&
+                const int hg = P.donate && s_ctl[3] && idle_snap + kDonateReserve > (avail_snap > 0 ? avail_snap : 0) &&
                                avail_snap < kQueueCap / 2 && ep != donate_epoch;
-                packed = (ep << 1) | hg;
+                /* end game: when this many warps starve, a warp parts with a chunk as soon as it keeps 32 nodes */
+                packed = (ep << 2) | ((idle_snap >= kEndgameIdle) << 1) | hg;
             }
             packed = __shfl_sync(kFull, packed, 0);
-            if ((packed & 1) && (w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= kDonateMinNodes) {
+            if ((packed & 1) && (w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= ((packed & 2) ? 64u : kDonateMinNodes)) {
                 /* somebody starves and no seeds are left: give away the shallowest chunk */
                 TRACE(P, GWARP, lane, 50);
-                donate_epoch = packed >> 1;
+                donate_epoch = packed >> 2;
                 donate_chunk(w, P);
             }
         }
