@@ -300,7 +300,7 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         }
         en->smem = coop_smem_bytes(en->warps, P.smem_hist_slots, P.hist_hashed);
         int grid = 0;
-        CU(coop_max_grid(en->device, en->warps, P.hist_hashed, en->smem, &grid), "occupancy query");
+        CU(coop_max_grid(en->device, en->warps, P.hist_hashed, (P.n_sets == 1u && P.n_times == 1u) ? 1 : 0, en->smem, &grid), "occupancy query");
         if (grid <= 0) return fail(PROCELL_ERR_CUDA, "cooperative kernel does not fit on this device");
         en->grid = grid;
         en->block = en->warps * 32;

@@ -89,7 +89,7 @@ struct SimParams {
 
 size_t coop_smem_bytes(int warps, uint32_t hist_slots, int hashed);
 cudaError_t launch_coop(const SimParams& p, int warps, int grid, cudaStream_t stream);
-cudaError_t coop_max_grid(int device, int warps, int hashed, size_t smem_bytes, int* grid_out);
+cudaError_t coop_max_grid(int device, int warps, int hashed, int plain, size_t smem_bytes, int* grid_out);
 cudaError_t launch_simple(const SimParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_queue_init(unsigned long long* q_seq, ControlBlock* ctl, cudaStream_t stream);
 cudaError_t launch_rng_ceiling(int grid, int block, int iters, const double* logtab, double mean, double sd,
