@@ -518,7 +518,7 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
         const uint64_t d = w.sd[idx];
         dlo = (uint32_t)d;
         retry = (uint32_t)(d >> 32);
-        const uint32_t set = dlo & 0xFFFFu;
+        const uint32_t set = PLAIN ? 0u : (dlo & 0xFFFFu);
         const uint32_t type = (dlo >> 16) & 63u;
         const double2 ms = musd[set * T + type];          /* generic pointer: shared-memory copy or the HBM table */
         const pcs_u32x4 blk = pcs_draw_rk((uint32_t)pc, set, retry, PCS_TAG_DIVISION, heap, P.rk);
@@ -801,8 +801,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 
         TRACE(P, GWARP, lane, 20);
         const uint32_t take = n < 32u ? n : 32u;
-        if (take == 32u) divide_iteration<true, HASHED, PLAIN>(w, P, s_log, s_hist, s_musd, take, lt_mask, multi_set, dc);
-        else divide_iteration<false, HASHED, PLAIN>(w, P, s_log, s_hist, s_musd, take, lt_mask, multi_set, dc);
+        /* PLAIN: one set and at most 64 types, so the (mean, sd) table is always the shared-memory copy (plain LDS) */
+        const double2* musd = PLAIN ? s_musd_buf : s_musd;
+        if (take == 32u) divide_iteration<true, HASHED, PLAIN>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc);
+        else divide_iteration<false, HASHED, PLAIN>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc);
 
         /* hunger probe, every 4th iteration.  The CTA keeps a snapshot of "how many warps are starving", "how many
          * donated chunks are waiting" and "where is the seed cursor" in shared memory.  Every 64th iteration
