@@ -545,7 +545,10 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
         }
         dc.cnt += first;
     }
-    /* all popped nodes have been read (their values fed the predicates above), so the slots may be overwritten */
+    /* all popped nodes have been read: every lane's loads have returned before it votes below (the predicates depend
+     * on the loaded values) and no lane stores before all have voted, so the slots may be overwritten.  The partial
+     * iteration is divergent above, so it states the ordering explicitly as well. */
+    if (!FULL) __syncwarp();
     w.top -= take;
     const unsigned b0 = __ballot_sync(kFull, int0);
     const unsigned b1 = __ballot_sync(kFull, int1);
@@ -818,7 +821,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                     cp_async16(s_snap, &ctl->idle);
                     cp_async16(s_snap + 4, &ctl->avail);
                     if (!multi_set && !s_ctl[3]) cp_async16(s_snap + 8, &ctl->cursor);
-                    s_ctl[5] = s_ctl[5] + 1;
+                    atomicAdd(const_cast<int*>(s_ctl) + 5, 1);      /* snapshot epoch */
                 }
                 const int idle_snap = s_snap[0], avail_snap = s_snap[4];
                 if (!multi_set && !s_ctl[3]) {
