@@ -56,6 +56,8 @@ SIGNATURES = {
     "procell_version": (C.c_char_p, []),
     "procell_read_histogram": (C.c_int, [C.c_char_p, C.POINTER(_f64p), C.POINTER(_u64p), C.POINTER(C.c_size_t)]),
     "procell_read_cell_types": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(CellType)), C.POINTER(C.c_size_t)]),
+    "procell_parse_histogram": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(_f64p), C.POINTER(_u64p), C.POINTER(C.c_size_t)]),
+    "procell_parse_cell_types": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.POINTER(CellType)), C.POINTER(C.c_size_t)]),
     "procell_write_histogram": (C.c_int, [C.c_char_p, C.c_int, C.c_size_t, C.c_size_t, _f64p, _i64p, _i64p]),
     "procell_free": (None, [C.c_void_p]),
     "procell_check_proportions": (C.c_int, [C.POINTER(CellType), C.c_size_t]),

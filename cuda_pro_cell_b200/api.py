@@ -51,6 +51,34 @@ def read_histogram(path: str):
     return values, freqs
 
 
+def parse_histogram(text: bytes):
+    """The histogram reader on text already in memory."""
+    lib = _lib.load()
+    text = bytes(text)
+    v, f, n = _f64p(), _u64p(), C.c_size_t()
+    check(lib.procell_parse_histogram(text, len(text), C.byref(v), C.byref(f), C.byref(n)))
+    try:
+        values = np.ctypeslib.as_array(v, shape=(max(n.value, 1),))[: n.value].copy()
+        freqs = np.ctypeslib.as_array(f, shape=(max(n.value, 1),))[: n.value].copy()
+    finally:
+        lib.procell_free(v)
+        lib.procell_free(f)
+    return values, freqs
+
+
+def parse_cell_types(text: bytes) -> np.ndarray:
+    """The cell-types reader on text already in memory (checks the proportion sum like the file reader)."""
+    lib = _lib.load()
+    text = bytes(text)
+    t, n = C.POINTER(CellType)(), C.c_size_t()
+    rc = lib.procell_parse_cell_types(text, len(text), C.byref(t), C.byref(n))
+    try:
+        check(rc)
+        return np.array([(t[i].proportion, t[i].mean, t[i].stddev) for i in range(n.value)], dtype=np.float64).reshape(-1, 3)
+    finally:
+        lib.procell_free(t)
+
+
 def read_cell_types(path: str) -> np.ndarray:
     lib = _lib.load()
     t, n = C.POINTER(CellType)(), C.c_size_t()

@@ -1,21 +1,13 @@
-/* hostio.cpp - text formats and the result-key plan (host only, no CUDA).
+/* hostio.cpp - the result-key plan and the proportion check (host only, no CUDA).
  *
- * Replaces the reference's src/io/parser.cu: load_fluorescences (:68-154), load_cell_types (:156-185),
- * assert_proportion_sum (:46-66), save_fluorescences (:187-217).  File formats are kept byte for byte:
- *   histogram : whitespace-separated "<double value> <uint64 frequency>" pairs, read until the first parse
- *               failure; frequency-0 lines skipped; order preserved; duplicates allowed
- *   types     : "<proportion> <mean> <stddev>" triples, type id = 0-based line index
- *   output    : rows with frequency > 0, ascending value, value printed with precision 10 (== %.10g),
- *               TAB, frequency, then with -r one TAB-separated count per type in file order
+ * Replaces, in the reference's src/io/parser.cu, the result-key precomputation of load_fluorescences (:68-154)
+ * and assert_proportion_sum (:46-66).  The text readers and the writer live in textio.cpp.
  */
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <fstream>
-#include <iostream>
-#include <sstream>
 #include <utility>
 
 #include "host_plan.h"
@@ -44,30 +36,6 @@ const char* procell_version(void) { return "procell-b200 0.1 (sm_100a)"; }
 
 void procell_free(void* p) { free(p); }
 
-int procell_read_histogram(const char* path, double** value, uint64_t** freq, size_t* n_lines)
-{
-    if (!path || !value || !freq || !n_lines) return fail(PROCELL_ERR_ARG, "procell_read_histogram: null argument");
-    std::ifstream in(path);
-    if (!in.is_open()) return fail(PROCELL_ERR_IO, std::string("cannot open histogram file ") + path);
-    std::vector<double> v;
-    std::vector<uint64_t> f;
-    double x = 0.0;
-    uint64_t c = 0;
-    while (in >> x >> c) {   /* parser.cu:103-106 */
-        v.push_back(x);
-        f.push_back(c);
-    }
-    *n_lines = v.size();
-    *value = static_cast<double*>(malloc((v.size() + 1) * sizeof(double)));
-    *freq = static_cast<uint64_t*>(malloc((v.size() + 1) * sizeof(uint64_t)));
-    if (!*value || !*freq) return fail(PROCELL_ERR_ARG, "out of host memory");
-    if (!v.empty()) {
-        memcpy(*value, v.data(), v.size() * sizeof(double));
-        memcpy(*freq, f.data(), f.size() * sizeof(uint64_t));
-    }
-    return PROCELL_OK;
-}
-
 int procell_check_proportions(const procell_cell_type* types, size_t n_types)
 {
     double sum = 0.0;    /* thrust::reduce from 0.0, left to right (parser.cu:52-58) */
@@ -75,48 +43,6 @@ int procell_check_proportions(const procell_cell_type* types, size_t n_types)
     double err = 1 / pow(10.0, 8.0);
     if (std::fabs(1.0 - sum) > err)
         return fail(PROCELL_ERR_PROPORTION, "ERROR: proportion distribution of cell types does not sum to 1, aborting.");
-    return PROCELL_OK;
-}
-
-int procell_read_cell_types(const char* path, procell_cell_type** types, size_t* n_types)
-{
-    if (!path || !types || !n_types) return fail(PROCELL_ERR_ARG, "procell_read_cell_types: null argument");
-    std::ifstream in(path);
-    if (!in.is_open()) return fail(PROCELL_ERR_IO, std::string("cannot open cell types file ") + path);
-    std::vector<procell_cell_type> t;
-    procell_cell_type c;
-    while (in >> c.proportion >> c.mean >> c.stddev) t.push_back(c);   /* parser.cu:167-175 */
-    *n_types = t.size();
-    *types = static_cast<procell_cell_type*>(malloc((t.size() + 1) * sizeof(procell_cell_type)));
-    if (!*types) return fail(PROCELL_ERR_ARG, "out of host memory");
-    if (!t.empty()) memcpy(*types, t.data(), t.size() * sizeof(procell_cell_type));
-    return procell_check_proportions(*types, *n_types);
-}
-
-int procell_write_histogram(const char* path, int save_ratio, size_t n_types, size_t n_rows,
-                            const double* row_value, const int64_t* row_freq, const int64_t* row_ratio)
-{
-    if (n_rows && (!row_value || !row_freq)) return fail(PROCELL_ERR_ARG, "procell_write_histogram: null rows");
-    if (save_ratio && n_rows && !row_ratio) return fail(PROCELL_ERR_ARG, "procell_write_histogram: null ratios");
-    std::ofstream file;
-    if (path) {
-        file.open(path);
-        if (!file.is_open()) return fail(PROCELL_ERR_IO, std::string("cannot open output file ") + path);
-    }
-    std::ostream& out = path ? static_cast<std::ostream&>(file) : std::cout;
-    std::ostringstream buf;
-    buf.precision(10);   /* parser.cu:194-195 */
-    for (size_t i = 0; i < n_rows; ++i) {
-        if (row_freq[i] <= 0) continue;
-        buf << row_value[i] << "\t" << row_freq[i];
-        if (save_ratio)
-            for (size_t j = 0; j < n_types; ++j) buf << "\t" << row_ratio[i * n_types + j];
-        buf << "\n";
-        if (buf.tellp() > (1 << 20)) { out << buf.str(); buf.str(std::string()); }
-    }
-    out << buf.str();
-    out.flush();
-    if (!out.good()) return fail(PROCELL_ERR_IO, "write failed");
     return PROCELL_OK;
 }
 

@@ -45,11 +45,14 @@ typedef struct procell_engine procell_engine; /* one GPU: resident tables, work 
 const char* procell_last_error(void);
 const char* procell_version(void);
 
-/* ---- text I/O ------------------------------------------------------------------------------- */
+/* ---- text I/O (streaming: one read() + in-place scan, one buffer per write(); csrc/textio.cpp) ---- */
 /* replaces io::load_fluorescences' reading loop (src/io/parser.cu:103-106): "<double> <uint64>" pairs
  * until the first parse failure; lines with frequency 0 are KEPT here (the plan skips them).
  * Arrays are malloc'd; release with procell_free. */
 int procell_read_histogram(const char* path, double** value, uint64_t** freq, size_t* n_lines);
+/* the same two readers on text already in memory (len bytes, no terminator needed) */
+int procell_parse_histogram(const char* text, size_t len, double** value, uint64_t** freq, size_t* n_lines);
+int procell_parse_cell_types(const char* text, size_t len, procell_cell_type** types, size_t* n_types);
 /* replaces io::load_cell_types (src/io/parser.cu:156-185): "<proportion> <mean> <stddev>" triples, file
  * order kept (type id = line index); checks the proportion sum. */
 int procell_read_cell_types(const char* path, procell_cell_type** types, size_t* n_types);
