@@ -84,6 +84,7 @@ struct procell_engine {
     bool loaded = false;
     int kernel = PROCELL_KERNEL_COOP;
     int warps = 16;
+    int ring = 1;                           /* 2: 256-node rings, two nodes per lane (16 warps) */
     int grid = 0, block = 0;
     size_t smem = 0;
     size_t counts_len = 0;
@@ -287,7 +288,10 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         const char* wenv = getenv("PROCELL_COOP_WARPS");     /* tuning knob: 16, 24 or 32 warps per CTA */
         const int wreq = wenv ? atoi(wenv) : 0;
         en->warps = (wreq == 16 || wreq == 24) ? wreq : 32;
-        const size_t fixed = coop_smem_bytes(en->warps, 0, 0);
+        const char* renv = getenv("PROCELL_COOP_NPL");       /* tuning knob: 2 = 16 warps, two nodes per lane */
+        en->ring = (renv && atoi(renv) == 2) ? 2 : 1;
+        if (en->ring == 2) en->warps = 16;
+        const size_t fixed = coop_smem_bytes(en->warps, en->ring, 0, 0);
         const size_t room = (size_t)max_smem > fixed ? (size_t)max_smem - fixed : 0;
         if (en->counts_len * 4 <= room) {            /* the whole key space fits: direct u32 table */
             P.hist_hashed = 0;
@@ -298,9 +302,9 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
             P.hist_hashed = 1;
             P.smem_hist_slots = slots;
         }
-        en->smem = coop_smem_bytes(en->warps, P.smem_hist_slots, P.hist_hashed);
+        en->smem = coop_smem_bytes(en->warps, en->ring, P.smem_hist_slots, P.hist_hashed);
         int grid = 0;
-        CU(coop_max_grid(en->device, en->warps, P.hist_hashed, (P.n_sets == 1u && P.n_times == 1u) ? 1 : 0, en->smem, &grid), "occupancy query");
+        CU(coop_max_grid(en->device, en->warps, en->ring, P.hist_hashed, (P.n_sets == 1u && P.n_times == 1u) ? 1 : 0, en->smem, &grid), "occupancy query");
         if (grid <= 0) return fail(PROCELL_ERR_CUDA, "cooperative kernel does not fit on this device");
         en->grid = grid;
         en->block = en->warps * 32;
@@ -335,7 +339,7 @@ int procell_engine_run(procell_engine* en, uint64_t seed, void* stream_v, int64_
     CU(cudaMemsetAsync(P.divisions, 0, en->n_sets * 8, stream), "zero divisions");
     CU(launch_queue_init(P.q_seq, P.ctl, stream), "launch k_queue_init");
     if (en->kernel == PROCELL_KERNEL_SIMPLE) CU(launch_simple(P, en->grid, stream), "launch k_proliferate_simple");
-    else CU(launch_coop(P, en->warps, en->grid, stream), "launch k_proliferate_coop");
+    else CU(launch_coop(P, en->warps, en->ring, en->grid, stream), "launch k_proliferate_coop");
     en->launches_last = 2;
     CU(cudaEventRecord(en->ev1, stream), "event record");
     return PROCELL_OK;

@@ -240,16 +240,30 @@ PCS_HD void pcs_sincos2pi(uint64_t v, double* s_out, double* c_out)
 
 /* ------------------------------------------------------------------ one Box-Muller pair from one Philox block
  * z0 = rad*sin, z1 = rad*cos with rad = sqrt(-2 ln u); child c of a division uses z_c.
- * u_override (refcompat seeding) replaces the radius uniform when > 0. */
-PCS_HD void pcs_normal_pair(pcs_u32x4 w, const double* tab, double u_override, double* z0, double* z1)
+ * u_override (refcompat seeding) replaces the radius uniform when > 0.
+ * The transform is given in two halves so that a kernel expanding several nodes per lane can run the polynomial
+ * halves of all of them before the square roots (whose slow-path branch ends a basic block); pcs_normal_pair is
+ * their composition, so the operation sequence per node is the same either way. */
+PCS_HD void pcs_normal_pair_polys(pcs_u32x4 w, const double* tab, double u_override, double* rad2, double* s, double* c)
 {
     double u = pcs_u53(w.x, w.y);
     if (u_override > 0.0) u = u_override;
-    double rad = PCS_SQRT(pcs_neg2log(u, tab));
-    double s, c;
-    pcs_sincos2pi(((uint64_t)w.w << 32) | (uint64_t)w.z, &s, &c);
+    *rad2 = pcs_neg2log(u, tab);
+    pcs_sincos2pi(((uint64_t)w.w << 32) | (uint64_t)w.z, s, c);
+}
+
+PCS_HD void pcs_normal_pair_finish(double rad2, double s, double c, double* z0, double* z1)
+{
+    double rad = PCS_SQRT(rad2);
     *z0 = PCS_MUL(rad, s);
     *z1 = PCS_MUL(rad, c);
+}
+
+PCS_HD void pcs_normal_pair(pcs_u32x4 w, const double* tab, double u_override, double* z0, double* z1)
+{
+    double rad2, s, c;
+    pcs_normal_pair_polys(w, tab, u_override, &rad2, &s, &c);
+    pcs_normal_pair_finish(rad2, s, c, z0, z1);
 }
 
 /* timer = mean + sd*z (one fma), accepted iff > 0 (cell.cu:106-122: redraw while rnd <= 0) */

@@ -38,7 +38,12 @@ namespace {
 #define TRACE(P, gw, lane, code) do { } while (0)
 #endif
 
-constexpr uint32_t kRingMask = kStackCap - 1;
+/* ring capacity of a warp: kStackCap nodes per node-per-lane of the instance (RING = 1: 128 nodes, the product shape
+ * with 32 warps; RING = 2: 256 nodes for the 16-warp instance whose full DIVIDE iteration expands two nodes per lane) */
+template <int RING> struct Ring {
+    static constexpr uint32_t kCap = (uint32_t)kStackCap * RING;
+    static constexpr uint32_t kMask = kCap - 1u;
+};
 constexpr int kSmemMusdEntries = 64;  /* (mean, sd) table cached in shared memory when n_sets * n_types fits */
 constexpr int kSmemCtlBytes = 128 + kSmemMusdEntries * 16;    /* control words (64 B) + three 16-byte snapshots of the control block */
 constexpr unsigned kFull = 0xFFFFFFFFu;
@@ -213,9 +218,10 @@ struct WarpCtx {
     int lane;
 };
 
+template <int RING>
 __device__ __forceinline__ void spill_bottom_chunk(WarpCtx& w, const SimParams& P)
 {
-    uint32_t idx = (w.bottom + w.lane) & kRingMask;
+    uint32_t idx = (w.bottom + w.lane) & Ring<RING>::kMask;
     unsigned long long* dst = w.spill + (size_t)(w.sp_top % kSpillCap) * kChunkWords;
     __stcg(dst + w.lane, w.sa[idx]);
     __stcg(dst + 32 + w.lane, w.sb[idx]);
@@ -227,12 +233,13 @@ __device__ __forceinline__ void spill_bottom_chunk(WarpCtx& w, const SimParams& 
     __syncwarp();
 }
 
+template <int RING>
 __device__ __forceinline__ void unspill_newest_chunk(WarpCtx& w)
 {
     w.sp_top -= 1;
     const unsigned long long* src = w.spill + (size_t)(w.sp_top % kSpillCap) * kChunkWords;
     w.bottom -= kChunkNodes;
-    uint32_t idx = (w.bottom + w.lane) & kRingMask;
+    uint32_t idx = (w.bottom + w.lane) & Ring<RING>::kMask;
     w.sa[idx] = __ldcg(src + w.lane);
     w.sb[idx] = __ldcg(src + 32 + w.lane);
     w.sc[idx] = __ldcg(src + 64 + w.lane);
@@ -299,6 +306,7 @@ __device__ __forceinline__ bool queue_read_ticket(const SimParams& P, int lane, 
 }
 
 /* hand the shallowest chunk (oldest spilled, else ring bottom) to the shared queue */
+template <int RING>
 __device__ __forceinline__ void donate_chunk(WarpCtx& w, const SimParams& P)
 {
     uint64_t a, b, c, d;
@@ -310,7 +318,7 @@ __device__ __forceinline__ void donate_chunk(WarpCtx& w, const SimParams& P)
         d = __ldcg(src + 96 + w.lane);
         w.sp_bottom += 1;
     } else {
-        uint32_t idx = (w.bottom + w.lane) & kRingMask;
+        uint32_t idx = (w.bottom + w.lane) & Ring<RING>::kMask;
         a = w.sa[idx]; b = w.sb[idx]; c = w.sc[idx]; d = w.sd[idx];
         w.bottom += kChunkNodes;
     }
@@ -323,6 +331,7 @@ __device__ __forceinline__ void donate_chunk(WarpCtx& w, const SimParams& P)
  * permit is available, claims a chunk with fetch-adds only (permit counter, then head ticket) - no CAS retry
  * storms, at most 148 concurrent pollers.  Quiescence (no active warp, no permit) is stable, so the warp that
  * observes it publishes it to its CTA through s_ctl[1]. */
+template <int RING>
 __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volatile int* s_ctl, unsigned long long deadline, uint32_t gwarp)
 {
     ControlBlock* ctl = P.ctl;
@@ -340,7 +349,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
             ticket = __shfl_sync(kFull, ticket, 0);
             uint64_t a, b, c, d;
             if (!queue_read_ticket(P, w.lane, ticket, a, b, c, d)) return false;     /* watchdog abort */
-            uint32_t idx = (w.top + w.lane) & kRingMask;
+            uint32_t idx = (w.top + w.lane) & Ring<RING>::kMask;
             w.sa[idx] = a; w.sb[idx] = b; w.sc[idx] = c; w.sd[idx] = d;
             w.top += kChunkNodes;
             __syncwarp();
@@ -399,7 +408,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
             ticket = __shfl_sync(kFull, ticket, 0);
             uint64_t a, b, c, d;
             if (!queue_read_ticket(P, w.lane, ticket, a, b, c, d)) return false;     /* watchdog abort */
-            uint32_t idx = (w.top + w.lane) & kRingMask;
+            uint32_t idx = (w.top + w.lane) & Ring<RING>::kMask;
             w.sa[idx] = a; w.sb[idx] = b; w.sc[idx] = c; w.sd[idx] = d;
             w.top += kChunkNodes;
             __syncwarp();
@@ -499,107 +508,149 @@ struct DivCount {
 /* ---- DIVIDE iteration: the lanes below `take` pop one node each (newest first), draw ONE Philox block -> one
  * Box-Muller pair -> both daughters' timers, classify the daughters and push the ones that will divide.
  * FULL = all 32 lanes have a node (the common case): straight-line code.  Otherwise the lanes without a node skip the
- * arithmetic, and every warp collective below is still executed by all 32 lanes with the full mask. */
-template <bool FULL, bool HASHED, bool PLAIN>
+ * arithmetic, and every warp collective below is still executed by all 32 lanes with the full mask.
+ * NPL = nodes per lane: 1, or 2 in the 16-warp instance with 256-node rings (RING = 2), where lane l expands the
+ * nodes top-1-l and top-33-l in one straight-line pass: two independent arithmetic chains for the scheduler to
+ * interleave, and the per-iteration overhead (loop control, constant loads, probes) is paid once per 64 divisions. */
+template <bool FULL, bool HASHED, bool PLAIN, int RING, int NPL>
 __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P, const double* s_log, uint32_t* s_hist,
                                                  const double2* musd, uint32_t take, unsigned lt_mask, bool multi_set,
                                                  DivCount& dc)
 {
+    static_assert(NPL == 1 || (FULL && RING >= NPL), "several nodes per lane: full iterations of a wide-ring instance only");
+    constexpr uint32_t kMask = Ring<RING>::kMask;
     const uint32_t T = P.n_types;
-    bool int0 = false, int1 = false;        /* daughter 0 / 1 lives on and will divide */
-    uint32_t rej = 0, leaf_inc = 0, leaf_key = 0, dlo = 0, retry = 0;
-    uint64_t heap = 0, pc = 0;
-    double t_div = 0.0, tc0 = 0.0, tc1 = 0.0;
-    if (FULL || (uint32_t)w.lane < take) {
-        const uint32_t idx = (w.top - 1u - (uint32_t)w.lane) & kRingMask;
-        t_div = pcs_bits2d(w.sa[idx]);
-        heap = w.sb[idx];
-        pc = w.sc[idx];
-        const uint64_t d = w.sd[idx];
-        dlo = (uint32_t)d;
-        retry = (uint32_t)(d >> 32);
-        const uint32_t set = PLAIN ? 0u : (dlo & 0xFFFFu);
-        const uint32_t type = (dlo >> 16) & 63u;
-        const double2 ms = musd[set * T + type];          /* generic pointer: shared-memory copy or the HBM table */
-        const pcs_u32x4 blk = pcs_draw_rk((uint32_t)pc, set, retry, PCS_TAG_DIVISION, heap, P.rk);
-        double z0, z1;
-        pcs_normal_pair(blk, s_log, 0.0, &z0, &z1);
-        const bool forced = retry >= PCS_MAX_RETRY;        /* 255 redraws failed: the timer is the mean */
-        const double tm0 = forced ? ms.x : pcs_timer(ms.x, ms.y, z0);
-        const double tm1 = forced ? ms.x : pcs_timer(ms.x, ms.y, z1);
-        const bool want0 = (dlo & (1u << 28)) != 0u, want1 = (dlo & (2u << 28)) != 0u;
-        const bool ok0 = want0 && (tm0 > 0.0 || forced), ok1 = want1 && (tm1 > 0.0 || forced);
-        tc0 = PCS_ADD(t_div, tm0);
-        tc1 = PCS_ADD(t_div, tm1);
-        const bool late0 = tc0 > P.t_max, late1 = tc1 > P.t_max;      /* proliferation.cu:404-410 */
-        const bool deeper = (dlo & (63u << 22)) != 0u;                /* f/2 > phi one level down (:323) */
-        leaf_inc = (uint32_t)(ok0 && late0) + (uint32_t)(ok1 && late1);
-        int0 = ok0 && !late0 && deeper;
-        int1 = ok1 && !late1 && deeper;
-        rej = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
-        leaf_key = (uint32_t)(pc >> 32) + T;
-        const uint32_t first = retry == 0u ? 1u : 0u;      /* a redraw is not another division */
-        if (multi_set && first && set != dc.set) {
-            if (dc.cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
-            dc.cnt = 0; dc.set = set;
+    bool int0[NPL], int1[NPL];              /* daughter 0 / 1 lives on and will divide */
+    uint32_t rej[NPL], leaf_inc[NPL], leaf_key[NPL], dlo[NPL], retry[NPL];
+    uint64_t heap[NPL], pc[NPL];
+    double t_div[NPL], tc0[NPL], tc1[NPL];
+    /* the arithmetic runs phase by phase over the lane's nodes (pop + Philox, polynomials, square roots, classify):
+     * with NPL = 2 that puts two independent chains side by side in every basic block */
+    pcs_u32x4 blk[NPL];
+    double rad2[NPL], sn[NPL], cs[NPL], z0[NPL], z1[NPL];
+    const bool mine = FULL || (uint32_t)w.lane < take;
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+        int0[s] = false; int1[s] = false;
+        rej[s] = 0; leaf_inc[s] = 0; leaf_key[s] = 0; dlo[s] = 0; retry[s] = 0;
+        heap[s] = 0; pc[s] = 0;
+        t_div[s] = 0.0; tc0[s] = 0.0; tc1[s] = 0.0;
+    }
+    if (mine) {
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) {
+            const uint32_t idx = (w.top - 1u - 32u * (uint32_t)s - (uint32_t)w.lane) & kMask;
+            t_div[s] = pcs_bits2d(w.sa[idx]);
+            heap[s] = w.sb[idx];
+            pc[s] = w.sc[idx];
+            const uint64_t d = w.sd[idx];
+            dlo[s] = (uint32_t)d;
+            retry[s] = (uint32_t)(d >> 32);
+            const uint32_t set = PLAIN ? 0u : (dlo[s] & 0xFFFFu);
+            blk[s] = pcs_draw_rk((uint32_t)pc[s], set, retry[s], PCS_TAG_DIVISION, heap[s], P.rk);
         }
-        dc.cnt += first;
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) pcs_normal_pair_polys(blk[s], s_log, 0.0, &rad2[s], &sn[s], &cs[s]);
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) pcs_normal_pair_finish(rad2[s], sn[s], cs[s], &z0[s], &z1[s]);
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) {
+            const uint32_t set = PLAIN ? 0u : (dlo[s] & 0xFFFFu);
+            const uint32_t type = (dlo[s] >> 16) & 63u;
+            const double2 ms = musd[set * T + type];          /* generic pointer: shared-memory copy or the HBM table */
+            const bool forced = retry[s] >= PCS_MAX_RETRY;     /* 255 redraws failed: the timer is the mean */
+            const double tm0 = forced ? ms.x : pcs_timer(ms.x, ms.y, z0[s]);
+            const double tm1 = forced ? ms.x : pcs_timer(ms.x, ms.y, z1[s]);
+            const bool want0 = (dlo[s] & (1u << 28)) != 0u, want1 = (dlo[s] & (2u << 28)) != 0u;
+            const bool ok0 = want0 && (tm0 > 0.0 || forced), ok1 = want1 && (tm1 > 0.0 || forced);
+            tc0[s] = PCS_ADD(t_div[s], tm0);
+            tc1[s] = PCS_ADD(t_div[s], tm1);
+            const bool late0 = tc0[s] > P.t_max, late1 = tc1[s] > P.t_max;  /* proliferation.cu:404-410 */
+            const bool deeper = (dlo[s] & (63u << 22)) != 0u;               /* f/2 > phi one level down (:323) */
+            leaf_inc[s] = (uint32_t)(ok0 && late0) + (uint32_t)(ok1 && late1);
+            int0[s] = ok0 && !late0 && deeper;
+            int1[s] = ok1 && !late1 && deeper;
+            rej[s] = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
+            leaf_key[s] = (uint32_t)(pc[s] >> 32) + T;
+            const uint32_t first = retry[s] == 0u ? 1u : 0u;   /* a redraw is not another division */
+            if (multi_set && first && set != dc.set) {
+                if (dc.cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
+                dc.cnt = 0; dc.set = set;
+            }
+            dc.cnt += first;
+        }
     }
     /* all popped nodes have been read: every lane's loads have returned before it votes below (the predicates depend
-     * on the loaded values) and no lane stores before all have voted, so the slots may be overwritten.  The partial
-     * iteration is divergent above, so it states the ordering explicitly as well. */
+     * on the loaded values of every node it popped) and no lane stores before all have voted on everything, so the
+     * slots may be overwritten.  The partial iteration is divergent above, so it states the ordering explicitly as well. */
     if (!FULL) __syncwarp();
     w.top -= take;
-    const unsigned b0 = __ballot_sync(kFull, int0);
-    const unsigned b1 = __ballot_sync(kFull, int1);
-    const unsigned br = __ballot_sync(kFull, rej != 0u);
-    const uint64_t child_c = ((pc >> 32) + T) << 32 | (pc & 0xFFFFFFFFull);
-    const uint64_t child_d = (uint64_t)((dlo | (3u << 28)) - (1u << 22));
-    if (int0) {
-        const uint32_t i0 = (w.top + __popc(b0 & lt_mask)) & kRingMask;
-        w.sa[i0] = pcs_d2bits(tc0); w.sb[i0] = heap * 2ull; w.sc[i0] = child_c; w.sd[i0] = child_d;
+    unsigned b0[NPL], b1[NPL], br[NPL];
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+        b0[s] = __ballot_sync(kFull, int0[s]);
+        b1[s] = __ballot_sync(kFull, int1[s]);
+        br[s] = __ballot_sync(kFull, rej[s] != 0u);
     }
-    w.top += __popc(b0);
-    if (int1) {
-        const uint32_t i1 = (w.top + __popc(b1 & lt_mask)) & kRingMask;
-        w.sa[i1] = pcs_d2bits(tc1); w.sb[i1] = heap * 2ull + 1ull; w.sc[i1] = child_c; w.sd[i1] = child_d;
-    }
-    w.top += __popc(b1);
-    if (br) {   /* a daughter's timer came out <= 0: redraw it in a later iteration (cell.cu:114-118) */
-        if (rej) {
-            const uint32_t ir = (w.top + __popc(br & lt_mask)) & kRingMask;
-            w.sa[ir] = pcs_d2bits(t_div); w.sb[ir] = heap; w.sc[ir] = pc;
-            w.sd[ir] = (uint64_t)((dlo & ~(3u << 28)) | (rej << 28)) | ((uint64_t)(retry + 1u) << 32);
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+        const uint64_t child_c = ((pc[s] >> 32) + T) << 32 | (pc[s] & 0xFFFFFFFFull);
+        const uint64_t child_d = (uint64_t)((dlo[s] | (3u << 28)) - (1u << 22));
+        if (int0[s]) {
+            const uint32_t i0 = (w.top + __popc(b0[s] & lt_mask)) & kMask;
+            w.sa[i0] = pcs_d2bits(tc0[s]); w.sb[i0] = heap[s] * 2ull; w.sc[i0] = child_c; w.sd[i0] = child_d;
         }
-        w.top += __popc(br);
+        w.top += __popc(b0[s]);
+        if (int1[s]) {
+            const uint32_t i1 = (w.top + __popc(b1[s] & lt_mask)) & kMask;
+            w.sa[i1] = pcs_d2bits(tc1[s]); w.sb[i1] = heap[s] * 2ull + 1ull; w.sc[i1] = child_c; w.sd[i1] = child_d;
+        }
+        w.top += __popc(b1[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+        if (br[s]) {   /* a daughter's timer came out <= 0: redraw it in a later iteration (cell.cu:114-118) */
+            if (rej[s]) {
+                const uint32_t ir = (w.top + __popc(br[s] & lt_mask)) & kMask;
+                w.sa[ir] = pcs_d2bits(t_div[s]); w.sb[ir] = heap[s]; w.sc[ir] = pc[s];
+                w.sd[ir] = (uint64_t)((dlo[s] & ~(3u << 28)) | (rej[s] << 28)) | ((uint64_t)(retry[s] + 1u) << 32);
+            }
+            w.top += __popc(br[s]);
+        }
     }
     __syncwarp();
-    if (PLAIN || P.n_times == 1u) {
-        warp_count_leaves<HASHED>(P, s_hist, leaf_key, leaf_inc);
-    } else {
-        /* time series: a daughter born at t_div that divides (or would divide) at tc is out of time at every
-         * checkpoint in [t_div, tc) */
-        const bool have0 = (rej & 1u) == 0u && (dlo & (1u << 28)) != 0u;      /* daughter 0 got its timer now */
-        const bool have1 = (rej & 2u) == 0u && (dlo & (2u << 28)) != 0u;
-        for (uint32_t j = 0; j < P.n_times; ++j) {
-            const double tj = P.times[j];
-            const bool born = t_div <= tj;
-            const uint32_t inc = (uint32_t)(have0 && born && tj < tc0) + (uint32_t)(have1 && born && tj < tc1);
-            warp_count_leaves<HASHED>(P, s_hist, leaf_key + j * P.time_stride, inc);
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+        if (PLAIN || P.n_times == 1u) {
+            warp_count_leaves<HASHED>(P, s_hist, leaf_key[s], leaf_inc[s]);
+        } else {
+            /* time series: a daughter born at t_div that divides (or would divide) at tc is out of time at every
+             * checkpoint in [t_div, tc) */
+            const bool have0 = (rej[s] & 1u) == 0u && (dlo[s] & (1u << 28)) != 0u;      /* daughter 0 got its timer now */
+            const bool have1 = (rej[s] & 2u) == 0u && (dlo[s] & (2u << 28)) != 0u;
+            for (uint32_t j = 0; j < P.n_times; ++j) {
+                const double tj = P.times[j];
+                const bool born = t_div[s] <= tj;
+                const uint32_t inc = (uint32_t)(have0 && born && tj < tc0[s]) + (uint32_t)(have1 && born && tj < tc1[s]);
+                warp_count_leaves<HASHED>(P, s_hist, leaf_key[s] + j * P.time_stride, inc);
+            }
         }
     }
 }
 
 }  // namespace
 
-template <int WARPS, bool HASHED, bool PLAIN>
+template <int WARPS, bool HASHED, bool PLAIN, int RING>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid_constant__ SimParams P)
 {
+    static_assert(RING == 1 || RING == 2, "ring of 128 or 256 nodes per warp");
+    constexpr uint32_t kCap = Ring<RING>::kCap, kMask = Ring<RING>::kMask;
+    constexpr uint32_t kLow = 32u * RING;        /* below this many nodes a warp looks for seed cells / spilled chunks first */
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_log = reinterpret_cast<double*>(smem_raw);
     volatile int* s_ctl = reinterpret_cast<volatile int*>(smem_raw + kLogTabDoubles * 8);   /* [0] poll lock, [1] quiescent */
     uint64_t* s_stack = reinterpret_cast<uint64_t*>(smem_raw + kLogTabDoubles * 8 + kSmemCtlBytes);
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + kLogTabDoubles * 8 + kSmemCtlBytes + (size_t)WARPS * 4 * kStackCap * 8);
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + kLogTabDoubles * 8 + kSmemCtlBytes + (size_t)WARPS * 4 * kCap * 8);
 
     double2* s_musd_buf = reinterpret_cast<double2*>(smem_raw + kLogTabDoubles * 8 + 128);
     const bool musd_cached = P.n_sets * P.n_types <= (uint32_t)kSmemMusdEntries;
@@ -621,10 +672,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     ControlBlock* ctl = P.ctl;
 
     WarpCtx w;
-    w.sa = s_stack + (size_t)warp * 4 * kStackCap;
-    w.sb = w.sa + kStackCap;
-    w.sc = w.sb + kStackCap;
-    w.sd = w.sc + kStackCap;
+    w.sa = s_stack + (size_t)warp * 4 * kCap;
+    w.sb = w.sa + kCap;
+    w.sc = w.sb + kCap;
+    w.sd = w.sc + kCap;
     w.bottom = 0; w.top = 0;
     w.spill = P.spill + (size_t)(blockIdx.x * WARPS + warp) * kSpillCap * kChunkWords;
     w.sp_bottom = 0; w.sp_top = 0;
@@ -659,8 +710,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 
     for (;;) {
         const uint32_t n = w.top - w.bottom;
-        if (n < 32u) {
-            if (w.sp_top != w.sp_bottom) { TRACE(P, GWARP, lane, 41); unspill_newest_chunk(w); continue; }
+        if (n < kLow) {
+            if (w.sp_top != w.sp_bottom) { TRACE(P, GWARP, lane, 41); unspill_newest_chunk<RING>(w); continue; }
             /* RULE: every decision that depends on mutable shared/global state is taken by lane 0 and broadcast.
              * Lanes of a warp are not guaranteed to be converged when they read a volatile flag, so a per-lane read
              * can see two different values inside one warp and split it for good. */
@@ -757,7 +808,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 if (have) so = build_seed(P, s_log, root, seed_set, bin);
                 const unsigned live = __ballot_sync(kFull, so.kind == 2);
                 if (so.kind == 2) {
-                    uint32_t idx = (w.top + __popc(live & lt_mask)) & kRingMask;
+                    uint32_t idx = (w.top + __popc(live & lt_mask)) & kMask;
                     w.sa[idx] = pcs_d2bits(so.t_div);
                     w.sb[idx] = 1ull;
                     w.sc[idx] = (uint64_t)root | ((uint64_t)so.key << 32);
@@ -777,11 +828,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
             }
             if (n == 0u) {
                 TRACE(P, GWARP, lane, 30);
-                if (!idle_wait(w, P, s_ctl, *s_deadline, GWARP)) break;
+                if (!idle_wait<RING>(w, P, s_ctl, *s_deadline, GWARP)) break;
                 continue;
             }
         }
-        if (n > (uint32_t)(kStackCap - 32)) { TRACE(P, GWARP, lane, 40); spill_bottom_chunk(w, P); continue; }
+        /* an iteration pops 32 * RING nodes at most and pushes twice as many: keep that much room in the ring */
+        if (n > kCap - 32u * RING) { TRACE(P, GWARP, lane, 40); spill_bottom_chunk<RING>(w, P); continue; }
 
         ++iter;
         if ((iter & 255u) == 0u) {       /* every 256 iterations: flush the 32-bit division counters, check the watchdog */
@@ -806,8 +858,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         const uint32_t take = n < 32u ? n : 32u;
         /* PLAIN: one set and at most 64 types, so the (mean, sd) table is always the shared-memory copy (plain LDS) */
         const double2* musd = PLAIN ? s_musd_buf : s_musd;
-        if (take == 32u) divide_iteration<true, HASHED, PLAIN>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc);
-        else divide_iteration<false, HASHED, PLAIN>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc);
+        if (RING == 2 && n >= 64u) divide_iteration<true, HASHED, PLAIN, RING, RING>(w, P, s_log, s_hist, musd, 64u, lt_mask, multi_set, dc);
+        else if (take == 32u) divide_iteration<true, HASHED, PLAIN, RING, 1>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc);
+        else divide_iteration<false, HASHED, PLAIN, RING, 1>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc);
 
         /* hunger probe, every 4th iteration.  The CTA keeps a snapshot of "how many warps are starving", "how many
          * donated chunks are waiting" and "where is the seed cursor" in shared memory.  Every 64th iteration
@@ -836,11 +889,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 packed = (ep << 2) | ((idle_snap >= kEndgameIdle) << 1) | hg;
             }
             packed = __shfl_sync(kFull, packed, 0);
-            if ((packed & 1) && (w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= ((packed & 2) ? 64u : kDonateMinNodes)) {
+            if ((packed & 1) && (w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= ((packed & 2) ? 64u : kDonateMinNodes * RING)) {
                 /* somebody starves and no seeds are left: give away the shallowest chunk */
                 TRACE(P, GWARP, lane, 50);
                 donate_epoch = packed >> 2;
-                donate_chunk(w, P);
+                donate_chunk<RING>(w, P);
             }
         }
     }
@@ -969,18 +1022,18 @@ __global__ void __launch_bounds__(256) k_rng_ceiling(int iters, const double* lo
 }
 
 /* ------------------------------------------------------------------------------------------------ host */
-size_t coop_smem_bytes(int warps, uint32_t hist_slots, int hashed)
+size_t coop_smem_bytes(int warps, int ring, uint32_t hist_slots, int hashed)
 {
-    return (size_t)kLogTabDoubles * 8 + kSmemCtlBytes + (size_t)warps * 4 * kStackCap * 8 + (size_t)hist_slots * (hashed ? 8 : 4);
+    return (size_t)kLogTabDoubles * 8 + kSmemCtlBytes + (size_t)warps * 4 * kStackCap * ring * 8 + (size_t)hist_slots * (hashed ? 8 : 4);
 }
 
-template <int WARPS, bool HASHED, bool PLAIN>
+template <int WARPS, bool HASHED, bool PLAIN, int RING>
 static cudaError_t coop_max_grid_t(int device, size_t smem_bytes, int* grid_out)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_proliferate_coop<WARPS, HASHED, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k_proliferate_coop<WARPS, HASHED, PLAIN, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     int per_sm = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<WARPS, HASHED, PLAIN>, WARPS * 32, smem_bytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<WARPS, HASHED, PLAIN, RING>, WARPS * 32, smem_bytes);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
@@ -988,33 +1041,38 @@ static cudaError_t coop_max_grid_t(int device, size_t smem_bytes, int* grid_out)
     return cudaSuccess;
 }
 
-/* the 12 instances: CTA shape (32 / 24 / 16 warps) x histogram mode x PLAIN */
-#define COOP_DISPATCH(warps, hashed, plain, X)                                                       \
+/* the 16 instances: CTA shape (32 / 24 / 16 warps with 128-node rings, 16 warps with 256-node rings and two nodes
+ * per lane) x histogram mode x PLAIN */
+#define COOP_DISPATCH(warps, ring, hashed, plain, X)                                                  \
     do {                                                                                             \
-        switch (((warps) == 32 ? 0 : (warps) == 24 ? 4 : 8) + ((hashed) ? 2 : 0) + ((plain) ? 1 : 0)) { \
-        case 0: X(32, false, false); break;  case 1: X(32, false, true); break;                      \
-        case 2: X(32, true, false); break;   case 3: X(32, true, true); break;                       \
-        case 4: X(24, false, false); break;  case 5: X(24, false, true); break;                      \
-        case 6: X(24, true, false); break;   case 7: X(24, true, true); break;                       \
-        case 8: X(16, false, false); break;  case 9: X(16, false, true); break;                      \
-        case 10: X(16, true, false); break;  default: X(16, true, true); break;                      \
+        switch (((ring) == 2 ? 12 : (warps) == 32 ? 0 : (warps) == 24 ? 4 : 8) + ((hashed) ? 2 : 0) + ((plain) ? 1 : 0)) { \
+        case 0: X(32, false, false, 1); break;  case 1: X(32, false, true, 1); break;                \
+        case 2: X(32, true, false, 1); break;   case 3: X(32, true, true, 1); break;                 \
+        case 4: X(24, false, false, 1); break;  case 5: X(24, false, true, 1); break;                \
+        case 6: X(24, true, false, 1); break;   case 7: X(24, true, true, 1); break;                 \
+        case 8: X(16, false, false, 1); break;  case 9: X(16, false, true, 1); break;                \
+        case 10: X(16, true, false, 1); break;  case 11: X(16, true, true, 1); break;                \
+        case 12: X(16, false, false, 2); break; case 13: X(16, false, true, 2); break;               \
+        case 14: X(16, true, false, 2); break;  default: X(16, true, true, 2); break;                \
         }                                                                                            \
     } while (0)
 
-cudaError_t coop_max_grid(int device, int warps, int hashed, int plain, size_t smem_bytes, int* grid_out)
+cudaError_t coop_max_grid(int device, int warps, int ring, int hashed, int plain, size_t smem_bytes, int* grid_out)
 {
-#define X(W, H, PL) return coop_max_grid_t<W, H, PL>(device, smem_bytes, grid_out)
-    COOP_DISPATCH(warps, hashed, plain, X);
+    if (ring == 2 && warps != 16) return cudaErrorInvalidValue;
+#define X(W, H, PL, R) return coop_max_grid_t<W, H, PL, R>(device, smem_bytes, grid_out)
+    COOP_DISPATCH(warps, ring, hashed, plain, X);
 #undef X
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_coop(const SimParams& p, int warps, int grid, cudaStream_t stream)
+cudaError_t launch_coop(const SimParams& p, int warps, int ring, int grid, cudaStream_t stream)
 {
-    const size_t smem = coop_smem_bytes(warps, p.smem_hist_slots, p.hist_hashed);
+    if (ring == 2 && warps != 16) return cudaErrorInvalidValue;
+    const size_t smem = coop_smem_bytes(warps, ring, p.smem_hist_slots, p.hist_hashed);
     const bool plain = coop_is_plain(p);
-#define X(W, H, PL) k_proliferate_coop<W, H, PL><<<grid, W * 32, smem, stream>>>(p)
-    COOP_DISPATCH(warps, p.hist_hashed, plain, X);
+#define X(W, H, PL, R) k_proliferate_coop<W, H, PL, R><<<grid, W * 32, smem, stream>>>(p)
+    COOP_DISPATCH(warps, ring, p.hist_hashed, plain, X);
 #undef X
     return cudaGetLastError();
 }

@@ -9,7 +9,7 @@ namespace procell_b200 {
 
 /* ---- geometry of the warp-cooperative kernel ---- */
 constexpr int kCoopWarpsMax = 32;              /* warps per CTA (16, 24 or 32), one CTA per SM */
-constexpr int kStackCap = 128;                 /* nodes per warp kept in shared memory (ring) */
+constexpr int kStackCap = 128;                 /* nodes per warp kept in shared memory (ring), times `ring` (1 or 2) */
 constexpr int kChunkNodes = 32;                /* spill / donation granule: one node per lane */
 constexpr int kChunkWords = 4 * kChunkNodes;   /* 4 x u64 fields per node, field-major */
 constexpr int kSpillCap = 128;                 /* private spill ring, chunks per warp */
@@ -87,9 +87,11 @@ struct SimParams {
     double times[8];              /* ascending */
 };
 
-size_t coop_smem_bytes(int warps, uint32_t hist_slots, int hashed);
-cudaError_t launch_coop(const SimParams& p, int warps, int grid, cudaStream_t stream);
-cudaError_t coop_max_grid(int device, int warps, int hashed, int plain, size_t smem_bytes, int* grid_out);
+/* ring = 1: 128-node ring per warp, one node per lane and iteration (warps = 32, 24 or 16);
+ * ring = 2: 256-node ring per warp, two nodes per lane in the full DIVIDE iteration (warps = 16 only) */
+size_t coop_smem_bytes(int warps, int ring, uint32_t hist_slots, int hashed);
+cudaError_t launch_coop(const SimParams& p, int warps, int ring, int grid, cudaStream_t stream);
+cudaError_t coop_max_grid(int device, int warps, int ring, int hashed, int plain, size_t smem_bytes, int* grid_out);
 cudaError_t launch_simple(const SimParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_queue_init(unsigned long long* q_seq, ControlBlock* ctl, cudaStream_t stream);
 cudaError_t launch_rng_ceiling(int grid, int block, int iters, const double* logtab, double mean, double sd,

@@ -1,0 +1,46 @@
+#!/usr/bin/env python3
+"""A/B of the kernel's run-time shape knobs in ONE process (one CUDA context): for every knob setting and workload,
+load the engine (the knobs are read at load time), run REPS times, report min / median kernel_ms and a checksum of
+the count tensor (all settings must agree: results do not depend on scheduling).
+
+  python tools/ab_knobs.py [REPS]      # prints one JSON line per (knob, workload)
+"""
+import json
+import os
+import statistics
+import sys
+import zlib
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from cuda_pro_cell_b200 import api, synth  # noqa: E402
+
+REPS = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+KNOBS = [{}, {"PROCELL_COOP_NPL": "2"}, {"PROCELL_COOP_WARPS": "16"}, {"PROCELL_COOP_WARPS": "24"}]
+WORK = [(2, 1.0, 0.0), (3, 0.1, 0.0), (5, 0.1, 0.0), (4, 0.1, 600.0)]
+
+for cfg, scale, t_override in WORK:
+    w = synth.workload(cfg, scale)
+    if t_override > 0:
+        w.t_max = t_override
+    plan = api.Plan(w.values, w.freqs, w.phi)
+    for knob in KNOBS:
+        for k in ("PROCELL_COOP_NPL", "PROCELL_COOP_WARPS"):
+            os.environ.pop(k, None)
+        os.environ.update(knob)
+        eng = api.Engine(0)
+        eng.load(plan, w.types, w.t_max, w.seed)
+        ms, crc, div = [], None, None
+        for i in range(REPS + 1):
+            eng.run()
+            r = eng.finish(fetch=(i == 0))
+            if i == 0:
+                crc = zlib.crc32(r.counts.tobytes())
+                div = int(r.divisions.sum())
+            else:
+                ms.append(r.stats["kernel_ms"])
+        print(json.dumps({"config": cfg, "scale": scale, "t_max": w.t_max, "knob": knob, "divisions": div, "crc": crc,
+                          "ms_min": min(ms), "ms_med": statistics.median(ms), "block": r.stats["block"],
+                          "Gdiv_s": div / min(ms) / 1e6}), flush=True)
+        eng.close()
