@@ -80,6 +80,31 @@ def test_result_independent_of_claim_unit(gpu_api, oracle):
         assert np.array_equal(got.counts, ref.counts)
 
 
+@pytest.mark.parametrize("knob", [{"PROCELL_COOP_WARPS": "16"}, {"PROCELL_COOP_WARPS": "24"}, {"PROCELL_COOP_NPL": "2"}])
+def test_result_independent_of_cta_shape(gpu_api, oracle, monkeypatch, knob):
+    """the tuning instances of the cooperative kernel (16 / 24 warps per CTA; 16 warps with 256-node rings expanding
+    two nodes per lane) must give the oracle's tensors too: results do not depend on scheduling.  The knobs are read
+    when the engine is loaded.  Covers the direct and the hashed histogram, spill + donation and the time series."""
+    for k, v in knob.items():
+        monkeypatch.setenv(k, v)
+    w = synth.workload(2, 0.05)
+    _, got, want = _run_both(gpu_api, oracle, w.values, w.freqs, w.phi, w.types, w.t_max, w.seed, 0)
+    assert got.stats["block"] == (768 if knob.get("PROCELL_COOP_WARPS") == "24" else 512)
+    assert np.array_equal(got.counts, want["counts"]) and np.array_equal(got.divisions, want["divisions"])
+    values, freqs = synth.synthetic_histogram(3000)
+    _, got, want = _run_both(gpu_api, oracle, values, freqs, 0.5, synth.sweep_types(1024)[::64], 168.0, 0x5EED0005, 0)
+    assert np.array_equal(got.counts, want["counts"]) and np.array_equal(got.divisions, want["divisions"])
+    _, got, want = _run_both(gpu_api, oracle, np.array([1000.0, 2000.0]), np.array([3, 2], dtype=np.uint64), 1e-7,
+                             np.array([[(1.0, 24.0, 4.0)]]), 420.0, 4, 0)
+    assert np.array_equal(got.counts, want["counts"]) and np.array_equal(got.divisions, want["divisions"])
+    plan = gpu_api.Plan(w.values, w.freqs, w.phi)
+    cps = [60.0, 150.0, 240.0]
+    ts = gpu_api.proliferate(plan, w.types, w.t_max, w.seed, checkpoints=cps)
+    monkeypatch.delenv(next(iter(knob)))
+    ref = gpu_api.proliferate(plan, w.types, w.t_max, w.seed, checkpoints=cps)
+    assert np.array_equal(ts.counts, ref.counts) and np.array_equal(ts.divisions, ref.divisions)
+
+
 def test_edge_cases(gpu_api, oracle):
     # t_max = 0: output histogram == input histogram (every seed is out of time at level 0)
     values, freqs = synth.synthetic_histogram(5000)
