@@ -48,7 +48,8 @@ constexpr int kSmemMusdEntries = 64;  /* (mean, sd) table cached in shared memor
 constexpr int kSmemCtlBytes = 128 + kSmemMusdEntries * 16;    /* control words (64 B) + three 16-byte snapshots of the control block */
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
-/* A node = a cell that WILL divide: 4 x u64, field-major in the ring
+/* A node = a cell that WILL divide: 4 x u64, kept in the ring as two 16-byte pairs (A,B) and (C,D) so that a pop is
+ * two LDS.128 and a push two STS.128; chunks in HBM (spill rings, donation queue) are field-major
  *   A  t_div   time of its division = birth time of its daughters (double bits)
  *   B  heap    tree path: root = 1, daughters 2h and 2h+1 (Philox counter words 2,3)
  *   C  root cell id | key << 32, key = count-tensor index of (set, bin, level of THIS node, type)
@@ -211,22 +212,48 @@ __device__ __noinline__ void watchdog_fire(const SimParams& P, uint32_t gwarp, i
 }
 
 struct WarpCtx {
-    uint64_t *sa, *sb, *sc, *sd;     /* ring fields: t_div bits, heap, root|keybase<<32, D */
+    ulonglong2 *ab, *cd;             /* ring: (t_div bits, heap) pairs and (root|keybase<<32, D) pairs */
     uint32_t bottom, top;            /* ring positions, n = top - bottom */
     unsigned long long* spill;       /* private spill ring */
     uint32_t sp_bottom, sp_top;
     int lane;
 };
 
+__device__ __forceinline__ void ring_load(const WarpCtx& w, uint32_t idx, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d)
+{
+    const ulonglong2 x = w.ab[idx], y = w.cd[idx];
+    a = x.x; b = x.y; c = y.x; d = y.y;
+}
+
+__device__ __forceinline__ void ring_store(WarpCtx& w, uint32_t idx, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
+{
+    w.ab[idx] = make_ulonglong2(a, b);
+    w.cd[idx] = make_ulonglong2(c, d);
+}
+
+/* the same under a predicate, as two predicated STS.128 instead of a branch around four stores */
+__device__ __forceinline__ void ring_store_if(WarpCtx& w, bool p, uint32_t idx, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
+{
+#ifdef PROCELL_BRANCHY_PUSH
+    if (p) ring_store(w, idx, a, b, c, d);
+#else
+    const unsigned sab = (unsigned)__cvta_generic_to_shared(w.ab + idx), scd = (unsigned)__cvta_generic_to_shared(w.cd + idx);
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.v2.u64 [%1], {%2, %3};\n\t@q st.shared.v2.u64 [%4], {%5, %6};\n\t}"
+                 :: "r"((unsigned)p), "r"(sab), "l"(a), "l"(b), "r"(scd), "l"(c), "l"(d) : "memory");
+#endif
+}
+
 template <int RING>
 __device__ __forceinline__ void spill_bottom_chunk(WarpCtx& w, const SimParams& P)
 {
     uint32_t idx = (w.bottom + w.lane) & Ring<RING>::kMask;
     unsigned long long* dst = w.spill + (size_t)(w.sp_top % kSpillCap) * kChunkWords;
-    __stcg(dst + w.lane, w.sa[idx]);
-    __stcg(dst + 32 + w.lane, w.sb[idx]);
-    __stcg(dst + 64 + w.lane, w.sc[idx]);
-    __stcg(dst + 96 + w.lane, w.sd[idx]);
+    uint64_t a, b, c, d;
+    ring_load(w, idx, a, b, c, d);
+    __stcg(dst + w.lane, a);
+    __stcg(dst + 32 + w.lane, b);
+    __stcg(dst + 64 + w.lane, c);
+    __stcg(dst + 96 + w.lane, d);
     w.bottom += kChunkNodes;
     w.sp_top += 1;
     if (w.sp_top - w.sp_bottom > (uint32_t)kSpillCap && w.lane == 0) atomicExch(&P.ctl->status, kStatusSpillOverflow);
@@ -240,10 +267,7 @@ __device__ __forceinline__ void unspill_newest_chunk(WarpCtx& w)
     const unsigned long long* src = w.spill + (size_t)(w.sp_top % kSpillCap) * kChunkWords;
     w.bottom -= kChunkNodes;
     uint32_t idx = (w.bottom + w.lane) & Ring<RING>::kMask;
-    w.sa[idx] = __ldcg(src + w.lane);
-    w.sb[idx] = __ldcg(src + 32 + w.lane);
-    w.sc[idx] = __ldcg(src + 64 + w.lane);
-    w.sd[idx] = __ldcg(src + 96 + w.lane);
+    ring_store(w, idx, __ldcg(src + w.lane), __ldcg(src + 32 + w.lane), __ldcg(src + 64 + w.lane), __ldcg(src + 96 + w.lane));
     __syncwarp();
 }
 
@@ -319,7 +343,7 @@ __device__ __forceinline__ void donate_chunk(WarpCtx& w, const SimParams& P)
         w.sp_bottom += 1;
     } else {
         uint32_t idx = (w.bottom + w.lane) & Ring<RING>::kMask;
-        a = w.sa[idx]; b = w.sb[idx]; c = w.sc[idx]; d = w.sd[idx];
+        ring_load(w, idx, a, b, c, d);
         w.bottom += kChunkNodes;
     }
     __syncwarp();
@@ -350,7 +374,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
             uint64_t a, b, c, d;
             if (!queue_read_ticket(P, w.lane, ticket, a, b, c, d)) return false;     /* watchdog abort */
             uint32_t idx = (w.top + w.lane) & Ring<RING>::kMask;
-            w.sa[idx] = a; w.sb[idx] = b; w.sc[idx] = c; w.sd[idx] = d;
+            ring_store(w, idx, a, b, c, d);
             w.top += kChunkNodes;
             __syncwarp();
             return true;
@@ -409,7 +433,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
             uint64_t a, b, c, d;
             if (!queue_read_ticket(P, w.lane, ticket, a, b, c, d)) return false;     /* watchdog abort */
             uint32_t idx = (w.top + w.lane) & Ring<RING>::kMask;
-            w.sa[idx] = a; w.sb[idx] = b; w.sc[idx] = c; w.sd[idx] = d;
+            ring_store(w, idx, a, b, c, d);
             w.top += kChunkNodes;
             __syncwarp();
             return true;
@@ -540,10 +564,9 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
 #pragma unroll
         for (int s = 0; s < NPL; ++s) {
             const uint32_t idx = (w.top - 1u - 32u * (uint32_t)s - (uint32_t)w.lane) & kMask;
-            t_div[s] = pcs_bits2d(w.sa[idx]);
-            heap[s] = w.sb[idx];
-            pc[s] = w.sc[idx];
-            const uint64_t d = w.sd[idx];
+            uint64_t a, d;
+            ring_load(w, idx, a, heap[s], pc[s], d);
+            t_div[s] = pcs_bits2d(a);
             dlo[s] = (uint32_t)d;
             retry[s] = (uint32_t)(d >> 32);
             const uint32_t set = PLAIN ? 0u : (dlo[s] & 0xFFFFu);
@@ -596,15 +619,11 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
     for (int s = 0; s < NPL; ++s) {
         const uint64_t child_c = ((pc[s] >> 32) + T) << 32 | (pc[s] & 0xFFFFFFFFull);
         const uint64_t child_d = (uint64_t)((dlo[s] | (3u << 28)) - (1u << 22));
-        if (int0[s]) {
-            const uint32_t i0 = (w.top + __popc(b0[s] & lt_mask)) & kMask;
-            w.sa[i0] = pcs_d2bits(tc0[s]); w.sb[i0] = heap[s] * 2ull; w.sc[i0] = child_c; w.sd[i0] = child_d;
-        }
+        const uint32_t i0 = (w.top + __popc(b0[s] & lt_mask)) & kMask;
+        ring_store_if(w, int0[s], i0, pcs_d2bits(tc0[s]), heap[s] * 2ull, child_c, child_d);
         w.top += __popc(b0[s]);
-        if (int1[s]) {
-            const uint32_t i1 = (w.top + __popc(b1[s] & lt_mask)) & kMask;
-            w.sa[i1] = pcs_d2bits(tc1[s]); w.sb[i1] = heap[s] * 2ull + 1ull; w.sc[i1] = child_c; w.sd[i1] = child_d;
-        }
+        const uint32_t i1 = (w.top + __popc(b1[s] & lt_mask)) & kMask;
+        ring_store_if(w, int1[s], i1, pcs_d2bits(tc1[s]), heap[s] * 2ull + 1ull, child_c, child_d);
         w.top += __popc(b1[s]);
     }
 #pragma unroll
@@ -612,8 +631,8 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
         if (br[s]) {   /* a daughter's timer came out <= 0: redraw it in a later iteration (cell.cu:114-118) */
             if (rej[s]) {
                 const uint32_t ir = (w.top + __popc(br[s] & lt_mask)) & kMask;
-                w.sa[ir] = pcs_d2bits(t_div[s]); w.sb[ir] = heap[s]; w.sc[ir] = pc[s];
-                w.sd[ir] = (uint64_t)((dlo[s] & ~(3u << 28)) | (rej[s] << 28)) | ((uint64_t)(retry[s] + 1u) << 32);
+                ring_store(w, ir, pcs_d2bits(t_div[s]), heap[s], pc[s],
+                           (uint64_t)((dlo[s] & ~(3u << 28)) | (rej[s] << 28)) | ((uint64_t)(retry[s] + 1u) << 32));
             }
             w.top += __popc(br[s]);
         }
@@ -672,10 +691,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     ControlBlock* ctl = P.ctl;
 
     WarpCtx w;
-    w.sa = s_stack + (size_t)warp * 4 * kCap;
-    w.sb = w.sa + kCap;
-    w.sc = w.sb + kCap;
-    w.sd = w.sc + kCap;
+    w.ab = reinterpret_cast<ulonglong2*>(s_stack + (size_t)warp * 4 * kCap);
+    w.cd = w.ab + kCap;
     w.bottom = 0; w.top = 0;
     w.spill = P.spill + (size_t)(blockIdx.x * WARPS + warp) * kSpillCap * kChunkWords;
     w.sp_bottom = 0; w.sp_top = 0;
@@ -809,10 +826,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 const unsigned live = __ballot_sync(kFull, so.kind == 2);
                 if (so.kind == 2) {
                     uint32_t idx = (w.top + __popc(live & lt_mask)) & kMask;
-                    w.sa[idx] = pcs_d2bits(so.t_div);
-                    w.sb[idx] = 1ull;
-                    w.sc[idx] = (uint64_t)root | ((uint64_t)so.key << 32);
-                    w.sd[idx] = (uint64_t)pack_dlo(seed_set, so.type, so.kdiv - 1u, 3u);
+                    ring_store(w, idx, pcs_d2bits(so.t_div), 1ull, (uint64_t)root | ((uint64_t)so.key << 32),
+                               (uint64_t)pack_dlo(seed_set, so.type, so.kdiv - 1u, 3u));
                 }
                 w.top += __popc(live);
                 __syncwarp();

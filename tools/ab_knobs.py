@@ -3,7 +3,8 @@
 load the engine (the knobs are read at load time), run REPS times, report min / median kernel_ms and a checksum of
 the count tensor (all settings must agree: results do not depend on scheduling).
 
-  python tools/ab_knobs.py [REPS]      # prints one JSON line per (knob, workload)
+  python tools/ab_knobs.py [REPS] [default,npl2,w16,w24]     # prints one JSON line per (knob, workload)
+  PROCELL_LIB=libprocell_b200_x.so python tools/ab_knobs.py 5 default       # another in-tree build of the library
 """
 import json
 import os
@@ -17,7 +18,9 @@ sys.path.insert(0, str(ROOT))
 from cuda_pro_cell_b200 import api, synth  # noqa: E402
 
 REPS = int(sys.argv[1]) if len(sys.argv) > 1 else 5
-KNOBS = [{}, {"PROCELL_COOP_NPL": "2"}, {"PROCELL_COOP_WARPS": "16"}, {"PROCELL_COOP_WARPS": "24"}]
+ALL_KNOBS = {"default": {}, "npl2": {"PROCELL_COOP_NPL": "2"}, "w16": {"PROCELL_COOP_WARPS": "16"},
+             "w24": {"PROCELL_COOP_WARPS": "24"}}
+KNOBS = [ALL_KNOBS[k] for k in (sys.argv[2].split(",") if len(sys.argv) > 2 else ALL_KNOBS)]
 WORK = [(2, 1.0, 0.0), (3, 0.1, 0.0), (5, 0.1, 0.0), (4, 0.1, 600.0)]
 
 for cfg, scale, t_override in WORK:
@@ -40,7 +43,7 @@ for cfg, scale, t_override in WORK:
                 div = int(r.divisions.sum())
             else:
                 ms.append(r.stats["kernel_ms"])
-        print(json.dumps({"config": cfg, "scale": scale, "t_max": w.t_max, "knob": knob, "divisions": div, "crc": crc,
+        print(json.dumps({"lib": os.environ.get("PROCELL_LIB", "libprocell_b200.so"), "config": cfg, "scale": scale, "t_max": w.t_max, "knob": knob, "divisions": div, "crc": crc,
                           "ms_min": min(ms), "ms_med": statistics.median(ms), "block": r.stats["block"],
                           "Gdiv_s": div / min(ms) / 1e6}), flush=True)
         eng.close()
