@@ -529,6 +529,29 @@ struct DivCount {
     uint32_t set, cnt;      /* divisions of parameter set `set` counted by this lane and not yet flushed */
 };
 
+/* The node rule for both daughters of one division (proliferation.cu:321-380, :404-410) given their standard normals.
+ * FRESH = the node is known to be a first draw with both daughters wanted (retry == 0, mask == 3): the common case,
+ * decided for the whole warp by one vote, drops the forced-timer selects and the wanted-daughter masks. */
+template <bool FRESH>
+__device__ __forceinline__ void classify_daughters(const SimParams& P, double2 ms, uint32_t dlo, uint32_t retry, double t_div,
+                                                   double z0, double z1, bool& int0, bool& int1, uint32_t& rej,
+                                                   uint32_t& leaf_inc, double& tc0, double& tc1)
+{
+    const bool forced = !FRESH && retry >= PCS_MAX_RETRY;      /* 255 redraws failed: the timer is the mean */
+    const double tm0 = forced ? ms.x : pcs_timer(ms.x, ms.y, z0);
+    const double tm1 = forced ? ms.x : pcs_timer(ms.x, ms.y, z1);
+    const bool want0 = FRESH || (dlo & (1u << 28)) != 0u, want1 = FRESH || (dlo & (2u << 28)) != 0u;
+    const bool ok0 = want0 && (tm0 > 0.0 || forced), ok1 = want1 && (tm1 > 0.0 || forced);
+    tc0 = PCS_ADD(t_div, tm0);
+    tc1 = PCS_ADD(t_div, tm1);
+    const bool late0 = tc0 > P.t_max, late1 = tc1 > P.t_max;  /* proliferation.cu:404-410 */
+    const bool deeper = (dlo & (63u << 22)) != 0u;           /* f/2 > phi one level down (:323) */
+    leaf_inc = (uint32_t)(ok0 && late0) + (uint32_t)(ok1 && late1);
+    int0 = ok0 && !late0 && deeper;
+    int1 = ok1 && !late1 && deeper;
+    rej = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
+}
+
 /* ---- DIVIDE iteration: the lanes below `take` pop one node each (newest first), draw ONE Philox block -> one
  * Box-Muller pair -> both daughters' timers, classify the daughters and push the ones that will divide.
  * FULL = all 32 lanes have a node (the common case): straight-line code.  Otherwise the lanes without a node skip the
@@ -553,6 +576,7 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
     pcs_u32x4 blk[NPL];
     double rad2[NPL], sn[NPL], cs[NPL], z0[NPL], z1[NPL];
     const bool mine = FULL || (uint32_t)w.lane < take;
+    bool fresh = false;
 #pragma unroll
     for (int s = 0; s < NPL; ++s) {
         int0[s] = false; int1[s] = false;
@@ -572,6 +596,14 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
             const uint32_t set = PLAIN ? 0u : (dlo[s] & 0xFFFFu);
             blk[s] = pcs_draw_rk((uint32_t)pc[s], set, retry[s], PCS_TAG_DIVISION, heap[s], P.rk);
         }
+#ifndef PROCELL_NO_FRESH_PATH
+        if (FULL) {     /* one vote: are all popped nodes first draws with both daughters wanted? (warp-uniform branch below) */
+            bool f = true;
+#pragma unroll
+            for (int s = 0; s < NPL; ++s) f = f && ((dlo[s] >> 28) | (retry[s] << 4)) == 3u;
+            fresh = __all_sync(kFull, f);
+        }
+#endif
 #pragma unroll
         for (int s = 0; s < NPL; ++s) pcs_normal_pair_polys(blk[s], s_log, 0.0, &rad2[s], &sn[s], &cs[s]);
 #pragma unroll
@@ -581,21 +613,10 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
             const uint32_t set = PLAIN ? 0u : (dlo[s] & 0xFFFFu);
             const uint32_t type = (dlo[s] >> 16) & 63u;
             const double2 ms = musd[set * T + type];          /* generic pointer: shared-memory copy or the HBM table */
-            const bool forced = retry[s] >= PCS_MAX_RETRY;     /* 255 redraws failed: the timer is the mean */
-            const double tm0 = forced ? ms.x : pcs_timer(ms.x, ms.y, z0[s]);
-            const double tm1 = forced ? ms.x : pcs_timer(ms.x, ms.y, z1[s]);
-            const bool want0 = (dlo[s] & (1u << 28)) != 0u, want1 = (dlo[s] & (2u << 28)) != 0u;
-            const bool ok0 = want0 && (tm0 > 0.0 || forced), ok1 = want1 && (tm1 > 0.0 || forced);
-            tc0[s] = PCS_ADD(t_div[s], tm0);
-            tc1[s] = PCS_ADD(t_div[s], tm1);
-            const bool late0 = tc0[s] > P.t_max, late1 = tc1[s] > P.t_max;  /* proliferation.cu:404-410 */
-            const bool deeper = (dlo[s] & (63u << 22)) != 0u;               /* f/2 > phi one level down (:323) */
-            leaf_inc[s] = (uint32_t)(ok0 && late0) + (uint32_t)(ok1 && late1);
-            int0[s] = ok0 && !late0 && deeper;
-            int1[s] = ok1 && !late1 && deeper;
-            rej[s] = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
+            if (fresh) classify_daughters<true>(P, ms, dlo[s], retry[s], t_div[s], z0[s], z1[s], int0[s], int1[s], rej[s], leaf_inc[s], tc0[s], tc1[s]);
+            else classify_daughters<false>(P, ms, dlo[s], retry[s], t_div[s], z0[s], z1[s], int0[s], int1[s], rej[s], leaf_inc[s], tc0[s], tc1[s]);
             leaf_key[s] = (uint32_t)(pc[s] >> 32) + T;
-            const uint32_t first = retry[s] == 0u ? 1u : 0u;   /* a redraw is not another division */
+            const uint32_t first = (fresh || retry[s] == 0u) ? 1u : 0u;   /* a redraw is not another division */
             if (multi_set && first && set != dc.set) {
                 if (dc.cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
                 dc.cnt = 0; dc.set = set;
