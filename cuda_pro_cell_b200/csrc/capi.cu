@@ -250,12 +250,17 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
 
     /* claim unit: 32 seed cells = one SEED iteration of a warp (small units keep the tail balanced: a warp claims
      * a new unit with one atomic whenever its stack runs low); smaller still when there are too few cells to
-     * give every warp of every GPU several units */
+     * give every warp of every GPU several units, larger when there are plenty */
     uint32_t unit = sp->shard_unit;
     if (unit == 0) {
         const double per_warp = (double)plan->n_cells * (double)S / (148.0 * kCoopWarpsMax * 4.0 * P.shard_world);
         unit = 32;
         while (unit > 1 && (double)unit > per_warp) unit >>= 1;
+#ifndef PROCELL_UNIT_MAX
+#define PROCELL_UNIT_MAX 256u
+#endif
+        /* large inputs: up to 256 cells per claim (8 SEED iterations) while every warp still gets 64 units or more */
+        while (unit < PROCELL_UNIT_MAX && (double)unit * 32.0 <= per_warp) unit <<= 1;
     }
     P.unit = unit;
     P.units_per_set = (uint32_t)((plan->n_cells + unit - 1) / unit);

@@ -21,7 +21,7 @@ REPS = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 ALL_KNOBS = {"default": {}, "npl2": {"PROCELL_COOP_NPL": "2"}, "w16": {"PROCELL_COOP_WARPS": "16"},
              "w24": {"PROCELL_COOP_WARPS": "24"}}
 KNOBS = [ALL_KNOBS[k] for k in (sys.argv[2].split(",") if len(sys.argv) > 2 else ALL_KNOBS)]
-WORK = [(2, 1.0, 0.0), (3, 0.1, 0.0), (5, 0.1, 0.0), (4, 0.1, 600.0)]
+WORK = [(2, 1.0, 0.0), (3, 0.1, 0.0), (3, 1.0, 0.0), (5, 0.1, 0.0), (4, 0.1, 600.0)]
 
 for cfg, scale, t_override in WORK:
     w = synth.workload(cfg, scale)

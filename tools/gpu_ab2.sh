@@ -19,10 +19,10 @@ import json
 rows=[json.loads(l) for l in open("gpurun_out/ab_$TAG.jsonl")]
 best={}
 for r in rows:
-    k=(r["config"],r["lib"],json.dumps(r["knob"]))
+    k=(r["config"],r["scale"],r["lib"],json.dumps(r["knob"]))
     best[k]=min(best.get(k,1e9),r["ms_min"])
 crc={}
-for r in rows: crc.setdefault(r["config"],set()).add(r["crc"])
+for r in rows: crc.setdefault((r["config"],r["scale"],r["t_max"]),set()).add((r["crc"],r["divisions"]))
 for k in sorted(best): print(k, "%.4f ms"%best[k])
 print("crc consistent:", all(len(v)==1 for v in crc.values()))
 PY
