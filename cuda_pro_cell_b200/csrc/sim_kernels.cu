@@ -390,14 +390,17 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
         __threadfence();
         atomicSub(&ctl->active, 1);
     }
-    const unsigned long long t0 = global_timer_ns();
-    unsigned backoff = 128;
-    for (;;) {
-        int state = 0;   /* 0 wait, 1 ticket taken, 2 exit */
-        unsigned long long ticket = 0;
-        if (w.lane == 0) {
+    /* The wait itself is lane 0's alone: the other lanes park at the shuffle below and issue nothing, so an idle warp
+     * costs a dozen instructions per poll instead of a warp-wide loop with a collective in it (idle polling was 10 % of
+     * all executed warp instructions of config 2 and competes with the last busy warps for issue slots). */
+    int state = 0;   /* 1 ticket taken, 2 exit */
+    unsigned long long ticket = 0;
+    if (w.lane == 0) {
+        const unsigned long long t0 = global_timer_ns();
+        unsigned backoff = 128;
+        for (;;) {
             if (s_ctl[1]) state = 2;
-            else if (atomicCAS(const_cast<int*>(s_ctl), 0, 1) == 0) {
+            else if (s_ctl[0] == 0 && atomicCAS(const_cast<int*>(s_ctl), 0, 1) == 0) {
                 /* `active` is read (acquire) BEFORE the permit counter: a warp that pushed and then went idle
                  * decremented `active` after its permit became visible, so active == 0 implies every permit is seen */
                 const int act = ld_acquire_s32(&ctl->active);
@@ -424,27 +427,24 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
                 __threadfence_block();
                 atomicExch(const_cast<int*>(s_ctl), 0);
             }
+            if (state != 0) break;
+            __nanosleep(backoff);
+            if (backoff < kIdleBackoffMaxNs) backoff <<= 1;
         }
-        state = __shfl_sync(kFull, state, 0);
-        if (state != 0 && w.lane == 0) {
-            atomicSub(&ctl->idle, 1);
-            atomicAdd(&ctl->idle_ns, global_timer_ns() - t0);
-            atomicAdd(&ctl->idle_waits, 1ull);
-        }
-        if (state == 2) return false;
-        if (state == 1) {
-            ticket = __shfl_sync(kFull, ticket, 0);
-            uint64_t a, b, c, d;
-            if (!queue_read_ticket(P, w.lane, ticket, a, b, c, d)) return false;     /* watchdog abort */
-            uint32_t idx = (w.top + w.lane) & Ring<RING>::kMask;
-            ring_store(w, idx, a, b, c, d);
-            w.top += kChunkNodes;
-            __syncwarp();
-            return true;
-        }
-        __nanosleep(backoff);
-        if (backoff < kIdleBackoffMaxNs) backoff <<= 1;
+        atomicSub(&ctl->idle, 1);
+        atomicAdd(&ctl->idle_ns, global_timer_ns() - t0);
+        atomicAdd(&ctl->idle_waits, 1ull);
     }
+    state = __shfl_sync(kFull, state, 0);
+    if (state == 2) return false;
+    ticket = __shfl_sync(kFull, ticket, 0);
+    uint64_t a, b, c, d;
+    if (!queue_read_ticket(P, w.lane, ticket, a, b, c, d)) return false;     /* watchdog abort */
+    uint32_t idx = (w.top + w.lane) & Ring<RING>::kMask;
+    ring_store(w, idx, a, b, c, d);
+    w.top += kChunkNodes;
+    __syncwarp();
+    return true;
 }
 
 /* result of building one seed cell (cell.cu:25-79 with type == -1, t == 0) */
