@@ -45,7 +45,9 @@ template <int RING> struct Ring {
     static constexpr uint32_t kMask = kCap - 1u;
 };
 constexpr int kSmemMusdEntries = 64;  /* (mean, sd) table cached in shared memory when n_sets * n_types fits */
-constexpr int kSmemCtlBytes = 128 + kSmemMusdEntries * 16;    /* control words (64 B) + three 16-byte snapshots of the control block */
+/* control words (64 B) + three 16-byte snapshots of the control block, then the type tables of small runs:
+ * (mean, sd) 16 B, cumulative proportion 8 B and selection order 1 B per entry */
+constexpr int kSmemCtlBytes = 128 + kSmemMusdEntries * (16 + 8 + 1);
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 /* A node = a cell that WILL divide: 4 x u64, kept in the ring as two 16-byte pairs (A,B) and (C,D) so that a pop is
@@ -472,9 +474,12 @@ __device__ __forceinline__ uint32_t find_bin(const SimParams& P, uint32_t root, 
  * The warp first finds root0's bin with a 32-ary search (every lane probes one boundary, a ballot counts the ones at
  * or below root0: two dependent loads for 1024 bins instead of ten); the lanes whose root lies beyond that bin's end
  * (sparse histograms) finish with a binary search above it. */
-__device__ __forceinline__ uint32_t find_bin_warp(const SimParams& P, uint32_t root0, int lane)
+__device__ __forceinline__ uint32_t find_bin_warp(const SimParams& P, uint32_t root0, int lane, uint32_t hint)
 {
+    /* hint: the bin of the previous SEED iteration's last root when this one continues the same claim unit (roots
+     * ascend within a unit, so bin_start[hint] <= root0 already holds), else 0xFFFFFFFF */
     uint32_t lo = 0, end = P.n_bins;                /* answer for root0 is in [lo, end) */
+    if (hint != 0xFFFFFFFFu && root0 < __ldg(P.bin_start + hint + 1u)) { lo = hint; end = hint + 1u; }
     while (end - lo > 1u) {
         const uint32_t step = (end - lo + 31u) >> 5;
         const uint32_t probe = lo + ((uint32_t)lane + 1u) * step;
@@ -487,8 +492,9 @@ __device__ __forceinline__ uint32_t find_bin_warp(const SimParams& P, uint32_t r
     return lo;
 }
 
+/* cum / sel / musd: the type tables of parameter set `set` (shared-memory copies or the HBM tables) */
 __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* s_log, uint32_t root, uint32_t set,
-                                              uint32_t bin)
+                                              uint32_t bin, const double* cum, const uint8_t* sel, const double2* musd)
 {
     SeedOut o;
     const uint32_t kd = __ldg(P.bin_kdiv + bin);
@@ -496,11 +502,11 @@ __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* 
     pcs_u32x4 w = pcs_draw_rk(root, set, 0u, PCS_TAG_SEED, 0ull, P.rk);
     const double u_type = pcs_u53(w.x, w.y);
     const double u_age = pcs_u53(w.z, w.w);
-    uint32_t j = 0;
-    for (; j + 1 < T; ++j)                                     /* cell.cu:81-104; Q17: none -> last */
-        if (u_type < __ldg(P.type_cum + (size_t)set * T + j)) break;
-    const uint32_t type = __ldg(P.type_sel + (size_t)set * T + j);
-    const double2 ms = __ldg(P.type_musd + (size_t)set * T + type);
+    uint32_t j = T - 1u;                                       /* cell.cu:81-104: the FIRST j with u < cum[j]; Q17: none -> last */
+    for (uint32_t i = T - 1u; i-- > 0u;)                       /* scanned downwards without a break: no divergence */
+        if (u_type < cum[i]) j = i;
+    const uint32_t type = sel[j];
+    const double2 ms = musd[type];
     o.type = type;
     o.kdiv = kd & 63u;
     o.key = (set * P.n_keys + __ldg(P.bin_keybase + bin)) * T + type;
@@ -698,8 +704,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 
     double2* s_musd_buf = reinterpret_cast<double2*>(smem_raw + kLogTabDoubles * 8 + 128);
     const bool musd_cached = P.n_sets * P.n_types <= (uint32_t)kSmemMusdEntries;
-    if (musd_cached && threadIdx.x < P.n_sets * P.n_types) s_musd_buf[threadIdx.x] = __ldg(P.type_musd + threadIdx.x);
+    double* s_cum_buf = reinterpret_cast<double*>(smem_raw + kLogTabDoubles * 8 + 128 + kSmemMusdEntries * 16);
+    uint8_t* s_sel_buf = reinterpret_cast<uint8_t*>(smem_raw + kLogTabDoubles * 8 + 128 + kSmemMusdEntries * 24);
+    if (musd_cached && threadIdx.x < P.n_sets * P.n_types) {
+        s_musd_buf[threadIdx.x] = __ldg(P.type_musd + threadIdx.x);
+        s_cum_buf[threadIdx.x] = __ldg(P.type_cum + threadIdx.x);
+        s_sel_buf[threadIdx.x] = __ldg(P.type_sel + threadIdx.x);
+    }
     const double2* s_musd = musd_cached ? s_musd_buf : P.type_musd;
+    const double* s_cum = musd_cached ? s_cum_buf : P.type_cum;
+    const uint8_t* s_sel = musd_cached ? s_sel_buf : P.type_sel;
     if (threadIdx.x < 2) s_ctl[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < kLogTabDoubles; i += blockDim.x) s_log[i] = __ldg(P.logtab + i);
     if (HASHED) {
@@ -724,6 +738,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     w.lane = lane;
 
     uint32_t seed_cur = 0, seed_end = 0, seed_set = 0;
+    uint32_t seed_hint = 0xFFFFFFFFu;    /* bin of the last root of the previous SEED iteration of the same claim unit */
     /* s_ctl[3]: 1 once the seed-unit cursor has run out; s_ctl[5]: snapshot epoch; s_ctl[6]: batch-refill lock;
      * s_snap: copies of the control block's idle count, permit count and seed cursor, refreshed by one lane of the
      * CTA every few iterations with cp.async and read from shared memory: busy warps never poll HBM. */
@@ -752,6 +767,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 
     for (;;) {
         const uint32_t n = w.top - w.bottom;
+        /* the two uncommon cases - too few nodes for a full iteration, too many for the pushes of one - share one test */
+        if (n - kLow > kCap - 32u * RING - kLow) {
         if (n < kLow) {
             if (w.sp_top != w.sp_bottom) { TRACE(P, GWARP, lane, 41); unspill_newest_chunk<RING>(w); continue; }
             /* RULE: every decision that depends on mutable shared/global state is taken by lane 0 and broadcast.
@@ -834,6 +851,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                     unsigned long long last = first + P.unit;
                     if (last > P.n_cells) last = P.n_cells;
                     seed_cur = (uint32_t)first; seed_end = (uint32_t)last; seed_set = set;
+                    seed_hint = 0xFFFFFFFFu;
                     if (seed_cur >= seed_end) { seed_cur = seed_end; continue; }
                 }
                 /* ---- SEED iteration: one seed cell per lane ---- */
@@ -845,9 +863,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 #ifdef PROCELL_LANE_BINSEARCH
                 const uint32_t bin = find_bin(P, root);
 #else
-                const uint32_t bin = find_bin_warp(P, root - (uint32_t)lane, lane);
+                const uint32_t bin = find_bin_warp(P, root - (uint32_t)lane, lane, seed_hint);
+                seed_hint = __shfl_sync(kFull, bin, 31);
 #endif
-                if (have) so = build_seed(P, s_log, root, seed_set, bin);
+                if (have) {     /* PLAIN: one set, the tables are always the shared-memory copies */
+                    const size_t tab = PLAIN ? 0u : (size_t)seed_set * P.n_types;
+                    so = build_seed(P, s_log, root, seed_set, bin, (PLAIN ? s_cum_buf : s_cum) + tab, (PLAIN ? s_sel_buf : s_sel) + tab,
+                                    (PLAIN ? s_musd_buf : s_musd) + tab);
+                }
                 const unsigned live = __ballot_sync(kFull, so.kind == 2);
                 if (so.kind == 2) {
                     uint32_t idx = (w.top + __popc(live & lt_mask)) & kMask;
@@ -872,28 +895,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 continue;
             }
         }
-        /* an iteration pops 32 * RING nodes at most and pushes twice as many: keep that much room in the ring */
-        if (n > kCap - 32u * RING) { TRACE(P, GWARP, lane, 40); spill_bottom_chunk<RING>(w, P); continue; }
-
-        ++iter;
-        if ((iter & 255u) == 0u) {       /* every 256 iterations: flush the 32-bit division counters, check the watchdog */
-            if (!multi_set) {
-                const uint32_t tot = __reduce_add_sync(kFull, dc.cnt);
-                if (lane == 0 && tot) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions), (unsigned long long)tot);
-                dc.cnt = 0;
-            } else if (dc.cnt > (1u << 30)) {
-                atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
-                dc.cnt = 0;
-            }
-            if (!HASHED && (iter & (kHistFlushIters - 1u)) == 0u) hist_drain(P, s_hist, lane);
-            int late = 0;
-            if (lane == 0) late = global_timer_ns() > *s_deadline;
-            if (__shfl_sync(kFull, late, 0)) {
-                watchdog_fire(P, GWARP, lane, 1, n, w.sp_top - w.sp_bottom, seed_cur, seed_end, iter, 0);
-                break;
-            }
+        else {      /* an iteration pops 32 * RING nodes at most and pushes twice as many: keep that much room in the ring */
+            TRACE(P, GWARP, lane, 40); spill_bottom_chunk<RING>(w, P); continue;
+        }
         }
 
+        ++iter;
         TRACE(P, GWARP, lane, 20);
         const uint32_t take = n < 32u ? n : 32u;
         /* PLAIN: one set and at most 64 types, so the (mean, sd) table is always the shared-memory copy (plain LDS) */
@@ -908,6 +915,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
          * block in HBM/L2 into shared memory: no registers, no waiting, the values simply turn up a little later.
          * Lane 0 reads the snapshot and decides, the warp follows (see RULE above). */
         if ((iter & kProbeMask) == 0u) {
+            if ((iter & 255u) == 0u) {       /* every 256 iterations: flush the 32-bit division counters, check the watchdog */
+                if (!multi_set) {
+                    const uint32_t tot = __reduce_add_sync(kFull, dc.cnt);
+                    if (lane == 0 && tot) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions), (unsigned long long)tot);
+                    dc.cnt = 0;
+                } else if (dc.cnt > (1u << 30)) {
+                    atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
+                    dc.cnt = 0;
+                }
+                if (!HASHED && (iter & (kHistFlushIters - 1u)) == 0u) hist_drain(P, s_hist, lane);
+                int late = 0;
+                if (lane == 0) late = global_timer_ns() > *s_deadline;
+                if (__shfl_sync(kFull, late, 0)) {
+                    watchdog_fire(P, GWARP, lane, 1, n, w.sp_top - w.sp_bottom, seed_cur, seed_end, iter, 0);
+                    break;
+                }
+            }
             int packed = 0;
             if (lane == 0) {
                 if (((iter + (uint32_t)warp * (kProbeMask + 1u)) & 63u) == 0u) {
@@ -981,7 +1005,8 @@ __global__ void __launch_bounds__(kSimpleThreads) k_proliferate_simple(const __g
         const uint32_t set = (uint32_t)(gi / P.n_cells);
         const uint32_t root = (uint32_t)(gi - (unsigned long long)set * P.n_cells);
         if (P.shard_world > 1u && (root / P.unit) % P.shard_world != P.shard_rank) continue;
-        SeedOut so = build_seed(P, s_log, root, set, find_bin(P, root));
+        const size_t tab = (size_t)set * P.n_types;
+        SeedOut so = build_seed(P, s_log, root, set, find_bin(P, root), P.type_cum + tab, P.type_sel + tab, P.type_musd + tab);
         if (so.kind == 1) atomicAdd(counts + so.key, 1ull);
         if (so.kind != 2) continue;
         const double2 ms = __ldg(P.type_musd + (size_t)set * T + so.type);
