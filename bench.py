@@ -9,7 +9,8 @@ ends with ONE NCCL reduce (sum, int64) of the count tensor + division counters t
   value     whole-job divisions/s, tables resident in HBM, CUDA-event time per step summed over K steps (L2 flushed
             between steps, outside the events), max over ranks
   e2e       the same metric through the C ABI with HOST buffers: histogram arrays -> plan -> H2D tables -> kernel ->
-            D2H count tensor -> merged rows, wall-clock per step bracketed by synchronize
+            D2H count tensor -> merged rows, wall-clock over all steps bracketed by synchronize (the host legs of
+            neighbouring steps overlap the kernel)
   roofline  instruction-issue roofline (this path is FP64/INT-issue bound, not HBM/tensor bound - DESIGN.md):
             achieved divisions/s over the RNG-only ceiling kernel measured in the same run; HBM figures for completeness
   cpu_baseline  the CPU oracle (oracle/, a port with the same Philox streams) on this box's host cores
@@ -212,7 +213,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-steps", type=int, default=100)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -296,19 +297,34 @@ def main():
     d2h = (n_counts + 1) * 8
     host_values, host_freqs = w.values.copy(), w.freqs.copy()
     e2e_div = 0
+
+    def merge(done):          # rank 0: count tensor -> merged output rows (what a caller reads)
+        nonlocal e2e_div
+        p_done, host_done = done
+        if rank == 0:
+            p_done.merge_rows(host_done[:n_counts].numpy().reshape(plan.n_keys, n_types))
+            e2e_div += int(host_done[n_counts])
+
     barrier()
     t0 = time.perf_counter()
+    # every step does all of its own work - plan from the host arrays, H2D tables, kernel, reduce, D2H, row merge; the
+    # host legs of neighbouring steps (plan of step i+1, row merge of step i-1) run while kernel i is on the GPU
+    p_next = api.Plan(host_values, host_freqs, w.phi)                      # parser.cu:68-154 work, on the host
+    prev = None
     for i in range(E):
-        p = api.Plan(host_values, host_freqs, w.phi)                       # parser.cu:68-154 work, on the host
+        p = p_next
         eng.load(p, w.types, w.t_max, w.seed + i, shard=shard)             # H2D tables
         eng.run(w.seed + 2000 + i, stream.cuda_stream, buf.data_ptr(), buf.data_ptr() + 8 * n_counts)
         if world > 1:
             dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
+        if i + 1 < E:
+            p_next = api.Plan(host_values, host_freqs, w.phi)
+        if prev is not None:
+            merge(prev)
         host = buf.cpu()                                                   # D2H count tensor + division counter
         eng.finish(stream.cuda_stream, fetch=False)
-        if rank == 0:
-            rf, rr = p.merge_rows(host[:n_counts].numpy().reshape(plan.n_keys, n_types))
-            e2e_div += int(host[n_counts])
+        prev = (p, host)
+    merge(prev)
     barrier()
     t_e2e = time.perf_counter() - t0
     t_e = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
@@ -335,8 +351,8 @@ def main():
                     "frac": per_gpu / ceiling,
                     "peak_source": "k_rng_ceiling measured live: one Philox4x32-10 block + Box-Muller pair + 2 timers per division, no tree/atomics",
                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this workload, from the
-                    # committed capture profiles/r1_coop32_config2_ncu_full.md (tables + count tensor + donated chunks)
-                    "traffic": 1419776 if world == 1 else None,
+                    # committed capture profiles/r1g_coop32_config2_ncu_full.md (tables + count tensor + donated chunks)
+                    "traffic": 774912 if world == 1 else None,
                     "hbm": {"achieved": alg_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
@@ -352,7 +368,8 @@ def main():
                 "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
                 "e2e": {"value": e2e_div / t_e2e if t_e2e > 0 else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "steps": E,
-                        "path": "api.Plan (host) -> procell_engine_load (H2D) -> procell_engine_run -> reduce -> D2H -> merge_rows"},
+                        "path": "api.Plan (host) -> procell_engine_load (H2D) -> procell_engine_run -> reduce -> D2H -> merge_rows; "
+                                "the plan of step i+1 and the row merge of step i-1 overlap kernel i"},
                 "gpu_launches": 2 * K, "kernels_per_step": ["k_queue_init", "k_proliferate_coop"],
                 "clocks": clocks, "roofline": roofline}
         if not args.no_cpu_baseline and world == 1:      # the CPU baseline is timed on rank 0 at N = 1 only

@@ -218,34 +218,37 @@ __device__ __noinline__ void watchdog_fire(const SimParams& P, uint32_t gwarp, i
 }
 
 struct WarpCtx {
-    ulonglong2 *ab, *cd;             /* ring: (t_div bits, heap) pairs and (root|keybase<<32, D) pairs */
+    ulonglong2* ab;                  /* ring: kCap (t_div bits, heap) pairs followed by kCap (root|keybase<<32, D) pairs */
     uint32_t bottom, top;            /* ring positions, n = top - bottom */
     unsigned long long* spill;       /* private spill ring */
     uint32_t sp_bottom, sp_top;
     int lane;
 };
 
+template <int RING>
 __device__ __forceinline__ void ring_load(const WarpCtx& w, uint32_t idx, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d)
 {
-    const ulonglong2 x = w.ab[idx], y = w.cd[idx];
+    const ulonglong2 x = w.ab[idx], y = w.ab[Ring<RING>::kCap + idx];    /* the second half: a constant offset */
     a = x.x; b = x.y; c = y.x; d = y.y;
 }
 
+template <int RING>
 __device__ __forceinline__ void ring_store(WarpCtx& w, uint32_t idx, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
 {
     w.ab[idx] = make_ulonglong2(a, b);
-    w.cd[idx] = make_ulonglong2(c, d);
+    w.ab[Ring<RING>::kCap + idx] = make_ulonglong2(c, d);
 }
 
 /* the same under a predicate, as two predicated STS.128 instead of a branch around four stores */
+template <int RING>
 __device__ __forceinline__ void ring_store_if(WarpCtx& w, bool p, uint32_t idx, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
 {
 #ifdef PROCELL_BRANCHY_PUSH
-    if (p) ring_store(w, idx, a, b, c, d);
+    if (p) ring_store<RING>(w, idx, a, b, c, d);
 #else
-    const unsigned sab = (unsigned)__cvta_generic_to_shared(w.ab + idx), scd = (unsigned)__cvta_generic_to_shared(w.cd + idx);
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.v2.u64 [%1], {%2, %3};\n\t@q st.shared.v2.u64 [%4], {%5, %6};\n\t}"
-                 :: "r"((unsigned)p), "r"(sab), "l"(a), "l"(b), "r"(scd), "l"(c), "l"(d) : "memory");
+    const unsigned sab = (unsigned)__cvta_generic_to_shared(w.ab + idx);
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.v2.u64 [%1], {%2, %3};\n\t@q st.shared.v2.u64 [%1+%6], {%4, %5};\n\t}"
+                 :: "r"((unsigned)p), "r"(sab), "l"(a), "l"(b), "l"(c), "l"(d), "n"(Ring<RING>::kCap * 16u) : "memory");
 #endif
 }
 
@@ -255,7 +258,7 @@ __device__ __forceinline__ void spill_bottom_chunk(WarpCtx& w, const SimParams& 
     uint32_t idx = (w.bottom + w.lane) & Ring<RING>::kMask;
     unsigned long long* dst = w.spill + (size_t)(w.sp_top % kSpillCap) * kChunkWords;
     uint64_t a, b, c, d;
-    ring_load(w, idx, a, b, c, d);
+    ring_load<RING>(w, idx, a, b, c, d);
     __stcg(dst + w.lane, a);
     __stcg(dst + 32 + w.lane, b);
     __stcg(dst + 64 + w.lane, c);
@@ -273,7 +276,7 @@ __device__ __forceinline__ void unspill_newest_chunk(WarpCtx& w)
     const unsigned long long* src = w.spill + (size_t)(w.sp_top % kSpillCap) * kChunkWords;
     w.bottom -= kChunkNodes;
     uint32_t idx = (w.bottom + w.lane) & Ring<RING>::kMask;
-    ring_store(w, idx, __ldcg(src + w.lane), __ldcg(src + 32 + w.lane), __ldcg(src + 64 + w.lane), __ldcg(src + 96 + w.lane));
+    ring_store<RING>(w, idx, __ldcg(src + w.lane), __ldcg(src + 32 + w.lane), __ldcg(src + 64 + w.lane), __ldcg(src + 96 + w.lane));
     __syncwarp();
 }
 
@@ -349,7 +352,7 @@ __device__ __forceinline__ void donate_chunk(WarpCtx& w, const SimParams& P)
         w.sp_bottom += 1;
     } else {
         uint32_t idx = (w.bottom + w.lane) & Ring<RING>::kMask;
-        ring_load(w, idx, a, b, c, d);
+        ring_load<RING>(w, idx, a, b, c, d);
         w.bottom += kChunkNodes;
     }
     __syncwarp();
@@ -380,7 +383,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
             uint64_t a, b, c, d;
             if (!queue_read_ticket(P, w.lane, ticket, a, b, c, d)) return false;     /* watchdog abort */
             uint32_t idx = (w.top + w.lane) & Ring<RING>::kMask;
-            ring_store(w, idx, a, b, c, d);
+            ring_store<RING>(w, idx, a, b, c, d);
             w.top += kChunkNodes;
             __syncwarp();
             return true;
@@ -443,7 +446,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
     uint64_t a, b, c, d;
     if (!queue_read_ticket(P, w.lane, ticket, a, b, c, d)) return false;     /* watchdog abort */
     uint32_t idx = (w.top + w.lane) & Ring<RING>::kMask;
-    ring_store(w, idx, a, b, c, d);
+    ring_store<RING>(w, idx, a, b, c, d);
     w.top += kChunkNodes;
     __syncwarp();
     return true;
@@ -599,7 +602,7 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
         for (int s = 0; s < NPL; ++s) {
             const uint32_t idx = (w.top - 1u - 32u * (uint32_t)s - (uint32_t)w.lane) & kMask;
             uint64_t a, d;
-            ring_load(w, idx, a, heap[s], pc[s], d);
+            ring_load<RING>(w, idx, a, heap[s], pc[s], d);
             t_div[s] = pcs_bits2d(a);
             dlo[s] = (uint32_t)d;
             retry[s] = (uint32_t)(d >> 32);
@@ -651,10 +654,10 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
         const uint64_t child_c = ((pc[s] >> 32) + T) << 32 | (pc[s] & 0xFFFFFFFFull);
         const uint64_t child_d = (uint64_t)((dlo[s] | (3u << 28)) - (1u << 22));
         const uint32_t i0 = (w.top + __popc(b0[s] & lt_mask)) & kMask;
-        ring_store_if(w, int0[s], i0, pcs_d2bits(tc0[s]), heap[s] * 2ull, child_c, child_d);
+        ring_store_if<RING>(w, int0[s], i0, pcs_d2bits(tc0[s]), heap[s] * 2ull, child_c, child_d);
         w.top += __popc(b0[s]);
         const uint32_t i1 = (w.top + __popc(b1[s] & lt_mask)) & kMask;
-        ring_store_if(w, int1[s], i1, pcs_d2bits(tc1[s]), heap[s] * 2ull + 1ull, child_c, child_d);
+        ring_store_if<RING>(w, int1[s], i1, pcs_d2bits(tc1[s]), heap[s] * 2ull + 1ull, child_c, child_d);
         w.top += __popc(b1[s]);
     }
 #pragma unroll
@@ -662,7 +665,7 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
         if (br[s]) {   /* a daughter's timer came out <= 0: redraw it in a later iteration (cell.cu:114-118) */
             if (rej[s]) {
                 const uint32_t ir = (w.top + __popc(br[s] & lt_mask)) & kMask;
-                ring_store(w, ir, pcs_d2bits(t_div[s]), heap[s], pc[s],
+                ring_store<RING>(w, ir, pcs_d2bits(t_div[s]), heap[s], pc[s],
                            (uint64_t)((dlo[s] & ~(3u << 28)) | (rej[s] << 28)) | ((uint64_t)(retry[s] + 1u) << 32));
             }
             w.top += __popc(br[s]);
@@ -731,7 +734,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 
     WarpCtx w;
     w.ab = reinterpret_cast<ulonglong2*>(s_stack + (size_t)warp * 4 * kCap);
-    w.cd = w.ab + kCap;
     w.bottom = 0; w.top = 0;
     w.spill = P.spill + (size_t)(blockIdx.x * WARPS + warp) * kSpillCap * kChunkWords;
     w.sp_bottom = 0; w.sp_top = 0;
@@ -874,7 +876,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 const unsigned live = __ballot_sync(kFull, so.kind == 2);
                 if (so.kind == 2) {
                     uint32_t idx = (w.top + __popc(live & lt_mask)) & kMask;
-                    ring_store(w, idx, pcs_d2bits(so.t_div), 1ull, (uint64_t)root | ((uint64_t)so.key << 32),
+                    ring_store<RING>(w, idx, pcs_d2bits(so.t_div), 1ull, (uint64_t)root | ((uint64_t)so.key << 32),
                                (uint64_t)pack_dlo(seed_set, so.type, so.kdiv - 1u, 3u));
                 }
                 w.top += __popc(live);

@@ -93,9 +93,28 @@ def test_plan_equals_oracle_plan(oracle):
         assert (a.n_bins, a.n_keys, a.n_rows, a.n_cells, a.phi) == (b.n_bins, b.n_keys, b.n_rows, b.n_cells, b.phi)
         assert np.array_equal(a.row_value, b.row_value) and np.array_equal(a.key_row, b.key_row)
         assert np.array_equal(a.bin_keybase, b.bin_keybase) and np.array_equal(a.bin_kdiv, b.bin_kdiv)
+    # the bucketed key ordering (bins by mantissa, keys by exponent) and its fallback to a plain sort: values related by
+    # powers of two (equal key values from different bins must share a row), unsorted and duplicate lines, a huge
+    # dynamic range, subnormal / zero / negative values (fallback), halvings that run into the subnormal range
+    cases = [
+        ([8.0, 4.0, 2.0, 1.0, 3.0, 6.0, 12.0, 1.5], [1] * 8, 0.7),
+        ([1000.0, 10.0, 1000.0, 500.0, 10.0, 2000.0], [3, 1, 2, 5, 7, 1], 3.0),
+        ([1e300, 1e-300, 1.0, 3e150, 7e-200], [1, 2, 3, 4, 5], 1e-305),
+        ([5e-324, 1e-310, 1.0, 4.0], [1, 1, 1, 1], 1e-320),
+        ([0.0, -2.0, 8.0, 16.0], [1, 1, 1, 1], 1.0),
+        ([3e-308, 6e-308, 1.2e-307], [2, 2, 2], 1e-323),
+        (list(rng.uniform(1.0, 2.0, 64) * 2.0 ** rng.integers(-40, 40, 64)), [1] * 64, 1e-9),
+        (list(np.repeat(rng.uniform(1.0, 2.0, 8), 8) * 2.0 ** np.tile(np.arange(8), 8)), [2] * 64, 0.01),
+    ]
+    for v, f, phi in cases:
+        v, f = np.array(v, dtype=np.float64), np.array(f, dtype=np.uint64)
+        a, b = api.Plan(v, f, phi), oracle.OraclePlan(v, f, phi)
+        assert (a.n_bins, a.n_keys, a.n_rows, a.n_cells, a.phi) == (b.n_bins, b.n_keys, b.n_rows, b.n_cells, b.phi)
+        assert np.array_equal(a.row_value, b.row_value) and np.array_equal(a.key_row, b.key_row)
+        assert (np.diff(a.row_value) > 0).all()
     w = synth.workload(2)
     a, b = api.Plan(w.values, w.freqs, w.phi), oracle.OraclePlan(w.values, w.freqs, w.phi)
-    assert np.array_equal(a.key_row, b.key_row) and a.n_keys == b.n_keys
+    assert np.array_equal(a.key_row, b.key_row) and a.n_keys == b.n_keys and np.array_equal(a.row_value, b.row_value)
     counts = rng.integers(0, 9, (a.n_keys, 4)).astype(np.int64)
     rf, rr = a.merge_rows(counts)
     assert int(rf.sum()) == int(counts.sum()) and np.array_equal(rr.sum(axis=1), rf)
