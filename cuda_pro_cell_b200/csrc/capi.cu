@@ -43,7 +43,13 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-const uint64_t kLogRows[1 << PCM_LOG_N_BITS][2] = { PCM_LOG_TABLE_ROWS };
+/* the math table of procell_spec.h: log rows, then sin/cos rows (bit patterns) */
+struct MathTable {
+    uint64_t log_rows[1 << PCM_LOG_N_BITS][2];
+    uint64_t sincos_rows[1 << PCM_SC_N_BITS][2];
+};
+const MathTable kLogRows = { { PCM_LOG_TABLE_ROWS }, { PCM_SINCOS_TABLE_ROWS } };
+static_assert(sizeof(MathTable) == (size_t)kLogTabDoubles * 8, "math table size");
 
 void set_round_keys(SimParams& P, uint64_t seed)
 {
@@ -115,7 +121,7 @@ int procell_engine_create(int device, procell_engine** out)
     en->device = device;
     en->sm_count = prop.multiProcessorCount;
     if (en->logtab.reserve(sizeof(kLogRows)) != cudaSuccess ||
-        cudaMemcpy(en->logtab.p, kLogRows, sizeof(kLogRows), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(en->logtab.p, &kLogRows, sizeof(kLogRows), cudaMemcpyHostToDevice) != cudaSuccess ||
         en->ctl.reserve(sizeof(ControlBlock)) != cudaSuccess ||
         en->q_seq.reserve(sizeof(unsigned long long) * kQueueCap) != cudaSuccess ||
         en->q_data.reserve(sizeof(unsigned long long) * (size_t)kQueueCap * kChunkWords) != cudaSuccess ||
@@ -683,7 +689,7 @@ int procell_rng_ceiling(int device, int iters, double* ms_out, double* pairs_out
     unsigned long long* d_sink = nullptr;
     CU(cudaMalloc(&d_tab, sizeof(kLogRows)), "alloc");
     CU(cudaMalloc(&d_sink, 16), "alloc");
-    CU(cudaMemcpy(d_tab, kLogRows, sizeof(kLogRows), cudaMemcpyHostToDevice), "upload");
+    CU(cudaMemcpy(d_tab, &kLogRows, sizeof(kLogRows), cudaMemcpyHostToDevice), "upload");
     CU(cudaMemset(d_sink, 0, 16), "memset");
     const int block = 256, grid = sms * 6;   /* 6 CTAs of 256 threads per SM fit at 34 registers: one full wave */
     cudaEvent_t e0, e1;

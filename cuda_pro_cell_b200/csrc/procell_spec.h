@@ -175,6 +175,10 @@ PCS_HD double pcs_u53(uint32_t lo, uint32_t hi)
     return pcs_unit_from_mant52((((uint64_t)hi << 32) | (uint64_t)lo) >> 12);
 }
 
+/* the math table every consumer passes as `tab`: 128 log rows {invc, logc}, then 256 sin/cos rows {sin, cos} */
+#define PCS_TAB_SINCOS (2 << PCM_LOG_N_BITS)
+#define PCS_TAB_DOUBLES (PCS_TAB_SINCOS + (2 << PCM_SC_N_BITS))
+
 /* ------------------------------------------------------------------ -2*ln(u), u in (0,1), normal double
  * tab: 128 rows {invc, logc} as 256 doubles (a shared-memory copy on the device).
  * log(u) = k*ln2 + logc_i + log1p(r),  r = z*invc_i - 1,  |r| <= 2^-8,  log1p by Taylor to r^6. */
@@ -201,41 +205,32 @@ PCS_HD double pcs_neg2log(double u, const double* tab)
 }
 
 /* ------------------------------------------------------------------ sin/cos(2*pi*V/2^64) from 64 random bits
- * octant q = top 3 bits; next 52 bits y (complemented in odd octants) -> theta = (pi/4)*(2y+1)*2^-53 in
- * (0, pi/4); Taylor sin to x^15, cos to x^16; octant symmetries by selects and sign flips (exact). */
-PCS_HD void pcs_sincos2pi(uint64_t v, double* s_out, double* c_out)
+ * sector j = top 8 bits (256 sectors of pi/128); the next 52 bits d in [1,2) give the offset from the sector's
+ * CENTRE, delta = fma(d, pi/128, -(3/2 - 2^-53) * pi/128) in (-pi/256, pi/256), never 0.  With the table row
+ * {S, C} = {sin c_j, cos c_j} of the centre angle:
+ *   sin(c+delta) = S + (S*(cos delta - 1) + C*sin delta),  cos(c+delta) = C + (C*(cos delta - 1) - S*sin delta)
+ * sin delta to delta^5 and cos delta - 1 to delta^6 (truncation 8e-18 and 1e-20): 12 FP64 operations and one
+ * 16-byte table load instead of 21 operations and the octant selects of a pi/4 reduction.
+ * tab_sc: 256 rows {sin, cos} as 512 doubles (a shared-memory copy on the device). */
+PCS_HD void pcs_sincos2pi(uint64_t v, const double* tab_sc, double* s_out, double* c_out)
 {
-    uint32_t q = (uint32_t)(v >> 61);
-    uint64_t y = (v >> 9) & 0x000FFFFFFFFFFFFFULL;
-    if (q & 1u) y ^= 0x000FFFFFFFFFFFFFULL;
-    double th = PCS_MUL(pcs_unit_from_mant52(y), PCS_C(PIO4));
-    double t2 = PCS_MUL(th, th);
-    double ps = PCS_C(SIN_S7);
-    ps = PCS_FMA(ps, t2, PCS_C(SIN_S6));
-    ps = PCS_FMA(ps, t2, PCS_C(SIN_S5));
-    ps = PCS_FMA(ps, t2, PCS_C(SIN_S4));
-    ps = PCS_FMA(ps, t2, PCS_C(SIN_S3));
-    ps = PCS_FMA(ps, t2, PCS_C(SIN_S2));
-    ps = PCS_FMA(ps, t2, PCS_C(SIN_S1));
-    double t3 = PCS_MUL(th, t2);
-    double sn = PCS_FMA(t3, ps, th);
-    double pc = PCS_C(COS_C8);
-    pc = PCS_FMA(pc, t2, PCS_C(COS_C7));
-    pc = PCS_FMA(pc, t2, PCS_C(COS_C6));
-    pc = PCS_FMA(pc, t2, PCS_C(COS_C5));
-    pc = PCS_FMA(pc, t2, PCS_C(COS_C4));
-    pc = PCS_FMA(pc, t2, PCS_C(COS_C3));
-    pc = PCS_FMA(pc, t2, PCS_C(COS_C2));
-    pc = PCS_FMA(pc, t2, PCS_C(COS_C1));
-    double cs = PCS_FMA(t2, pc, 1.0);
-    /* q: 0 (s,c) 1 (c,s) 2 (c,-s) 3 (s,-c) 4 (-s,-c) 5 (-c,-s) 6 (-c,s) 7 (-s,c) */
-    bool swap = ((q + 1u) & 2u) != 0u;
-    double a = swap ? cs : sn;
-    double b = swap ? sn : cs;
-    uint64_t sa = (uint64_t)(q >> 2) << 63;                 /* sin negative in octants 4..7 */
-    uint64_t sb = (uint64_t)(((q + 2u) >> 2) & 1u) << 63;   /* cos negative in octants 2..5 */
-    *s_out = pcs_bits2d(pcs_d2bits(a) ^ sa);
-    *c_out = pcs_bits2d(pcs_d2bits(b) ^ sb);
+    uint32_t j = (uint32_t)(v >> (64 - PCM_SC_N_BITS));
+    uint64_t m = (v >> (12 - PCM_SC_N_BITS)) & 0x000FFFFFFFFFFFFFULL;
+    double d = pcs_bits2d(0x3FF0000000000000ULL | m);            /* [1,2) */
+    double dl = PCS_FMA(d, PCS_C(SC_A), PCS_C(SC_B));
+    double d2 = PCS_MUL(dl, dl);
+    double ps = PCS_FMA(PCS_C(SD_S2), d2, PCS_C(SD_S1));
+    double d3 = PCS_MUL(dl, d2);
+    double sd = PCS_FMA(d3, ps, dl);                            /* sin delta */
+    double pc = PCS_FMA(PCS_C(CM_C3), d2, PCS_C(CM_C2));
+    pc = PCS_FMA(pc, d2, PCS_C(CM_C1));
+    double cm = PCS_MUL(pc, d2);                                /* cos delta - 1 */
+    double sj = tab_sc[2 * j];
+    double cj = tab_sc[2 * j + 1];
+    double ts = PCS_FMA(sj, cm, sj);
+    double tc = PCS_FMA(cj, cm, cj);
+    *s_out = PCS_FMA(cj, sd, ts);
+    *c_out = PCS_FMA(-sj, sd, tc);
 }
 
 /* ------------------------------------------------------------------ one Box-Muller pair from one Philox block
@@ -249,7 +244,7 @@ PCS_HD void pcs_normal_pair_polys(pcs_u32x4 w, const double* tab, double u_overr
     double u = pcs_u53(w.x, w.y);
     if (u_override > 0.0) u = u_override;
     *rad2 = pcs_neg2log(u, tab);
-    pcs_sincos2pi(((uint64_t)w.w << 32) | (uint64_t)w.z, s, c);
+    pcs_sincos2pi(((uint64_t)w.w << 32) | (uint64_t)w.z, tab + PCS_TAB_SINCOS, s, c);
 }
 
 PCS_HD void pcs_normal_pair_finish(double rad2, double s, double c, double* z0, double* z1)

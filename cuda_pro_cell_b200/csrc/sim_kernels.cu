@@ -30,6 +30,8 @@
 
 namespace procell_b200 {
 
+static_assert(kLogTabDoubles == PCS_TAB_DOUBLES, "math table size");
+
 namespace {
 
 #ifdef PROCELL_TRACE

@@ -14,7 +14,7 @@ constexpr int kChunkNodes = 32;                /* spill / donation granule: one 
 constexpr int kChunkWords = 4 * kChunkNodes;   /* 4 x u64 fields per node, field-major */
 constexpr int kSpillCap = 128;                 /* private spill ring, chunks per warp */
 constexpr int kQueueCap = 8192;                /* shared donation queue, chunks (power of two) */
-constexpr int kLogTabDoubles = 256;
+constexpr int kLogTabDoubles = 768;           /* math table: 128 log rows {invc, logc} + 256 sin/cos rows (procell_spec.h) */
 constexpr int kSimpleThreads = 128;
 constexpr int kSimpleStack = 136;              /* >= 2*63 + slack entries per thread */
 
@@ -49,7 +49,7 @@ struct SimParams {
     const double* type_cum;       /* running proportion sums in selection order (descending proportion) */
     const uint8_t* type_sel;      /* file id of the j-th type in selection order */
     const double2* type_musd;     /* (mean, sd) by file id */
-    const double* logtab;         /* 128 x {invc, logc} */
+    const double* logtab;         /* the math table: 128 x {invc, logc}, then 256 x {sin, cos} */
     /* outputs */
     long long* counts;            /* [n_sets][n_keys][n_types] */
     long long* divisions;         /* [n_sets] */

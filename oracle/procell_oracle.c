@@ -48,6 +48,7 @@ static double as_f64(uint64_t u) { orc_pun p; p.u = u; return p.d; }
 static uint64_t as_u64(double d) { orc_pun p; p.d = d; return p.u; }
 
 static const uint64_t log_rows[1 << PCM_LOG_N_BITS][2] = { PCM_LOG_TABLE_ROWS };
+static const uint64_t sincos_rows[1 << PCM_SC_N_BITS][2] = { PCM_SINCOS_TABLE_ROWS };
 
 /* ------------------------------------------------------------------------------------------------
  * Philox4x32-10.  ctr[4], key[2]; ten rounds of (mulhi, mullo, xor), key bumped by the Weyl constants.
@@ -114,38 +115,29 @@ double oracle_neg2log(double u)
     return lg * -2.0;
 }
 
-/* sin and cos of 2*pi*v/2^64 */
+/* sin and cos of 2*pi*v/2^64: the circle is cut into 256 sectors; the top 8 bits pick the sector, the next 52 the
+ * offset from the sector's centre angle c, |offset| < pi/256; angle-addition with short series for the offset */
 void oracle_sincos2pi(uint64_t v, double* sin_out, double* cos_out)
 {
-    static const uint64_t S[7] = { PCM_BITS_SIN_S1, PCM_BITS_SIN_S2, PCM_BITS_SIN_S3, PCM_BITS_SIN_S4,
-                                   PCM_BITS_SIN_S5, PCM_BITS_SIN_S6, PCM_BITS_SIN_S7 };
-    static const uint64_t C[8] = { PCM_BITS_COS_C1, PCM_BITS_COS_C2, PCM_BITS_COS_C3, PCM_BITS_COS_C4,
-                                   PCM_BITS_COS_C5, PCM_BITS_COS_C6, PCM_BITS_COS_C7, PCM_BITS_COS_C8 };
-    unsigned oct = (unsigned)(v >> 61);
-    uint64_t frac = (v >> 9) & 0xFFFFFFFFFFFFFull;
-    if (oct & 1) frac = (~frac) & 0xFFFFFFFFFFFFFull;       /* reflect: 1 - y */
-    double theta = unit_from_mantissa(frac) * as_f64(PCM_BITS_PIO4);
-    double x2 = theta * theta;
-    double ps = as_f64(S[6]);
-    for (int j = 5; j >= 0; --j) ps = fma(ps, x2, as_f64(S[j]));
-    double x3 = theta * x2;
-    double sn = fma(x3, ps, theta);
-    double pc = as_f64(C[7]);
-    for (int j = 6; j >= 0; --j) pc = fma(pc, x2, as_f64(C[j]));
-    double cs = fma(x2, pc, 1.0);
-    double s, c;
-    switch (oct) {
-    case 0: s = sn;  c = cs;  break;
-    case 1: s = cs;  c = sn;  break;
-    case 2: s = cs;  c = -sn; break;
-    case 3: s = sn;  c = -cs; break;
-    case 4: s = -sn; c = -cs; break;
-    case 5: s = -cs; c = -sn; break;
-    case 6: s = -cs; c = sn;  break;
-    default: s = -sn; c = cs; break;
-    }
-    *sin_out = s;
-    *cos_out = c;
+    unsigned sector = (unsigned)(v >> 56);
+    uint64_t frac = (v >> 4) & 0xFFFFFFFFFFFFFull;
+    double one_to_two = as_f64(0x3FF0000000000000ull | frac);
+    double off = fma(one_to_two, as_f64(PCM_BITS_SC_A), as_f64(PCM_BITS_SC_B));
+    double off2 = off * off;
+    /* sin(off) = off + off^3 * (S1 + S2 off^2) */
+    double sin_poly = fma(as_f64(PCM_BITS_SD_S2), off2, as_f64(PCM_BITS_SD_S1));
+    double off3 = off * off2;
+    double sin_off = fma(off3, sin_poly, off);
+    /* cos(off) - 1 = off^2 * (C1 + off^2 * (C2 + C3 off^2)) */
+    double cos_poly = fma(as_f64(PCM_BITS_CM_C3), off2, as_f64(PCM_BITS_CM_C2));
+    cos_poly = fma(cos_poly, off2, as_f64(PCM_BITS_CM_C1));
+    double cos_off_m1 = cos_poly * off2;
+    double sin_c = as_f64(sincos_rows[sector][0]);
+    double cos_c = as_f64(sincos_rows[sector][1]);
+    double sin_part = fma(sin_c, cos_off_m1, sin_c);      /* sin c * cos off */
+    double cos_part = fma(cos_c, cos_off_m1, cos_c);      /* cos c * cos off */
+    *sin_out = fma(cos_c, sin_off, sin_part);
+    *cos_out = fma(-sin_c, sin_off, cos_part);
 }
 
 /* one Philox block -> two independent standard normals; u_forced > 0 replaces the radius uniform */

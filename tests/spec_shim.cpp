@@ -3,7 +3,9 @@
  * the header the kernels include states the same operation sequence as the oracle (bit-for-bit). */
 #include "../cuda_pro_cell_b200/csrc/procell_spec.h"
 
-static const uint64_t kRows[1 << PCM_LOG_N_BITS][2] = { PCM_LOG_TABLE_ROWS };
+static const struct { uint64_t log_rows[1 << PCM_LOG_N_BITS][2]; uint64_t sincos_rows[1 << PCM_SC_N_BITS][2]; } kTab =
+    { { PCM_LOG_TABLE_ROWS }, { PCM_SINCOS_TABLE_ROWS } };
+static const double* const kRows = reinterpret_cast<const double*>(&kTab);
 
 extern "C" {
 void shim_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out)
@@ -17,12 +19,12 @@ void shim_draw(uint32_t root, uint32_t set, uint32_t retry, uint32_t tag, uint64
     out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = o.w;
 }
 double shim_u53(uint32_t lo, uint32_t hi) { return pcs_u53(lo, hi); }
-double shim_neg2log(double u) { return pcs_neg2log(u, reinterpret_cast<const double*>(kRows)); }
-void shim_sincos2pi(uint64_t v, double* s, double* c) { pcs_sincos2pi(v, s, c); }
+double shim_neg2log(double u) { return pcs_neg2log(u, kRows); }
+void shim_sincos2pi(uint64_t v, double* s, double* c) { pcs_sincos2pi(v, kRows + PCS_TAB_SINCOS, s, c); }
 void shim_normal_pair(const uint32_t* w, double u_forced, double* z)
 {
     pcs_u32x4 b; b.x = w[0]; b.y = w[1]; b.z = w[2]; b.w = w[3];
-    pcs_normal_pair(b, reinterpret_cast<const double*>(kRows), u_forced, &z[0], &z[1]);
+    pcs_normal_pair(b, kRows, u_forced, &z[0], &z[1]);
 }
 double shim_timer(double mean, double sd, double z) { return pcs_timer(mean, sd, z); }
 }

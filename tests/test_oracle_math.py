@@ -65,15 +65,17 @@ def test_neg2log_accuracy(oracle):
         assert abs(got - want) <= mpmath.mpf(2) ** -51 * want + mpmath.mpf("2e-18"), u
 
 
-def test_sincos_accuracy_all_octants(oracle):
+def test_sincos_accuracy_all_sectors(oracle):
+    """sin/cos(2 pi v / 2^64): 8 sector bits + 52 offset bits, offset = fma(d, pi/128, -(3/2 - 2^-53) pi/128)"""
     rng = np.random.default_rng(11)
     worst = 0.0
     vs = [int(x) for x in rng.integers(0, 2**64, 4000, dtype=np.uint64)]
-    vs += [q << 61 for q in range(8)] + [(q << 61) | ((1 << 61) - 1) for q in range(8)]
+    vs += [j << 56 for j in range(256)] + [(j << 56) | ((1 << 56) - 1) for j in range(256)]
+    vs += [(j << 56) | (1 << 55) for j in range(0, 256, 7)]
     for v in vs:
         s, c = oracle.sincos2pi(v)
-        q, y = v >> 61, (v >> 9) & ((1 << 52) - 1)
-        ang = (mpmath.mpf(q) + mpmath.mpf(2 * y + 1) / 2**53) * mpmath.pi / 4
+        j, m = v >> 56, (v >> 4) & ((1 << 52) - 1)
+        ang = (mpmath.mpf(j) + mpmath.mpf(2 * m + 1) / 2**53) * mpmath.pi / 128      # the angle the bits stand for
         worst = max(worst, float(abs(mpmath.sin(ang) - s)), float(abs(mpmath.cos(ang) - c)))
         assert abs(s * s + c * c - 1.0) < 1e-15
     assert worst < 3e-16
