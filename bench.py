@@ -351,8 +351,8 @@ def main():
                     "frac": per_gpu / ceiling,
                     "peak_source": "k_rng_ceiling measured live: one Philox4x32-10 block + Box-Muller pair + 2 timers per division, no tree/atomics",
                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this workload, from the
-                    # committed capture profiles/r1g_coop32_config2_ncu_full.md (tables + count tensor + donated chunks)
-                    "traffic": 774912 if world == 1 else None,
+                    # committed capture profiles/r1h_coop32_config2_ncu_full.md (tables + count tensor + donated chunks)
+                    "traffic": 777216 if world == 1 else None,
                     "hbm": {"achieved": alg_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
