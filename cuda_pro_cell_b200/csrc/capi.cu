@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -389,7 +390,9 @@ int procell_engine_finish(procell_engine* en, void* stream_v, int64_t* counts, i
                     msg += " | active " + std::to_string(cbs.active) + " idle " + std::to_string(cbs.idle) + " avail " +
                            std::to_string(cbs.avail) + " cursor " + std::to_string(cbs.cursor) + " head " +
                            std::to_string(cbs.q_head) + " tail " + std::to_string(cbs.q_tail) + " status " + std::to_string(cbs.status);
+                    cudaStreamDestroy(side);
                 }
+                cudaEventDestroy(done);
                 return fail(PROCELL_ERR_OVERFLOW, msg);
             }
             std::this_thread::sleep_for(std::chrono::milliseconds(1));
@@ -520,9 +523,15 @@ struct NcclApi {
     int (*GroupEnd)() = nullptr;
     int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
-    bool load()
+    std::once_flag once;
+    bool ok = false;
+    bool load()     /* thread-safe: the library is looked up once per process */
     {
-        if (handle) return true;
+        std::call_once(once, [this] { ok = load_once(); });
+        return ok;
+    }
+    bool load_once()
+    {
         handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (!handle) return false;
