@@ -7,17 +7,18 @@
  * The reference materialises every tree level densely in HBM (N*2^d 40-byte cells) and recurses by one
  * dynamic-parallelism launch per block per level.  Here nothing but the count tensor ever reaches HBM:
  *
- * k_proliferate_coop - persistent, one CTA per SM, 16 warps.  Each warp owns a 128-node ring in shared
- *   memory.  An iteration is warp-uniform: either SEED (32 lanes build 32 seed cells: type pick, first timer,
- *   initial age; living roots are pushed) or DIVIDE (32 lanes pop the 32 newest = deepest nodes, each draws ONE
- *   Philox block -> one Box-Muller pair -> both daughters' timers, classifies the daughters as leaf / dropped /
- *   internal and pushes the internal ones).  While a warp holds fewer than 32 nodes every node is expanded each
- *   iteration (the breadth-first warm-up); from 32 on, expansion is depth-first, and the ring overflows in
- *   32-node chunks into a private spill ring in HBM.  Starving warps are fed through a bounded MPMC queue of
- *   chunks that busy warps fill from the BOTTOM of their stacks (the shallowest nodes = the largest subtrees).
- *   Leaves are counted in a shared-memory u32 histogram keyed (bin, k, type) with __match_any_sync aggregation;
- *   u32 slots cannot wrap: every warp drains the CTA's table into the int64 tensor in HBM every 2^20 of its own
- *   DIVIDE iterations (see kHistFlushIters), the rest is flushed at the end.
+ * k_proliferate_coop - persistent, one CTA per SM, 32 warps (16 / 24 as tuning shapes).  Each warp owns a 128-node
+ *   ring in shared memory.  An iteration is warp-uniform: either SEED (32 lanes build 32 seed cells: bin, type,
+ *   first timer, initial age; living roots are pushed) or DIVIDE (32 lanes pop the 32 newest = deepest nodes, each
+ *   draws ONE Philox block -> one Box-Muller pair -> both daughters' timers, classifies the daughters as leaf /
+ *   dropped / internal and pushes the internal ones with predicated 16-byte stores).  While a warp holds fewer than
+ *   32 nodes every node is expanded each iteration (the breadth-first warm-up); from 32 on, expansion is depth-first,
+ *   and the ring overflows in 32-node chunks into a private spill ring in HBM.  Starving warps are fed through a
+ *   bounded MPMC queue of chunks that busy warps fill from the BOTTOM of their stacks (the shallowest nodes = the
+ *   largest subtrees).  Leaves are counted in a shared-memory histogram keyed (bin, k, type): a u32 table with one
+ *   fire-and-forget atomic per lane when the key space fits (the slots cannot wrap: every warp drains the CTA's
+ *   table into the int64 tensor in HBM every 2^20 of its own DIVIDE iterations, see kHistFlushIters), else a
+ *   direct-mapped {key, count} cache updated after __match_any_sync merging; the rest is flushed at the end.
  *
  * k_proliferate_simple - one thread per lineage with a local-memory stack and global atomics: the bring-up
  *   kernel, kept as an independent device-side cross-check of the cooperative one.
