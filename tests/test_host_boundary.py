@@ -161,3 +161,64 @@ def test_cli_messages_match_the_reference(tmp_path):
     assert (r.returncode, r.stdout) == (1, "ERROR: proportion distribution of cell types does not sum to 1, aborting.\n")
     r = _cli("-h", str(tmp_path / "nope"), "-c", str(c), "-t", "5")
     assert r.returncode == 1 and "cannot open histogram file" in r.stdout
+
+
+_REF_BIN = ROOT / "oracle" / "_ref" / "procell_ref"
+
+_CLI_CASES = [
+    ["--bogus"], ["-x"], ["extra"], ["-t", "5", "extra"], ["--bogus", "--help"],
+    ["-h"], ["-h", "a", "-h", "b"], ["--histogram", "a", "-h", "b"], ["-c"], ["-c", "a", "--cell-types", "b"],
+    ["-t"], ["-t", "-3"], ["-t", "abc"], ["-t", "-0"], ["-t", "1e3x"], ["-t", "0", "-t", "1"], ["-t", "1.5", "--time-max", "2"],
+    ["-p"], ["-p", "0"], ["-p", "-1"], ["-p", "abc"], ["-p", "1e-400"], ["-p", "1", "--phi-min", "2"],
+    ["-d"], ["-d", "0"], ["-d", "24"], ["-d", "x"], ["-d", "3.7"], ["-d", "23", "-d", "2"],
+    ["-r", "-r"], ["-r", "--track-ratio"], ["-o"], ["-o", "x", "-o", "y"], ["--output-histogram", "x", "-o", "y"],
+    [], ["-o", "x"], ["-h", "a"], ["-h", "a", "-c", "b"], ["-p", "1"], ["-h", "a", "-c", "b", "-p", "1"],
+    ["-h", "a", "-t", "5", "-p", "1"], ["-c", "b", "-t", "5", "-p", "1"],
+]
+
+
+@pytest.mark.skipif(not _REF_BIN.exists(), reason="the reference binary is built only where /root/reference exists (make -C oracle ref)")
+@pytest.mark.parametrize("argv", _CLI_CASES, ids=lambda a: " ".join(a) or "(none)")
+def test_cli_rejections_equal_the_reference_binary(argv):
+    """Every command line the reference rejects BEFORE it touches CUDA (cmdargs.cpp:11-76 runs first, main.cu:18-24)
+    is fed to the unmodified reference binary and to `procell`: same stdout, same exit status.  The one deliberate
+    difference: -p is optional here, as the reference's README documents (README.md:98-102), so the reference's
+    "--phi-min (-p)" line in the list of missing arguments has no counterpart."""
+    ref = subprocess.run([str(_REF_BIN)] + argv, capture_output=True, text=True, timeout=60)
+    new = _cli(*argv)
+    want = "".join(l for l in ref.stdout.splitlines(keepends=True) if l != "--phi-min (-p)\n")
+    if want == "The following missing arguments are required:\n":     # only -p was missing there: not an error here
+        pytest.skip("the reference rejects this line for the missing -p alone")
+    assert ref.returncode == 1 and ref.stderr == ""
+    assert (new.returncode, new.stdout, new.stderr) == (1, want, "")
+
+
+_TYPE_FILES = [          # (text of the cell-types file, does its proportion column sum to 1 within 1e-8 as read?)
+    ("0.5 10 1\n0.5 20 2\n", True), ("0.5 10 1\n0.50000001 20 2\n", True), ("0.5 10 1\n0.500000011 20 2\n", False),
+    ("0.5 10 1\n0.49999999 20 2\n", True), ("0.5 10 1\n0.499999989 20 2\n", False), ("0.1 1 1\n0.2 1 1\n0.7 -1 -1\n", True),
+    ("1 10 1\n", True), ("", False), ("0.5 10\n", False), ("0.5 10 1 0.5 20 2", True), ("0.5 10 1\nx 1 1\n0.5 2 2\n", False),
+    ("0.25 1 1\n0.25 1 1\n0.25 1 1\n0.25 1 1 trailing", True), ("1e0 5 5\n", True), ("0.3 1 1\n0.3 1 1\n0.4\n", False),
+]
+
+
+@pytest.mark.skipif(not _REF_BIN.exists(), reason="the reference binary is built only where /root/reference exists (make -C oracle ref)")
+@pytest.mark.parametrize("text,sums", _TYPE_FILES)
+def test_proportion_check_equals_the_reference_binary(tmp_path, text, sums):
+    """The reference reads both files and checks the proportions (parser.cu:46-66,156-185) before its first CUDA call,
+    so on a box without a GPU its verdict on a cell-types file is observable: rejected with the message on stdout and
+    status 1, or accepted (it then dies in its first CUDA call).  `procell` must draw the same line at 1e-8."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("on a GPU box the reference would run the simulation")
+    h, c = tmp_path / "h.txt", tmp_path / "c.txt"
+    h.write_text("10 5\n")
+    c.write_text(text)
+    argv = ["-h", str(h), "-c", str(c), "-t", "5", "-p", "1"]
+    ref = subprocess.run([str(_REF_BIN)] + argv, capture_output=True, text=True, timeout=60)
+    new = _cli(*argv)
+    msg = "ERROR: proportion distribution of cell types does not sum to 1, aborting.\n"
+    assert ((ref.returncode, ref.stdout) == (1, msg)) == (not sums)
+    if sums:
+        assert new.returncode == 1 and "no CUDA device" in new.stdout and msg not in new.stdout
+    else:
+        assert (new.returncode, new.stdout) == (1, msg)
