@@ -27,7 +27,10 @@ def kernels(lib):
             continue
         mi = re.match(r'^\s*/\*[0-9a-f]{4,}\*/\s+(.*?);', l)
         if mi and name:
-            res[name].append(re.sub(r'`\(\.L_x_\d+\)', 'L', mi.group(1)).strip())
+            insn = re.sub(r'`\(\.L_x_\d+\)', 'L', mi.group(1)).strip()
+            # names of anonymous-namespace callees carry a hash of the source PATH: the same code built in another
+            # directory must still compare equal
+            res[name].append(re.sub(r'(_INTERNAL_|_GLOBAL__N__)[0-9a-f]{8}_', r'\1', insn))
     return res
 
 
