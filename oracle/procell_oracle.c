@@ -304,6 +304,8 @@ typedef struct {
     int refcompat;
     int64_t* counts;        /* [n_keys][n_types] for this set, type index = file order */
     int64_t divisions;
+    /* subtree sharding (shard_level L >= 1, world > 1): see oracle_simulate */
+    uint32_t sub_level, sub_world, sub_rank;
 } orc_ctx;
 
 /* truncated-normal timers for the children in `want` (bit c = child c) of the division at `heap` */
@@ -349,8 +351,12 @@ static void expand_root(orc_ctx* cx, uint32_t root, unsigned bin)
         acc += cx->types[j].prop;
         if (u_type < acc) { ty = &cx->types[j]; break; }
     }
+    /* with subtree sharding every rank walks the first sub_level levels of EVERY lineage; what those levels count
+     * is credited to one rank only, root % world */
+    const int sub = cx->sub_level > 0;
+    const int low_owner = !sub || root % cx->sub_world == cx->sub_rank;
     if (ty->mean < 0.0) {                                 /* quiescent: timer = -1, t = 0 -> out_of_time */
-        count_leaf(cx, bin, 0, ty->id);
+        if (low_owner) count_leaf(cx, bin, 0, ty->id);
         return;
     }
     double timer[2];
@@ -358,7 +364,7 @@ static void expand_root(orc_ctx* cx, uint32_t root, unsigned bin)
     division_timers(cx, root, 0ull, ty, 2u, cx->refcompat ? u_type : 0.0, timer);
     double t0 = timer[1] * u_age;                         /* cell.cu:124-143: t = timer * U' */
     double t_div = t0 + timer[1];
-    if (t_div > cx->t_max) { count_leaf(cx, bin, 0, ty->id); return; }     /* proliferation.cu:404-410 */
+    if (t_div > cx->t_max) { if (low_owner) count_leaf(cx, bin, 0, ty->id); return; }     /* proliferation.cu:404-410 */
     if (p->bin_kdiv[bin] == 0) return;                    /* f/2 <= phi: silently dropped (Q6) */
 
     orc_node stack[2 * ORC_MAX_LEVEL + 4];
@@ -367,13 +373,19 @@ static void expand_root(orc_ctx* cx, uint32_t root, unsigned bin)
     while (sp > 0) {
         orc_node nd = stack[--sp];
         unsigned level = 63u - (unsigned)__builtin_clzll(nd.heap);
-        cx->divisions += 1;
+        /* a node below the shard level is expanded by every rank and credited to one; from the shard level on a node
+         * exists on one rank only */
+        const int credit = !sub || level >= cx->sub_level || low_owner;
+        if (credit) cx->divisions += 1;
         division_timers(cx, root, nd.heap, ty, 3u, 0.0, timer);
         for (unsigned c = 0; c < 2; ++c) {
             double t_child = nd.t_div + timer[c];         /* child.t = parent.t + parent.timer; + own timer */
-            if (t_child > cx->t_max) count_leaf(cx, bin, level + 1, ty->id);
+            if (t_child > cx->t_max) { if (credit) count_leaf(cx, bin, level + 1, ty->id); }
             else if (level + 1 < p->bin_kdiv[bin]) {
-                stack[sp].heap = 2 * nd.heap + c; stack[sp].t_div = t_child; ++sp;
+                const uint64_t child = 2 * nd.heap + c;
+                /* the subtree under a node AT the shard level belongs to rank (root + heap) mod world */
+                if (sub && level + 1 == cx->sub_level && (root + (uint32_t)child) % cx->sub_world != cx->sub_rank) continue;
+                stack[sp].heap = child; stack[sp].t_div = t_child; ++sp;
             }
             /* else: alive, in time, f/2 <= phi -> vanishes uncounted */
         }
@@ -382,12 +394,19 @@ static void expand_root(orc_ctx* cx, uint32_t root, unsigned bin)
 
 /* counts: [n_sets][n_keys][n_types] int64 (zeroed here); divisions: [n_sets].
  * types: [n_sets][n_types][3] = proportion, mean, sd in FILE order.
- * Roots in [root_begin, root_end) with (root / shard_unit) % shard_world == shard_rank are simulated. */
+ * shard_level == 0: roots in [root_begin, root_end) with (root / shard_unit) % shard_world == shard_rank are simulated
+ *   (whole lineages per rank).
+ * shard_level == L >= 1 (subtree sharding, SURVEY 8e: "for config 4 subtree granularity is required for balance"):
+ *   every rank builds every seed cell and expands every node of tree level < L (root = level 0); level-0 leaves and
+ *   the divisions and leaves of nodes below level L are credited to rank root % world; a daughter AT level L that will
+ *   divide is kept by rank (root + heap) % world alone, and everything under it is that rank's.  The ranks' tensors
+ *   sum to the unsharded result because the random stream is keyed by (root, tree path), not by who expands a node. */
 int oracle_simulate(const oracle_plan* p, const double* types, size_t n_types, size_t n_sets, double t_max,
                     uint64_t seed, int refcompat, uint64_t root_begin, uint64_t root_end,
-                    uint32_t shard_unit, uint32_t shard_world, uint32_t shard_rank, int n_threads,
+                    uint32_t shard_unit, uint32_t shard_world, uint32_t shard_rank, uint32_t shard_level, int n_threads,
                     int64_t* counts, int64_t* divisions)
 {
+    if (shard_level > 62) return -3;
     if (n_types == 0 || n_types > 64 || n_sets == 0 || n_sets > 65536) return -1;
     if (p->n_cells > 0xFFFFFFFFull) return -2;
     if (root_end > p->n_cells) root_end = p->n_cells;
@@ -410,6 +429,7 @@ int oracle_simulate(const oracle_plan* p, const double* types, size_t n_types, s
             orc_ctx cx;
             cx.plan = p; cx.types = sorted; cx.n_types = n_types; cx.set = (uint32_t)s; cx.t_max = t_max;
             cx.seed = seed; cx.refcompat = refcompat; cx.divisions = 0;
+            cx.sub_level = shard_world > 1 ? shard_level : 0; cx.sub_world = shard_world; cx.sub_rank = shard_rank;
             cx.counts = (int64_t*)calloc(per_set ? per_set : 1, sizeof(int64_t));
 #pragma omp for schedule(dynamic, 1)
             for (size_t b = 0; b < p->n_bins; ++b) {
@@ -417,7 +437,7 @@ int oracle_simulate(const oracle_plan* p, const double* types, size_t n_types, s
                 if (lo < root_begin) lo = root_begin;
                 if (hi > root_end) hi = root_end;
                 for (uint64_t r = lo; r < hi; ++r) {
-                    if ((r / shard_unit) % shard_world != shard_rank) continue;
+                    if (!cx.sub_level && (r / shard_unit) % shard_world != shard_rank) continue;
                     expand_root(&cx, (uint32_t)r, (unsigned)b);
                 }
             }

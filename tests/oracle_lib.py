@@ -52,7 +52,7 @@ def lib():
         L.oracle_check_proportions.argtypes = [_f64p, C.c_size_t]
         L.oracle_check_proportions.restype = C.c_int
         L.oracle_simulate.argtypes = [C.c_void_p, _f64p, C.c_size_t, C.c_size_t, C.c_double, C.c_uint64, C.c_int,
-                                      C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                                      C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
                                       _i64p, _i64p]
         L.oracle_simulate.restype = C.c_int
         L.oracle_merge_rows.argtypes = [C.c_void_p, _i64p, C.c_size_t, _i64p, _i64p]
@@ -109,8 +109,9 @@ class OraclePlan:
 
 
 def simulate(plan: OraclePlan, types, t_max, seed, refcompat=False, root_begin=0, root_end=None,
-             shard=(0, 1, 1), n_threads=0):
-    """types: array [n_sets][n_types][3] or [n_types][3]; shard = (rank, world, unit).  Returns dict(counts[S,K,T], divisions[S],
+             shard=(0, 1, 1), n_threads=0, shard_level=0):
+    """types: array [n_sets][n_types][3] or [n_types][3]; shard = (rank, world, unit); shard_level >= 1 selects subtree
+    sharding (every rank walks the first levels of every lineage, see oracle_simulate).  Returns dict(counts[S,K,T], divisions[S],
     row_freq[S,R], row_ratio[S,R,T])."""
     t = np.ascontiguousarray(types, dtype=np.float64)
     if t.ndim == 2:
@@ -122,7 +123,7 @@ def simulate(plan: OraclePlan, types, t_max, seed, refcompat=False, root_begin=0
         root_end = plan.n_cells
     rc = lib().oracle_simulate(plan.h, t.ctypes.data_as(_f64p), n_types, n_sets, float(t_max), C.c_uint64(seed),
                                int(bool(refcompat)), C.c_uint64(root_begin), C.c_uint64(root_end),
-                               int(shard[2]) or 1, int(shard[1]) or 1, int(shard[0]), int(n_threads),
+                               int(shard[2]) or 1, int(shard[1]) or 1, int(shard[0]), int(shard_level), int(n_threads),
                                counts.ctypes.data_as(_i64p), divisions.ctypes.data_as(_i64p))
     if rc != 0:
         raise RuntimeError("oracle_simulate failed rc=%d" % rc)

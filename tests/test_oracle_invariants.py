@@ -95,6 +95,33 @@ def test_shards_partition_the_run(oracle):
         assert sum(int(x["divisions"][0]) for x in parts) == int(whole["divisions"][0])
 
 
+def test_subtree_shards_partition_the_run_and_balance_deep_trees(oracle):
+    """Subtree sharding (oracle_simulate, shard_level >= 1): every rank walks the first levels of every
+    lineage, a subtree at the shard level belongs to one rank.  The ranks' tensors sum to the unsharded run for any
+    level and world size - also when the level is deeper than the trees - and on the config-4 shape (1 % of the seed
+    cells own almost all divisions) the busiest rank carries a few per cent more than the mean instead of ~40 %."""
+    v, f, p = _plan(oracle, 3000, 0.5)
+    whole = oracle.simulate(p, [synth.TYPES_CONFIG2], 200.0, 6)
+    for world, level in ((2, 1), (3, 2), (8, 5), (5, 40)):
+        parts = [oracle.simulate(p, [synth.TYPES_CONFIG2], 200.0, 6, shard=(r, world, 32), shard_level=level) for r in range(world)]
+        assert np.array_equal(sum(x["counts"] for x in parts), whole["counts"])
+        assert sum(int(x["divisions"][0]) for x in parts) == int(whole["divisions"][0])
+        assert all(int(x["divisions"][0]) > 0 for x in parts)
+    v, f = synth.synthetic_histogram(10000)
+    p = oracle.OraclePlan(v, f, 1e-7)
+    whole = oracle.simulate(p, [synth.TYPES_CONFIG4], 300.0, 0x5EED0004)
+
+    def busiest_over_mean(level):
+        parts = [oracle.simulate(p, [synth.TYPES_CONFIG4], 300.0, 0x5EED0004, shard=(r, 8, 32), shard_level=level) for r in range(8)]
+        assert np.array_equal(sum(x["counts"] for x in parts), whole["counts"])
+        d = [int(x["divisions"][0]) for x in parts]
+        assert sum(d) == int(whole["divisions"][0])
+        return max(d) * 8 / sum(d)
+
+    by_lineage, by_subtree = busiest_over_mean(0), busiest_over_mean(6)
+    assert by_lineage > 1.25 and by_subtree < 1.05, (by_lineage, by_subtree)
+
+
 def test_seed_and_set_change_the_stream_but_not_the_law(oracle):
     v, f, p = _plan(oracle, 20000, 1.0)
     a = oracle.simulate(p, [synth.TYPES_CONFIG1], 168.0, 100)
