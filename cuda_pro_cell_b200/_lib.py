@@ -22,7 +22,7 @@ class SimParams(C.Structure):
     _fields_ = [("types", C.POINTER(CellType)), ("n_types", C.c_size_t), ("n_sets", C.c_size_t),
                 ("t_max", C.c_double), ("seed", C.c_uint64), ("seeding_mode", C.c_int), ("kernel", C.c_int),
                 ("shard_rank", C.c_uint32), ("shard_world", C.c_uint32), ("shard_unit", C.c_uint32),
-                ("checkpoints", C.POINTER(C.c_double)), ("n_checkpoints", C.c_size_t)]
+                ("checkpoints", C.POINTER(C.c_double)), ("n_checkpoints", C.c_size_t), ("shard_level", C.c_uint32)]
 
 
 class RunStats(C.Structure):

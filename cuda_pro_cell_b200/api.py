@@ -149,7 +149,7 @@ class Plan:
             pass
 
 
-def _make_params(types: np.ndarray, t_max, seed, seeding_mode, kernel, shard, checkpoints=None):
+def _make_params(types: np.ndarray, t_max, seed, seeding_mode, kernel, shard, checkpoints=None, shard_level=0):
     n_sets, n_types, _ = types.shape
     p = SimParams()
     if checkpoints is not None:
@@ -165,6 +165,7 @@ def _make_params(types: np.ndarray, t_max, seed, seeding_mode, kernel, shard, ch
     p.seeding_mode = int(seeding_mode)
     p.kernel = int(kernel)
     p.shard_rank, p.shard_world, p.shard_unit = int(shard[0]), int(shard[1]), int(shard[2])
+    p.shard_level = int(shard_level)
     return p
 
 
@@ -183,12 +184,13 @@ def _stats_dict(st: RunStats) -> dict:
 
 
 def proliferate(plan: Plan, types, t_max: float, seed: int = 0x5EED0000, seeding_mode: int = SEEDING_IDEAL,
-                kernel: int = KERNEL_COOP, device: int = 0, shard=(0, 1, 0), checkpoints=None) -> Result:
+                kernel: int = KERNEL_COOP, device: int = 0, shard=(0, 1, 0), checkpoints=None, shard_level: int = 0) -> Result:
     """One-shot host-buffer call (what the CLI uses).  shard = (rank, world, unit).  With `checkpoints` (ascending,
-    at most 8; the last replaces t_max) counts gets a leading checkpoint axis."""
+    at most 8; the last replaces t_max) counts gets a leading checkpoint axis.  shard_level >= 1 (with world > 1)
+    shards subtrees at that tree level instead of whole lineages (procell_sim_params.shard_level)."""
     lib = _lib.load()
     t = _types_array(types)
-    p = _make_params(t, t_max, seed, seeding_mode, kernel, shard, checkpoints)
+    p = _make_params(t, t_max, seed, seeding_mode, kernel, shard, checkpoints, shard_level)
     shape = (t.shape[0], plan.n_keys, t.shape[1])
     if checkpoints is not None:
         shape = (len(checkpoints),) + shape
@@ -201,11 +203,12 @@ def proliferate(plan: Plan, types, t_max: float, seed: int = 0x5EED0000, seeding
 
 
 def proliferate_multi(plan: Plan, types, t_max: float, seed: int = 0x5EED0000, n_gpus: int = 0,
-                      seeding_mode: int = SEEDING_IDEAL, kernel: int = KERNEL_COOP) -> Result:
-    """One process, n_gpus GPUs of this box (0 = all): sharded seed-cell units + one NCCL reduce onto GPU 0."""
+                      seeding_mode: int = SEEDING_IDEAL, kernel: int = KERNEL_COOP, shard_level: int = 0) -> Result:
+    """One process, n_gpus GPUs of this box (0 = all): sharded seed-cell units (or, with shard_level >= 1, subtrees at
+    that tree level) + one NCCL reduce onto GPU 0."""
     lib = _lib.load()
     t = _types_array(types)
-    p = _make_params(t, t_max, seed, seeding_mode, kernel, (0, 1, 0))
+    p = _make_params(t, t_max, seed, seeding_mode, kernel, (0, 1, 0), None, shard_level)
     shape = (t.shape[0], plan.n_keys, t.shape[1])
     flat = np.zeros(max(int(np.prod(shape)), 1), dtype=np.int64)
     div = np.zeros(t.shape[0], dtype=np.int64)
@@ -228,9 +231,9 @@ class Engine:
         self.shape = None
 
     def load(self, plan: Plan, types, t_max: float, seed: int = 0x5EED0000, seeding_mode: int = SEEDING_IDEAL,
-             kernel: int = KERNEL_COOP, shard=(0, 1, 0), checkpoints=None) -> None:
+             kernel: int = KERNEL_COOP, shard=(0, 1, 0), checkpoints=None, shard_level: int = 0) -> None:
         t = _types_array(types)
-        p = _make_params(t, t_max, seed, seeding_mode, kernel, shard, checkpoints)
+        p = _make_params(t, t_max, seed, seeding_mode, kernel, shard, checkpoints, shard_level)
         check(_lib.load().procell_engine_load(self.h, plan.h, C.byref(p)))
         self.plan = plan
         self.seed = seed

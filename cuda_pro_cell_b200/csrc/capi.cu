@@ -167,6 +167,9 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     if ((double)M * (double)S * (double)K * (double)T >= 4294967296.0)
         return fail(PROCELL_ERR_ARG, "n_checkpoints * n_sets * n_keys * n_types must be below 2^32");
     if (sp->shard_world > 1 && sp->shard_rank >= sp->shard_world) return fail(PROCELL_ERR_ARG, "shard_rank >= shard_world");
+    const bool subtree = sp->shard_level > 0 && sp->shard_world > 1;
+    if (subtree && (sp->shard_level > 30 || S != 1 || M != 1 || sp->kernel != PROCELL_KERNEL_COOP))
+        return fail(PROCELL_ERR_ARG, "subtree sharding needs shard_level <= 30, the cooperative kernel, one parameter set and one checkpoint");
     for (size_t s = 0; s < S; ++s) {
         int rc = procell_check_proportions(sp->types + s * T, T);
         if (rc != PROCELL_OK) return rc;
@@ -246,8 +249,11 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     P.q_data = (unsigned long long*)en->q_data.p;
     P.n_bins = (uint32_t)B; P.n_types = (uint32_t)T; P.n_sets = (uint32_t)S; P.n_keys = (uint32_t)K;
     P.n_cells = (uint32_t)plan->n_cells;
-    P.shard_world = sp->shard_world > 1 ? sp->shard_world : 1;
-    P.shard_rank = sp->shard_world > 1 ? sp->shard_rank : 0;
+    P.shard_world = (sp->shard_world > 1 && !subtree) ? sp->shard_world : 1;
+    P.shard_rank = (sp->shard_world > 1 && !subtree) ? sp->shard_rank : 0;
+    P.sub_world = subtree ? sp->shard_world : 1;      /* subtree sharding: every GPU claims every seed unit */
+    P.sub_rank = subtree ? sp->shard_rank : 0;
+    P.sub_limit = subtree ? 1ull << sp->shard_level : 0ull;
     P.refcompat = sp->seeding_mode == PROCELL_SEEDING_REFCOMPAT;
     P.t_max = times[M - 1];
     P.n_times = (uint32_t)M;
@@ -303,6 +309,7 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         const char* renv = getenv("PROCELL_COOP_NPL");       /* tuning knob: 2 = 16 warps, two nodes per lane */
         en->ring = (renv && atoi(renv) == 2) ? 2 : 1;
         if (en->ring == 2) en->warps = 16;
+        if (subtree) { en->warps = 32; en->ring = 1; }       /* the subtree-sharding instances exist in the product shape only */
         const size_t fixed = coop_smem_bytes(en->warps, en->ring, 0, 0);
         const size_t room = (size_t)max_smem > fixed ? (size_t)max_smem - fixed : 0;
         if (en->counts_len * 4 <= room) {            /* the whole key space fits: direct u32 table */
@@ -316,7 +323,8 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         }
         en->smem = coop_smem_bytes(en->warps, en->ring, P.smem_hist_slots, P.hist_hashed);
         int grid = 0;
-        CU(coop_max_grid(en->device, en->warps, en->ring, P.hist_hashed, (P.n_sets == 1u && P.n_times == 1u) ? 1 : 0, en->smem, &grid), "occupancy query");
+        if (subtree) CU(coop_max_grid_subtree(en->device, P.hist_hashed, en->smem, &grid), "occupancy query");
+        else CU(coop_max_grid(en->device, en->warps, en->ring, P.hist_hashed, (P.n_sets == 1u && P.n_times == 1u) ? 1 : 0, en->smem, &grid), "occupancy query");
         if (grid <= 0) return fail(PROCELL_ERR_CUDA, "cooperative kernel does not fit on this device");
         en->grid = grid;
         en->block = en->warps * 32;

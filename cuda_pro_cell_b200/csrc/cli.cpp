@@ -8,7 +8,7 @@
  * (README.md:98-102; the reference code wrongly requires it, cmdargs.cpp:48-49), default = smallest value
  * with a non-zero frequency (parser.cu:80-96).  -d/--tree-depth (1..23) is accepted and ignored: it only
  * sized the reference's dense level arrays.  Extensions (not in the reference): --seed, --seeding,
- * --kernel, --device, --gpus, --checkpoints, --stats.
+ * --kernel, --device, --gpus, --shard-level, --checkpoints, --stats.
  */
 #include <cstdio>
 #include <cstdlib>
@@ -31,6 +31,7 @@ struct Args {
     int kernel = PROCELL_KERNEL_COOP;
     int device = 0;
     int gpus = 1;
+    int shard_level = 0;
     std::vector<double> checkpoints;
 };
 
@@ -50,6 +51,7 @@ void usage()
         "      --kernel coop|simple\n"
         "      --device N               CUDA device index\n"
         "      --gpus N                 shard the seed cells over N GPUs of this box (0 = all), one NCCL reduce\n"
+        "      --shard-level L          with --gpus: shard SUBTREES at tree level L instead of whole lineages (deep trees)\n"
         "      --checkpoints T1,T2,...  also write the histogram at these earlier times (FILE.t<T>), one tree expansion\n"
         "      --stats                  print run statistics as JSON on stderr\n";
 }
@@ -144,6 +146,10 @@ extern "C" int procell_main(int argc, char** argv)
         } else if (s == "--gpus" && i < argc - 1) {
             a.gpus = atoi(argv[++i]);
             r = 1;
+        } else if (s == "--shard-level" && i < argc - 1) {
+            a.shard_level = atoi(argv[++i]);
+            if (a.shard_level < 0 || a.shard_level > 30) { std::cout << "Option --shard-level requires an integer value >= 0 && <= 30" << std::endl; return 1; }
+            r = 1;
         } else if (s == "--checkpoints" && i < argc - 1) {
             /* extension: histograms at several times from one expansion; -o FILE gets the last one, FILE.t<time> the others */
             std::string list = argv[++i];
@@ -194,7 +200,7 @@ extern "C" int procell_main(int argc, char** argv)
         procell_sim_params sp;
         memset(&sp, 0, sizeof sp);
         sp.types = types; sp.n_types = n_types; sp.n_sets = 1; sp.t_max = a.t_max; sp.seed = a.seed;
-        sp.seeding_mode = a.seeding; sp.kernel = a.kernel;
+        sp.seeding_mode = a.seeding; sp.kernel = a.kernel; sp.shard_level = (uint32_t)a.shard_level;
         if (!a.checkpoints.empty()) {
             if (a.checkpoints.back() != a.t_max) a.checkpoints.push_back(a.t_max);     /* -t is always the last one */
             sp.checkpoints = a.checkpoints.data();

@@ -575,7 +575,7 @@ __device__ __forceinline__ void classify_daughters(const SimParams& P, double2 m
  * NPL = nodes per lane: 1, or 2 in the 16-warp instance with 256-node rings (RING = 2), where lane l expands the
  * nodes top-1-l and top-33-l in one straight-line pass: two independent arithmetic chains for the scheduler to
  * interleave, and the per-iteration overhead (loop control, constant loads, probes) is paid once per 64 divisions. */
-template <bool FULL, bool HASHED, bool PLAIN, int RING, int NPL>
+template <bool FULL, bool HASHED, bool PLAIN, int RING, int NPL, bool SUBTREE>
 __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P, const double* s_log, uint32_t* s_hist,
                                                  const double2* musd, uint32_t take, unsigned lt_mask, bool multi_set,
                                                  DivCount& dc)
@@ -632,7 +632,19 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
             if (fresh) classify_daughters<true>(P, ms, dlo[s], retry[s], t_div[s], z0[s], z1[s], int0[s], int1[s], rej[s], leaf_inc[s], tc0[s], tc1[s]);
             else classify_daughters<false>(P, ms, dlo[s], retry[s], t_div[s], z0[s], z1[s], int0[s], int1[s], rej[s], leaf_inc[s], tc0[s], tc1[s]);
             leaf_key[s] = (uint32_t)(pc[s] >> 32) + T;
-            const uint32_t first = (fresh || retry[s] == 0u) ? 1u : 0u;   /* a redraw is not another division */
+            uint32_t first = (fresh || retry[s] == 0u) ? 1u : 0u;   /* a redraw is not another division */
+            if (SUBTREE && heap[s] < P.sub_limit) {
+                /* subtree sharding: a node below the shard level is expanded by EVERY GPU (same stream, same outcome);
+                 * its division and the leaves among its daughters are credited to GPU root % world only, and of its
+                 * daughters AT the shard level this GPU keeps the ones with (root + heap) % world == rank */
+                const uint32_t root = (uint32_t)pc[s];
+                if (root % P.sub_world != P.sub_rank) { leaf_inc[s] = 0u; first = 0u; }
+                if (heap[s] >= (P.sub_limit >> 1)) {
+                    const uint32_t h0 = root + (uint32_t)heap[s] * 2u;
+                    int0[s] = int0[s] && h0 % P.sub_world == P.sub_rank;
+                    int1[s] = int1[s] && (h0 + 1u) % P.sub_world == P.sub_rank;
+                }
+            }
             if (multi_set && first && set != dc.set) {
                 if (dc.cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
                 dc.cnt = 0; dc.set = set;
@@ -696,10 +708,12 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
 
 }  // namespace
 
-template <int WARPS, bool HASHED, bool PLAIN, int RING>
+/* SUBTREE: the subtree-sharding rule of multi-GPU runs of deep trees (SimParams::sub_world > 1) compiled in */
+template <int WARPS, bool HASHED, bool PLAIN, int RING, bool SUBTREE>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid_constant__ SimParams P)
 {
     static_assert(RING == 1 || RING == 2, "ring of 128 or 256 nodes per warp");
+    static_assert(!SUBTREE || (PLAIN && RING == 1), "subtree sharding: one parameter set, one checkpoint, one node per lane");
     constexpr uint32_t kCap = Ring<RING>::kCap, kMask = Ring<RING>::kMask;
     constexpr uint32_t kLow = 32u * RING;        /* below this many nodes a warp looks for seed cells / spilled chunks first */
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -885,7 +899,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 w.top += __popc(live);
                 __syncwarp();
                 if (PLAIN || P.n_times == 1u) {
-                    warp_count_leaves<HASHED>(P, s_hist, so.key, so.kind == 1 ? 1u : 0u);
+                    /* subtree sharding: every GPU builds every seed cell, GPU root % world counts its level-0 leaf */
+                    const bool credit = !SUBTREE || root % P.sub_world == P.sub_rank;
+                    warp_count_leaves<HASHED>(P, s_hist, so.key, (so.kind == 1 && credit) ? 1u : 0u);
                 } else {        /* a seed cell exists from the start: out of time at every checkpoint before t_div */
                     for (uint32_t j = 0; j < P.n_times; ++j) {
                         const uint32_t inc = (have && so.count0 && (so.quiescent || P.times[j] < so.t_div)) ? 1u : 0u;
@@ -910,9 +926,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         const uint32_t take = n < 32u ? n : 32u;
         /* PLAIN: one set and at most 64 types, so the (mean, sd) table is always the shared-memory copy (plain LDS) */
         const double2* musd = PLAIN ? s_musd_buf : s_musd;
-        if (RING == 2 && n >= 64u) divide_iteration<true, HASHED, PLAIN, RING, RING>(w, P, s_log, s_hist, musd, 64u, lt_mask, multi_set, dc);
-        else if (take == 32u) divide_iteration<true, HASHED, PLAIN, RING, 1>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc);
-        else divide_iteration<false, HASHED, PLAIN, RING, 1>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc);
+        if (RING == 2 && n >= 64u) divide_iteration<true, HASHED, PLAIN, RING, RING, SUBTREE>(w, P, s_log, s_hist, musd, 64u, lt_mask, multi_set, dc);
+        else if (take == 32u) divide_iteration<true, HASHED, PLAIN, RING, 1, SUBTREE>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc);
+        else divide_iteration<false, HASHED, PLAIN, RING, 1, SUBTREE>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc);
 
         /* hunger probe, every 8th iteration (every 4th costs 1.8 % on config 2).  The CTA keeps a snapshot of "how many warps are starving", "how many
          * donated chunks are waiting" and "where is the seed cursor" in shared memory.  Every 64th iteration
@@ -1100,10 +1116,10 @@ size_t coop_smem_bytes(int warps, int ring, uint32_t hist_slots, int hashed)
 template <int WARPS, bool HASHED, bool PLAIN, int RING>
 static cudaError_t coop_max_grid_t(int device, size_t smem_bytes, int* grid_out)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_proliferate_coop<WARPS, HASHED, PLAIN, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k_proliferate_coop<WARPS, HASHED, PLAIN, RING, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     int per_sm = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<WARPS, HASHED, PLAIN, RING>, WARPS * 32, smem_bytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<WARPS, HASHED, PLAIN, RING, false>, WARPS * 32, smem_bytes);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
@@ -1111,7 +1127,7 @@ static cudaError_t coop_max_grid_t(int device, size_t smem_bytes, int* grid_out)
     return cudaSuccess;
 }
 
-/* the 16 instances: CTA shape (32 / 24 / 16 warps with 128-node rings, 16 warps with 256-node rings and two nodes
+/* the 16 instances without the subtree-sharding rule: CTA shape (32 / 24 / 16 warps with 128-node rings, 16 warps with 256-node rings and two nodes
  * per lane) x histogram mode x PLAIN */
 #define COOP_DISPATCH(warps, ring, hashed, plain, X)                                                  \
     do {                                                                                             \
@@ -1136,12 +1152,33 @@ cudaError_t coop_max_grid(int device, int warps, int ring, int hashed, int plain
     return cudaErrorInvalidValue;
 }
 
+cudaError_t coop_max_grid_subtree(int device, int hashed, size_t smem_bytes, int* grid_out)
+{
+    int per_sm = 0, sms = 0;
+    cudaError_t e = hashed ? cudaFuncSetAttribute(k_proliferate_coop<32, true, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)
+                           : cudaFuncSetAttribute(k_proliferate_coop<32, false, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = hashed ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<32, true, true, 1, true>, 1024, smem_bytes)
+               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<32, false, true, 1, true>, 1024, smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    *grid_out = per_sm * sms;
+    return cudaSuccess;
+}
+
 cudaError_t launch_coop(const SimParams& p, int warps, int ring, int grid, cudaStream_t stream)
 {
     if (ring == 2 && warps != 16) return cudaErrorInvalidValue;
     const size_t smem = coop_smem_bytes(warps, ring, p.smem_hist_slots, p.hist_hashed);
     const bool plain = coop_is_plain(p);
-#define X(W, H, PL, R) k_proliferate_coop<W, H, PL, R><<<grid, W * 32, smem, stream>>>(p)
+    if (p.sub_world > 1u) {
+        if (warps != 32 || ring != 1 || !plain) return cudaErrorInvalidValue;
+        if (p.hist_hashed) k_proliferate_coop<32, true, true, 1, true><<<grid, 1024, smem, stream>>>(p);
+        else k_proliferate_coop<32, false, true, 1, true><<<grid, 1024, smem, stream>>>(p);
+        return cudaGetLastError();
+    }
+#define X(W, H, PL, R) k_proliferate_coop<W, H, PL, R, false><<<grid, W * 32, smem, stream>>>(p)
     COOP_DISPATCH(warps, ring, p.hist_hashed, plain, X);
 #undef X
     return cudaGetLastError();

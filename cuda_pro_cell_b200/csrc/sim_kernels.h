@@ -85,6 +85,13 @@ struct SimParams {
     uint32_t n_times;             /* 1..8 */
     uint32_t time_stride;         /* n_sets * n_keys * n_types */
     double times[8];              /* ascending */
+    /* subtree sharding (deep trees): appended LAST so that the parameter-block offsets of everything above -
+     * and with them the machine code of the other kernel instances - stay as they are.  sub_world > 1: this GPU builds
+     * EVERY seed cell and expands every node whose heap index is below sub_limit = 2^L (tree level < L); what those
+     * nodes count is credited to GPU root % sub_world; a daughter at level L that will divide is kept by GPU
+     * (root + heap) % sub_world alone.  shard_world / shard_rank are 1 / 0 in this mode. */
+    uint32_t sub_world, sub_rank;
+    unsigned long long sub_limit;
 };
 
 /* ring = 1: 128-node ring per warp, one node per lane and iteration (warps = 32, 24 or 16);
@@ -92,6 +99,9 @@ struct SimParams {
 size_t coop_smem_bytes(int warps, int ring, uint32_t hist_slots, int hashed);
 cudaError_t launch_coop(const SimParams& p, int warps, int ring, int grid, cudaStream_t stream);
 cudaError_t coop_max_grid(int device, int warps, int ring, int hashed, int plain, size_t smem_bytes, int* grid_out);
+/* the subtree-sharding instances (p.sub_world > 1): 32 warps, 128-node rings, one parameter set, one checkpoint;
+ * launch_coop picks them by p.sub_world */
+cudaError_t coop_max_grid_subtree(int device, int hashed, size_t smem_bytes, int* grid_out);
 cudaError_t launch_simple(const SimParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_queue_init(unsigned long long* q_seq, ControlBlock* ctl, cudaStream_t stream);
 cudaError_t launch_rng_ceiling(int grid, int block, int iters, const double* logtab, double mean, double sd,

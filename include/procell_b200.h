@@ -98,6 +98,13 @@ typedef struct procell_sim_params {
      * [m][n_sets][n_keys][n_types]; slice j equals a run with t_max = checkpoints[j] and the same seed, bit for bit. */
     const double* checkpoints;
     size_t n_checkpoints;
+    /* subtree sharding (extension; multi-GPU runs of DEEP trees, where a handful of lineages own all the work and
+     * sharding whole lineages leaves the GPUs unevenly loaded): 0 = off, the rule above.  L >= 1 with shard_world > 1:
+     * every GPU builds every seed cell and expands every node of tree level < L (cheap: at most 2^L nodes per
+     * lineage); what those nodes count is credited to GPU root % shard_world; a daughter at level L that will divide
+     * is kept by GPU (root + heap index) % shard_world alone.  The GPUs' tensors still sum to the single-GPU result
+     * bit for bit.  Needs the cooperative kernel, one parameter set, one checkpoint, L <= 30; shard_unit is ignored. */
+    uint32_t shard_level;
 } procell_sim_params;
 
 typedef struct procell_run_stats {

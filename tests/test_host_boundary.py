@@ -222,3 +222,35 @@ def test_proportion_check_equals_the_reference_binary(tmp_path, text, sums):
         assert new.returncode == 1 and "no CUDA device" in new.stdout and msg not in new.stdout
     else:
         assert (new.returncode, new.stdout) == (1, msg)
+
+
+def test_python_structs_match_the_c_header(tmp_path):
+    """ctypes mirrors of the C-ABI structs against the header itself: a C program prints sizeof / offsetof of every
+    struct that crosses the boundary by pointer; a field added on one side only would shift everything behind it."""
+    import shutil
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    structs = {"procell_cell_type": _lib.CellType, "procell_sim_params": _lib.SimParams, "procell_run_stats": _lib.RunStats,
+               "procell_input": _lib.SimInput, "procell_output": _lib.SimOutput}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "procell_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["return 0;", "}"]
+    src, exe = tmp_path / "abi.c", tmp_path / "abi"
+    src.write_text("\n".join(lines))
+    subprocess.run([cc, "-std=c11", "-I", str(ROOT / "include"), "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, "%s.%s" % (cname, fname)
+    # and the header has no field the mirror lacks: same number of members (counted from the header text)
+    header = (ROOT / "include" / "procell_b200.h").read_text()
+    for cname, cls in structs.items():
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), header, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        members = [d for decl in body.split(";") if decl.strip() for d in decl.split(",")]
+        assert len(members) == len(cls._fields_), "%s: header has %d members, the ctypes mirror %d" % (cname, len(members), len(cls._fields_))

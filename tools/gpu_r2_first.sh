@@ -1,0 +1,32 @@
+#!/bin/bash
+# First GPU visit after a session without GPU access (round 1 ended with the GPU budget spent).
+#   gpurun --timeout 900 -- 'bash tools/gpu_r2_first.sh'            (1 GPU)
+#   gpurun --gpus 8 --timeout 600 -- 'bash tools/gpu_r2_first.sh 8'  (adds the multi-GPU legs)
+# 1. the regular parity suite (the 16 kernel instances of round 1 are byte-identical, tools/sass_same.py)
+# 2. the code paths that have never run on a GPU (PROCELL_TEST_NEW=1): subtree sharding
+# 3. bench line; 4. with 8 GPUs: config 4 at full size, lineage sharding vs subtree sharding at level 6
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+N=${1:-1}
+export PROCELL_WATCHDOG_S=60
+timeout 300 python -m pytest tests -m gpu -x -q --timeout 120 > gpurun_out/pytest_gpu_r2a.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_r2a.log
+PROCELL_TEST_NEW=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 120 -k "subtree" > gpurun_out/pytest_gpu_r2a_new.log 2>&1; echo "pytest (new paths) rc=$?"; tail -5 gpurun_out/pytest_gpu_r2a_new.log
+timeout 300 python bench.py --steps 200 --warmup 5 > gpurun_out/bench_r2a.json 2> gpurun_out/bench_r2a.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/bench_r2a.json
+if [ "$N" -ge 2 ]; then
+cat > /tmp/sub.py <<'PY'
+import sys, time, json; sys.path.insert(0, '.')
+import numpy as np
+from cuda_pro_cell_b200 import api, synth
+n = int(sys.argv[1])
+w = synth.workload(4, 1.0)
+plan = api.Plan(w.values, w.freqs, w.phi)
+out = {}
+for level in (0, 4, 6, 8):
+    api.proliferate_multi(plan, w.types, 400.0, w.seed, n_gpus=n, shard_level=level)          # warm-up (contexts, NCCL)
+    t = time.time(); r = api.proliferate_multi(plan, w.types, w.t_max, w.seed, n_gpus=n, shard_level=level); dt = time.time() - t
+    out[level] = dict(wall_s=dt, kernel_ms=r.stats["kernel_ms"], divisions=int(r.divisions.sum()), checksum=int((r.counts * np.arange(1, r.counts.size + 1).reshape(r.counts.shape) % 1000003).sum()))
+    print(level, out[level], flush=True)
+json.dump(out, open("gpurun_out/config4_subtree_%dgpu.json" % n, "w"), indent=1)
+PY
+timeout 400 python /tmp/sub.py $N 2>&1 | tail -6
+fi
