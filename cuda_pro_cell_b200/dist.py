@@ -25,6 +25,17 @@ def owner_of_seed(root: int, world: int, unit: int = DEFAULT_SHARD_UNIT) -> int:
     return (root // unit) % world
 
 
+def owner_of_shared_node(root: int, world: int) -> int:
+    """Subtree sharding (procell_sim_params.shard_level = L >= 1): every rank expands the nodes of tree level < L; what
+    they count (level-0 leaves, their divisions, the leaves among their daughters) is credited to this rank."""
+    return root % world
+
+
+def owner_of_subtree(root: int, heap: int, world: int) -> int:
+    """... and a daughter at level L (heap index in [2^L, 2^(L+1))) that will divide is kept by this rank alone."""
+    return ((root + (heap & 0xFFFFFFFF)) & 0xFFFFFFFF) % world
+
+
 def packed_buffer(n_sets: int, n_keys: int, n_types: int, device) -> torch.Tensor:
     """counts [n_sets*n_keys*n_types] followed by divisions [n_sets]: one tensor, so one collective."""
     return torch.zeros(n_sets * n_keys * n_types + n_sets, dtype=torch.int64, device=device)

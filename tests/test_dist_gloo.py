@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, shard_level=0):
     sys.path.insert(0, str(ROOT))
     sys.path.insert(0, str(ROOT / "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -34,7 +34,7 @@ def _worker(rank, world, port, out_path):
     plan = oracle_lib.OraclePlan(w.values, w.freqs, w.phi)
     shard = pdist.shard_spec(unit=64)
     assert shard == (rank, world, 64)
-    part = oracle_lib.simulate(plan, w.types, w.t_max, w.seed, shard=shard, n_threads=2)
+    part = oracle_lib.simulate(plan, w.types, w.t_max, w.seed, shard=shard, n_threads=2, shard_level=shard_level)
     n_sets, n_keys, n_types = part["counts"].shape
     buf = pdist.packed_buffer(n_sets, n_keys, n_types, "cpu")
     counts, div = pdist.unpack(buf, n_sets, n_keys, n_types)
@@ -53,6 +53,24 @@ def test_two_rank_reduce_equals_unsharded(tmp_path):
     out = tmp_path / "result.txt"
     mp.spawn(_worker, args=(2, _free_port(), str(out)), nprocs=2, join=True)
     assert out.read_text() == "ok"
+
+
+def test_two_rank_reduce_equals_unsharded_with_subtree_sharding(tmp_path):
+    """the same exchange step when the ranks share the first tree levels and own subtrees at level 3"""
+    out = tmp_path / "result.txt"
+    mp.spawn(_worker, args=(2, _free_port(), str(out), 3), nprocs=2, join=True)
+    assert out.read_text() == "ok"
+
+
+def test_subtree_owner_functions():
+    sys.path.insert(0, str(ROOT))
+    from cuda_pro_cell_b200 import dist as pdist
+    for world in (2, 3, 8):
+        kids = [pdist.owner_of_subtree(r, h, world) for r in (0, 5, 4096) for h in range(64, 128)]
+        assert set(kids) == set(range(world))                      # the 64 subtrees of a lineage spread over all ranks
+        assert pdist.owner_of_subtree(7, 64, world) == (7 + 64) % world
+        assert pdist.owner_of_subtree(0xFFFFFFFF, 2, world) == 1 % world      # 32-bit wrap, as on the device
+        assert pdist.owner_of_shared_node(13, world) == 13 % world
 
 
 def test_owner_function_matches_the_shard_rule():
