@@ -1,17 +1,14 @@
 #!/usr/bin/env python3
-"""First GPU contact: timings of both kernels on the BASELINE configs, the RNG ceiling, and a few runs of the
-unmodified reference binary (oracle/_ref/procell_ref) on config 1.  Writes gpurun_out/first_light.json."""
+"""First GPU contact: timings of the kernels on the BASELINE configs and the RNG ceiling.  Writes
+gpurun_out/first_light.json.  (The reference binary is timed by `bench.py --impl reference` only.)"""
 import json
-import subprocess
 import sys
-import time
 from pathlib import Path
 
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, str(ROOT / "tests"))
 from cuda_pro_cell_b200 import api, synth  # noqa: E402
 
 OUT = ROOT / "gpurun_out"
@@ -55,31 +52,6 @@ try:
     print("rng ceiling", res["rng_ceiling"], flush=True)
 except Exception as e:
     res["rng_ceiling"] = {"error": str(e)}
-
-# ---- the reference binary on config 1 (needs -p; wall-clock seeded, so space the runs by > 1 s)
-ref = ROOT / "oracle" / "_ref" / "procell_ref"
-if ref.exists():
-    w = synth.workload(1)
-    (OUT / "cfg1_hist.txt").write_text(synth.histogram_text(w.values, w.freqs))
-    (OUT / "cfg1_types.txt").write_text(synth.types_text(w.types[0]))
-    runs = []
-    for i, (tmax, phi) in enumerate(()):
-        out = OUT / ("ref_cfg1_run%d.txt" % i)
-        t0 = time.time()
-        r = subprocess.run([str(ref), "-h", str(OUT / "cfg1_hist.txt"), "-c", str(OUT / "cfg1_types.txt"), "-t", str(tmax),
-                            "-p", repr(phi), "-o", str(out), "-r"], capture_output=True, text=True, timeout=600)
-        dt = time.time() - t0
-        rows = [ln.split("\t") for ln in out.read_text().splitlines()] if out.exists() else []
-        tot = sum(int(x[1]) for x in rows)
-        mass = sum(float(x[0]) * int(x[1]) for x in rows)
-        runs.append(dict(t_max=tmax, phi=phi, rc=r.returncode, wall_s=dt, start_unix=int(t0), rows=len(rows), total=tot,
-                         mass=mass, stdout=r.stdout[-300:], stderr=r.stderr[-300:]))
-        print("ref run", runs[-1], flush=True)
-        time.sleep(1.2)
-    res["reference_cfg1"] = runs
-    res["cfg1_input_mass"] = float((w.values * w.freqs).sum())
-else:
-    res["reference_cfg1"] = "binary missing"
 
 (OUT / "first_light.json").write_text(json.dumps(res, indent=1))
 print("done")
