@@ -214,6 +214,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--e2e-engines", type=int, default=1,
+                    help="engines (each with its own stream, count tensor and pinned host buffer) the end-to-end leg keeps in "
+                         "flight: 1 = one step at a time (measured in round 1); 2 = the D2H of step i and the H2D of step i+2 "
+                         "overlap kernel i+1 (written without GPU access: opt-in until it has been run on a B200)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -305,12 +309,51 @@ def main():
             p_done.merge_rows(host_done[:n_counts].numpy().reshape(plan.n_keys, n_types))
             e2e_div += int(host_done[n_counts])
 
+    n_eng = max(1, args.e2e_engines)
+    if n_eng > 1:
+        # several steps in flight: slot k = (engine, non-blocking stream, device count tensor, pinned host tensor).  Every
+        # step still does all of its own work (plan, H2D tables, kernel, reduce, D2H, row merge); a slot is reused only after
+        # its previous step has been read back, checked (finish: device status word) and merged.
+        engs = [eng] + [api.Engine(local_rank) for _ in range(n_eng - 1)]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(n_eng)]
+        bufs = [torch.zeros_like(buf) for _ in range(n_eng)]
+        hosts = [torch.zeros(buf.shape, dtype=buf.dtype).pin_memory() for _ in range(n_eng)]
+        inflight = [None] * n_eng
     barrier()
     t0 = time.perf_counter()
     # every step does all of its own work - plan from the host arrays, H2D tables, kernel, reduce, D2H, row merge; the
     # host legs of neighbouring steps (plan of step i+1, row merge of step i-1) run while kernel i is on the GPU
-    p_next = api.Plan(host_values, host_freqs, w.phi)                      # parser.cu:68-154 work, on the host
     prev = None
+    if n_eng > 1:
+
+        def retire(k):
+            p_k, ev_k = inflight[k]
+            ev_k.synchronize()
+            engs[k].finish(streams[k].cuda_stream, fetch=False)
+            merge((p_k, hosts[k]))
+            inflight[k] = None
+
+        for i in range(E):
+            k = i % n_eng
+            if inflight[k] is not None:
+                retire(k)
+            p = api.Plan(host_values, host_freqs, w.phi)
+            engs[k].load(p, w.types, w.t_max, w.seed + i, shard=shard)
+            engs[k].run(w.seed + 2000 + i, streams[k].cuda_stream, bufs[k].data_ptr(), bufs[k].data_ptr() + 8 * n_counts)
+            with torch.cuda.stream(streams[k]):
+                if world > 1:
+                    dist.reduce(bufs[k], dst=0, op=dist.ReduceOp.SUM)
+                hosts[k].copy_(bufs[k], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(streams[k])
+            inflight[k] = (p, ev)
+        for j in range(n_eng):
+            k = (E + j) % n_eng
+            if inflight[k] is not None:
+                retire(k)
+        E_done, E = E, 0          # the single-engine loop below does not run
+    else:
+        p_next = api.Plan(host_values, host_freqs, w.phi)                  # parser.cu:68-154 work, on the host
     for i in range(E):
         p = p_next
         eng.load(p, w.types, w.t_max, w.seed + i, shard=shard)             # H2D tables
@@ -324,9 +367,15 @@ def main():
         host = buf.cpu()                                                   # D2H count tensor + division counter
         eng.finish(stream.cuda_stream, fetch=False)
         prev = (p, host)
-    merge(prev)
+    if n_eng > 1:
+        E = E_done
+    else:
+        merge(prev)
     barrier()
     t_e2e = time.perf_counter() - t0
+    if n_eng > 1:
+        for extra in engs[1:]:
+            extra.close()
     t_e = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
@@ -368,6 +417,7 @@ def main():
                 "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
                 "e2e": {"value": e2e_div / t_e2e if t_e2e > 0 else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "steps": E,
+                        "engines_in_flight": n_eng,
                         "path": "api.Plan (host) -> procell_engine_load (H2D) -> procell_engine_run -> reduce -> D2H -> merge_rows; "
                                 "the plan of step i+1 and the row merge of step i-1 overlap kernel i"},
                 "gpu_launches": 2 * K, "kernels_per_step": ["k_queue_init", "k_proliferate_coop"],

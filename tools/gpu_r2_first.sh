@@ -12,6 +12,16 @@ export PROCELL_WATCHDOG_S=60
 timeout 300 python -m pytest tests -m gpu -x -q --timeout 120 > gpurun_out/pytest_gpu_r2a.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_r2a.log
 PROCELL_TEST_NEW=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 120 -k "subtree" > gpurun_out/pytest_gpu_r2a_new.log 2>&1; echo "pytest (new paths) rc=$?"; tail -5 gpurun_out/pytest_gpu_r2a_new.log
 timeout 300 python bench.py --steps 200 --warmup 5 > gpurun_out/bench_r2a.json 2> gpurun_out/bench_r2a.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/bench_r2a.json
+timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-engines 2 > gpurun_out/bench_r2a_e2e2.json 2> gpurun_out/bench_r2a_e2e2.err; echo "bench (2 engines in flight) rc=$?"
+python - <<'PY'
+import json
+for f in ("bench_r2a", "bench_r2a_e2e2"):
+    try:
+        d = json.loads(open("gpurun_out/%s.json" % f).read().strip().splitlines()[-1])
+        print(f, "value %.4g  e2e %.4g  frac %.3f" % (d["value"], d["e2e"]["value"], d["roofline"]["frac"]))
+    except Exception as e:
+        print(f, "unreadable:", e)
+PY
 if [ "$N" -ge 2 ]; then
 cat > /tmp/sub.py <<'PY'
 import sys, time, json; sys.path.insert(0, '.')
