@@ -293,6 +293,7 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     const char* denv = getenv("PROCELL_NO_DONATE");
     P.donate = !(denv && atoi(denv) == 1);
     en->kernel = sp->kernel;
+    P.hist_setdirect = 0;
     if (en->kernel == PROCELL_KERNEL_SIMPLE) {
         en->block = kSimpleThreads;
         en->grid = en->sm_count * 8;
@@ -312,9 +313,19 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         if (subtree) { en->warps = 32; en->ring = 1; }       /* the subtree-sharding instances exist in the product shape only */
         const size_t fixed = coop_smem_bytes(en->warps, en->ring, 0, 0);
         const size_t room = (size_t)max_smem > fixed ? (size_t)max_smem - fixed : 0;
+        /* sweeps whose whole key space does not fit but ONE set's does: a direct table of the CTA's current set
+         * (kernel MODE kModeSetDirect).  Written without GPU access: on request only (PROCELL_SWEEP_DIRECT=1) until
+         * it has passed the parity suite on a B200. */
+        const char* sdenv = getenv("PROCELL_SWEEP_DIRECT");
+        P.hist_setdirect = 0;
         if (en->counts_len * 4 <= room) {            /* the whole key space fits: direct u32 table */
             P.hist_hashed = 0;
             P.smem_hist_slots = (uint32_t)en->counts_len;
+        } else if (sdenv && atoi(sdenv) == 1 && S > 1 && M == 1 && !subtree && en->warps == 32 && en->ring == 1 &&
+                   K * T * 4 <= room) {
+            P.hist_hashed = 0;
+            P.hist_setdirect = 1;
+            P.smem_hist_slots = (uint32_t)(K * T);
         } else {                                     /* direct-mapped {key,count} cache, power-of-two slots */
             uint32_t slots = 1;
             while ((size_t)slots * 2 * 8 <= room) slots *= 2;
@@ -323,7 +334,8 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         }
         en->smem = coop_smem_bytes(en->warps, en->ring, P.smem_hist_slots, P.hist_hashed);
         int grid = 0;
-        if (subtree) CU(coop_max_grid_subtree(en->device, P.hist_hashed, en->smem, &grid), "occupancy query");
+        if (P.hist_setdirect) CU(coop_max_grid_setdirect(en->device, en->smem, &grid), "occupancy query");
+        else if (subtree) CU(coop_max_grid_subtree(en->device, P.hist_hashed, en->smem, &grid), "occupancy query");
         else CU(coop_max_grid(en->device, en->warps, en->ring, P.hist_hashed, (P.n_sets == 1u && P.n_times == 1u) ? 1 : 0, en->smem, &grid), "occupancy query");
         if (grid <= 0) return fail(PROCELL_ERR_CUDA, "cooperative kernel does not fit on this device");
         en->grid = grid;

@@ -52,6 +52,9 @@ constexpr int kSmemMusdEntries = 64;  /* (mean, sd) table cached in shared memor
  * (mean, sd) 16 B, cumulative proportion 8 B and selection order 1 B per entry */
 constexpr int kSmemCtlBytes = 128 + kSmemMusdEntries * (16 + 8 + 1);
 constexpr unsigned kFull = 0xFFFFFFFFu;
+/* kernel MODE: 0 = the kernel as measured in round 1; 1 = subtree sharding compiled in (multi-GPU runs of deep trees);
+ * 2 = sweeps with a set-relative direct histogram table and a CTA-wide rendezvous at batch switches */
+constexpr int kModeBase = 0, kModeSubtree = 1, kModeSetDirect = 2;
 
 /* A node = a cell that WILL divide: 4 x u64, kept in the ring as two 16-byte pairs (A,B) and (C,D) so that a pop is
  * two LDS.128 and a push two STS.128; chunks in HBM (spill rings, donation queue) are field-major
@@ -178,6 +181,31 @@ __device__ __noinline__ void hist_drain(const SimParams& P, uint32_t* s_hist, in
     }
 }
 
+/* ---- sweeps with a set-relative direct table (kernel MODE kModeSetDirect) ----
+ * A sweep's key space (n_sets x n_keys x n_types) does not fit in shared memory, but ONE parameter set's does, and a
+ * CTA works on one set at a time (batches).  The CTA's u32 table then holds the counts of the set whose first key is
+ * `base` (kept in shared memory, s_ctl[7]); a leaf of any other set - a donated chunk from another CTA at the very end
+ * of the run - goes straight to the int64 tensor in HBM.  `base` changes only inside setdirect_rendezvous, while every
+ * warp of the CTA is parked there without a node, so no add can be in flight across a change.  Against the hashed
+ * cache this removes MATCH + two ballots + a 64-bit CAS loop per DIVIDE iteration and every eviction. */
+__device__ __forceinline__ void count_leaves_setdirect(const SimParams& P, uint32_t* s_hist, uint32_t key, uint32_t inc, uint32_t base)
+{
+    if (inc > 0u) {
+        const uint32_t rel = key - base;
+        if (rel < P.smem_hist_slots) atomicAdd(&s_hist[rel], inc);
+        else atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + key, (unsigned long long)inc);
+    }
+}
+
+__device__ __noinline__ void hist_drain_at(const SimParams& P, uint32_t* s_hist, int lane, uint32_t base)
+{
+    for (uint32_t i = (uint32_t)lane; i < P.smem_hist_slots; i += 32u) {
+        if (*reinterpret_cast<volatile uint32_t*>(s_hist + i) == 0u) continue;
+        const uint32_t v = atomicExch(s_hist + i, 0u);
+        if (v) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + base + i, (unsigned long long)v);
+    }
+}
+
 /* every lane of the warp calls this; each may carry `inc` (0, 1 or 2) leaves for `key`.
  * direct mode: every lane issues its own shared atomic; the shared-memory atomic unit serialises equal addresses
  *   faster than any merging in registers (measured: config 2 1.64 -> 1.46 ms).
@@ -218,6 +246,59 @@ __device__ __noinline__ void watchdog_fire(const SimParams& P, uint32_t gwarp, i
         __threadfence();
         atomicCAS(&P.ctl->status, kStatusOk, kStatusWatchdog);
     }
+}
+
+/* MODE kModeSetDirect: a warp that holds no node and finds the CTA's batch used up comes here.  The LAST of the CTA's
+ * warps to arrive - every other one is parked in the wait below, none holds a node, no add is in flight - drains the
+ * table of the old set into the int64 tensor, takes the next batch from the global cursor, re-bases the table on that
+ * batch's set and releases the others.  shared control words: s_ctl[7] table base (first key of the CTA's set),
+ * s_ctl[12] arrivals of this round, s_ctl[13] round number.  Waiting is lane 0's alone (see idle_wait) and bounded by
+ * the watchdog deadline; false = abort. */
+template <int WARPS>
+__device__ __forceinline__ bool setdirect_rendezvous(const SimParams& P, volatile int* s_ctl, uint32_t* s_hist,
+                                                     unsigned long long* s_batch, int lane, uint32_t gwarp)
+{
+    __threadfence_block();      /* this warp's shared atomics are performed before its arrival is counted */
+    __syncwarp();
+    int role = 0;               /* 1 last to arrive: does the switch, 2 released, 3 abort */
+    if (lane == 0) {
+        const int round = s_ctl[13];
+        const int arrived = atomicAdd(const_cast<int*>(s_ctl) + 12, 1) + 1;
+        if (arrived == WARPS) role = 1;
+        else {
+            const unsigned long long deadline = *reinterpret_cast<volatile unsigned long long*>(const_cast<int*>(s_ctl) + 10);
+            unsigned backoff = 64;
+            for (;;) {
+                if (s_ctl[13] != round) { role = 2; break; }
+                __nanosleep(backoff);
+                if (backoff < 1024u) backoff <<= 1;
+                if (global_timer_ns() > deadline || ld_volatile_s32(&P.ctl->status) != kStatusOk) { role = 3; break; }
+            }
+        }
+    }
+    role = __shfl_sync(kFull, role, 0);
+    if (role == 2) return true;
+    if (role == 3) {
+        watchdog_fire(P, gwarp, lane, 4, (unsigned long long)s_ctl[12], (unsigned long long)s_ctl[13], 0, 0, 0, 0);
+        return false;
+    }
+    hist_drain_at(P, s_hist, lane, (uint32_t)s_ctl[7]);
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned long long g = atomicAdd(&P.ctl->cursor, 1ull);
+        if (g >= P.total_batches) {
+            s_ctl[3] = 1;                                   /* no batch left anywhere: the base stays where it is */
+            atomicMin(&P.ctl->t_exhausted, global_timer_ns());
+        } else {
+            s_ctl[7] = (int)((uint32_t)(g / P.batches_per_set) * P.smem_hist_slots);
+            atomicExch(s_batch, g << 24);
+        }
+        s_ctl[12] = 0;
+        __threadfence_block();
+        atomicAdd(const_cast<int*>(s_ctl) + 13, 1);         /* release the parked warps */
+    }
+    __syncwarp();
+    return true;
 }
 
 struct WarpCtx {
@@ -575,11 +656,12 @@ __device__ __forceinline__ void classify_daughters(const SimParams& P, double2 m
  * NPL = nodes per lane: 1, or 2 in the 16-warp instance with 256-node rings (RING = 2), where lane l expands the
  * nodes top-1-l and top-33-l in one straight-line pass: two independent arithmetic chains for the scheduler to
  * interleave, and the per-iteration overhead (loop control, constant loads, probes) is paid once per 64 divisions. */
-template <bool FULL, bool HASHED, bool PLAIN, int RING, int NPL, bool SUBTREE>
+template <bool FULL, bool HASHED, bool PLAIN, int RING, int NPL, int MODE>
 __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P, const double* s_log, uint32_t* s_hist,
                                                  const double2* musd, uint32_t take, unsigned lt_mask, bool multi_set,
-                                                 DivCount& dc)
+                                                 DivCount& dc, uint32_t hist_base)
 {
+    constexpr bool SUBTREE = MODE == kModeSubtree, SETDIRECT = MODE == kModeSetDirect;
     static_assert(NPL == 1 || (FULL && RING >= NPL), "several nodes per lane: full iterations of a wide-ring instance only");
     constexpr uint32_t kMask = Ring<RING>::kMask;
     const uint32_t T = P.n_types;
@@ -689,7 +771,9 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
     __syncwarp();
 #pragma unroll
     for (int s = 0; s < NPL; ++s) {
-        if (PLAIN || P.n_times == 1u) {
+        if (SETDIRECT) {
+            count_leaves_setdirect(P, s_hist, leaf_key[s], leaf_inc[s], hist_base);
+        } else if (PLAIN || P.n_times == 1u) {
             warp_count_leaves<HASHED>(P, s_hist, leaf_key[s], leaf_inc[s]);
         } else {
             /* time series: a daughter born at t_div that divides (or would divide) at tc is out of time at every
@@ -708,12 +792,15 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
 
 }  // namespace
 
-/* SUBTREE: the subtree-sharding rule of multi-GPU runs of deep trees (SimParams::sub_world > 1) compiled in */
-template <int WARPS, bool HASHED, bool PLAIN, int RING, bool SUBTREE>
+/* MODE: kModeBase, kModeSubtree (the subtree-sharding rule of multi-GPU runs of deep trees, SimParams::sub_world > 1)
+ * or kModeSetDirect (sweeps: set-relative direct histogram table, SimParams::hist_setdirect) */
+template <int WARPS, bool HASHED, bool PLAIN, int RING, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid_constant__ SimParams P)
 {
+    constexpr bool SUBTREE = MODE == kModeSubtree, SETDIRECT = MODE == kModeSetDirect;
     static_assert(RING == 1 || RING == 2, "ring of 128 or 256 nodes per warp");
     static_assert(!SUBTREE || (PLAIN && RING == 1), "subtree sharding: one parameter set, one checkpoint, one node per lane");
+    static_assert(!SETDIRECT || (!PLAIN && !HASHED && RING == 1), "set-relative table: sweeps, u32 slots, one node per lane");
     constexpr uint32_t kCap = Ring<RING>::kCap, kMask = Ring<RING>::kMask;
     constexpr uint32_t kLow = 32u * RING;        /* below this many nodes a warp looks for seed cells / spilled chunks first */
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -768,6 +855,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         s_ctl[2] = 0; s_ctl[3] = P.total_local_units == 0; s_ctl[4] = 0; s_ctl[5] = 0; s_ctl[6] = 0;
         for (int i = 0; i < 12; ++i) s_snap[i] = 0;
         *s_batch = (0xFFFFFFFFFFull << 24) | 0x800000ull;   /* no batch yet (invalid id; offset bits leave room for increments) */
+        if (SETDIRECT) { s_ctl[7] = 0; s_ctl[12] = 0; s_ctl[13] = 0; }
     }
     __syncthreads();
     DivCount dc;
@@ -802,7 +890,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 if (seed_cur == seed_end) {
                     TRACE(P, GWARP, lane, 10);
                     uint32_t set = 0, j = 0;
-                    bool got = false;
+                    bool got = false, wait_switch = false;
                     if (!multi_set) {
                         unsigned long long c = 0;
                         if (lane == 0) c = atomicAdd(&ctl->cursor, 1ull);
@@ -826,6 +914,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                                 }
                                 if (status == 0) {
                                     if (s_ctl[3]) status = 2;
+                                    else if (SETDIRECT) status = 4;        /* batch used up: the CTA switches sets together */
                                     else if ((spin & 1023) == 1023 && global_timer_ns() > *s_deadline) status = 3;
                                     else if (atomicCAS(const_cast<int*>(s_ctl) + 6, 0, 1) == 0) {
                                         /* batch used up: one warp of the CTA fetches the next one */
@@ -852,8 +941,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                                 break;
                             } else if (status == 2) {
                                 break;
+                            } else if (SETDIRECT && status == 4) {
+                                wait_switch = true;
+                                break;
                             }
                         }
+                    }
+                    if (SETDIRECT && wait_switch) {
+                        /* the last nodes of the old set are expanded first (partial DIVIDE iterations below); only a
+                         * warp without any node may wait for the switch */
+                        if (n != 0u) goto divide_now;
+                        if (!setdirect_rendezvous<WARPS>(P, s_ctl, s_hist, s_batch, lane, GWARP)) break;
+                        continue;
                     }
                     if (!got) {
                         if (lane == 0) { s_ctl[3] = 1; atomicMin(&ctl->t_exhausted, global_timer_ns()); }
@@ -898,7 +997,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 }
                 w.top += __popc(live);
                 __syncwarp();
-                if (PLAIN || P.n_times == 1u) {
+                if (SETDIRECT) {
+                    count_leaves_setdirect(P, s_hist, so.key, so.kind == 1 ? 1u : 0u, (uint32_t)s_ctl[7]);
+                } else if (PLAIN || P.n_times == 1u) {
                     /* subtree sharding: every GPU builds every seed cell, GPU root % world counts its level-0 leaf */
                     const bool credit = !SUBTREE || root % P.sub_world == P.sub_rank;
                     warp_count_leaves<HASHED>(P, s_hist, so.key, (so.kind == 1 && credit) ? 1u : 0u);
@@ -921,14 +1022,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         }
         }
 
+    divide_now:
         ++iter;
         TRACE(P, GWARP, lane, 20);
         const uint32_t take = n < 32u ? n : 32u;
+        const uint32_t hist_base = SETDIRECT ? (uint32_t)s_ctl[7] : 0u;     /* changes only while this warp is parked in the rendezvous */
         /* PLAIN: one set and at most 64 types, so the (mean, sd) table is always the shared-memory copy (plain LDS) */
         const double2* musd = PLAIN ? s_musd_buf : s_musd;
-        if (RING == 2 && n >= 64u) divide_iteration<true, HASHED, PLAIN, RING, RING, SUBTREE>(w, P, s_log, s_hist, musd, 64u, lt_mask, multi_set, dc);
-        else if (take == 32u) divide_iteration<true, HASHED, PLAIN, RING, 1, SUBTREE>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc);
-        else divide_iteration<false, HASHED, PLAIN, RING, 1, SUBTREE>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc);
+        if (RING == 2 && n >= 64u) divide_iteration<true, HASHED, PLAIN, RING, RING, MODE>(w, P, s_log, s_hist, musd, 64u, lt_mask, multi_set, dc, hist_base);
+        else if (take == 32u) divide_iteration<true, HASHED, PLAIN, RING, 1, MODE>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc, hist_base);
+        else divide_iteration<false, HASHED, PLAIN, RING, 1, MODE>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc, hist_base);
 
         /* hunger probe, every 8th iteration (every 4th costs 1.8 % on config 2).  The CTA keeps a snapshot of "how many warps are starving", "how many
          * donated chunks are waiting" and "where is the seed cursor" in shared memory.  Every 64th iteration
@@ -945,7 +1048,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                     atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
                     dc.cnt = 0;
                 }
-                if (!HASHED && (iter & (kHistFlushIters - 1u)) == 0u) hist_drain(P, s_hist, lane);
+                if (!HASHED && (iter & (kHistFlushIters - 1u)) == 0u) {
+                    if (SETDIRECT) hist_drain_at(P, s_hist, lane, hist_base);
+                    else hist_drain(P, s_hist, lane);
+                }
                 int late = 0;
                 if (lane == 0) late = global_timer_ns() > *s_deadline;
                 if (__shfl_sync(kFull, late, 0)) {
@@ -1000,9 +1106,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
             if ((uint32_t)e) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + (uint32_t)(e >> 32), (unsigned long long)(uint32_t)e);
         }
     } else {
+        const uint32_t flush_base = SETDIRECT ? (uint32_t)s_ctl[7] : 0u;
         for (uint32_t i = threadIdx.x; i < P.smem_hist_slots; i += blockDim.x) {
             uint32_t v = s_hist[i];
-            if (v) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + i, (unsigned long long)v);
+            if (v) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + flush_base + i, (unsigned long long)v);
         }
     }
 }
@@ -1116,10 +1223,10 @@ size_t coop_smem_bytes(int warps, int ring, uint32_t hist_slots, int hashed)
 template <int WARPS, bool HASHED, bool PLAIN, int RING>
 static cudaError_t coop_max_grid_t(int device, size_t smem_bytes, int* grid_out)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_proliferate_coop<WARPS, HASHED, PLAIN, RING, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k_proliferate_coop<WARPS, HASHED, PLAIN, RING, kModeBase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     int per_sm = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<WARPS, HASHED, PLAIN, RING, false>, WARPS * 32, smem_bytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<WARPS, HASHED, PLAIN, RING, kModeBase>, WARPS * 32, smem_bytes);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
@@ -1155,11 +1262,24 @@ cudaError_t coop_max_grid(int device, int warps, int ring, int hashed, int plain
 cudaError_t coop_max_grid_subtree(int device, int hashed, size_t smem_bytes, int* grid_out)
 {
     int per_sm = 0, sms = 0;
-    cudaError_t e = hashed ? cudaFuncSetAttribute(k_proliferate_coop<32, true, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)
-                           : cudaFuncSetAttribute(k_proliferate_coop<32, false, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = hashed ? cudaFuncSetAttribute(k_proliferate_coop<32, true, true, 1, kModeSubtree>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)
+                           : cudaFuncSetAttribute(k_proliferate_coop<32, false, true, 1, kModeSubtree>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
-    e = hashed ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<32, true, true, 1, true>, 1024, smem_bytes)
-               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<32, false, true, 1, true>, 1024, smem_bytes);
+    e = hashed ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<32, true, true, 1, kModeSubtree>, 1024, smem_bytes)
+               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<32, false, true, 1, kModeSubtree>, 1024, smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    *grid_out = per_sm * sms;
+    return cudaSuccess;
+}
+
+cudaError_t coop_max_grid_setdirect(int device, size_t smem_bytes, int* grid_out)
+{
+    int per_sm = 0, sms = 0;
+    cudaError_t e = cudaFuncSetAttribute(k_proliferate_coop<32, false, false, 1, kModeSetDirect>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<32, false, false, 1, kModeSetDirect>, 1024, smem_bytes);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
@@ -1172,13 +1292,18 @@ cudaError_t launch_coop(const SimParams& p, int warps, int ring, int grid, cudaS
     if (ring == 2 && warps != 16) return cudaErrorInvalidValue;
     const size_t smem = coop_smem_bytes(warps, ring, p.smem_hist_slots, p.hist_hashed);
     const bool plain = coop_is_plain(p);
-    if (p.sub_world > 1u) {
-        if (warps != 32 || ring != 1 || !plain) return cudaErrorInvalidValue;
-        if (p.hist_hashed) k_proliferate_coop<32, true, true, 1, true><<<grid, 1024, smem, stream>>>(p);
-        else k_proliferate_coop<32, false, true, 1, true><<<grid, 1024, smem, stream>>>(p);
+    if (p.hist_setdirect) {
+        if (warps != 32 || ring != 1 || plain || p.hist_hashed || p.n_times != 1u || p.sub_world > 1u) return cudaErrorInvalidValue;
+        k_proliferate_coop<32, false, false, 1, kModeSetDirect><<<grid, 1024, smem, stream>>>(p);
         return cudaGetLastError();
     }
-#define X(W, H, PL, R) k_proliferate_coop<W, H, PL, R, false><<<grid, W * 32, smem, stream>>>(p)
+    if (p.sub_world > 1u) {
+        if (warps != 32 || ring != 1 || !plain) return cudaErrorInvalidValue;
+        if (p.hist_hashed) k_proliferate_coop<32, true, true, 1, kModeSubtree><<<grid, 1024, smem, stream>>>(p);
+        else k_proliferate_coop<32, false, true, 1, kModeSubtree><<<grid, 1024, smem, stream>>>(p);
+        return cudaGetLastError();
+    }
+#define X(W, H, PL, R) k_proliferate_coop<W, H, PL, R, kModeBase><<<grid, W * 32, smem, stream>>>(p)
     COOP_DISPATCH(warps, ring, p.hist_hashed, plain, X);
 #undef X
     return cudaGetLastError();

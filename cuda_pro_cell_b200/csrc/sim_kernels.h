@@ -92,6 +92,9 @@ struct SimParams {
      * (root + heap) % sub_world alone.  shard_world / shard_rank are 1 / 0 in this mode. */
     uint32_t sub_world, sub_rank;
     unsigned long long sub_limit;
+    /* sweeps: 1 = the shared-memory table is a direct u32 table of ONE parameter set (smem_hist_slots = n_keys *
+     * n_types), re-based at batch switches behind a CTA-wide rendezvous (kernel MODE kModeSetDirect) */
+    int hist_setdirect;
 };
 
 /* ring = 1: 128-node ring per warp, one node per lane and iteration (warps = 32, 24 or 16);
@@ -102,6 +105,8 @@ cudaError_t coop_max_grid(int device, int warps, int ring, int hashed, int plain
 /* the subtree-sharding instances (p.sub_world > 1): 32 warps, 128-node rings, one parameter set, one checkpoint;
  * launch_coop picks them by p.sub_world */
 cudaError_t coop_max_grid_subtree(int device, int hashed, size_t smem_bytes, int* grid_out);
+/* the sweep instance with a set-relative direct table (p.hist_setdirect): 32 warps, 128-node rings */
+cudaError_t coop_max_grid_setdirect(int device, size_t smem_bytes, int* grid_out);
 cudaError_t launch_simple(const SimParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_queue_init(unsigned long long* q_seq, ControlBlock* ctl, cudaStream_t stream);
 cudaError_t launch_rng_ceiling(int grid, int block, int iters, const double* logtab, double mean, double sd,

@@ -32,7 +32,7 @@ def _res_usage():
 def test_kernel_instances_fit_their_cta_shape():
     usage = _res_usage()
     coop = {k: v for k, v in usage.items() if "k_proliferate_coop" in k}
-    assert len(coop) == 18, "CTA shapes (32 / 24 / 16 warps, 16 warps x 2 nodes per lane) x histogram mode x PLAIN + 2 subtree-sharding instances"
+    assert len(coop) == 19, "CTA shapes (32 / 24 / 16 warps, 16 warps x 2 nodes per lane) x histogram mode x PLAIN + 2 subtree-sharding instances + the set-direct sweep instance"
     for name, u in coop.items():
         warps = int(re.search(r"coopILi(\d+)E", name).group(1))
         plain = re.search(r"coopILi\d+ELb[01]ELb1E", name) is not None

@@ -475,3 +475,38 @@ def test_single_process_multi_gpu_subtree_sharding(gpu_api, oracle, n_gpus):
     want = oracle.simulate(oplan, types, 360.0, 4)
     got = gpu_api.proliferate_multi(plan, types, 360.0, 4, n_gpus=n_gpus, shard_level=6)
     assert np.array_equal(got.counts, want["counts"]) and np.array_equal(got.divisions, want["divisions"])
+
+
+@_new_path
+@pytest.mark.parametrize("shape", ["sweep32", "many_small_sets", "two_deep_sets", "unit1", "sharded"])
+def test_sweep_with_set_relative_table_bit_exact(gpu_api, oracle, monkeypatch, shape):
+    """PROCELL_SWEEP_DIRECT=1: sweeps keep a direct u32 table of the CTA's current parameter set in shared memory and
+    switch sets behind a CTA-wide rendezvous (kernel MODE 2) instead of the hashed {key, count} cache.  Same tensor as
+    the oracle and as the hashed instance; `two_deep_sets` ends with donated chunks of the other set (global path)."""
+    shard = (0, 1, 0)
+    if shape == "sweep32":
+        values, freqs = synth.synthetic_histogram(3000)
+        types, t_max, phi = synth.sweep_types(1024)[::32], 168.0, 0.5
+    elif shape == "many_small_sets":
+        values, freqs = synth.synthetic_histogram(300)
+        types, t_max, phi = synth.sweep_types(1024)[::4], 168.0, 0.5
+    elif shape == "two_deep_sets":
+        values, freqs = synth.synthetic_histogram(600)
+        types, t_max, phi = np.array([synth.TYPES_CONFIG4, [(0.02, 20.0, 3.0), (0.28, 86.3, 26.8), (0.70, -1.0, -1.0)]]), 330.0, 1e-7
+    elif shape == "unit1":
+        values, freqs = synth.synthetic_histogram(2000)
+        types, t_max, phi, shard = synth.sweep_types(1024)[::128], 168.0, 0.5, (0, 1, 1)
+    else:
+        values, freqs = synth.synthetic_histogram(4000)
+        types, t_max, phi, shard = synth.sweep_types(1024)[::64], 200.0, 0.5, (1, 3, 32)
+    plan, oplan = gpu_api.Plan(values, freqs, phi), oracle.OraclePlan(values, freqs, phi)
+    want = oracle.simulate(oplan, types, t_max, 0x5EED0005, shard=shard if shard[1] > 1 else (0, 1, 1))
+    monkeypatch.delenv("PROCELL_SWEEP_DIRECT", raising=False)
+    hashed = gpu_api.proliferate(plan, types, t_max, 0x5EED0005, shard=shard)
+    monkeypatch.setenv("PROCELL_SWEEP_DIRECT", "1")
+    got = gpu_api.proliferate(plan, types, t_max, 0x5EED0005, shard=shard)
+    assert got.stats["smem_bytes"] != hashed.stats["smem_bytes"], "the set-relative instance was not selected"
+    assert np.array_equal(got.divisions, want["divisions"]) and np.array_equal(got.counts, want["counts"])
+    assert np.array_equal(hashed.counts, want["counts"])
+    again = gpu_api.proliferate(plan, types, t_max, 0x5EED0005, shard=shard)
+    assert np.array_equal(again.counts, got.counts)

@@ -10,7 +10,30 @@ mkdir -p gpurun_out
 N=${1:-1}
 export PROCELL_WATCHDOG_S=60
 timeout 300 python -m pytest tests -m gpu -x -q --timeout 120 > gpurun_out/pytest_gpu_r2a.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_r2a.log
-PROCELL_TEST_NEW=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 120 -k "subtree" > gpurun_out/pytest_gpu_r2a_new.log 2>&1; echo "pytest (new paths) rc=$?"; tail -5 gpurun_out/pytest_gpu_r2a_new.log
+PROCELL_TEST_NEW=1 timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 120 -k "subtree or set_relative" > gpurun_out/pytest_gpu_r2a_new.log 2>&1; echo "pytest (new paths) rc=$?"; tail -5 gpurun_out/pytest_gpu_r2a_new.log
+# config 5 (1024 sets x 1e6 cells) and a tenth of it: hashed cache against the set-relative direct table
+cat > /tmp/sweep_ab.py <<'PY'
+import os, sys, json; sys.path.insert(0, '.')
+import numpy as np
+from cuda_pro_cell_b200 import api, synth
+out = {}
+for scale in (0.1, 1.0):
+    w = synth.workload(5, scale)
+    plan = api.Plan(w.values, w.freqs, w.phi)
+    for mode in ("0", "1"):
+        os.environ["PROCELL_SWEEP_DIRECT"] = mode
+        eng = api.Engine(0); eng.load(plan, w.types, w.t_max, w.seed)
+        best = None
+        for _ in range(3):
+            eng.run(); r = eng.finish(fetch=True)
+            best = r.stats if best is None or r.stats["kernel_ms"] < best["kernel_ms"] else best
+        chk = int((r.counts.reshape(-1)[::7].astype(np.uint64) * np.arange(1, r.counts.size // 7 + 2, dtype=np.uint64)[: len(r.counts.reshape(-1)[::7])]).sum() % (1 << 61))
+        out["scale%g_direct%s" % (scale, mode)] = dict(kernel_ms=best["kernel_ms"], divisions=int(r.divisions.sum()), smem=best["smem_bytes"], checksum=chk, idle_warp_us=best["idle_warp_us"])
+        print(scale, mode, out["scale%g_direct%s" % (scale, mode)], flush=True)
+        eng.close()
+json.dump(out, open("gpurun_out/config5_setdirect_ab.json", "w"), indent=1)
+PY
+timeout 300 python /tmp/sweep_ab.py 2>&1 | tail -5
 timeout 300 python bench.py --steps 200 --warmup 5 > gpurun_out/bench_r2a.json 2> gpurun_out/bench_r2a.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/bench_r2a.json
 timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-engines 2 > gpurun_out/bench_r2a_e2e2.json 2> gpurun_out/bench_r2a_e2e2.err; echo "bench (2 engines in flight) rc=$?"
 python - <<'PY'

@@ -22,8 +22,8 @@ def kernels(lib):
     for l in out.splitlines():
         m = re.match(r'\s*\.section\s+\.text\.(\S+?),', l)
         if m:
-            # k_proliferate_coop gained a fifth template argument (SUBTREE); <..., false> is the kernel it was before
-            name = re.sub(r'(k_proliferate_coopILi\d+ELb[01]ELb[01]ELi\d+E)Lb0E(EEvNS_9SimParamsE)', r'\1\2', m.group(1))
+            # k_proliferate_coop gained a fifth template argument (MODE); <..., 0> is the kernel it was before
+            name = re.sub(r'(k_proliferate_coopILi\d+ELb[01]ELb[01]ELi\d+E)L[bi]0E(EEvNS_9SimParamsE)', r'\1\2', m.group(1))
             res[name] = []
             continue
         mi = re.match(r'^\s*/\*[0-9a-f]{4,}\*/\s+(.*?);', l)
@@ -33,7 +33,7 @@ def kernels(lib):
             # directory must still compare equal
             insn = re.sub(r'(_INTERNAL_|_GLOBAL__N__)[0-9a-f]{8}_', r'\1', insn)
             insn = re.sub(r'\$__internal_\d+_\$', '$__internal_$', insn)      # libdevice helpers are numbered per file
-            res[name].append(re.sub(r'(k_proliferate_coopILi\d+ELb[01]ELb[01]ELi\d+E)Lb0E(EEvNS_9SimParamsE)', r'\1\2', insn))
+            res[name].append(re.sub(r'(k_proliferate_coopILi\d+ELb[01]ELb[01]ELi\d+E)L[bi]0E(EEvNS_9SimParamsE)', r'\1\2', insn))
     return res
 
 
