@@ -64,3 +64,20 @@ def test_product_instance_keeps_its_sass_level_shape():
     assert "DFMA" in text and "MUFU.RSQ64H" in text
     counts, _ = sass_lines.account([l for l in lines], "outer")       # whole file: only a smoke test of the tool
     assert sum(counts.values()) > 10000
+
+
+def test_setdirect_rendezvous_protocol_model(tmp_path):
+    """The CTA-level protocol of kernel MODE 2 (sweeps with a set-relative table: claim, park, last warp drains /
+    fetches / re-bases / releases) as a host program with threads for warps: it must terminate with exactly the
+    expected tensor for several CTA / warp / set / unit shapes (tests/models/setdirect_protocol_model.cpp)."""
+    from pathlib import Path
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no C++ compiler")
+    src = Path(__file__).resolve().parent / "models" / "setdirect_protocol_model.cpp"
+    exe = tmp_path / "model"
+    subprocess.run([cxx, "-std=c++17", "-O2", "-pthread", "-o", str(exe), str(src)], check=True)
+    for shape in (("4", "8", "37", "23"), ("2", "32", "50", "100"), ("8", "4", "5", "3"), ("3", "5", "1", "1"), ("5", "16", "64", "29")):
+        for _ in range(3):
+            r = subprocess.run([str(exe), *shape], capture_output=True, text=True, timeout=120)
+            assert r.returncode == 0, (shape, r.stdout)
