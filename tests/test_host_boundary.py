@@ -151,7 +151,9 @@ def test_cli_messages_match_the_reference(tmp_path):
     assert r.returncode == 1 and r.stdout.splitlines() == ["The following missing arguments are required:",
                                                            "--histogram (-h)", "--cell-types (-c)", "--t-max (-t)"]
     r = _cli("--help")
-    assert r.returncode == 0 and "--histogram" in r.stdout
+    assert r.returncode == 0 and "--histogram" in r.stdout and "--shard-level" in r.stdout
+    r = _cli("--shard-level", "31")      # extension flags follow the reference's message style
+    assert (r.returncode, r.stdout) == (1, "Option --shard-level requires an integer value >= 0 && <= 30\n")
     # -p is optional (README.md:98-102); both long spellings parse; bad proportions abort before any GPU work
     h, c = tmp_path / "h.txt", tmp_path / "c.txt"
     h.write_text("10 5\n")
