@@ -269,12 +269,13 @@ __device__ __forceinline__ bool setdirect_rendezvous(const SimParams& P, volatil
     if (lane == 0) {
         const int round = s_ctl[13];
         const int arrived = atomicAdd(const_cast<int*>(s_ctl) + 12, 1) + 1;
-        if (arrived == WARPS) role = 1;
+        if (s_ctl[3]) role = 2;              /* another warp has just found the cursor exhausted: nothing to switch to */
+        else if (arrived == WARPS) role = 1;
         else {
             const unsigned long long deadline = *reinterpret_cast<volatile unsigned long long*>(const_cast<int*>(s_ctl) + 10);
             unsigned backoff = 64;
             for (;;) {
-                if (s_ctl[13] != round) { role = 2; break; }
+                if (s_ctl[13] != round || s_ctl[3]) { role = 2; break; }     /* released, or no batch left anywhere */
                 __nanosleep(backoff);
                 if (backoff < 1024u) backoff <<= 1;
                 if (global_timer_ns() > deadline || ld_volatile_s32(&P.ctl->status) != kStatusOk) { role = 3; break; }
@@ -919,7 +920,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                                 }
                                 if (status == 0) {
                                     if (s_ctl[3]) status = 2;
-                                    else if (SETDIRECT) status = 4;        /* batch used up: the CTA switches sets together */
+                                    else if (SETDIRECT) {
+                                        /* batch used up.  If no batch is left ANYWHERE there will be no further switch:
+                                         * say so at once (the table keeps its base), so that this CTA's busy warps start
+                                         * handing work to the idle ones instead of everyone parking behind the slowest.
+                                         * Otherwise the CTA switches sets together. */
+                                        if (ld_acquire_u64(&ctl->cursor) >= P.total_batches) {
+                                            s_ctl[3] = 1;
+                                            atomicMin(&ctl->t_exhausted, global_timer_ns());
+                                            status = 2;
+                                        } else status = 4;
+                                    }
                                     else if ((spin & 1023) == 1023 && global_timer_ns() > *s_deadline) status = 3;
                                     else if (atomicCAS(const_cast<int*>(s_ctl) + 6, 0, 1) == 0) {
                                         /* batch used up: one warp of the CTA fetches the next one */
