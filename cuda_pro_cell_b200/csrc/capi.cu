@@ -314,15 +314,18 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         const size_t fixed = coop_smem_bytes(en->warps, en->ring, 0, 0);
         const size_t room = (size_t)max_smem > fixed ? (size_t)max_smem - fixed : 0;
         /* sweeps whose whole key space does not fit but ONE set's does: a direct table of the CTA's current set
-         * (kernel MODE kModeSetDirect).  Written without GPU access: on request only (PROCELL_SWEEP_DIRECT=1) until
-         * it has passed the parity suite on a B200. */
+         * (kernel MODE kModeSetDirect).  The CTA's warps meet at every batch switch, which pays off only when a batch
+         * keeps them busy for a while: measured on a B200, config 5 at full size (30 units per warp and batch) runs in
+         * 60.7 ms instead of 70.4 ms, a tenth of it (3 units per warp and batch) in 8.0 ms instead of 6.8 ms.  Default:
+         * on from 24 units per warp and batch; PROCELL_SWEEP_DIRECT=1 / 0 forces it on / off. */
         const char* sdenv = getenv("PROCELL_SWEEP_DIRECT");
+        const bool sd_forced_on = sdenv && atoi(sdenv) == 1, sd_forced_off = sdenv && atoi(sdenv) == 0;
+        const bool sd_wanted = sd_forced_on || (!sd_forced_off && (double)P.batch_units >= 24.0 * 32.0);
         P.hist_setdirect = 0;
         if (en->counts_len * 4 <= room) {            /* the whole key space fits: direct u32 table */
             P.hist_hashed = 0;
             P.smem_hist_slots = (uint32_t)en->counts_len;
-        } else if (sdenv && atoi(sdenv) == 1 && S > 1 && M == 1 && !subtree && en->warps == 32 && en->ring == 1 &&
-                   K * T * 4 <= room) {
+        } else if (sd_wanted && S > 1 && M == 1 && !subtree && en->warps == 32 && en->ring == 1 && K * T * 4 <= room) {
             P.hist_hashed = 0;
             P.hist_setdirect = 1;
             P.smem_hist_slots = (uint32_t)(K * T);

@@ -20,10 +20,10 @@
  *   table into the int64 tensor in HBM every 2^20 of its own DIVIDE iterations, see kHistFlushIters), else a
  *   direct-mapped {key, count} cache updated after __match_any_sync merging; the rest is flushed at the end.
  *
- *   Two further compile-time modes of the same kernel exist and were written in a session without GPU access (selected
- *   on request only until they have passed parity on a B200; the MODE 0 instances are byte-identical to the verified
- *   build): MODE 1 = subtree sharding for multi-GPU runs of deep trees, MODE 2 = sweeps with a direct table of the
- *   CTA's current parameter set and a CTA-wide rendezvous at batch switches.
+ *   Two further compile-time modes of the same kernel: MODE 1 = subtree sharding for multi-GPU runs of deep trees,
+ *   MODE 2 = sweeps with a direct table of the CTA's current parameter set and a CTA-wide rendezvous at batch switches
+ *   (config 5: 70.4 -> 60.7 ms).  Both are bit-exact against the oracle on a B200 (profiles/r1i_*); the MODE 0
+ *   instances are byte-identical to the build the round-1 measurements were made with.
  *
  * k_proliferate_simple - one thread per lineage with a local-memory stack and global atomics: the bring-up
  *   kernel, kept as an independent device-side cross-check of the cooperative one.

@@ -417,11 +417,12 @@ def test_simulate_one_call_equals_oracle_rows(gpu_api, oracle, n_sets):
     assert divisions == int(want["divisions"].sum())
 
 
-# ---- code paths built in a session without GPU access ------------------------------------------------------------
-# The subtree-sharding kernel instances (k_proliferate_coop<32, *, true, 1, true>) were written and compiled while no
-# GPU was reachable; the 16 instances that existed before are byte-identical to the GPU-verified build
-# (tools/sass_same.py).  Until these tests have passed once on a B200 they run only on request
-# (PROCELL_TEST_NEW=1, tools/gpu_r2_first.sh), so that an unproven path cannot break the parity suite of a round end.
+# ---- kernel modes added in the last session of round 1 -------------------------------------------------------------
+# The subtree-sharding instances (MODE 1) and the set-relative sweep instance (MODE 2) were written while no GPU was
+# reachable; the 16 MODE 0 instances are byte-identical to the GPU-verified build (tools/sass_same.py).  With the last
+# GPU seconds of the round both modes were run against the oracle by tools/gpu_new_paths_quick.py (10 of 10 and 4 of 4
+# cases bit-exact, profiles/r1i_*), but these pytest cases themselves have not run on a GPU yet, so they run on
+# request (PROCELL_TEST_NEW=1, tools/gpu_r2_first.sh) until they have, and cannot break the parity suite of a round end.
 import os
 
 _new_path = pytest.mark.skipif(os.environ.get("PROCELL_TEST_NEW") != "1",
@@ -501,7 +502,7 @@ def test_sweep_with_set_relative_table_bit_exact(gpu_api, oracle, monkeypatch, s
         types, t_max, phi, shard = synth.sweep_types(1024)[::64], 200.0, 0.5, (1, 3, 32)
     plan, oplan = gpu_api.Plan(values, freqs, phi), oracle.OraclePlan(values, freqs, phi)
     want = oracle.simulate(oplan, types, t_max, 0x5EED0005, shard=shard if shard[1] > 1 else (0, 1, 1))
-    monkeypatch.delenv("PROCELL_SWEEP_DIRECT", raising=False)
+    monkeypatch.setenv("PROCELL_SWEEP_DIRECT", "0")
     hashed = gpu_api.proliferate(plan, types, t_max, 0x5EED0005, shard=shard)
     monkeypatch.setenv("PROCELL_SWEEP_DIRECT", "1")
     got = gpu_api.proliferate(plan, types, t_max, 0x5EED0005, shard=shard)
