@@ -52,7 +52,7 @@ def test_product_instance_keeps_its_sass_level_shape():
     lines = sass_lines.disassemble(str(_lib.LIB_PATH))
     body = None
     for name, b in sass_lines.sections(lines):
-        if "k_proliferate_coopILi32ELb0ELb1ELi1E" in name:      # 32 warps, direct histogram, PLAIN: config 2's kernel
+        if "k_proliferate_coopILi32ELb0ELb1ELi1ELi0E" in name:  # 32 warps, direct histogram, PLAIN, MODE 0: config 2's kernel
             body = [l for l in b if sass_lines.INSN_RE.match(l)]
     assert body, "product instance not found in the library"
     text = "\n".join(body)

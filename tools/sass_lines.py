@@ -74,7 +74,7 @@ def account(body, by):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("lib", nargs="?", default=os.path.join(ROOT, "cuda_pro_cell_b200", "libprocell_b200.so"))
-    ap.add_argument("--kernel", default="k_proliferate_coopILi32ELb0ELb1E")
+    ap.add_argument("--kernel", default="k_proliferate_coopILi32ELb0ELb1ELi1ELi0E")
     ap.add_argument("--by", default="outer", choices=["outer", "inner", "chain"])
     ap.add_argument("--top", type=int, default=0)
     ap.add_argument("--range", default="", help="only outer lines A-B of sim_kernels.cu, e.g. 504-591")
