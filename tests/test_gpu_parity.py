@@ -511,3 +511,33 @@ def test_sweep_with_set_relative_table_bit_exact(gpu_api, oracle, monkeypatch, s
     assert np.array_equal(hashed.counts, want["counts"])
     again = gpu_api.proliferate(plan, types, t_max, 0x5EED0005, shard=shard)
     assert np.array_equal(again.counts, got.counts)
+
+
+@_new_path
+def test_periodic_drain_of_the_set_relative_table(gpu_api, oracle, tmp_path):
+    """MODE 2 with the drain period set to 256 iterations (libprocell_b200_drain256.so): warps drain the CTA's table
+    into the tensor at the current base (hist_drain_at) while the other warps keep adding.  4 sets of config-2-like
+    parameters on 5e5 cells: ~2e8 divisions, over a thousand iterations per warp."""
+    import os
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    lib = root / "cuda_pro_cell_b200" / "libprocell_b200_drain256.so"
+    out = tmp_path / "drain.npz"
+    types = np.array([[(0.40, 48.33 + 2 * i, 21.6), (0.25, 86.3, 26.8 - i), (0.17, 24.0 + i, 6.0), (0.18, -1.0, -1.0)] for i in range(4)])
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from cuda_pro_cell_b200 import api, synth\n"
+        "v, f = synth.synthetic_histogram(500000)\n"
+        "plan = api.Plan(v, f, 0.5)\n"
+        "types = np.array(%r)\n"
+        "r = api.proliferate(plan, types, 240.0, 11)\n"
+        "assert r.stats['smem_bytes'] == 138944 + 4 * plan.n_keys * 4, 'the set-relative instance was not selected'\n"
+        "np.savez(%r, counts=r.counts, divisions=r.divisions)\n" % (str(root), types.tolist(), str(out)))
+    env = dict(os.environ, PROCELL_LIB=lib.name, PROCELL_SWEEP_DIRECT="1", PROCELL_WATCHDOG_S="30")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=150)
+    got = np.load(out)
+    v, f = synth.synthetic_histogram(500000)
+    want = oracle.simulate(oracle.OraclePlan(v, f, 0.5), types, 240.0, 11)
+    assert np.array_equal(got["divisions"], want["divisions"]) and np.array_equal(got["counts"], want["counts"])
