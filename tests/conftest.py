@@ -9,6 +9,12 @@ for p in (str(ROOT), str(ROOT / "tests")):
         sys.path.insert(0, p)
 
 
+# A kernel that does not end aborts itself after this many seconds (device-side watchdog, read at engine load) instead of
+# the library's default of an hour: a hang in a test must cost a failed test, not the GPU box.
+import os
+os.environ.setdefault("PROCELL_WATCHDOG_S", "120")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
