@@ -61,6 +61,16 @@ for level in (0, 4, 6, 8):
     out[level] = dict(wall_s=dt, kernel_ms=r.stats["kernel_ms"], divisions=int(r.divisions.sum()), checksum=int((r.counts * np.arange(1, r.counts.size + 1).reshape(r.counts.shape) % 1000003).sum()))
     print(level, out[level], flush=True)
 json.dump(out, open("gpurun_out/config4_subtree_%dgpu.json" % n, "w"), indent=1)
+# BASELINE configs[2]: 1e8 seed cells sharded over the GPUs of the box (strong scaling of one run, one ncclReduce)
+w = synth.workload(3, 1.0)
+plan = api.Plan(w.values, w.freqs, w.phi)
+res = {}
+for g in sorted({1, 2, n // 2, n} - {0}):
+    api.proliferate_multi(plan, w.types, w.t_max, w.seed, n_gpus=g)
+    t = time.time(); r = api.proliferate_multi(plan, w.types, w.t_max, w.seed, n_gpus=g); dt = time.time() - t
+    res[g] = dict(wall_s=dt, kernel_ms=r.stats["kernel_ms"], divisions=int(r.divisions.sum()))
+    print("config 3 on", g, "GPU(s):", res[g], flush=True)
+json.dump(res, open("gpurun_out/config3_strong_scaling_%dgpu.json" % n, "w"), indent=1)
 PY
-timeout 400 python /tmp/sub.py $N 2>&1 | tail -6
+timeout 500 python /tmp/sub.py $N 2>&1 | tail -12
 fi
