@@ -603,7 +603,8 @@ int procell_proliferate_multi(const procell_plan* plan, const procell_sim_params
         procell_sim_params sp = *params;
         sp.shard_rank = (uint32_t)i;
         sp.shard_world = (uint32_t)n_gpus;
-        if (sp.shard_unit == 0) sp.shard_unit = 32;
+        /* shard_unit == 0: every engine derives the same claim unit from (cells, sets, world) in procell_engine_load,
+         * so the GPUs agree on who owns which unit - and large inputs get 256-cell units (config 3: -4 %) */
         rc = procell_engine_load(eng[i], plan, &sp);
         if (rc == PROCELL_OK && cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking) != cudaSuccess)
             rc = fail(PROCELL_ERR_CUDA, "cudaStreamCreate failed");
