@@ -127,7 +127,7 @@ int procell_proliferate(const procell_plan* plan, const procell_sim_params* para
                         int64_t* counts, int64_t* divisions, procell_run_stats* stats);
 
 /* Same, on the first n_gpus GPUs of this box from ONE process (n_gpus <= 0: all): seed-cell units (shard_unit cells;
- * 0 = chosen from the input size, 32 to 256) are
+ * 0 = chosen from the input size, 1 to 256) are
  * sharded GPU-strided, every GPU runs the same kernel on its units, and one ncclReduce(sum, int64) over NVLink
  * combines the count tensors on GPU 0.  The result equals the single-GPU result bit for bit.  The reference is
  * single-GPU (device 0 hard-coded, src/simulation/proliferation.cu:38).  NCCL is loaded with dlopen. */
