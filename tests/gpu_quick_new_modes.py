@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Seconds-long parity check of the kernel modes that were written without GPU access (no torch, no pytest):
-  python tools/gpu_new_paths_quick.py subtree | setdirect
+  python tests/gpu_quick_new_modes.py subtree | setdirect
 Prints one PASS / FAIL line per case.  Run each mode in its own process under `timeout`, with PROCELL_WATCHDOG_S small."""
 import os
 import sys
@@ -9,7 +9,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, str(ROOT / "tests"))
+sys.path.insert(0, str(ROOT / "tests"))      # the oracle binding lives with the tests: this script is a test tool
 import numpy as np  # noqa: E402
 from cuda_pro_cell_b200 import api, synth  # noqa: E402
 import oracle_lib  # noqa: E402  (the checker; this script is a test tool)

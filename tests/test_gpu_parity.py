@@ -420,7 +420,7 @@ def test_simulate_one_call_equals_oracle_rows(gpu_api, oracle, n_sets):
 # ---- kernel modes added in the last session of round 1 -------------------------------------------------------------
 # The subtree-sharding instances (MODE 1) and the set-relative sweep instance (MODE 2) were written while no GPU was
 # reachable; the 16 MODE 0 instances are byte-identical to the GPU-verified build (tools/sass_same.py).  With the last
-# GPU seconds of the round both modes were run against the oracle by tools/gpu_new_paths_quick.py (10 of 10 and 4 of 4
+# GPU seconds of the round both modes were run against the oracle by tests/gpu_quick_new_modes.py (10 of 10 and 4 of 4
 # cases bit-exact, profiles/r1i_*), but these pytest cases themselves have not run on a GPU yet, so they run on
 # request (PROCELL_TEST_NEW=1, tools/gpu_r2_first.sh) until they have, and cannot break the parity suite of a round end.
 import os
