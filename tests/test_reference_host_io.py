@@ -199,3 +199,39 @@ def test_written_file_is_read_back_identically_by_the_reference(ref, tmp_path):
     v, f = api.read_histogram(p)
     assert np.array_equal(_bits(v), _bits(want["value"])) and np.array_equal(f, want["freq"]) and (f > 0).all()
     assert int(f.sum()) == int(freq.sum())
+
+
+def test_random_histograms_equal_load_fluorescences(ref, tmp_path):
+    """300 random histogram files (values on a coarse grid so that equal values, exact halves and values equal to phi
+    occur; zero frequencies; explicit and default phi) through the reference's loader and this build's reader + plan."""
+    rng = np.random.default_rng(424242)
+    p = tmp_path / "h.txt"
+    for it in range(300):
+        n = int(rng.integers(1, 40))
+        style = it % 3
+        if style == 0:
+            vals = rng.choice([0.25, 0.5, 1.0, 2.0, 3.0, 4.0, 6.0, 8.0, 12.0, 16.0, 100.0, 1024.0], n)
+        elif style == 1:
+            vals = np.round(rng.lognormal(3.0, 2.0, n), 3)
+        else:
+            vals = rng.integers(1, 50, n).astype(np.float64) * 0.5
+        freqs = rng.integers(0, 6, n) * rng.integers(0, 2, n)
+        phi = [0.0, 0.5, float(vals.min()), float(vals.max()) / 4.0][int(rng.integers(0, 4))]
+        p.write_text("".join("%.17g %d\n" % (v, f) for v, f in zip(vals, freqs)))
+        want = ref_histogram(ref, p, phi)
+        v, f = api.read_histogram(p)
+        keep = f > 0
+        assert np.array_equal(_bits(v[keep]), _bits(want["value"])) and np.array_equal(f[keep], want["freq"])
+        if not keep.any() or phi > float(v[keep].max()) * 2:
+            continue
+        plan = api.Plan(v, f, phi)
+        assert plan.phi == want["phi"] and plan.n_cells == want["total"] and plan.n_bins == len(want["value"])
+        dead = want["rows"] == want["phi"] if not (want["value"] == want["phi"]).any() else np.zeros(len(want["rows"]), bool)
+        assert np.array_equal(_bits(plan.row_value), _bits(want["rows"][~dead])), (it, vals.tolist(), freqs.tolist(), phi)
+        # every (bin, level) key points at the row that holds value / 2^level
+        kb, kd = plan.bin_keybase, plan.bin_kdiv & 63
+        for b, val in enumerate(v[keep]):
+            for k in range(int(kd[b]) + 1):
+                row = plan.key_row[kb[b] + k]
+                if row != 0xFFFFFFFF:
+                    assert plan.row_value[row] == val / 2.0 ** k
