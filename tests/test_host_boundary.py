@@ -256,3 +256,32 @@ def test_python_structs_match_the_c_header(tmp_path):
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         members = [d for decl in body.split(";") if decl.strip() for d in decl.split(",")]
         assert len(members) == len(cls._fields_), "%s: header has %d members, the ctypes mirror %d" % (cname, len(members), len(cls._fields_))
+
+
+@pytest.mark.skipif(not _REF_BIN.exists(), reason="the reference binary is built only where /root/reference exists (make -C oracle ref)")
+def test_random_command_lines_are_rejected_like_the_reference_binary():
+    """300 random sequences of the reference's flags, stray words and values: whatever the reference rejects (status 1,
+    before any CUDA call) `procell` rejects with the same stdout - same precedence between "invalid option", "already
+    given", "requires ..." and the list of missing arguments.  (-p is optional here: that line is dropped.)"""
+    import random
+    rng = random.Random(7)
+    flags = ["-h", "--histogram", "-c", "--cell-types", "-t", "--time-max", "-o", "--output-histogram", "-p", "--phi-min",
+             "-d", "--tree-depth", "-r", "--track-ratio", "--bogus", "-x", "extra"]
+    vals = ["a", "b", "1", "0", "-1", "1.5", "abc", "24", "23", "0.0", "1e-3", "", "-r", "-t", "3.7", "1e400", "-0"]
+    compared = 0
+    for _ in range(300):
+        argv = []
+        for _ in range(rng.randrange(0, 7)):
+            argv.append(rng.choice(flags))
+            if rng.random() < 0.7:
+                argv.append(rng.choice(vals))
+        ref = subprocess.run([str(_REF_BIN)] + argv, capture_output=True, text=True, timeout=60)
+        if ref.returncode != 1:
+            continue                    # accepted: the reference goes on to CUDA and dies there without a GPU
+        want = "".join(l for l in ref.stdout.splitlines(keepends=True) if l != "--phi-min (-p)\n")
+        if want == "The following missing arguments are required:\n":
+            continue
+        new = _cli(*argv)
+        assert (new.returncode, new.stdout) == (1, want), argv
+        compared += 1
+    assert compared > 200
