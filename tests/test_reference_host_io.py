@@ -170,7 +170,9 @@ def test_cell_types_reader_and_sort_equal_load_cell_types(ref, tmp_path, text):
 
 
 def _rows(rng, n, n_types):
-    value = np.sort(np.concatenate([rng.lognormal(3.0, 3.0, n - 6), [0.1, 1.0, 1234567890.125, 1e-5, 99999.999995, 1e15]]))
+    special = [0.1, 1.0, 1234567890.125, 1e-5, 99999.999995, 1e15, 5e-324, 1e-310, 9.9999999995e9, 0.000099999999995,
+               1e100, 2.0 ** 53, 1.0 / 3.0, 9999999999.5, 0.00001234567890123, 1.7e308]   # %.10g corner cases
+    value = np.sort(np.concatenate([rng.lognormal(3.0, 3.0, n - len(special)), special]))
     freq = rng.integers(0, 5_000_000, n).astype(np.uint64)
     freq[rng.integers(0, n, n // 5)] = 0                           # rows with frequency 0 are not written
     ratio = rng.integers(0, 2_000_000, (n, max(n_types, 1))).astype(np.int32)
