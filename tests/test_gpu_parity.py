@@ -541,3 +541,19 @@ def test_periodic_drain_of_the_set_relative_table(gpu_api, oracle, tmp_path):
     v, f = synth.synthetic_histogram(500000)
     want = oracle.simulate(oracle.OraclePlan(v, f, 0.5), types, 240.0, 11)
     assert np.array_equal(got["divisions"], want["divisions"]) and np.array_equal(got["counts"], want["counts"])
+
+
+@_new_path
+def test_single_counts_beyond_2_to_32(gpu_api):
+    """the reference's 32-bit counters wrap; here a single (bin, level) count may exceed 2^32.  sd = 0 makes
+    the tree deterministic: 5 seed cells, 33 generations, 2^33 leaves per lineage in ONE key (4e10 divisions, about half
+    a second), checked against the closed form - no oracle could follow in seconds."""
+    from closed_forms import check_sigma_zero_tree
+
+    def sim(values, freqs, phi, types, t_max):
+        plan = gpu_api.Plan(values, freqs, phi)
+        r = gpu_api.proliferate(plan, types, t_max, 5)
+        return r.counts[0], r.divisions[0], int(plan.bin_keybase[0])
+
+    a, b = check_sigma_zero_tree(sim, 5, 33)
+    assert max(a, b) > 1 << 32

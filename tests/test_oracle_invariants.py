@@ -72,6 +72,20 @@ def test_sigma_zero_closed_form(oracle):
     assert abs(n3 - 500 / 3) < 5 * np.sqrt(500 * (1 / 3) * (2 / 3))
 
 
+def test_sigma_zero_tree_closed_form_at_depth(oracle):
+    """the same closed form as a shared checker (tests/closed_forms.py); the GPU runs it at depth 33, where single
+    counts exceed 2^32 (test_gpu_parity.py)"""
+    from closed_forms import check_sigma_zero_tree
+
+    def sim(values, freqs, phi, types, t_max):
+        p = oracle.OraclePlan(values, freqs, phi)
+        r = oracle.simulate(p, types, t_max, 5)
+        return r["counts"][0], r["divisions"][0], int(p.bin_keybase[0])
+
+    for n_seeds, k_hi in ((6, 12), (3, 15), (40, 5)):
+        check_sigma_zero_tree(sim, n_seeds, k_hi)
+
+
 def test_key_space_and_row_merge(oracle):
     # 8 and 4 share the rows 4, 2, 1: equal value/2^k from different (bin, k) merge into one output row
     p = oracle.OraclePlan(np.array([8.0, 4.0, 3.0]), np.array([1, 1, 1], dtype=np.uint64), 1.0)

@@ -10,7 +10,7 @@ mkdir -p gpurun_out
 N=${1:-1}
 export PROCELL_WATCHDOG_S=60
 timeout 300 python -m pytest tests -m gpu -x -q --timeout 120 > gpurun_out/pytest_gpu_r2a.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_r2a.log
-PROCELL_TEST_NEW=1 timeout 500 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 150 -k "subtree or set_relative" > gpurun_out/pytest_gpu_r2a_new.log 2>&1; echo "pytest (new paths) rc=$?"; tail -5 gpurun_out/pytest_gpu_r2a_new.log
+PROCELL_TEST_NEW=1 timeout 500 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 150 -k "subtree or set_relative or beyond_2_to_32" > gpurun_out/pytest_gpu_r2a_new.log 2>&1; echo "pytest (new paths) rc=$?"; tail -5 gpurun_out/pytest_gpu_r2a_new.log
 # config 5 (1024 sets x 1e6 cells) and a tenth of it: hashed cache against the set-relative direct table
 cat > /tmp/sweep_ab.py <<'PY'
 import os, sys, json; sys.path.insert(0, '.')
