@@ -1,22 +1,28 @@
 #!/usr/bin/env python3
 """bench.py - simulated cell divisions per second of the proliferation hot path on N B200s of one node.
 
-A step = one full simulation of the workload (BASELINE.json configs[1] shape: 1e6 seed cells per GPU, 3
-proliferating types + quiescent, t_max = 240, -r per-type counts, phi = 0.5; ~1.1e8 divisions per GPU).
-N > 1 is weak scaling: the histogram holds N x 1e6 cells, seed-cell units are sharded rank-strided, and the step
-ends with ONE NCCL reduce (sum, int64) of the count tensor + division counters to rank 0.
+Workload of the headline (`value`, `e2e`): BASELINE.json configs[1] - 1e6 seed cells per GPU, 3 proliferating types +
+quiescent, t_max = 240, -r per-type counts, phi = 0.5; ~1.1e8 divisions per simulation and GPU.
+A STEP is one batch of B such simulations (--batch, default 32; each with its own Philox seed, each its own launch
+and - at N > 1 - its own NCCL reduce), so that the driver's 20 steps cover ~0.7 s of GPU time instead of 22 ms.
+N > 1 is weak scaling: the histogram holds N x 1e6 cells, seed-cell units are sharded rank-strided, every simulation
+ends with ONE NCCL reduce (sum, int64) of count tensor + division counter to rank 0; the reduce of simulation i runs on
+a second stream and overlaps simulation i + 1 (two count tensors used alternately).
 
-  value     whole-job divisions/s, tables resident in HBM, CUDA-event time per step summed over K steps (L2 flushed
-            between steps, outside the events), max over ranks
-  e2e       the same metric through the C ABI with HOST buffers: histogram arrays -> plan -> H2D tables -> kernel ->
-            D2H count tensor -> merged rows, wall-clock over all steps bracketed by synchronize (the host legs of
-            neighbouring steps overlap the kernel)
-  roofline  instruction-issue roofline (this path is FP64/INT-issue bound, not HBM/tensor bound - DESIGN.md):
-            achieved divisions/s over the RNG-only ceiling kernel measured in the same run; HBM figures for completeness
+  value       whole-job divisions/s, tables resident in HBM: CUDA-event time of the K steps (L2 flushed between steps,
+              outside the events), max over ranks
+  e2e         the same metric through the C ABI with HOST buffers: histogram arrays -> plan -> H2D tables -> kernel ->
+              [reduce] -> D2H count tensor -> merged rows, wall clock bracketed by synchronize, two engines in flight
+  per_config  BASELINE configs 2..5 at full size, each with its own ms, divisions/s and roofline fraction; at N > 1
+              config 3 and config 5 are sharded over the ranks by seed-cell units and config 4 by subtrees (strong scaling)
+  roofline    instruction-issue roofline (FP64/INT-issue bound path, neither HBM nor tensor - DESIGN.md section 5):
+              achieved divisions/s over the RNG-only ceiling kernel measured in the same run, with the hardware-unit
+              fractions of the committed ncu capture beside it; HBM figures for completeness
   cpu_baseline  the CPU oracle (oracle/, a port with the same Philox streams) on this box's host cores
+  verify      N > 1: the reduced tensor of one simulation equals, bit for bit, the same simulation run unsharded on rank 0
 
---impl reference times the UNMODIFIED reference CUDA build (oracle/_ref/procell_ref, one B200, whole-process wall
-clock: it has no internal timers and no resident mode) on the largest BASELINE config it can run.
+--impl reference times the reference's own CUDA build (oracle/_ref/, one B200, one process per step) on the SAME input
+file; see run_reference().
 """
 import argparse
 import json
@@ -40,6 +46,8 @@ UNIT = "divisions/s"
 CELLS_PER_GPU = 1_000_000
 FLUSH_BYTES = 256 << 20
 SHARD_UNIT = 32
+WORKLOAD_TEXT = ("BASELINE configs[1]: 1e6 seed cells per GPU (synthetic 1024-channel histogram), types 0.40/48.33/21.6 "
+                 "0.25/86.3/26.8 0.17/24/6 + 0.18 quiescent, t_max=240, phi=0.5, -r")
 
 
 def workload_for(n_gpus: int):
@@ -52,52 +60,77 @@ def workload_for(n_gpus: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and clock-event (throttle) reasons of one GPU sampled every 20 ms through NVML from a thread, started
+    BEFORE warm-up; stop() summarises the samples that fell inside the timed region [t0, t1].  Falls back to an
+    `nvidia-smi -lms 100` child process when pynvml is not importable."""
+    NAMES = {"hw_slowdown": "nvmlClocksEventReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksEventReasonHwThermalSlowdown",
+             "sw_thermal_slowdown": "nvmlClocksEventReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksEventReasonSwPowerCap"}
 
     def __init__(self, index: int):
         self.index = index
-        self.lines = []
-        self.proc = None
+        self.samples = []          # (perf_counter, sm_mhz, reason bits)
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.smi = None
+        self.how = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {k: getattr(pynvml, v) for k, v in self.NAMES.items()}
 
-    def _pump(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            def pump():
+                while not self.stop_flag.is_set():
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        rs = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        self.samples.append((time.perf_counter(), mhz, [k for k, b in bits.items() if rs & b]))
+                    except Exception:
+                        pass
+                    self.stop_flag.wait(0.02)
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+            self.thread = threading.Thread(target=pump, daemon=True)
+            self.thread.start()
+            self.how = "pynvml, 20 ms"
+        except Exception:
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                self.smi = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                             "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+                def pump_smi():
+                    for ln in self.smi.stdout:
+                        f = [x.strip() for x in ln.split(",")]
+                        try:
+                            self.max_mhz = float(f[1])
+                            self.samples.append((time.perf_counter(), float(f[0]),
+                                                 [k for k, v in zip(self.NAMES, f[2:6]) if v.lower().startswith("active")]))
+                        except (ValueError, IndexError):
+                            pass
+
+                self.thread = threading.Thread(target=pump_smi, daemon=True)
+                self.thread.start()
+                self.how = "nvidia-smi -lms 100"
+            except OSError:
+                self.how = None
+
+    def stop(self, t0: float, t1: float):
+        self.stop_flag.set()
+        if self.smi is not None:
+            self.smi.terminate()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if self.how is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        reasons = sorted({r for s in inside for r in s[2]})
+        return {"sm_mhz": statistics.median(s[1] for s in inside) if inside else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(inside), "samples_total": len(self.samples), "how": self.how}
 
 
 def cpu_baseline(w, max_seconds=25.0):
@@ -121,110 +154,181 @@ def cpu_baseline(w, max_seconds=25.0):
             "sample": "%d full run(s) of the 1e6-cell config-2 workload (%.3g divisions, %.2f s)" % (runs, div_total, t_total)}
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# reference arm
+# --------------------------------------------------------------------------------------------------------------------
+def _ref_run(binary, tmp, wl, t_max, limit):
+    """one process of a reference build on the files in tmp; returns (wall_s, leaf total) or None on failure"""
+    o = tmp / "o.txt"
+    if o.exists():
+        o.unlink()
+    cmd = [str(binary), "-h", str(tmp / "h.txt"), "-c", str(tmp / "c.txt"), "-t", repr(float(t_max)), "-p", repr(float(wl.phi)),
+           "-o", str(o)] + (["-r"] if wl.track_ratio else [])
+    t0 = time.perf_counter()
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=limit)
+    except subprocess.TimeoutExpired:
+        return None
+    dt = time.perf_counter() - t0
+    if r.returncode != 0 or not o.exists():
+        return None
+    leaves = sum(int(ln.split("\t")[1]) for ln in o.read_text().splitlines() if ln.strip())
+    return dt, leaves
+
+
 def run_reference(args):
-    """--impl reference: the unmodified reference CUDA binary, whole-process wall clock per step."""
+    """--impl reference: the reference's own CUDA build on one B200, one process per step, on the SAME input as our arm
+    (configs[1], 1e6 cells, written to the text files both executables read).
+
+    Which binary: the unmodified build (oracle/_ref/procell_ref) silently loses subtrees on sm_100 from 2e4 cells on
+    (CDP2's pending-launch pool; tests/golden/ref_cfg2_*.json), so for this input the arm uses
+    oracle/_ref/procell_ref_pl = the same sources plus the ONE line BASELINE.md section 2 permits,
+    cudaDeviceSetLimit(cudaLimitDevRuntimePendingLaunchCount, N) (oracle/Makefile `refpl`, diff in
+    oracle/_ref/procell_ref_pl.diff).  A run is accepted only if its leaf total is within 2 % of the Philox oracle's
+    expectation for the same input (the two are equal in law; run-to-run spread of the total is ~0.1 %).
+    What is reported: the reference has no timers and no resident mode, so a step is a whole process.  `value` =
+    divisions / (wall - floor), where floor = the same command with -t 0 (context creation, file parsing, seed
+    population; no division) - the simulation alone, the quantity our event-timed arm measures; the whole-process
+    figure is given beside it (`process_value`), and so is the config-1 command line, wall clock, for the CLI-vs-CLI
+    comparison.  If no build simulates the 1e6-cell input credibly, the line says so (`unavailable_config2`) and
+    carries configs[0] (1e4 cells), which the unmodified reference does run correctly."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    ref = ROOT / "oracle" / "_ref" / "procell_ref"
     import oracle_lib
     from cuda_pro_cell_b200 import synth
+    refdir = ROOT / "oracle" / "_ref"
     w = workload_for(1)
-    cfg = {"workload": "BASELINE configs[1]: 1e6 seed cells, types 0.40/48.33/21.6 0.25/86.3/26.8 0.17/24/6 + 0.18 quiescent, "
-                       "t_max=240, phi=0.5, -r", "n_cells": int(w.n_cells), "l2": "n/a (separate process per step)"}
+    cfg = {"workload": WORKLOAD_TEXT, "n_cells": int(w.n_cells), "l2": "n/a (separate process per step)"}
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg}
-    if not ref.exists():
+    binaries = [b for b in (refdir / "procell_ref_pl", refdir / "procell_ref") if b.exists()]
+    if not binaries:
         # no reference binary on this box: time the oracle port on all host cores instead
         cb = cpu_baseline(w)
         line.update({"value": cb["value"], "ms_per_step": None, "cpu_baseline": cb,
                      "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                     "note": "oracle/_ref/procell_ref missing; oracle port timed instead"})
+                     "note": "oracle/_ref/procell_ref* missing; oracle port timed instead"})
         print(json.dumps(line))
         return 0
-    # expected divisions of the workload (equal in law to the reference's): from the oracle, once
     tmp = Path(tempfile.mkdtemp(prefix="procell_ref_"))
-    steps_total = max(1, args.warmup) + args.steps
-    # the reference silently loses subtrees on sm_100 once levels get wide (tests/golden/ref_cfg2_*.json: 7 % of the
-    # expected leaves at 1e6 cells, 25 % at 2e4, correct at 2e3), so walk down until its leaf total is credible
-    attempts = [(w, "configs[1] full (1e6 cells)")]
-    for scale, label in ((0.1, "1e5"), (0.01, "1e4"), (0.002, "2e3")):
-        attempts.append((synth.workload(2, scale), "configs[1] shape at %s cells (larger inputs lose subtrees on the reference build)" % label))
-    attempts.append((synth.workload(1), "configs[0] (1e4 cells, t_max=168)"))
-    for wl, label in attempts:
+    budget_s = 170.0
+    t_begin = time.perf_counter()
+
+    def measure(binary, wl, label, max_steps):
+        """floor + up to max_steps timed processes; None unless every run's leaf total is credible"""
         (tmp / "h.txt").write_text(synth.histogram_text(wl.values, wl.freqs))
         (tmp / "c.txt").write_text(synth.types_text(wl.types[0]))
-        cmd = [str(ref), "-h", str(tmp / "h.txt"), "-c", str(tmp / "c.txt"), "-t", repr(float(wl.t_max)),
-               "-p", repr(float(wl.phi)), "-o", str(tmp / "o.txt")] + (["-r"] if wl.track_ratio else [])
         oplan = oracle_lib.OraclePlan(wl.values, wl.freqs, wl.phi)
         expect = oracle_lib.simulate(oplan, wl.types, wl.t_max, wl.seed)
-        exp_div = int(expect["divisions"].sum())
-        exp_leaves = int(expect["row_freq"].sum())
-        times, ok, leaves = [], True, []
-        n_warm, n_steps, i = max(1, args.warmup), args.steps, 0
-        while i < n_warm + n_steps:
-            t0 = time.perf_counter()
-            try:
-                r = subprocess.run(cmd, capture_output=True, text=True, timeout=150)
-            except subprocess.TimeoutExpired:
-                ok = False
-                break
-            dt = time.perf_counter() - t0
-            if r.returncode != 0 or not (tmp / "o.txt").exists():
-                ok = False
-                break
-            got = sum(int(ln.split("\t")[1]) for ln in (tmp / "o.txt").read_text().splitlines() if ln.strip())
-            leaves.append(got)
-            if abs(got - exp_leaves) > 0.2 * exp_leaves:   # lost subtrees (CDP2 pending-launch pool) or truncation
-                ok = False
-                break
-            if i == 0:   # bound the whole arm to ~2.5 minutes: each step is a whole process (>= 1.05 s apart)
-                n_warm = 1
-                n_steps = max(3, min(args.steps, int(150.0 / max(dt, 1.05)) - 1))
-            else:
-                times.append(dt)
-            (tmp / "o.txt").unlink()
-            if dt < 1.05:
-                time.sleep(1.05 - dt)      # the reference seeds from time(NULL): keep runs in distinct seconds
-            i += 1
-        if ok and times:
-            total = sum(times)
-            value = exp_div * len(times) / total
-            cfg["workload_run"] = label
-            line.update({"value": value, "ms_per_step": 1e3 * total / len(times), "steps": len(times),
-                         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
-                                          "sample": "%s; unmodified reference CUDA build (sm_100, CDP2) on one B200, "
-                                                    "whole-process wall clock, %d runs; divisions = oracle expectation %d "
-                                                    "(reference leaves %s vs expected %d)"
-                                                    % (label, len(times), exp_div, leaves[-3:], exp_leaves)},
-                         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-            print(json.dumps(line))
-            return 0
-    line.update({"unavailable": "reference binary failed on every attempted input"})
+        exp_div, exp_leaves = int(expect["divisions"].sum()), int(expect["row_freq"].sum())
+        floors = []
+        for _ in range(2):
+            f = _ref_run(binary, tmp, wl, 0.0, 120)
+            if f is None:
+                return None
+            floors.append(f[0])
+            time.sleep(max(0.0, 1.05 - f[0]))
+        floor = min(floors)
+        first = _ref_run(binary, tmp, wl, wl.t_max, 160)         # warm-up step; also sizes the loop
+        if first is None or abs(first[1] - exp_leaves) > 0.02 * exp_leaves:
+            return {"ok": False, "leaves": None if first is None else first[1], "expected_leaves": exp_leaves}
+        left = budget_s - (time.perf_counter() - t_begin)
+        n = max(1, min(max_steps, int(left / max(first[0] + 0.2, 1.1))))
+        times, leaves = [], []
+        for _ in range(n):
+            time.sleep(max(0.0, 1.05 - (times[-1] if times else first[0])))   # the reference seeds from time(NULL)
+            r = _ref_run(binary, tmp, wl, wl.t_max, 160)
+            if r is None or abs(r[1] - exp_leaves) > 0.02 * exp_leaves:
+                return {"ok": False, "leaves": None if r is None else r[1], "expected_leaves": exp_leaves}
+            times.append(r[0])
+            leaves.append(r[1])
+        wall = sum(times) / len(times)
+        sim = max(wall - floor, 1e-6)
+        return {"ok": True, "label": label, "binary": binary.name, "steps": len(times), "wall_s": wall, "floor_s": floor, "sim_s": sim,
+                "divisions": exp_div, "leaves": leaves[-3:], "expected_leaves": exp_leaves}
+
+    # the config-1 command line, wall clock (what the unmodified reference certainly runs): CLI-vs-CLI figure
+    w1 = synth.workload(1)
+    cli1 = measure(refdir / "procell_ref" if (refdir / "procell_ref").exists() else binaries[0], w1, "configs[0]", 3)
+    result, rejected = None, []
+    for b in binaries:
+        if time.perf_counter() - t_begin > budget_s - 40:
+            break
+        m = measure(b, w, "configs[1] full (1e6 cells)", args.steps)
+        if m and m.get("ok"):
+            result = m
+            break
+        rejected.append({"binary": b.name, "result": m})
+    if result is None and cli1 and cli1.get("ok"):
+        result = cli1
+        cfg["workload"] = "BASELINE configs[0]: 1e4 seed cells, types 0.53/48.33/21.6 0.29/86.3/26.8 + 0.18 quiescent, t_max=168, phi=min bin"
+        cfg["n_cells"] = int(w1.n_cells)
+        line["unavailable_config2"] = "no reference build simulates the 1e6-cell input credibly on sm_100: %s" % json.dumps(rejected)
+    if result is None:
+        line.update({"unavailable": "reference binary failed on every attempted input: %s" % json.dumps(rejected)})
+        print(json.dumps(line))
+        return 0
+    value = result["divisions"] / result["sim_s"]
+    cfg["workload_run"] = result["label"]
+    patch = ""
+    if result["binary"] != "procell_ref":
+        d = refdir / (result["binary"] + ".diff")
+        patch = d.read_text().strip() if d.exists() else "cudaDeviceSetLimit(cudaLimitDevRuntimePendingLaunchCount, N)"
+    line.update({"value": value, "ms_per_step": 1e3 * result["sim_s"], "steps": result["steps"],
+                 "process_value": result["divisions"] / result["wall_s"], "process_wall_ms_per_step": 1e3 * result["wall_s"],
+                 "process_start_floor_ms": 1e3 * result["floor_s"],
+                 "reference_binary": result["binary"], "reference_patch": patch or "none (unmodified)",
+                 "timing": "value = divisions / (process wall - floor); floor = same command with -t 0 (context, parsing, seed population)",
+                 "cli_config1": None if not (cli1 and cli1.get("ok")) else
+                 {"wall_ms": 1e3 * cli1["wall_s"], "floor_ms": 1e3 * cli1["floor_s"], "divisions": cli1["divisions"], "binary": cli1["binary"]},
+                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
+                                  "sample": "%s; reference CUDA build %s (sm_100, CDP2) on one B200, %d process(es); divisions = oracle "
+                                            "expectation %d (reference leaves %s vs expected %d)"
+                                            % (result["label"], result["binary"], result["steps"], result["divisions"],
+                                               result["leaves"], result["expected_leaves"])},
+                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line))
     return 0
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------------------------
+def hw_fractions():
+    """hardware-unit fractions of the dominant kernel from the committed ncu captures (profiles/*_hw_fractions.json,
+    written by tools/summarize_profile.py --fractions from `ncu --set full` reports of this build)"""
+    best = None
+    for p in sorted((ROOT / "profiles").glob("*_hw_fractions.json")):
+        try:
+            best = (p.name, json.loads(p.read_text()))
+        except Exception:
+            pass
+    return best
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="simulations per step (each its own launch, seed and reduce)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=100)
-    ap.add_argument("--e2e-engines", type=int, default=1,
+    ap.add_argument("--no-per-config", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=8, help="steps (batches of --batch simulations) of the end-to-end leg")
+    ap.add_argument("--e2e-engines", type=int, default=2,
                     help="engines (each with its own stream, count tensor and pinned host buffer) the end-to-end leg keeps in "
-                         "flight: 1 = one step at a time (measured in round 1); 2 = the D2H of step i and the H2D of step i+2 "
-                         "overlap kernel i+1 (written without GPU access: opt-in until it has been run on a B200)")
+                         "flight: with 2 the D2H of simulation i and the H2D of simulation i+2 overlap kernel i+1")
+    ap.add_argument("--serial-reduce", action="store_true", help="N > 1: reduce on the compute stream (no overlap with the next simulation)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import torch.distributed as dist
-    from cuda_pro_cell_b200 import api
+    from cuda_pro_cell_b200 import api, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
@@ -239,7 +343,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
-    K = args.steps
+    K = max(1, args.steps)
+    B = max(1, args.batch)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                      # before warm-up: the first samples exist when the timed region starts
 
     w = workload_for(world)
     n_types = w.types.shape[1]
@@ -248,14 +357,41 @@ def main():
     shard = (rank, world, SHARD_UNIT)
     eng.load(plan, w.types, w.t_max, w.seed, shard=shard)
     n_counts = plan.n_keys * n_types
-    buf = torch.zeros(n_counts + 1, dtype=torch.int64, device=dev)        # counts + division counter: one reduce
+    bufs = [torch.zeros(n_counts + 1, dtype=torch.int64, device=dev) for _ in range(2)]   # counts + division counter: one reduce
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
+    comm = torch.cuda.Stream(device=dev) if world > 1 and not args.serial_reduce else None
+    div_acc = torch.zeros(1, dtype=torch.int64, device=dev)
+    reduced = [None, None]                   # event: the reduce that last read bufs[k] is over
 
-    def step(seed):
+    def simulate(seed, k, accumulate):
+        """one simulation into bufs[k]; N > 1: its reduce runs on the communication stream and overlaps the next one"""
+        buf = bufs[k]
+        if reduced[k] is not None:
+            stream.wait_event(reduced[k])
         eng.run(seed, stream.cuda_stream, buf.data_ptr(), buf.data_ptr() + 8 * n_counts)
-        if world > 1:
-            dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
+        if world > 1 and comm is not None:
+            done = torch.cuda.Event()
+            done.record(stream)
+            with torch.cuda.stream(comm):
+                comm.wait_event(done)
+                dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
+                if accumulate:
+                    div_acc.add_(buf[n_counts:])
+                ev = torch.cuda.Event()
+                ev.record(comm)
+            reduced[k] = ev
+        else:
+            if world > 1:
+                dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
+            if accumulate:
+                div_acc.add_(buf[n_counts:])
+
+    def step(first_seed, accumulate):
+        for j in range(B):
+            simulate(first_seed + j, j & 1, accumulate)
+        if comm is not None:
+            stream.wait_stream(comm)         # a step ends when its last reduce has ended
 
     def barrier():
         if world > 1:
@@ -264,127 +400,118 @@ def main():
 
     for i in range(W):
         flush.fill_(i)
-        step(w.seed + i)
+        step(w.seed + 100000 * i, False)
     barrier()
-    # status check once before timing (finish() synchronises and reads the device status word)
-    eng.finish(stream.cuda_stream, fetch=False)
+    eng.finish(stream.cuda_stream, fetch=False)      # status word (sticky on the device): no failure during warm-up
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    div_acc = torch.zeros(1, dtype=torch.int64, device=dev)
     barrier()
     t_wall0 = time.perf_counter()
     for i in range(K):
         flush.fill_(i & 0xFF)                      # L2 flush (256 MiB > 126 MB L2), outside the event pair
         evs[i][0].record(stream)
-        step(w.seed + 1000 + i)
+        step(w.seed + 1000 + i * B, True)
         evs[i][1].record(stream)
-        div_acc += buf[n_counts:]                  # exact division total of the timed steps (after the end event)
     barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
+    t_wall1 = time.perf_counter()
+    t_wall = t_wall1 - t_wall0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     gpu_ms = sum(a.elapsed_time(b) for a, b in evs)
     t_ms = torch.tensor([gpu_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     gpu_ms = float(t_ms.item())
-    eng.finish(stream.cuda_stream, fetch=False)    # device status word: no pool overflow / watchdog abort
+    # the device status word is sticky: a pool overflow / watchdog abort in ANY simulation since the last finish is still there
+    eng.finish(stream.cuda_stream, fetch=False)
     div_timed = int(div_acc.item())                # rank 0 holds the reduced totals
-    div_per_step = div_timed / K
+    div_per_sim = div_timed / (K * B)
     value = div_timed / (gpu_ms * 1e-3) if rank == 0 else 0.0
 
+    # ---- N > 1: the reduced tensor of one simulation == the same simulation unsharded on rank 0 (outside any timed region)
+    verify = None
+    if world > 1:
+        simulate(w.seed + 77, 0, False)
+        barrier()
+        if rank == 0:
+            whole = api.Engine(local_rank)
+            whole.load(plan, w.types, w.t_max, w.seed, shard=(0, 1, SHARD_UNIT))
+            ref = torch.zeros_like(bufs[0])
+            whole.run(w.seed + 77, stream.cuda_stream, ref.data_ptr(), ref.data_ptr() + 8 * n_counts)
+            whole.finish(stream.cuda_stream, fetch=False)
+            verify = {"reduced_tensor_equals_single_gpu_run": bool(torch.equal(ref, bufs[0])), "divisions": int(ref[n_counts].item()),
+                      "what": "count tensor + division counter of one %d-rank simulation after the NCCL reduce vs the same seed "
+                              "run unsharded on rank 0" % world}
+            whole.close()
+        barrier()
+
     # ---- end to end through the C ABI with host buffers
-    E = max(1, args.e2e_steps)
+    E = max(1, args.e2e_steps) * B           # simulations of the end-to-end leg
     h2d = plan.n_bins * 4 * 2 + plan.n_bins + 4 + w.types.size // 3 * (8 + 1 + 16) + 256 * 8
     d2h = (n_counts + 1) * 8
     host_values, host_freqs = w.values.copy(), w.freqs.copy()
     e2e_div = 0
-
-    def merge(done):          # rank 0: count tensor -> merged output rows (what a caller reads)
-        nonlocal e2e_div
-        p_done, host_done = done
-        if rank == 0:
-            p_done.merge_rows(host_done[:n_counts].numpy().reshape(plan.n_keys, n_types))
-            e2e_div += int(host_done[n_counts])
-
     n_eng = max(1, args.e2e_engines)
-    if n_eng > 1:
-        # several steps in flight: slot k = (engine, non-blocking stream, device count tensor, pinned host tensor).  Every
-        # step still does all of its own work (plan, H2D tables, kernel, reduce, D2H, row merge); a slot is reused only after
-        # its previous step has been read back, checked (finish: device status word) and merged.
-        engs = [eng] + [api.Engine(local_rank) for _ in range(n_eng - 1)]
-        streams = [torch.cuda.Stream(device=dev) for _ in range(n_eng)]
-        bufs = [torch.zeros_like(buf) for _ in range(n_eng)]
-        hosts = [torch.zeros(buf.shape, dtype=buf.dtype).pin_memory() for _ in range(n_eng)]
-        inflight = [None] * n_eng
+    engs = [eng] + [api.Engine(local_rank) for _ in range(n_eng - 1)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_eng)]
+    dbufs = [torch.zeros(n_counts + 1, dtype=torch.int64, device=dev) for _ in range(n_eng)]
+    hosts = [torch.zeros(n_counts + 1, dtype=torch.int64).pin_memory() for _ in range(n_eng)]
+    inflight = [None] * n_eng
+
+    def retire(k):
+        """slot k: wait for its D2H, check the device status word, merge the rows (what a caller reads)"""
+        nonlocal e2e_div
+        p_k, ev_k = inflight[k]
+        ev_k.synchronize()
+        engs[k].finish(streams[k].cuda_stream, fetch=False)
+        if rank == 0:
+            p_k.merge_rows(hosts[k][:n_counts].numpy().reshape(plan.n_keys, n_types))
+            e2e_div += int(hosts[k][n_counts])
+        inflight[k] = None
+
     barrier()
     t0 = time.perf_counter()
-    # every step does all of its own work - plan from the host arrays, H2D tables, kernel, reduce, D2H, row merge; the
-    # host legs of neighbouring steps (plan of step i+1, row merge of step i-1) run while kernel i is on the GPU
-    prev = None
-    if n_eng > 1:
-
-        def retire(k):
-            p_k, ev_k = inflight[k]
-            ev_k.synchronize()
-            engs[k].finish(streams[k].cuda_stream, fetch=False)
-            merge((p_k, hosts[k]))
-            inflight[k] = None
-
-        for i in range(E):
-            k = i % n_eng
-            if inflight[k] is not None:
-                retire(k)
-            p = api.Plan(host_values, host_freqs, w.phi)
-            engs[k].load(p, w.types, w.t_max, w.seed + i, shard=shard)
-            engs[k].run(w.seed + 2000 + i, streams[k].cuda_stream, bufs[k].data_ptr(), bufs[k].data_ptr() + 8 * n_counts)
-            with torch.cuda.stream(streams[k]):
-                if world > 1:
-                    dist.reduce(bufs[k], dst=0, op=dist.ReduceOp.SUM)
-                hosts[k].copy_(bufs[k], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(streams[k])
-            inflight[k] = (p, ev)
-        for j in range(n_eng):
-            k = (E + j) % n_eng
-            if inflight[k] is not None:
-                retire(k)
-        E_done, E = E, 0          # the single-engine loop below does not run
-    else:
-        p_next = api.Plan(host_values, host_freqs, w.phi)                  # parser.cu:68-154 work, on the host
+    # every simulation does all of its own work - plan from the host arrays, H2D tables, kernel, reduce, D2H, row merge; a
+    # slot (engine, stream, device tensor, pinned host tensor) is reused only after its previous simulation has been read
+    # back, checked and merged, so with two slots the host legs and copies of one overlap the kernel of the other
     for i in range(E):
-        p = p_next
-        eng.load(p, w.types, w.t_max, w.seed + i, shard=shard)             # H2D tables
-        eng.run(w.seed + 2000 + i, stream.cuda_stream, buf.data_ptr(), buf.data_ptr() + 8 * n_counts)
-        if world > 1:
-            dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
-        if i + 1 < E:
-            p_next = api.Plan(host_values, host_freqs, w.phi)
-        if prev is not None:
-            merge(prev)
-        host = buf.cpu()                                                   # D2H count tensor + division counter
-        eng.finish(stream.cuda_stream, fetch=False)
-        prev = (p, host)
-    if n_eng > 1:
-        E = E_done
-    else:
-        merge(prev)
+        k = i % n_eng
+        if inflight[k] is not None:
+            retire(k)
+        p = api.Plan(host_values, host_freqs, w.phi)                      # parser.cu:68-154 work, on the host
+        engs[k].load(p, w.types, w.t_max, w.seed + i, shard=shard)        # H2D tables (asynchronous, pinned staging)
+        engs[k].run(w.seed + 2000 + i, streams[k].cuda_stream, dbufs[k].data_ptr(), dbufs[k].data_ptr() + 8 * n_counts)
+        with torch.cuda.stream(streams[k]):
+            if world > 1:
+                dist.reduce(dbufs[k], dst=0, op=dist.ReduceOp.SUM)
+            hosts[k].copy_(dbufs[k], non_blocking=True)                   # D2H count tensor + division counter
+            ev = torch.cuda.Event()
+            ev.record(streams[k])
+        inflight[k] = (p, ev)
+    for j in range(n_eng):
+        k = (E + j) % n_eng
+        if inflight[k] is not None:
+            retire(k)
     barrier()
     t_e2e = time.perf_counter() - t0
-    if n_eng > 1:
-        for extra in engs[1:]:
-            extra.close()
+    for extra in engs[1:]:
+        extra.close()
     t_e = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     t_e2e = float(t_e.item())
 
+    # ---- RNG-only ceiling kernel, measured now on this GPU (rank 0)
+    ceiling = None
     if rank == 0:
-        # ---- roofline: the RNG-only ceiling kernel, measured now on this GPU
         ms_c, pairs = api.rng_ceiling(local_rank, 4096)
         ceiling = pairs / (ms_c * 1e-3)
+
+    # ---- per-config records: BASELINE configs 2..5 at full size (strong scaling over the ranks at N > 1)
+    per_config = None
+    if not args.no_per_config:
+        per_config = run_per_config(api, synth, torch, dist, dev, local_rank, rank, world, stream, barrier, ceiling)
+
+    if rank == 0:
         per_gpu = value / world
         peaks = {}
         try:
@@ -393,35 +520,44 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         alg_bytes = float(h2d + d2h)          # tables read once + count tensor written once per launch
-        ms_step = gpu_ms / K
+        ms_sim = gpu_ms / (K * B)
+        hw = hw_fractions()
         roofline = {"bound": "issue",
                     "bound_detail": "FP64 + INT instruction issue; neither HBM nor tensor bound (DESIGN.md section 5)",
                     "achieved": per_gpu / 1e9, "peak": ceiling / 1e9, "unit": "Gdivisions/s per GPU",
                     "frac": per_gpu / ceiling,
                     "peak_source": "k_rng_ceiling measured live: one Philox4x32-10 block + Box-Muller pair + 2 timers per division, no tree/atomics",
-                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this workload, from the
-                    # committed capture profiles/r1h_coop32_config2_ncu_full.md (tables + count tensor + donated chunks)
-                    "traffic": 777216 if world == 1 else None,
-                    "hbm": {"achieved": alg_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                    "traffic": None,
+                    "hbm": {"achieved": alg_bytes / (ms_sim * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": alg_bytes / (ms_sim * 1e-3) / 1e9 / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                             "algorithmic_bytes_per_launch": alg_bytes}}
+        if hw is not None:
+            # hardware-unit fractions of k_proliferate_coop on this workload and of the ceiling kernel itself, from the
+            # committed `ncu --set full` capture of this build (not measured live: a profiler cannot run inside a bench)
+            roofline["hardware"] = dict(hw[1], source="profiles/" + hw[0])
+            roofline["traffic"] = hw[1].get("config2", {}).get("dram_bytes_per_launch") if world == 1 else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": gpu_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "BASELINE configs[1]: 1e6 seed cells per GPU (synthetic 1024-channel histogram), types "
-                                       "0.40/48.33/21.6 0.25/86.3/26.8 0.17/24/6 + 0.18 quiescent, t_max=240, phi=0.5, -r",
-                           "n_cells": int(plan.n_cells), "divisions_per_step": div_per_step,
-                           "sharding": "seed-cell units of %d, rank-strided; one NCCL reduce(sum,int64) per step" % SHARD_UNIT,
+                "config": {"workload": WORKLOAD_TEXT, "n_cells": int(plan.n_cells), "simulations_per_step": B,
+                           "divisions_per_simulation": div_per_sim, "ms_per_simulation": ms_sim,
+                           "sharding": "seed-cell units of %d, rank-strided; one NCCL reduce(sum,int64) per simulation%s"
+                                       % (SHARD_UNIT, "" if comm is None else ", on a second stream (overlaps the next simulation)"),
                            "l2": "flushed between steps (256 MiB write), outside the timed events"},
-                "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
-                "e2e": {"value": e2e_div / t_e2e if t_e2e > 0 else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h), "steps": E,
+                "wall_ms_per_step_incl_flush": 1e3 * t_wall / K, "timed_region_s": gpu_ms * 1e-3,
+                "e2e": {"value": e2e_div / t_e2e if t_e2e > 0 else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * B,
+                        "d2h_bytes_per_step": int(d2h) * B, "steps": E // B, "simulations": E,
+                        "h2d_bytes_per_simulation": int(h2d), "d2h_bytes_per_simulation": int(d2h),
                         "engines_in_flight": n_eng,
-                        "path": "api.Plan (host) -> procell_engine_load (H2D) -> procell_engine_run -> reduce -> D2H -> merge_rows; "
-                                "the plan of step i+1 and the row merge of step i-1 overlap kernel i"},
-                "gpu_launches": 2 * K, "kernels_per_step": ["k_queue_init", "k_proliferate_coop"],
+                        "path": "api.Plan (host) -> procell_engine_load (H2D, pinned staging) -> procell_engine_run -> reduce -> D2H -> "
+                                "merge_rows, per simulation; %d engine(s) in flight" % n_eng},
+                "gpu_launches": 2 * K * B, "kernels_per_simulation": ["k_queue_init", "k_proliferate_coop"],
                 "clocks": clocks, "roofline": roofline}
+        if verify is not None:
+            line["verify"] = verify
+        if per_config is not None:
+            line["per_config"] = per_config
         if not args.no_cpu_baseline and world == 1:      # the CPU baseline is timed on rank 0 at N = 1 only
             line["cpu_baseline"] = cpu_baseline(w)
         print(json.dumps(line))
@@ -429,6 +565,79 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def run_per_config(api, synth, torch, dist, dev, local_rank, rank, world, stream, barrier, ceiling):
+    """BASELINE configs 2..5 at full size, one record each: ms per simulation (CUDA events, max over ranks), divisions/s,
+    fraction of the live RNG ceiling - by divisions, and by DRAWS (seed cells + divisions: every seed cell also costs a
+    Philox block and a Box-Muller timer, and configs 3 and 5 are seed-heavy).  N > 1 is STRONG scaling here: the one input
+    is sharded over the ranks - seed-cell units (configs 2, 3, 5; unit chosen by the library) or subtrees at tree level 6
+    (config 4: a hundred fast lineages own all the work) - and rank 0 checks the reduced tensor against the same simulation
+    unsharded on its own GPU."""
+    out = {}
+    plans = [(2, 1, 10, 0), (3, 1, 10, 0), (4, 1, 2, 6 if world > 1 else 0), (5, 1, 4, 0)]
+    for config, n_warm, n_timed, level in plans:
+        w = synth.workload(config)
+        plan = api.Plan(w.values, w.freqs, w.phi)
+        n_sets, n_types = w.types.shape[0], w.types.shape[1]
+        n_counts = n_sets * plan.n_keys * n_types
+        eng = api.Engine(local_rank)
+        eng.load(plan, w.types, w.t_max, w.seed, shard=(rank, world, 0), shard_level=level)
+        buf = torch.zeros(n_counts + n_sets, dtype=torch.int64, device=dev)
+
+        def sim():
+            eng.run(w.seed, stream.cuda_stream, buf.data_ptr(), buf.data_ptr() + 8 * n_counts)
+            if world > 1:
+                dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
+
+        for _ in range(n_warm):
+            sim()
+        barrier()
+        evs = []
+        for _ in range(n_timed):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            sim()
+            b.record(stream)
+            evs.append((a, b))
+        barrier()
+        st = eng.finish(stream.cuda_stream, fetch=False).stats
+        ms = sum(a.elapsed_time(b) for a, b in evs) / n_timed
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        idle = torch.tensor([st["idle_warp_us"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(idle, op=dist.ReduceOp.MAX)
+        rec = None
+        if rank == 0:
+            divisions = int(buf[n_counts:].sum().item())
+            draws = divisions + int(plan.n_cells) * n_sets
+            rec = {"n_cells": int(plan.n_cells), "n_sets": n_sets, "t_max": w.t_max, "divisions": divisions, "ms": ms,
+                   "value": divisions / (ms * 1e-3), "unit": UNIT, "scaling": "strong" if world > 1 else "single GPU",
+                   "sharding": "single GPU" if world == 1 else ("subtrees at tree level %d" % level if level else "seed-cell units, rank-strided"),
+                   "smem_bytes": st["smem_bytes"], "grid": st["grid"], "idle_warp_us_max_rank": float(idle.item()),
+                   "warps": st["grid"] * st["block"] // 32,
+                   "roofline": {"frac": divisions / (ms * 1e-3) / world / ceiling,
+                                "frac_draws": draws / (ms * 1e-3) / world / ceiling,
+                                "peak": ceiling / 1e9, "unit": "G/s per GPU",
+                                "note": "frac = divisions/s per GPU over the live RNG ceiling; frac_draws counts seed cells too"}}
+            if world > 1:
+                whole = api.Engine(local_rank)
+                whole.load(plan, w.types, w.t_max, w.seed)
+                ref = torch.zeros_like(buf)
+                whole.run(w.seed, stream.cuda_stream, ref.data_ptr(), ref.data_ptr() + 8 * n_counts)
+                ws = whole.finish(stream.cuda_stream, fetch=False).stats
+                rec["reduced_tensor_equals_single_gpu_run"] = bool(torch.equal(ref, buf))
+                rec["single_gpu_ms_on_rank0"] = ws["kernel_ms"]
+                whole.close()
+        barrier()
+        eng.close()
+        if rank == 0:
+            out["config%d" % config] = rec
+        del buf
+    return out if rank == 0 else None
 
 
 if __name__ == "__main__":

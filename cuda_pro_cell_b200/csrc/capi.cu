@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -80,8 +81,18 @@ struct procell_engine {
     int device = 0;
     int sm_count = 0;
     DevBuf tables, logtab;                  /* tables: plan + type tables, one packed allocation */
-    void* stage = nullptr;                  /* pinned host staging for the packed tables */
-    size_t stage_cap = 0;
+    /* pinned host staging for the packed tables: two buffers used alternately, so that the upload of load i+1 may be
+     * written while the asynchronous copy of load i is still in flight */
+    void* stage[2] = { nullptr, nullptr };
+    size_t stage_cap[2] = { 0, 0 };
+    cudaEvent_t stage_done[2] = { nullptr, nullptr };   /* recorded behind the copy that reads stage[k] */
+    int stage_next = 0;
+    cudaStream_t up_stream = nullptr;       /* the table upload runs here, ordered behind the previous run (ev1) */
+    cudaEvent_t up_done = nullptr;          /* the next run waits for it on its own stream */
+    bool up_pending = false;
+    bool ran = false;                       /* a run has been queued since creation (ev1 is recorded) */
+    long long* last_counts = nullptr;       /* where the last run wrote: the engine's tensor or the caller's */
+    long long* last_divisions = nullptr;
     DevBuf dbg, fit_key_channel, fit_target, fit_out;
     uint32_t fit_channels = 0;
     std::vector<double> plan_row_value;     /* copies of what fitness needs, so the plan may be destroyed after load */
@@ -126,6 +137,11 @@ int procell_engine_create(int device, procell_engine** out)
         en->ctl.reserve(sizeof(ControlBlock)) != cudaSuccess ||
         en->q_seq.reserve(sizeof(unsigned long long) * kQueueCap) != cudaSuccess ||
         en->q_data.reserve(sizeof(unsigned long long) * (size_t)kQueueCap * kChunkWords) != cudaSuccess ||
+        cudaMemset(en->ctl.p, 0, sizeof(ControlBlock)) != cudaSuccess ||      /* the status word is sticky: k_queue_init never clears it */
+        cudaStreamCreateWithFlags(&en->up_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&en->up_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&en->stage_done[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&en->stage_done[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&en->ev0) != cudaSuccess || cudaEventCreate(&en->ev1) != cudaSuccess) {
         cudaError_t le = cudaGetLastError();
         procell_engine_destroy(en);
@@ -141,7 +157,12 @@ void procell_engine_destroy(procell_engine* en)
     cudaSetDevice(en->device);
     DevBuf* bufs[] = { &en->tables, &en->logtab, &en->counts, &en->dbg, &en->fit_key_channel, &en->fit_target, &en->fit_out, &en->ctl, &en->q_seq, &en->q_data, &en->spill };
     for (DevBuf* b : bufs) b->release();
-    if (en->stage) cudaFreeHost(en->stage);
+    if (en->up_stream) { cudaStreamSynchronize(en->up_stream); cudaStreamDestroy(en->up_stream); }
+    for (int k = 0; k < 2; ++k) {
+        if (en->stage[k]) cudaFreeHost(en->stage[k]);
+        if (en->stage_done[k]) cudaEventDestroy(en->stage_done[k]);
+    }
+    if (en->up_done) cudaEventDestroy(en->up_done);
     if (en->ev0) cudaEventDestroy(en->ev0);
     if (en->ev1) cudaEventDestroy(en->ev1);
     delete en;
@@ -187,13 +208,16 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     const size_t off_musd = off_cum + align16(S * T * 8);
     const size_t off_sel = off_musd + align16(S * T * 16);
     const size_t table_bytes = off_sel + align16(S * T);
-    if (table_bytes > en->stage_cap) {
-        if (en->stage) cudaFreeHost(en->stage);
-        en->stage = nullptr; en->stage_cap = 0;
-        CU(cudaMallocHost(&en->stage, table_bytes), "alloc pinned staging");
-        en->stage_cap = table_bytes;
+    const int sk = en->stage_next;
+    en->stage_next ^= 1;
+    CU(cudaEventSynchronize(en->stage_done[sk]), "wait for the staging buffer");   /* its last copy (two loads ago) is over */
+    if (table_bytes > en->stage_cap[sk]) {
+        if (en->stage[sk]) cudaFreeHost(en->stage[sk]);
+        en->stage[sk] = nullptr; en->stage_cap[sk] = 0;
+        CU(cudaMallocHost(&en->stage[sk], table_bytes), "alloc pinned staging");
+        en->stage_cap[sk] = table_bytes;
     }
-    unsigned char* st = static_cast<unsigned char*>(en->stage);
+    unsigned char* st = static_cast<unsigned char*>(en->stage[sk]);
     uint32_t* h_start = reinterpret_cast<uint32_t*>(st + off_start);
     uint32_t* h_keybase = reinterpret_cast<uint32_t*>(st + off_keybase);
     uint8_t* h_kdiv = st + off_kdiv;
@@ -221,8 +245,18 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
             h_musd[s * T + j] = make_double2(ty[j].mean, ty[j].stddev);
         }
     }
-    CU(en->tables.reserve(table_bytes), "alloc tables");
-    CU(cudaMemcpy(en->tables.p, st, table_bytes, cudaMemcpyHostToDevice), "upload tables");
+    /* asynchronous upload on the engine's own stream: ordered behind the previous run of this engine (which may still
+     * be reading the tables) and ahead of the next one (procell_engine_run makes its stream wait for up_done); the host
+     * does not wait, so with two engines in flight the copy hides behind the other engine's kernel */
+    if (table_bytes > en->tables.cap || !en->tables.p) {
+        if (en->ran) CU(cudaEventSynchronize(en->ev1), "previous run");      /* the old allocation may still be in use */
+        CU(en->tables.reserve(table_bytes), "alloc tables");
+    }
+    if (en->ran) CU(cudaStreamWaitEvent(en->up_stream, en->ev1, 0), "order upload behind the previous run");
+    CU(cudaMemcpyAsync(en->tables.p, st, table_bytes, cudaMemcpyHostToDevice, en->up_stream), "upload tables");
+    CU(cudaEventRecord(en->stage_done[sk], en->up_stream), "event record");
+    CU(cudaEventRecord(en->up_done, en->up_stream), "event record");
+    en->up_pending = true;
     unsigned char* dt = static_cast<unsigned char*>(en->tables.p);
 
     en->counts_len = M * S * K * T;
@@ -232,6 +266,7 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     en->plan_key_row = plan->key_row;
     en->fit_channels = 0;
     /* one allocation: the count tensor followed by the division counters, so that a multi-GPU run needs ONE reduce */
+    if ((en->counts_len + S) * 8 > en->counts.cap && en->ran) CU(cudaEventSynchronize(en->ev1), "previous run");
     CU(en->counts.reserve((en->counts_len + S) * 8), "alloc counts");
 
     SimParams& P = en->P;
@@ -369,14 +404,20 @@ int procell_engine_run(procell_engine* en, uint64_t seed, void* stream_v, int64_
     if (d_counts) P.counts = (long long*)d_counts;
     if (d_divisions) P.divisions = (long long*)d_divisions;
     en->timed = true;
+    en->last_counts = P.counts;
+    en->last_divisions = P.divisions;
+    if (en->up_pending) {       /* the tables of the last load are on their way on the upload stream */
+        CU(cudaStreamWaitEvent(stream, en->up_done, 0), "order run behind the table upload");
+        en->up_pending = false;
+    }
     CU(cudaEventRecord(en->ev0, stream), "event record");
-    CU(cudaMemsetAsync(P.counts, 0, en->counts_len * 8, stream), "zero counts");
-    CU(cudaMemsetAsync(P.divisions, 0, en->n_sets * 8, stream), "zero divisions");
-    CU(launch_queue_init(P.q_seq, P.ctl, stream), "launch k_queue_init");
+    /* one launch resets queue + control block and zeroes the count tensor and the division counters */
+    CU(launch_queue_init(P.q_seq, P.ctl, P.counts, en->counts_len, P.divisions, en->n_sets, en->sm_count, stream), "launch k_queue_init");
     if (en->kernel == PROCELL_KERNEL_SIMPLE) CU(launch_simple(P, en->grid, stream), "launch k_proliferate_simple");
     else CU(launch_coop(P, en->warps, en->ring, en->grid, stream), "launch k_proliferate_coop");
     en->launches_last = 2;
     CU(cudaEventRecord(en->ev1, stream), "event record");
+    en->ran = true;
     return PROCELL_OK;
 }
 
@@ -427,6 +468,9 @@ int procell_engine_finish(procell_engine* en, void* stream_v, int64_t* counts, i
     CU(cudaMemcpy(&cb, en->ctl.p, sizeof(ControlBlock), cudaMemcpyDeviceToHost), "read status");
     const int status = cb.status;
     if (status != kStatusOk) {
+        /* the word is sticky on the device (any run since the last finish may have set it): clear it now that it is
+         * being reported, so that the engine can be used again */
+        cudaMemset(reinterpret_cast<unsigned char*>(en->ctl.p) + offsetof(ControlBlock, status), 0, sizeof(int));
         std::string msg = "device work pool failure, status " + std::to_string(status);
         if (status == kStatusWatchdog && en->dbg.p) {      /* where were the warps when the watchdog fired */
             const size_t nw = (size_t)en->grid * en->warps;
@@ -448,9 +492,12 @@ int procell_engine_finish(procell_engine* en, void* stream_v, int64_t* counts, i
         }
         return fail(PROCELL_ERR_OVERFLOW, msg);
     }
-    if (counts) CU(cudaMemcpy(counts, en->counts.p, en->counts_len * 8, cudaMemcpyDeviceToHost), "download counts");
+    /* results are read from where the LAST run wrote them: the engine's own tensor or the caller's device buffers */
+    const long long* src_counts = en->last_counts ? en->last_counts : (const long long*)en->counts.p;
+    const long long* src_div = en->last_divisions ? en->last_divisions : (const long long*)en->counts.p + en->counts_len;
+    if (counts) CU(cudaMemcpy(counts, src_counts, en->counts_len * 8, cudaMemcpyDeviceToHost), "download counts");
     std::vector<int64_t> div(en->n_sets);
-    CU(cudaMemcpy(div.data(), (long long*)en->counts.p + en->counts_len, en->n_sets * 8, cudaMemcpyDeviceToHost), "download divisions");
+    CU(cudaMemcpy(div.data(), src_div, en->n_sets * 8, cudaMemcpyDeviceToHost), "download divisions");
     if (divisions) memcpy(divisions, div.data(), en->n_sets * 8);
     if (stats) {
         stats->divisions = 0;

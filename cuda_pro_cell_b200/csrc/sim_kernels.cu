@@ -396,8 +396,9 @@ __device__ __forceinline__ bool queue_push(const SimParams& P, int lane, uint64_
     __syncwarp();
     if (lane == 0) {
         st_release_u64(P.q_seq + slot, pos + 1);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&P.ctl->pending), 1ull);   /* the chunk counts as pending work ... */
         __threadfence();
-        atomicAdd(&P.ctl->avail, 1);          /* one more permit, only after the chunk is published */
+        atomicAdd(&P.ctl->avail, 1);          /* ... before its permit exists; the permit only after the chunk is published */
     }
     return true;
 }
@@ -464,7 +465,12 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
         int fast = 0;
         unsigned long long ticket = 0;
         if (w.lane == 0 && ld_acquire_s32(&ctl->avail) > 0) {
-            if (atomicSub(&ctl->avail, 1) > 0) { ticket = atomicAdd(&ctl->q_head, 1ull); fast = 1; }
+            if (atomicSub(&ctl->avail, 1) > 0) {
+                ticket = atomicAdd(&ctl->q_head, 1ull);
+                fast = 1;
+                /* warp and chunk were two units of pending work, now they are one */
+                atomicAdd(reinterpret_cast<unsigned long long*>(&ctl->pending), ~0ull);
+            }
             else atomicAdd(&ctl->avail, 1);                       /* lost the race for the last permit */
         }
         fast = __shfl_sync(kFull, fast, 0);
@@ -484,6 +490,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
         atomicAdd(&ctl->idle, 1);
         __threadfence();
         atomicSub(&ctl->active, 1);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&ctl->pending), ~0ull);
     }
     /* The wait itself is lane 0's alone: the other lanes park at the shuffle below and issue nothing, so an idle warp
      * costs a dozen instructions per poll instead of a warp-wide loop with a collective in it (idle polling was 10 % of
@@ -496,8 +503,12 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
         for (;;) {
             if (s_ctl[1]) state = 2;
             else if (s_ctl[0] == 0 && atomicCAS(const_cast<int*>(s_ctl), 0, 1) == 0) {
-                /* `active` is read (acquire) BEFORE the permit counter: a warp that pushed and then went idle
-                 * decremented `active` after its permit became visible, so active == 0 implies every permit is seen */
+                /* Termination reads ONE word: `pending` = warps that hold or may find work + published chunks not yet
+                 * claimed.  A chunk enters it before its permit exists, an idle warp that claims a chunk takes the
+                 * chunk's place in it (no change), and a warp leaves it only on going idle - so it is 0 only when no
+                 * work exists anywhere, and then for good.  (The earlier test, active == 0 and then avail == 0, could
+                 * be fooled by a warp that re-activated and took the last permit between the two reads.) */
+                const long long pend = (long long)ld_acquire_u64(reinterpret_cast<const unsigned long long*>(&ctl->pending));
                 const int act = ld_acquire_s32(&ctl->active);
                 const int av = ld_acquire_s32(&ctl->avail);
                 const int st = ld_volatile_s32(&ctl->status);
@@ -505,7 +516,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
                 else if (av > 0) {
                     atomicAdd(&ctl->active, 1);                    /* re-activate BEFORE taking work */
                     if (atomicSub(&ctl->avail, 1) > 0) {
-                        ticket = atomicAdd(&ctl->q_head, 1ull);
+                        ticket = atomicAdd(&ctl->q_head, 1ull);    /* this warp takes the chunk's place in `pending` */
                         state = 1;
                     } else {                                       /* lost the race for the last permit */
                         atomicAdd(&ctl->avail, 1);
@@ -513,7 +524,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
                         atomicSub(&ctl->active, 1);
                     }
                 }
-                else if (act == 0) state = 2;
+                else if (pend == 0) state = 2;
                 else if (global_timer_ns() > deadline) {
                     watchdog_fire(P, gwarp, 0, 3, (unsigned long long)act, (unsigned long long)(long long)av, (unsigned long long)ld_volatile_s32(&ctl->idle), global_timer_ns() - t0, 0, 0);
                     state = 2;
@@ -871,6 +882,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     int donate_epoch = -1;
 
     if (lane == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&ctl->pending), 1ull);
         atomicAdd(&ctl->active, 1);
         atomicMin(&ctl->t_start, global_timer_ns());
     }
@@ -906,8 +918,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                     } else {
                         /* s_batch = batch id << 24 | next unit offset; one 64-bit shared atomicAdd claims a unit.
                          * Lane 0 runs the whole protocol and broadcasts (status, set, unit). */
+                        int status = 0;          /* 0 retry, 1 got a unit, 2 no seed units left, 3 watchdog, 4 wait for the switch */
                         for (int spin = 0; spin < 1000000 && !got; ++spin) {
-                            int status = 0;      /* 0 retry, 1 got a unit, 2 no seed units left, 3 watchdog */
+                            status = 0;
                             if (lane == 0) {
                                 const unsigned long long old = atomicAdd(s_batch, 1ull);
                                 const uint32_t off = (uint32_t)old & 0xFFFFFFu;
@@ -962,6 +975,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                                 break;
                             }
                         }
+                        if (!got && status == 0) {
+                            /* a million rounds without an answer (a refill-lock holder that never returns): that is a
+                             * failure, not "no seed units left" - abort the launch instead of dropping the batch's units */
+                            watchdog_fire(P, GWARP, lane, 5, 0, 0, 0, 0, 0, 0);
+                            break;
+                        }
+                        if (!got && status == 3) break;
                     }
                     if (SETDIRECT && wait_switch) {
                         /* the last nodes of the old set are expanded first (partial DIVIDE iterations below); only a
@@ -1189,16 +1209,22 @@ __global__ void __launch_bounds__(kSimpleThreads) k_proliferate_simple(const __g
 }
 
 /* ------------------------------------------------------------------------------------------------ */
-__global__ void k_queue_init(unsigned long long* q_seq, ControlBlock* ctl)
+__global__ void __launch_bounds__(256) k_queue_init(unsigned long long* q_seq, ControlBlock* ctl, unsigned long long* counts,
+                                                    size_t n_counts, unsigned long long* divisions, size_t n_divisions)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < kQueueCap) q_seq[i] = (unsigned long long)i;
-    /* the whole control block, padding included (it is copied in 16-byte pieces and read back by the host) */
-    constexpr int kWords = (int)(sizeof(ControlBlock) / 8);
-    if (i < kWords) {
-        const bool ones = i == (int)(offsetof(ControlBlock, t_start) / 8) || i == (int)(offsetof(ControlBlock, t_exhausted) / 8);
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (size_t)kQueueCap) q_seq[i] = (unsigned long long)i;
+    /* the whole control block, padding included (it is copied in 16-byte pieces and read back by the host) - except
+     * the status word, which stays as it is: a failure of ANY run since the host last looked must still be there when
+     * it looks again (procell_engine_finish reads and then clears it) */
+    constexpr size_t kWords = sizeof(ControlBlock) / 8;
+    if (i < kWords && i != offsetof(ControlBlock, status) / 8) {
+        const bool ones = i == offsetof(ControlBlock, t_start) / 8 || i == offsetof(ControlBlock, t_exhausted) / 8;
         reinterpret_cast<unsigned long long*>(ctl)[i] = ones ? ~0ull : 0ull;
     }
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = i; k < n_counts; k += stride) counts[k] = 0ull;
+    for (size_t k = i; k < n_divisions; k += stride) divisions[k] = 0ull;
 }
 
 /* RNG-only ceiling: the per-division arithmetic (one Philox block, one Box-Muller pair, two timers, two time
@@ -1331,9 +1357,16 @@ cudaError_t launch_simple(const SimParams& p, int grid, cudaStream_t stream)
     return cudaGetLastError();
 }
 
-cudaError_t launch_queue_init(unsigned long long* q_seq, ControlBlock* ctl, cudaStream_t stream)
+cudaError_t launch_queue_init(unsigned long long* q_seq, ControlBlock* ctl, long long* counts, size_t n_counts,
+                              long long* divisions, size_t n_divisions, int sm_count, cudaStream_t stream)
 {
-    k_queue_init<<<(kQueueCap + 255) / 256, 256, 0, stream>>>(q_seq, ctl);
+    static_assert(offsetof(ControlBlock, status) % 8 == 0 && sizeof(ControlBlock) / 8 <= (size_t)kQueueCap, "control block layout");
+    /* enough threads for the queue slots; for large tensors a grid-stride loop from 8 CTAs per SM */
+    size_t blocks = (kQueueCap + 255) / 256;
+    const size_t want = (n_counts + 255) / 256, cap = (size_t)(sm_count > 0 ? sm_count : 148) * 8;
+    if (want > blocks) blocks = want < cap ? want : cap;
+    k_queue_init<<<(unsigned)blocks, 256, 0, stream>>>(q_seq, ctl, reinterpret_cast<unsigned long long*>(counts), n_counts,
+                                                      reinterpret_cast<unsigned long long*>(divisions), n_divisions);
     return cudaGetLastError();
 }
 

@@ -37,7 +37,12 @@ struct alignas(128) ControlBlock {
     int avail;                      int pad7[31];   /* published chunks not yet claimed (permits) */
     /* diagnostics (globaltimer ns): first warp start, seed cursor exhausted, last warp exit; warp-ns spent waiting
      * for donated work (summed over warps) and the number of such waits */
-    unsigned long long t_start, t_exhausted, t_end, idle_ns, idle_waits, pad6[11];
+    unsigned long long t_start, t_exhausted, t_end, idle_ns, idle_waits;
+    /* warps that hold or may still find work + published chunks nobody has claimed yet.  It is the ONE word the
+     * termination test reads: a chunk is added to it before its permit is published and a warp leaves it only when it
+     * goes idle, so it can reach 0 only when no work exists anywhere, and then stays 0 */
+    long long pending;
+    unsigned long long pad6[10];
 };
 
 struct SimParams {
@@ -108,7 +113,10 @@ cudaError_t coop_max_grid_subtree(int device, int hashed, size_t smem_bytes, int
 /* the sweep instance with a set-relative direct table (p.hist_setdirect): 32 warps, 128-node rings */
 cudaError_t coop_max_grid_setdirect(int device, size_t smem_bytes, int* grid_out);
 cudaError_t launch_simple(const SimParams& p, int grid, cudaStream_t stream);
-cudaError_t launch_queue_init(unsigned long long* q_seq, ControlBlock* ctl, cudaStream_t stream);
+/* resets the queue and the control block (the status word excepted: it is sticky until the host has read it) and
+ * zeroes the count tensor and the division counters of the run - one launch instead of a kernel and two memsets */
+cudaError_t launch_queue_init(unsigned long long* q_seq, ControlBlock* ctl, long long* counts, size_t n_counts,
+                              long long* divisions, size_t n_divisions, int sm_count, cudaStream_t stream);
 cudaError_t launch_rng_ceiling(int grid, int block, int iters, const double* logtab, double mean, double sd,
                                double t_max, const uint32_t* rk, unsigned long long* sink,
                                cudaStream_t stream);

@@ -374,6 +374,76 @@ def test_large_configs_bit_exact(gpu_api, oracle, config, scale):
     assert np.array_equal(got.counts, want["counts"])
 
 
+def test_config3_full_size_bit_exact(gpu_api, oracle):
+    """BASELINE config 3 at FULL size: 1e8 seed cells, default phi (smallest non-empty bin), t_max 336 -
+    2.8e8 divisions.  The oracle follows on all host cores in a few seconds."""
+    w = synth.workload(3)
+    assert w.n_cells == 100_000_000 and w.phi == 0.0
+    plan = gpu_api.Plan(w.values, w.freqs, w.phi)
+    oplan = oracle.OraclePlan(w.values, w.freqs, w.phi)
+    got = gpu_api.proliferate(plan, w.types, w.t_max, w.seed)
+    want = oracle.simulate(oplan, w.types, w.t_max, w.seed)
+    assert np.array_equal(got.divisions, want["divisions"])
+    assert np.array_equal(got.counts, want["counts"])
+    assert int(got.counts.sum()) > 10**8          # the run really was the full-size one
+
+
+def test_config5_full_size_bit_exact_on_the_set_relative_instance(gpu_api, oracle):
+    """BASELINE config 5 at FULL size: 1024 parameter sets x 1e6 cells in ONE launch (3.8e9 divisions).  At this size
+    procell_engine_load selects the sweep instance with the set-relative direct table (kernel MODE 2) by itself - no
+    environment knob - and that is asserted from the launch's shared-memory size: math table + control words + 32 rings
+    (coop_smem_bytes with 0 slots = 138 944 B) plus ONE set's keys x types x 4 B, not the hashed cache's power of two."""
+    w = synth.workload(5)
+    assert w.types.shape[0] == 1024 and w.n_cells == 1_000_000
+    plan = gpu_api.Plan(w.values, w.freqs, w.phi)
+    oplan = oracle.OraclePlan(w.values, w.freqs, w.phi)
+    got = gpu_api.proliferate(plan, w.types, w.t_max, w.seed)
+    n_types = w.types.shape[1]
+    assert got.stats["smem_bytes"] == 138944 + plan.n_keys * n_types * 4, "the set-relative instance was not selected"
+    want = oracle.simulate(oplan, w.types, w.t_max, w.seed)
+    assert np.array_equal(got.divisions, want["divisions"])
+    assert np.array_equal(got.counts, want["counts"])
+
+
+def _config4_golden():
+    from pathlib import Path
+    return np.load(Path(__file__).parent / "golden" / "oracle_config4_full.npz")
+
+
+def test_config4_full_size_equals_the_committed_oracle_tensor(gpu_api):
+    """BASELINE config 4 at FULL size (1e4 cells, phi 1e-7, t_max 720, 30 generations, 8.1e10 divisions): the oracle
+    needs minutes for it, so its whole tensor is committed (tests/golden/oracle_config4_full.npz, made on the CPU by
+    tests/golden/make_full_size_golden.py) and the GPU's tensor must equal it bit for bit, division total included."""
+    g = _config4_golden()
+    w = synth.workload(4)
+    assert int(g["seed"]) == w.seed and float(g["t_max"]) == w.t_max == 720.0
+    plan = gpu_api.Plan(w.values, w.freqs, w.phi)
+    assert plan.n_keys == int(g["n_keys"]) and plan.n_cells == int(g["n_cells"])
+    got = gpu_api.proliferate(plan, w.types, w.t_max, w.seed)
+    assert np.array_equal(got.divisions, g["divisions"])
+    assert np.array_equal(got.counts, g["counts"])
+    assert int(got.divisions[0]) > 5 * 10**10
+
+
+@pytest.mark.timeout(500)
+def test_config4_full_size_shard_against_the_live_oracle(gpu_api, oracle):
+    """The same run, one rank of eight, GPU and oracle side by side at t_max 720: subtree sharding at level 6
+    (procell_sim_params.shard_level; every rank walks the first 6 levels of every lineage, a subtree at level 6 belongs
+    to rank (root + heap) % 8) gives this rank an eighth of the 8.1e10 divisions, which the oracle follows on all host
+    cores within the time limit; lineage sharding (level 0) of another rank is checked at t_max 600."""
+    w = synth.workload(4)
+    plan = gpu_api.Plan(w.values, w.freqs, w.phi)
+    oplan = oracle.OraclePlan(w.values, w.freqs, w.phi)
+    got = gpu_api.proliferate(plan, w.types, w.t_max, w.seed, shard=(3, 8, 32), shard_level=6)
+    want = oracle.simulate(oplan, w.types, w.t_max, w.seed, shard=(3, 8, 32), shard_level=6)
+    assert np.array_equal(got.counts, want["counts"]) and np.array_equal(got.divisions, want["divisions"])
+    whole = int(_config4_golden()["divisions"][0])
+    assert 0.10 * whole < int(got.divisions[0]) < 0.15 * whole      # an eighth of the run, balanced
+    got = gpu_api.proliferate(plan, w.types, 600.0, w.seed, shard=(5, 8, 32))
+    want = oracle.simulate(oplan, w.types, 600.0, w.seed, shard=(5, 8, 32))
+    assert np.array_equal(got.counts, want["counts"]) and np.array_equal(got.divisions, want["divisions"])
+
+
 def test_periodic_drain_bit_exact(gpu_api, oracle, tmp_path):
     """The direct-mode u32 count table is drained into the int64 tensor every 2^20 iterations of a warp (wrap
     protection, sim_kernels.cu hist_drain).  libprocell_b200_drain256.so is the same library with the period set to
@@ -417,19 +487,10 @@ def test_simulate_one_call_equals_oracle_rows(gpu_api, oracle, n_sets):
     assert divisions == int(want["divisions"].sum())
 
 
-# ---- kernel modes added in the last session of round 1 -------------------------------------------------------------
-# The subtree-sharding instances (MODE 1) and the set-relative sweep instance (MODE 2) were written while no GPU was
-# reachable; the 16 MODE 0 instances are byte-identical to the GPU-verified build (tools/sass_same.py).  With the last
-# GPU seconds of the round both modes were run against the oracle by tests/gpu_quick_new_modes.py (10 of 10 and 4 of 4
-# cases bit-exact, profiles/r1i_*), but these pytest cases themselves have not run on a GPU yet, so they run on
-# request (PROCELL_TEST_NEW=1, tools/gpu_r2_first.sh) until they have, and cannot break the parity suite of a round end.
+# ---- kernel modes 1 (subtree sharding) and 2 (set-relative sweep table) ---------------------------------------------
 import os
 
-_new_path = pytest.mark.skipif(os.environ.get("PROCELL_TEST_NEW") != "1",
-                               reason="not yet run on a GPU: set PROCELL_TEST_NEW=1 (tools/gpu_r2_first.sh)")
 
-
-@_new_path
 @pytest.mark.parametrize("phi", [1e-3, 1e-7])        # 15 k slots: direct shared-memory histogram; 25 k: the hashed one
 @pytest.mark.parametrize("world,level", [(2, 1), (3, 4), (8, 6), (4, 30)])
 def test_subtree_shards_bit_exact(gpu_api, oracle, world, level, phi):
@@ -450,7 +511,6 @@ def test_subtree_shards_bit_exact(gpu_api, oracle, world, level, phi):
     assert np.array_equal(total, whole["counts"]) and div == int(whole["divisions"][0])
 
 
-@_new_path
 def test_subtree_sharding_argument_checks(gpu_api):
     v, f = synth.synthetic_histogram(500)
     plan = gpu_api.Plan(v, f, 0.5)
@@ -465,7 +525,6 @@ def test_subtree_sharding_argument_checks(gpu_api):
     assert np.array_equal(a.counts, b.counts)
 
 
-@_new_path
 @pytest.mark.parametrize("n_gpus", [2, 8])
 def test_single_process_multi_gpu_subtree_sharding(gpu_api, oracle, n_gpus):
     if _n_gpus() < n_gpus:
@@ -478,7 +537,6 @@ def test_single_process_multi_gpu_subtree_sharding(gpu_api, oracle, n_gpus):
     assert np.array_equal(got.counts, want["counts"]) and np.array_equal(got.divisions, want["divisions"])
 
 
-@_new_path
 @pytest.mark.parametrize("shape", ["sweep32", "many_small_sets", "two_deep_sets", "unit1", "sharded"])
 def test_sweep_with_set_relative_table_bit_exact(gpu_api, oracle, monkeypatch, shape):
     """PROCELL_SWEEP_DIRECT=1: sweeps keep a direct u32 table of the CTA's current parameter set in shared memory and
@@ -513,7 +571,6 @@ def test_sweep_with_set_relative_table_bit_exact(gpu_api, oracle, monkeypatch, s
     assert np.array_equal(again.counts, got.counts)
 
 
-@_new_path
 def test_periodic_drain_of_the_set_relative_table(gpu_api, oracle, tmp_path):
     """MODE 2 with the drain period set to 256 iterations (libprocell_b200_drain256.so): warps drain the CTA's table
     into the tensor at the current base (hist_drain_at) while the other warps keep adding.  4 sets of config-2-like
@@ -543,7 +600,6 @@ def test_periodic_drain_of_the_set_relative_table(gpu_api, oracle, tmp_path):
     assert np.array_equal(got["divisions"], want["divisions"]) and np.array_equal(got["counts"], want["counts"])
 
 
-@_new_path
 def test_single_counts_beyond_2_to_32(gpu_api):
     """the reference's 32-bit counters wrap; here a single (bin, level) count may exceed 2^32.  sd = 0 makes
     the tree deterministic: 5 seed cells, 33 generations, 2^33 leaves per lineage in ONE key (4e10 divisions, about half
