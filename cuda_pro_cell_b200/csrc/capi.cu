@@ -329,6 +329,8 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     P.donate = !(denv && atoi(denv) == 1);
     en->kernel = sp->kernel;
     P.hist_setdirect = 0;
+    P.slot_mode = 0;
+    P.kstride = (uint32_t)T;
     if (en->kernel == PROCELL_KERNEL_SIMPLE) {
         en->block = kSimpleThreads;
         en->grid = en->sm_count * 8;
@@ -357,7 +359,26 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         const bool sd_forced_on = sdenv && atoi(sdenv) == 1, sd_forced_off = sdenv && atoi(sdenv) == 0;
         const bool sd_wanted = sd_forced_on || (!sd_forced_off && (double)P.batch_units >= 24.0 * 32.0);
         P.hist_setdirect = 0;
-        if (en->counts_len * 4 <= room) {            /* the whole key space fits: direct u32 table */
+        /* one parameter set, one checkpoint (the PLAIN instances): the table is laid out by SLOTS - proliferating types
+         * per key, then one row per bin for the quiescent types, which are only ever counted at level 0 (sim_kernels.h) */
+        const bool plain = S == 1 && M == 1;
+        uint32_t n_prolif = 0, n_quiet = 0;
+        for (size_t j = 0; j < T; ++j) {
+            const bool q = sp->types[j].mean < 0.0;
+            P.type_rank[j] = (uint8_t)(q ? n_quiet : n_prolif);
+            if (q) P.quiet_type[n_quiet++] = (uint8_t)j; else P.prolif_type[n_prolif++] = (uint8_t)j;
+        }
+        const size_t slot_count = K * n_prolif + B * n_quiet;
+        P.kstride = (uint32_t)T;
+        P.slot_mode = 0;
+        P.n_prolif = n_prolif; P.n_quiet = n_quiet;
+        P.slot_prolif_end = (uint32_t)(K * n_prolif);
+        if (plain && slot_count * 4 <= room) {
+            P.hist_hashed = 0;
+            P.slot_mode = 1;
+            P.kstride = n_prolif;
+            P.smem_hist_slots = (uint32_t)slot_count;
+        } else if (!plain && en->counts_len * 4 <= room) {   /* the whole key space fits: direct u32 table indexed by key */
             P.hist_hashed = 0;
             P.smem_hist_slots = (uint32_t)en->counts_len;
         } else if (sd_wanted && S > 1 && M == 1 && !subtree && en->warps == 32 && en->ring == 1 && K * T * 4 <= room) {

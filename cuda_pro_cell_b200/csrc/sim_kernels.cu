@@ -177,12 +177,25 @@ constexpr unsigned kIdleBackoffMaxNs = PROCELL_IDLE_BACKOFF_MAX_NS;   /* idle wa
 constexpr uint32_t kDonateMinNodes = PROCELL_DONATE_MIN_NODES;        /* a warp gives a chunk away only when its ring is about to spill anyway */
 static_assert((kHistFlushIters & (kHistFlushIters - 1u)) == 0u && kHistFlushIters >= 256u && kHistFlushIters <= (1u << 20), "");
 
+/* slot of the shared-memory table -> index of the count tensor (SimParams::slot_mode; identity otherwise).  Only the
+ * drains use it: a few thousand integer divisions per CTA and drain. */
+__device__ __forceinline__ uint32_t slot_key(const SimParams& P, uint32_t s)
+{
+    if (!P.slot_mode) return s;
+    if (s < P.slot_prolif_end) {
+        const uint32_t bk = s / P.n_prolif;
+        return bk * P.n_types + P.prolif_type[s - bk * P.n_prolif];
+    }
+    const uint32_t q = s - P.slot_prolif_end, bin = q / P.n_quiet;
+    return __ldg(P.bin_keybase + bin) * P.n_types + P.quiet_type[q - bin * P.n_quiet];
+}
+
 __device__ __noinline__ void hist_drain(const SimParams& P, uint32_t* s_hist, int lane)
 {
     for (uint32_t i = (uint32_t)lane; i < P.smem_hist_slots; i += 32u) {
         if (*reinterpret_cast<volatile uint32_t*>(s_hist + i) == 0u) continue;
         const uint32_t v = atomicExch(s_hist + i, 0u);
-        if (v) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + i, (unsigned long long)v);
+        if (v) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + slot_key(P, i), (unsigned long long)v);
     }
 }
 
@@ -556,6 +569,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
 /* result of building one seed cell (cell.cu:25-79 with type == -1, t == 0) */
 struct SeedOut {
     uint32_t key;       /* count-tensor index of (set, bin, level 0, type) */
+    uint32_t keybase;   /* first key of the bin (slot layout of the PLAIN direct instances) */
     uint32_t type, kdiv;
     int kind;           /* 0 dropped, 1 leaf at level 0, 2 living root */
     int count0;         /* level-0 leaves of this bin are output rows (value >= phi) */
@@ -613,7 +627,8 @@ __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* 
     const double2 ms = musd[type];
     o.type = type;
     o.kdiv = kd & 63u;
-    o.key = (set * P.n_keys + __ldg(P.bin_keybase + bin)) * T + type;
+    o.keybase = __ldg(P.bin_keybase + bin);
+    o.key = (set * P.n_keys + o.keybase) * T + type;
     const bool count0 = (kd & 0x80u) != 0u;
     o.count0 = count0;
     o.quiescent = ms.x < 0.0;
@@ -682,6 +697,9 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
     static_assert(NPL == 1 || (FULL && RING >= NPL), "several nodes per lane: full iterations of a wide-ring instance only");
     constexpr uint32_t kMask = Ring<RING>::kMask;
     const uint32_t T = P.n_types;
+    /* the key field of a node advances by KS per tree level: n_types, or - PLAIN direct instances, whose table is laid
+     * out by slots - the number of proliferating types */
+    const uint32_t KS = (PLAIN && !HASHED) ? P.kstride : T;
     bool int0[NPL], int1[NPL];              /* daughter 0 / 1 lives on and will divide */
     uint32_t rej[NPL], leaf_inc[NPL], leaf_key[NPL], dlo[NPL], retry[NPL];
     uint64_t heap[NPL], pc[NPL];
@@ -730,7 +748,7 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
             const double2 ms = musd[set * T + type];          /* generic pointer: shared-memory copy or the HBM table */
             if (fresh) classify_daughters<true>(P, ms, dlo[s], retry[s], t_div[s], z0[s], z1[s], int0[s], int1[s], rej[s], leaf_inc[s], tc0[s], tc1[s]);
             else classify_daughters<false>(P, ms, dlo[s], retry[s], t_div[s], z0[s], z1[s], int0[s], int1[s], rej[s], leaf_inc[s], tc0[s], tc1[s]);
-            leaf_key[s] = (uint32_t)(pc[s] >> 32) + T;
+            leaf_key[s] = (uint32_t)(pc[s] >> 32) + KS;
             uint32_t first = (fresh || retry[s] == 0u) ? 1u : 0u;   /* a redraw is not another division */
             if (SUBTREE && heap[s] < P.sub_limit) {
                 /* subtree sharding: a node below the shard level is expanded by EVERY GPU (same stream, same outcome);
@@ -765,7 +783,7 @@ __device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P,
     }
 #pragma unroll
     for (int s = 0; s < NPL; ++s) {
-        const uint64_t child_c = ((pc[s] >> 32) + T) << 32 | (pc[s] & 0xFFFFFFFFull);
+        const uint64_t child_c = ((pc[s] >> 32) + KS) << 32 | (pc[s] & 0xFFFFFFFFull);
         const uint64_t child_d = (uint64_t)((dlo[s] | (3u << 28)) - (1u << 22));
         const uint32_t i0 = (w.top + __popc(b0[s] & lt_mask)) & kMask;
         ring_store_if<RING>(w, int0[s], i0, pcs_d2bits(tc0[s]), heap[s] * 2ull, child_c, child_d);
@@ -819,6 +837,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     static_assert(!SUBTREE || (PLAIN && RING == 1), "subtree sharding: one parameter set, one checkpoint, one node per lane");
     static_assert(!SETDIRECT || (!PLAIN && !HASHED && RING == 1), "set-relative table: sweeps, u32 slots, one node per lane");
     constexpr uint32_t kCap = Ring<RING>::kCap, kMask = Ring<RING>::kMask;
+    constexpr bool SLOT = PLAIN && !HASHED;      /* the u32 table is laid out by slots (SimParams::slot_mode is set) */
     constexpr uint32_t kLow = 32u * RING;        /* below this many nodes a warp looks for seed cells / spilled chunks first */
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_log = reinterpret_cast<double*>(smem_raw);
@@ -1013,7 +1032,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 const uint32_t root = seed_cur + lane;
                 const bool have = root < seed_end;
                 seed_cur = (seed_end - seed_cur > 32u) ? seed_cur + 32u : seed_end;
-                SeedOut so; so.kind = 0; so.key = 0; so.type = 0; so.kdiv = 0; so.t_div = 0.0; so.count0 = 0; so.quiescent = 0;
+                SeedOut so; so.kind = 0; so.key = 0; so.keybase = 0; so.type = 0; so.kdiv = 0; so.t_div = 0.0; so.count0 = 0; so.quiescent = 0;
 #ifdef PROCELL_LANE_BINSEARCH
                 const uint32_t bin = find_bin(P, root);
 #else
@@ -1024,6 +1043,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                     const size_t tab = PLAIN ? 0u : (size_t)seed_set * P.n_types;
                     so = build_seed(P, s_log, root, seed_set, bin, (PLAIN ? s_cum_buf : s_cum) + tab, (PLAIN ? s_sel_buf : s_sel) + tab,
                                     (PLAIN ? s_musd_buf : s_musd) + tab);
+                }
+                if (SLOT && have) {     /* the node and the table work with slots: see SimParams::slot_mode */
+                    const uint32_t rk = P.type_rank[so.type];
+                    so.key = so.quiescent ? P.slot_prolif_end + bin * P.n_quiet + rk : so.keybase * P.n_prolif + rk;
                 }
                 const unsigned live = __ballot_sync(kFull, so.kind == 2);
                 if (so.kind == 2) {
@@ -1145,7 +1168,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         const uint32_t flush_base = SETDIRECT ? (uint32_t)s_ctl[7] : 0u;
         for (uint32_t i = threadIdx.x; i < P.smem_hist_slots; i += blockDim.x) {
             uint32_t v = s_hist[i];
-            if (v) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + flush_base + i, (unsigned long long)v);
+            if (v) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + flush_base + (SLOT ? slot_key(P, i) : i), (unsigned long long)v);
         }
     }
 }

@@ -100,6 +100,20 @@ struct SimParams {
     /* sweeps: 1 = the shared-memory table is a direct u32 table of ONE parameter set (smem_hist_slots = n_keys *
      * n_types), re-based at batch switches behind a CTA-wide rendezvous (kernel MODE kModeSetDirect) */
     int hist_setdirect;
+    /* slot layout of the shared-memory count table of the PLAIN direct instances (one parameter set, one checkpoint,
+     * u32 table).  The count tensor is [key][type], but a quiescent type is only ever counted at tree level 0 of a bin,
+     * so the TABLE keeps the proliferating types only, [key][n_prolif], followed by one row per bin for the quiescent
+     * ones, [bin][n_quiet]: n_keys * n_prolif + n_bins * n_quiet slots instead of n_keys * n_types.  That is what lets
+     * deep-tree runs (config 4: 10 422 keys x 3 types = 31 266 counters, one type quiescent) keep the direct table
+     * instead of the hashed cache.  A node carries its SLOT (stride kstride = n_prolif per tree level); slots are
+     * translated to tensor indices only when the table is drained (slot_key in sim_kernels.cu). */
+    uint32_t kstride;             /* stride of the node's key field per tree level: n_prolif in slot mode, else n_types */
+    uint32_t slot_mode;           /* 1: the table is laid out by slots (PLAIN direct instances only) */
+    uint32_t slot_prolif_end;     /* n_keys * n_prolif: first slot of the quiescent rows */
+    uint32_t n_prolif, n_quiet;
+    uint8_t type_rank[64];        /* file id -> rank among the proliferating (or among the quiescent) types */
+    uint8_t prolif_type[64];      /* rank -> file id */
+    uint8_t quiet_type[64];
 };
 
 /* ring = 1: 128-node ring per warp, one node per lane and iteration (warps = 32, 24 or 16);
