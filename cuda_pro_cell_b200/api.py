@@ -271,6 +271,10 @@ class Engine:
                                                  out.ctypes.data_as(_f64p)))
         return out
 
+    def fitness_in_launch(self) -> bool:
+        """True if the last fitness() was computed by the simulation launch itself (target set before run())."""
+        return bool(_lib.load().procell_engine_fitness_in_launch(self.h))
+
     def close(self):
         if getattr(self, "h", None):
             _lib.load().procell_engine_destroy(self.h)
@@ -317,6 +321,13 @@ def rng_ceiling(device: int = 0, iters: int = 2048):
     ms, pairs = C.c_double(), C.c_double()
     check(_lib.load().procell_rng_ceiling(int(device), int(iters), C.byref(ms), C.byref(pairs)))
     return ms.value, pairs.value
+
+
+def rng_ceiling_variants(device: int = 0, iters: int = 2048):
+    """[(ms, pairs)] of the three shapes of the RNG-only loop (rng_ceiling reports the fastest)."""
+    ms, pairs = (C.c_double * 3)(), (C.c_double * 3)()
+    check(_lib.load().procell_rng_ceiling_variants(int(device), int(iters), ms, pairs))
+    return [(ms[i], pairs[i]) for i in range(3)]
 
 
 class CmdArgs:

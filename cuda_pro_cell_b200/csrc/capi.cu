@@ -20,6 +20,7 @@
 #include "host_plan.h"
 #include "procell_math_tables.inc"
 #include "sim_kernels.h"
+#include "fitness_device.h"
 
 #include <chrono>
 #include <cstdlib>
@@ -93,6 +94,8 @@ struct procell_engine {
     bool ran = false;                       /* a run has been queued since creation (ev1 is recorded) */
     long long* last_counts = nullptr;       /* where the last run wrote: the engine's tensor or the caller's */
     long long* last_divisions = nullptr;
+    bool fit_in_launch = false;             /* the last run computed the sweep fitness itself (fit_out holds it) */
+    bool fit_last_from_launch = false;      /* ... and the last procell_engine_fitness call returned that */
     DevBuf dbg, fit_key_channel, fit_target, fit_out;
     uint32_t fit_channels = 0;
     std::vector<double> plan_row_value;     /* copies of what fitness needs, so the plan may be destroyed after load */
@@ -207,7 +210,8 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     const size_t off_cum = off_kdiv + align16(B + 1);
     const size_t off_musd = off_cum + align16(S * T * 8);
     const size_t off_sel = off_musd + align16(S * T * 16);
-    const size_t table_bytes = off_sel + align16(S * T);
+    const size_t off_rank = off_sel + align16(S * T);          /* set 0's types by kind: proliferating ids, then quiescent ids */
+    const size_t table_bytes = off_rank + align16(T);
     const int sk = en->stage_next;
     en->stage_next ^= 1;
     CU(cudaEventSynchronize(en->stage_done[sk]), "wait for the staging buffer");   /* its last copy (two loads ago) is over */
@@ -224,6 +228,12 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     double* h_cum = reinterpret_cast<double*>(st + off_cum);
     double2* h_musd = reinterpret_cast<double2*>(st + off_musd);
     uint8_t* h_sel = st + off_sel;
+    {
+        uint8_t* h_rank = st + off_rank;
+        size_t n = 0;
+        for (size_t j = 0; j < T; ++j) if (!(sp->types[j].mean < 0.0)) h_rank[n++] = (uint8_t)j;
+        for (size_t j = 0; j < T; ++j) if (sp->types[j].mean < 0.0) h_rank[n++] = (uint8_t)j;
+    }
     for (size_t b = 0; b <= B; ++b) h_start[b] = (uint32_t)plan->bin_start[b];
     for (size_t b = 0; b < B; ++b) {
         h_keybase[b] = plan->bin_keybase[b];
@@ -363,11 +373,11 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
          * per key, then one row per bin for the quiescent types, which are only ever counted at level 0 (sim_kernels.h) */
         const bool plain = S == 1 && M == 1;
         uint32_t n_prolif = 0, n_quiet = 0;
+        P.quiet_mask = 0ull;
         for (size_t j = 0; j < T; ++j) {
-            const bool q = sp->types[j].mean < 0.0;
-            P.type_rank[j] = (uint8_t)(q ? n_quiet : n_prolif);
-            if (q) P.quiet_type[n_quiet++] = (uint8_t)j; else P.prolif_type[n_prolif++] = (uint8_t)j;
+            if (sp->types[j].mean < 0.0) { P.quiet_mask |= 1ull << j; ++n_quiet; } else ++n_prolif;
         }
+        P.rank_type = (const uint8_t*)(dt + off_rank);
         const size_t slot_count = K * n_prolif + B * n_quiet;
         P.kstride = (uint32_t)T;
         P.slot_mode = 0;
@@ -427,6 +437,23 @@ int procell_engine_run(procell_engine* en, uint64_t seed, void* stream_v, int64_
     en->timed = true;
     en->last_counts = P.counts;
     en->last_divisions = P.divisions;
+    /* sweep fitness in the same launch: a target is set, the run is an unsharded sweep on the cooperative kernel, and
+     * the accumulators fit in the (by then flushed) shared-memory table.  PROCELL_FITNESS_FUSED=0 keeps the separate pass. */
+    P.fit_channels = 0;
+    en->fit_in_launch = false;
+    {
+        const char* fenv = getenv("PROCELL_FITNESS_FUSED");
+        const size_t table_bytes = (size_t)P.smem_hist_slots * (P.hist_hashed ? 8 : 4);
+        if (en->fit_channels != 0 && en->kernel == PROCELL_KERNEL_COOP && !(P.n_sets == 1u && P.n_times == 1u) &&
+            P.shard_world == 1u && P.sub_world == 1u && !(fenv && atoi(fenv) == 0) &&
+            fitness_smem_bytes(en->fit_channels) <= table_bytes) {
+            P.fit_channels = en->fit_channels;
+            P.fit_key_channel = (const uint32_t*)en->fit_key_channel.p;
+            P.fit_target = (const double*)en->fit_target.p;
+            P.fit_out = (double*)en->fit_out.p;
+            en->fit_in_launch = true;
+        }
+    }
     if (en->up_pending) {       /* the tables of the last load are on their way on the upload stream */
         CU(cudaStreamWaitEvent(stream, en->up_done, 0), "order run behind the table upload");
         en->up_pending = false;
@@ -584,6 +611,7 @@ int procell_engine_set_target(procell_engine* en, const double* value, const uin
     CU(cudaMemcpy(en->fit_key_channel.p, key_channel.data(), (n_keys + 1) * 4, cudaMemcpyHostToDevice), "upload key_channel");
     CU(cudaMemcpy(en->fit_target.p, share.data(), n_channels * 8, cudaMemcpyHostToDevice), "upload target");
     en->fit_channels = (uint32_t)n_channels;
+    en->fit_in_launch = false;          /* whatever the last run computed was for another target */
     return PROCELL_OK;
 }
 
@@ -594,6 +622,13 @@ int procell_engine_fitness(procell_engine* en, void* stream_v, const int64_t* d_
     cudaStream_t stream = (cudaStream_t)stream_v;
     CU(cudaSetDevice(en->device), "cudaSetDevice");
     const long long* counts = d_counts ? (const long long*)d_counts : (const long long*)en->counts.p;
+    /* the run that produced this tensor computed the distances in its own launch: only 8 bytes per set are left to do */
+    en->fit_last_from_launch = en->fit_in_launch && counts == en->last_counts;
+    if (en->fit_last_from_launch) {
+        CU(cudaMemcpyAsync(fitness, en->fit_out.p, en->n_sets * 8, cudaMemcpyDeviceToHost, stream), "download fitness");
+        CU(cudaStreamSynchronize(stream), "fitness download");
+        return PROCELL_OK;
+    }
     counts += (en->n_times - 1) * (size_t)en->P.time_stride;       /* time series: fitness of the last checkpoint */
     CU(launch_sweep_fitness(counts, (const uint32_t*)en->fit_key_channel.p, (const double*)en->fit_target.p,
                             (uint32_t)en->n_sets, en->P.n_keys, en->P.n_types, en->fit_channels, (double*)en->fit_out.p, stream),
@@ -602,6 +637,8 @@ int procell_engine_fitness(procell_engine* en, void* stream_v, const int64_t* d_
     CU(cudaStreamSynchronize(stream), "fitness kernel");
     return PROCELL_OK;
 }
+
+int procell_engine_fitness_in_launch(const procell_engine* en) { return en && en->fit_last_from_launch ? 1 : 0; }
 
 /* ---- single-process multi-GPU: seed-cell units sharded over the GPUs of one box, ONE ncclReduce(sum, int64) ---- */
 namespace {
@@ -779,10 +816,12 @@ void procell_output_free(procell_output* out)
     out->n_rows = 0;
 }
 
-int procell_rng_ceiling(int device, int iters, double* ms_out, double* pairs_out)
+/* all shapes of the RNG-only loop, each timed once after a warm-up: ms[v] and pairs[v] for v = 0..2 */
+int procell_rng_ceiling_variants(int device, int iters, double* ms_out, double* pairs_out)
 {
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(PROCELL_ERR_CUDA, "no CUDA device available");
+    if (!ms_out || !pairs_out) return fail(PROCELL_ERR_ARG, "procell_rng_ceiling_variants: null argument");
     CU(cudaSetDevice(device), "cudaSetDevice");
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), "query SMs");
@@ -792,22 +831,43 @@ int procell_rng_ceiling(int device, int iters, double* ms_out, double* pairs_out
     CU(cudaMalloc(&d_sink, 16), "alloc");
     CU(cudaMemcpy(d_tab, &kLogRows, sizeof(kLogRows), cudaMemcpyHostToDevice), "upload");
     CU(cudaMemset(d_sink, 0, 16), "memset");
-    const int block = 256, grid = sms * 6;   /* 6 CTAs of 256 threads per SM fit at 34 registers: one full wave */
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     SimParams K{};
     set_round_keys(K, 0x0000000200000001ull);
-    CU(launch_rng_ceiling(grid, block, 16, d_tab, 48.33, 21.6, 168.0, K.rk, d_sink, nullptr), "warm-up launch");
-    cudaEventRecord(e0);
-    CU(launch_rng_ceiling(grid, block, iters, d_tab, 48.33, 21.6, 168.0, K.rk, d_sink, nullptr), "launch");
-    cudaEventRecord(e1);
-    CU(cudaEventSynchronize(e1), "rng ceiling kernel");
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    if (ms_out) *ms_out = ms;
-    if (pairs_out) *pairs_out = (double)grid * block * (double)iters;
+    int rc = PROCELL_OK;
+    for (int v = 0; v < kRngCeilingVariants && rc == PROCELL_OK; ++v) {
+        const int block = 256, grid = sms * rng_ceiling_ctas_per_sm(v);     /* exactly one full wave */
+        const int it = iters / rng_ceiling_chains(v);
+        cudaError_t e = launch_rng_ceiling(v, grid, block, 16, d_tab, 48.33, 21.6, 168.0, K.rk, d_sink, nullptr);   /* warm-up */
+        if (e == cudaSuccess) {
+            cudaEventRecord(e0);
+            e = launch_rng_ceiling(v, grid, block, it, d_tab, 48.33, 21.6, 168.0, K.rk, d_sink, nullptr);
+            cudaEventRecord(e1);
+        }
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "rng ceiling kernel"); break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        ms_out[v] = ms;
+        pairs_out[v] = (double)grid * block * (double)it * rng_ceiling_chains(v);
+    }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(d_tab); cudaFree(d_sink);
+    return rc;
+}
+
+/* the ceiling the roofline is quoted against: the fastest shape (most pairs per ms) */
+int procell_rng_ceiling(int device, int iters, double* ms_out, double* pairs_out)
+{
+    double ms[kRngCeilingVariants], pairs[kRngCeilingVariants];
+    const int rc = procell_rng_ceiling_variants(device, iters, ms, pairs);
+    if (rc != PROCELL_OK) return rc;
+    int best = 0;
+    for (int v = 1; v < kRngCeilingVariants; ++v)
+        if (pairs[v] / ms[v] > pairs[best] / ms[best]) best = v;
+    if (ms_out) *ms_out = ms[best];
+    if (pairs_out) *pairs_out = pairs[best];
     return PROCELL_OK;
 }
 

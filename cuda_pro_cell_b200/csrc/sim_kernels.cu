@@ -33,6 +33,7 @@
 #include <cstddef>
 
 #include "procell_spec.h"
+#include "fitness_device.h"
 
 namespace procell_b200 {
 
@@ -184,10 +185,10 @@ __device__ __forceinline__ uint32_t slot_key(const SimParams& P, uint32_t s)
     if (!P.slot_mode) return s;
     if (s < P.slot_prolif_end) {
         const uint32_t bk = s / P.n_prolif;
-        return bk * P.n_types + P.prolif_type[s - bk * P.n_prolif];
+        return bk * P.n_types + __ldg(P.rank_type + (s - bk * P.n_prolif));
     }
     const uint32_t q = s - P.slot_prolif_end, bin = q / P.n_quiet;
-    return __ldg(P.bin_keybase + bin) * P.n_types + P.quiet_type[q - bin * P.n_quiet];
+    return __ldg(P.bin_keybase + bin) * P.n_types + __ldg(P.rank_type + P.n_prolif + (q - bin * P.n_quiet));
 }
 
 __device__ __noinline__ void hist_drain(const SimParams& P, uint32_t* s_hist, int lane)
@@ -568,8 +569,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
 
 /* result of building one seed cell (cell.cu:25-79 with type == -1, t == 0) */
 struct SeedOut {
-    uint32_t key;       /* count-tensor index of (set, bin, level 0, type) */
-    uint32_t keybase;   /* first key of the bin (slot layout of the PLAIN direct instances) */
+    uint32_t key;       /* count-tensor index of (set, bin, level 0, type) - or, SLOT, the table slot (SimParams::slot_mode) */
     uint32_t type, kdiv;
     int kind;           /* 0 dropped, 1 leaf at level 0, 2 living root */
     int count0;         /* level-0 leaves of this bin are output rows (value >= phi) */
@@ -610,7 +610,11 @@ __device__ __forceinline__ uint32_t find_bin_warp(const SimParams& P, uint32_t r
     return lo;
 }
 
-/* cum / sel / musd: the type tables of parameter set `set` (shared-memory copies or the HBM tables) */
+/* cum / sel / musd: the type tables of parameter set `set` (shared-memory copies or the HBM tables).
+ * SLOT (PLAIN direct instances of the cooperative kernel): key is the slot of the shared-memory table instead of the
+ * tensor index - proliferating types per key, then one row per bin for the quiescent types; a type's rank among its
+ * kind is the number of types of that kind with a smaller file id (a popcount under SimParams::quiet_mask). */
+template <bool SLOT>
 __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* s_log, uint32_t root, uint32_t set,
                                               uint32_t bin, const double* cum, const uint8_t* sel, const double2* musd)
 {
@@ -627,8 +631,14 @@ __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* 
     const double2 ms = musd[type];
     o.type = type;
     o.kdiv = kd & 63u;
-    o.keybase = __ldg(P.bin_keybase + bin);
-    o.key = (set * P.n_keys + o.keybase) * T + type;
+    const uint32_t keybase = __ldg(P.bin_keybase + bin);
+    if (SLOT) {
+        const unsigned long long below = (1ull << type) - 1ull;
+        o.key = ms.x < 0.0 ? P.slot_prolif_end + bin * P.n_quiet + (uint32_t)__popcll(P.quiet_mask & below)
+                           : keybase * P.n_prolif + (uint32_t)__popcll(~P.quiet_mask & below);
+    } else {
+        o.key = (set * P.n_keys + keybase) * T + type;
+    }
     const bool count0 = (kd & 0x80u) != 0u;
     o.count0 = count0;
     o.quiescent = ms.x < 0.0;
@@ -1032,7 +1042,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 const uint32_t root = seed_cur + lane;
                 const bool have = root < seed_end;
                 seed_cur = (seed_end - seed_cur > 32u) ? seed_cur + 32u : seed_end;
-                SeedOut so; so.kind = 0; so.key = 0; so.keybase = 0; so.type = 0; so.kdiv = 0; so.t_div = 0.0; so.count0 = 0; so.quiescent = 0;
+                SeedOut so; so.kind = 0; so.key = 0; so.type = 0; so.kdiv = 0; so.t_div = 0.0; so.count0 = 0; so.quiescent = 0;
 #ifdef PROCELL_LANE_BINSEARCH
                 const uint32_t bin = find_bin(P, root);
 #else
@@ -1041,12 +1051,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 #endif
                 if (have) {     /* PLAIN: one set, the tables are always the shared-memory copies */
                     const size_t tab = PLAIN ? 0u : (size_t)seed_set * P.n_types;
-                    so = build_seed(P, s_log, root, seed_set, bin, (PLAIN ? s_cum_buf : s_cum) + tab, (PLAIN ? s_sel_buf : s_sel) + tab,
+                    so = build_seed<SLOT>(P, s_log, root, seed_set, bin, (PLAIN ? s_cum_buf : s_cum) + tab, (PLAIN ? s_sel_buf : s_sel) + tab,
                                     (PLAIN ? s_musd_buf : s_musd) + tab);
-                }
-                if (SLOT && have) {     /* the node and the table work with slots: see SimParams::slot_mode */
-                    const uint32_t rk = P.type_rank[so.type];
-                    so.key = so.quiescent ? P.slot_prolif_end + bin * P.n_quiet + rk : so.keybase * P.n_prolif + rk;
                 }
                 const unsigned live = __ballot_sync(kFull, so.kind == 2);
                 if (so.kind == 2) {
@@ -1171,6 +1177,27 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
             if (v) atomicAdd(reinterpret_cast<unsigned long long*>(P.counts) + flush_base + (SLOT ? slot_key(P, i) : i), (unsigned long long)v);
         }
     }
+    /* ---- fitness of the sweep in the same launch.  Every CTA of the grid is resident (one per SM), so they can meet:
+     * a CTA arrives once its own flush is performed (fence), the last arrival releases everybody, and the sets are
+     * shared out CTA-strided.  The slabs were written by L2 atomics moments ago - 104 MB for config 5, which fits the
+     * 126 MB L2 - and are read back with ld.global.cg; 8 bytes per set leave the GPU instead of the tensor. */
+    if (!PLAIN && P.fit_channels != 0u) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(&ctl->done_ctas, 1ull);
+            while (ld_acquire_u64(&ctl->done_ctas) < (unsigned long long)gridDim.x) {
+                __nanosleep(256);
+                if (global_timer_ns() > *s_deadline) { atomicCAS(&ctl->status, kStatusOk, kStatusWatchdog); break; }
+            }
+        }
+        __syncthreads();
+        unsigned long long* s_acc = reinterpret_cast<unsigned long long*>(s_hist);     /* the table has been flushed: reuse it */
+        const long long* slab0 = P.counts + (size_t)(P.n_times - 1u) * P.time_stride;   /* time series: the last checkpoint */
+        for (uint32_t set = blockIdx.x; set < P.n_sets; set += gridDim.x)
+            fitness_of_set<true>(slab0 + (size_t)set * P.n_keys * P.n_types, P.fit_key_channel, P.fit_target, P.n_keys, P.n_types,
+                                 P.fit_channels, s_acc, P.fit_out + set);
+    }
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -1193,7 +1220,7 @@ __global__ void __launch_bounds__(kSimpleThreads) k_proliferate_simple(const __g
         const uint32_t root = (uint32_t)(gi - (unsigned long long)set * P.n_cells);
         if (P.shard_world > 1u && (root / P.unit) % P.shard_world != P.shard_rank) continue;
         const size_t tab = (size_t)set * P.n_types;
-        SeedOut so = build_seed(P, s_log, root, set, find_bin(P, root), P.type_cum + tab, P.type_sel + tab, P.type_musd + tab);
+        SeedOut so = build_seed<false>(P, s_log, root, set, find_bin(P, root), P.type_cum + tab, P.type_sel + tab, P.type_musd + tab);
         if (so.kind == 1) atomicAdd(counts + so.key, 1ull);
         if (so.kind != 2) continue;
         const double2 ms = __ldg(P.type_musd + (size_t)set * T + so.type);
@@ -1251,32 +1278,61 @@ __global__ void __launch_bounds__(256) k_queue_init(unsigned long long* q_seq, C
 }
 
 /* RNG-only ceiling: the per-division arithmetic (one Philox block, one Box-Muller pair, two timers, two time
- * updates, four compares) with no tree, no stack and no atomics */
+ * updates, four compares) with no tree, no stack and no atomics.  Three shapes of the same loop are built, and the
+ * roofline is quoted against the FASTEST of them measured live (a ceiling that could be raised by reshaping the loop
+ * would flatter the product kernel):
+ *   variant 0: one chain per thread, 256-thread CTAs, 6 CTAs per SM (48 warps; the shape measured in round 1)
+ *   variant 1: one chain per thread, register budget forced to 32 -> 8 CTAs per SM (64 warps, full occupancy)
+ *   variant 2: two independent chains per thread, 4 CTAs per SM (32 warps, twice the instruction-level parallelism) */
 struct RoundKeys { uint32_t rk[20]; };
 
-__global__ void __launch_bounds__(256) k_rng_ceiling(int iters, const double* logtab, double mean, double sd, double t_max,
-                                                     const __grid_constant__ RoundKeys K, unsigned long long* sink)
+template <int CHAINS>
+__device__ __forceinline__ void rng_ceiling_body(int iters, const double* logtab, double mean, double sd, double t_max,
+                                                 const RoundKeys& K, unsigned long long* sink)
 {
     __shared__ double s_log[kLogTabDoubles];
     for (int i = threadIdx.x; i < kLogTabDoubles; i += blockDim.x) s_log[i] = __ldg(logtab + i);
     __syncthreads();
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long acc = 0;
-    double t = 0.0;
-    uint64_t heap = 1;
+    double t[CHAINS];
+    uint64_t heap[CHAINS];
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) { t[c] = 0.0; heap[c] = 1; }
     for (int i = 0; i < iters; ++i) {
-        pcs_u32x4 blk = pcs_draw_rk(tid, 0u, 0u, PCS_TAG_DIVISION, heap, K.rk);
-        double z0, z1;
-        pcs_normal_pair(blk, s_log, 0.0, &z0, &z1);
-        const double a = pcs_timer(mean, sd, z0), b = pcs_timer(mean, sd, z1);
-        const double ta = PCS_ADD(t, a), tb = PCS_ADD(t, b);
-        acc += (a > 0.0) + (b > 0.0) + (ta > t_max) + (tb > t_max);
-        t = (ta > t_max) ? 0.0 : ta;
-        heap = heap * 2ull + (blk.x & 1u);
-        if (heap >> 62) heap = 1;
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c) {
+            pcs_u32x4 blk = pcs_draw_rk(tid, (uint32_t)c, 0u, PCS_TAG_DIVISION, heap[c], K.rk);
+            double z0, z1;
+            pcs_normal_pair(blk, s_log, 0.0, &z0, &z1);
+            const double a = pcs_timer(mean, sd, z0), b = pcs_timer(mean, sd, z1);
+            const double ta = PCS_ADD(t[c], a), tb = PCS_ADD(t[c], b);
+            acc += (a > 0.0) + (b > 0.0) + (ta > t_max) + (tb > t_max);
+            t[c] = (ta > t_max) ? 0.0 : ta;
+            heap[c] = heap[c] * 2ull + (blk.x & 1u);
+            if (heap[c] >> 62) heap[c] = 1;
+        }
     }
     if (acc == 0xFFFFFFFFFFFFFFFFull) sink[0] = acc;
     atomicAdd(sink + 1, acc & 1ull);
+}
+
+__global__ void __launch_bounds__(256) k_rng_ceiling(int iters, const double* logtab, double mean, double sd, double t_max,
+                                                     const __grid_constant__ RoundKeys K, unsigned long long* sink)
+{
+    rng_ceiling_body<1>(iters, logtab, mean, sd, t_max, K, sink);
+}
+
+__global__ void __launch_bounds__(256, 8) k_rng_ceiling_occ(int iters, const double* logtab, double mean, double sd, double t_max,
+                                                            const __grid_constant__ RoundKeys K, unsigned long long* sink)
+{
+    rng_ceiling_body<1>(iters, logtab, mean, sd, t_max, K, sink);
+}
+
+__global__ void __launch_bounds__(256, 4) k_rng_ceiling_ilp2(int iters, const double* logtab, double mean, double sd, double t_max,
+                                                             const __grid_constant__ RoundKeys K, unsigned long long* sink)
+{
+    rng_ceiling_body<2>(iters, logtab, mean, sd, t_max, K, sink);
 }
 
 /* ------------------------------------------------------------------------------------------------ host */
@@ -1393,12 +1449,17 @@ cudaError_t launch_queue_init(unsigned long long* q_seq, ControlBlock* ctl, long
     return cudaGetLastError();
 }
 
-cudaError_t launch_rng_ceiling(int grid, int block, int iters, const double* logtab, double mean, double sd,
+int rng_ceiling_ctas_per_sm(int variant) { return variant == 1 ? 8 : variant == 2 ? 4 : 6; }
+int rng_ceiling_chains(int variant) { return variant == 2 ? 2 : 1; }
+
+cudaError_t launch_rng_ceiling(int variant, int grid, int block, int iters, const double* logtab, double mean, double sd,
                                double t_max, const uint32_t* rk, unsigned long long* sink, cudaStream_t stream)
 {
     RoundKeys K;
     for (int i = 0; i < 20; ++i) K.rk[i] = rk[i];
-    k_rng_ceiling<<<grid, block, 0, stream>>>(iters, logtab, mean, sd, t_max, K, sink);
+    if (variant == 1) k_rng_ceiling_occ<<<grid, block, 0, stream>>>(iters, logtab, mean, sd, t_max, K, sink);
+    else if (variant == 2) k_rng_ceiling_ilp2<<<grid, block, 0, stream>>>(iters, logtab, mean, sd, t_max, K, sink);
+    else k_rng_ceiling<<<grid, block, 0, stream>>>(iters, logtab, mean, sd, t_max, K, sink);
     return cudaGetLastError();
 }
 

@@ -42,7 +42,8 @@ struct alignas(128) ControlBlock {
      * termination test reads: a chunk is added to it before its permit is published and a warp leaves it only when it
      * goes idle, so it can reach 0 only when no work exists anywhere, and then stays 0 */
     long long pending;
-    unsigned long long pad6[10];
+    unsigned long long done_ctas;   /* CTAs whose tables are flushed: the grid-wide rendezvous in front of the fused sweep fitness */
+    unsigned long long pad6[9];
 };
 
 struct SimParams {
@@ -111,9 +112,15 @@ struct SimParams {
     uint32_t slot_mode;           /* 1: the table is laid out by slots (PLAIN direct instances only) */
     uint32_t slot_prolif_end;     /* n_keys * n_prolif: first slot of the quiescent rows */
     uint32_t n_prolif, n_quiet;
-    uint8_t type_rank[64];        /* file id -> rank among the proliferating (or among the quiescent) types */
-    uint8_t prolif_type[64];      /* rank -> file id */
-    uint8_t quiet_type[64];
+    unsigned long long quiet_mask;    /* bit j: type j (file id) is quiescent; a type's rank among its kind is a popcount below j */
+    const uint8_t* rank_type;     /* [n_prolif] file ids of the proliferating types, then [n_quiet] of the quiescent ones (drains only) */
+    /* fitness of a sweep in the same launch: when fit_channels > 0 the CTAs meet once all tables are
+     * flushed and share the parameter sets among them; each set's slab is re-binned onto the target's channels straight
+     * from L2 and its Hellinger distance written to fit_out[set] (fitness_device.h) */
+    uint32_t fit_channels;
+    const uint32_t* fit_key_channel;   /* [n_keys] key -> target channel, 0xFFFFFFFF = not an output row */
+    const double* fit_target;          /* [fit_channels] target shares */
+    double* fit_out;                   /* [n_sets] */
 };
 
 /* ring = 1: 128-node ring per warp, one node per lane and iteration (warps = 32, 24 or 16);
@@ -131,7 +138,11 @@ cudaError_t launch_simple(const SimParams& p, int grid, cudaStream_t stream);
  * zeroes the count tensor and the division counters of the run - one launch instead of a kernel and two memsets */
 cudaError_t launch_queue_init(unsigned long long* q_seq, ControlBlock* ctl, long long* counts, size_t n_counts,
                               long long* divisions, size_t n_divisions, int sm_count, cudaStream_t stream);
-cudaError_t launch_rng_ceiling(int grid, int block, int iters, const double* logtab, double mean, double sd,
+/* variant 0..2: see k_rng_ceiling in sim_kernels.cu */
+constexpr int kRngCeilingVariants = 3;
+int rng_ceiling_ctas_per_sm(int variant);
+int rng_ceiling_chains(int variant);
+cudaError_t launch_rng_ceiling(int variant, int grid, int block, int iters, const double* logtab, double mean, double sd,
                                double t_max, const uint32_t* rk, unsigned long long* sink,
                                cudaStream_t stream);
 

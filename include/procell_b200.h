@@ -187,10 +187,19 @@ size_t procell_engine_counts_len(const procell_engine* engine); /* n_sets*n_keys
  * stream, on the engine's own count tensor (d_counts NULL) or on the caller's device tensor. fitness: host [n_sets]. */
 int procell_engine_set_target(procell_engine* engine, const double* value, const uint64_t* freq, size_t n_channels);
 int procell_engine_fitness(procell_engine* engine, void* stream, const int64_t* d_counts, double* fitness);
+/* When the target was set BEFORE procell_engine_run and the run was an unsharded sweep (n_sets > 1 or checkpoints) on
+ * the cooperative kernel, the simulation kernel computes the distances itself at the end of the same launch - the CTAs
+ * meet once their tables are flushed and re-bin the slabs straight from L2 - and procell_engine_fitness only downloads
+ * 8 bytes per set.  Same arithmetic, same bits as the separate pass (csrc/fitness_device.h).  Returns 1 if the last
+ * procell_engine_fitness call was served that way, 0 if it ran the separate kernel (PROCELL_FITNESS_FUSED=0 forces 0). */
+int procell_engine_fitness_in_launch(const procell_engine* engine);
 
 /* RNG-only micro-kernel: per thread `iters` Philox blocks + Box-Muller pairs + timers into a register
  * accumulator (the instruction-issue ceiling the roofline fraction is quoted against).  Returns ms. */
 int procell_rng_ceiling(int device, int iters, double* ms_out, double* pairs_out);
+/* The loop exists in three shapes (48 warps per SM; 64 warps per SM at 32 registers; two independent chains per thread):
+ * procell_rng_ceiling reports the FASTEST, this one all of them - ms_out[3], pairs_out[3]. */
+int procell_rng_ceiling_variants(int device, int iters, double* ms_out, double* pairs_out);
 
 /* ---- the `procell` command line (src/main.cu:18-34 + src/io/cmdargs.cpp:11-76) ---------------- */
 /* Returns the process exit code; prints errors to stdout as the reference does. */
