@@ -261,11 +261,27 @@ def run_reference(args):
             result = m
             break
         rejected.append({"binary": b.name, "result": m})
+    # the largest configs[1]-SHAPED input a reference build simulates correctly: 1e5 cells with the pending-launch pool
+    # raised (leaf total 99.8 % of the oracle's expectation, fluorescence mass conserved - profiles/r2a_ref_probe.json).
+    # Beyond that the reference's own 16-bit grid size (proliferation.cu:245, SURVEY Q8: at most 65535 x 1024 cells per
+    # launch) truncates the dense level arrays, whatever the pool: 1e6 cells x 2^7 levels is past it.
+    shape_1e5 = None
+    if result is None and (refdir / "procell_ref_pl").exists() and time.perf_counter() - t_begin < budget_s - 30:
+        w5 = synth.workload(2, 0.1)
+        shape_1e5 = measure(refdir / "procell_ref_pl", w5, "configs[1] shape at 1e5 cells", 3)
+    if shape_1e5 and shape_1e5.get("ok"):
+        line["config2_shape_1e5_cells"] = {
+            "value": shape_1e5["divisions"] / shape_1e5["sim_s"], "unit": UNIT, "divisions": shape_1e5["divisions"],
+            "sim_ms": 1e3 * shape_1e5["sim_s"], "process_wall_ms": 1e3 * shape_1e5["wall_s"], "floor_ms": 1e3 * shape_1e5["floor_s"],
+            "binary": shape_1e5["binary"], "leaves": shape_1e5["leaves"], "expected_leaves": shape_1e5["expected_leaves"],
+            "note": "same types, t_max, phi and -r as configs[1], a tenth of the cells: the largest input of that shape the reference "
+                    "build gets right; our arm carries the same input as per_config.config2_shape_1e5_cells"}
     if result is None and cli1 and cli1.get("ok"):
         result = cli1
         cfg["workload"] = "BASELINE configs[0]: 1e4 seed cells, types 0.53/48.33/21.6 0.29/86.3/26.8 + 0.18 quiescent, t_max=168, phi=min bin"
         cfg["n_cells"] = int(w1.n_cells)
-        line["unavailable_config2"] = "no reference build simulates the 1e6-cell input credibly on sm_100: %s" % json.dumps(rejected)
+        line["unavailable_config2"] = ("no reference build simulates the 1e6-cell input credibly on sm_100 (16-bit grid size, "
+                                       "proliferation.cu:245; pending-launch pool): %s" % json.dumps(rejected))
     if result is None:
         line.update({"unavailable": "reference binary failed on every attempted input: %s" % json.dumps(rejected)})
         print(json.dumps(line))
@@ -321,6 +337,7 @@ def main():
     ap.add_argument("--e2e-engines", type=int, default=2,
                     help="engines (each with its own stream, count tensor and pinned host buffer) the end-to-end leg keeps in "
                          "flight: with 2 the D2H of simulation i and the H2D of simulation i+2 overlap kernel i+1")
+    ap.add_argument("--engines", type=int, default=2, help="resident engines the device-timed leg alternates between (1 or 2)")
     ap.add_argument("--serial-reduce", action="store_true", help="N > 1: reduce on the compute stream (no overlap with the next simulation)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -353,43 +370,56 @@ def main():
     w = workload_for(world)
     n_types = w.types.shape[1]
     plan = api.Plan(w.values, w.freqs, w.phi)
-    eng = api.Engine(local_rank)
     shard = (rank, world, SHARD_UNIT)
-    eng.load(plan, w.types, w.t_max, w.seed, shard=shard)
+    # two resident engines (own control block, queue, spill rings, count tensor), each on its own stream and used
+    # alternately: the reset kernel and the launch latency of simulation i + 1 hide behind simulation i (its CTAs start as
+    # the CTAs of simulation i retire).  --engines 1 gives the one-engine, one-stream figure of round 1.
+    n_head = max(1, min(2, args.engines))
+    engs_h = [api.Engine(local_rank) for _ in range(n_head)]
+    for e in engs_h:
+        e.load(plan, w.types, w.t_max, w.seed, shard=shard)
+    eng = engs_h[0]
     n_counts = plan.n_keys * n_types
     bufs = [torch.zeros(n_counts + 1, dtype=torch.int64, device=dev) for _ in range(2)]   # counts + division counter: one reduce
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
+    estreams = [torch.cuda.Stream(device=dev) for _ in range(n_head)]
     comm = torch.cuda.Stream(device=dev) if world > 1 and not args.serial_reduce else None
-    div_acc = torch.zeros(1, dtype=torch.int64, device=dev)
+    div_accs = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(2)]
     reduced = [None, None]                   # event: the reduce that last read bufs[k] is over
 
     def simulate(seed, k, accumulate):
-        """one simulation into bufs[k]; N > 1: its reduce runs on the communication stream and overlaps the next one"""
-        buf = bufs[k]
+        """one simulation into bufs[k] on engine k % n_head; N > 1: its reduce runs on the communication stream and overlaps the next one"""
+        buf, st, e = bufs[k], estreams[k % n_head], engs_h[k % n_head]
         if reduced[k] is not None:
-            stream.wait_event(reduced[k])
-        eng.run(seed, stream.cuda_stream, buf.data_ptr(), buf.data_ptr() + 8 * n_counts)
+            st.wait_event(reduced[k])
+        e.run(seed, st.cuda_stream, buf.data_ptr(), buf.data_ptr() + 8 * n_counts)
         if world > 1 and comm is not None:
             done = torch.cuda.Event()
-            done.record(stream)
+            done.record(st)
             with torch.cuda.stream(comm):
                 comm.wait_event(done)
                 dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
                 if accumulate:
-                    div_acc.add_(buf[n_counts:])
+                    div_accs[k].add_(buf[n_counts:])
                 ev = torch.cuda.Event()
                 ev.record(comm)
             reduced[k] = ev
         else:
-            if world > 1:
-                dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
-            if accumulate:
-                div_acc.add_(buf[n_counts:])
+            with torch.cuda.stream(st):
+                if world > 1:
+                    dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
+                if accumulate:
+                    div_accs[k].add_(buf[n_counts:])
+            # buffer k is only ever touched on this stream (one engine: both buffers on the one stream): stream order protects it
 
     def step(first_seed, accumulate):
+        for st in estreams:
+            st.wait_stream(stream)           # behind the L2 flush and the start event on the main stream
         for j in range(B):
             simulate(first_seed + j, j & 1, accumulate)
+        for st in estreams:
+            stream.wait_stream(st)
         if comm is not None:
             stream.wait_stream(comm)         # a step ends when its last reduce has ended
 
@@ -402,7 +432,8 @@ def main():
         flush.fill_(i)
         step(w.seed + 100000 * i, False)
     barrier()
-    eng.finish(stream.cuda_stream, fetch=False)      # status word (sticky on the device): no failure during warm-up
+    for e, st in zip(engs_h, estreams):
+        e.finish(st.cuda_stream, fetch=False)        # status word (sticky on the device): no failure during warm-up
 
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
@@ -422,8 +453,9 @@ def main():
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     gpu_ms = float(t_ms.item())
     # the device status word is sticky: a pool overflow / watchdog abort in ANY simulation since the last finish is still there
-    eng.finish(stream.cuda_stream, fetch=False)
-    div_timed = int(div_acc.item())                # rank 0 holds the reduced totals
+    for e, st in zip(engs_h, estreams):
+        e.finish(st.cuda_stream, fetch=False)
+    div_timed = int(sum(d.item() for d in div_accs))      # rank 0 holds the reduced totals
     div_per_sim = div_timed / (K * B)
     value = div_timed / (gpu_ms * 1e-3) if rank == 0 else 0.0
 
@@ -451,7 +483,7 @@ def main():
     host_values, host_freqs = w.values.copy(), w.freqs.copy()
     e2e_div = 0
     n_eng = max(1, args.e2e_engines)
-    engs = [eng] + [api.Engine(local_rank) for _ in range(n_eng - 1)]
+    engs = (engs_h + [api.Engine(local_rank) for _ in range(n_eng)])[:n_eng]
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_eng)]
     dbufs = [torch.zeros(n_counts + 1, dtype=torch.int64, device=dev) for _ in range(n_eng)]
     hosts = [torch.zeros(n_counts + 1, dtype=torch.int64).pin_memory() for _ in range(n_eng)]
@@ -493,8 +525,10 @@ def main():
             retire(k)
     barrier()
     t_e2e = time.perf_counter() - t0
-    for extra in engs[1:]:
+    for extra in engs:
         extra.close()
+    for e in engs_h:
+        e.close()
     t_e = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
@@ -547,6 +581,7 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD_TEXT, "n_cells": int(plan.n_cells), "simulations_per_step": B,
                            "divisions_per_simulation": div_per_sim, "ms_per_simulation": ms_sim,
+                           "engines": "%d resident engine(s), alternating, each on its own stream" % n_head,
                            "sharding": "seed-cell units of %d, rank-strided; one NCCL reduce(sum,int64) per simulation%s"
                                        % (SHARD_UNIT, "" if comm is None else ", on a second stream (overlaps the next simulation)"),
                            "l2": "flushed between steps (256 MiB write), outside the timed events"},
@@ -572,6 +607,29 @@ def main():
     return 0
 
 
+def cli_wall_config1(synth, w):
+    """the `procell` command line on configs[0], whole-process wall clock (what bench.py --impl reference reports for the
+    reference binary as cli_config1), and the same command with -t 0 (process start, CUDA context, parsing: no division)"""
+    from cuda_pro_cell_b200 import _lib
+    tmp = Path(tempfile.mkdtemp(prefix="procell_cli_"))
+    (tmp / "h.txt").write_text(synth.histogram_text(w.values, w.freqs))
+    (tmp / "c.txt").write_text(synth.types_text(w.types[0]))
+
+    def run(t_max):
+        cmd = [str(_lib.CLI_PATH), "-h", str(tmp / "h.txt"), "-c", str(tmp / "c.txt"), "-t", repr(float(t_max)), "-p", repr(float(w.phi)),
+               "-o", str(tmp / "o.txt")]
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+        return time.perf_counter() - t0 if r.returncode == 0 else None
+
+    floors = [run(0.0) for _ in range(2)]
+    walls = [run(w.t_max) for _ in range(3)]
+    if any(x is None for x in floors + walls):
+        return {"cli_wall_ms": None}
+    return {"cli_wall_ms": 1e3 * sum(walls) / len(walls), "cli_floor_ms": 1e3 * min(floors),
+            "cli_note": "`procell -h -c -t 168 -p -o`, whole process incl. CUDA context creation, mean of 3; floor = same with -t 0"}
+
+
 def run_per_config(api, synth, torch, dist, dev, local_rank, rank, world, stream, barrier, ceiling):
     """BASELINE configs 2..5 at full size, one record each: ms per simulation (CUDA events, max over ranks), divisions/s,
     fraction of the live RNG ceiling - by divisions, and by DRAWS (seed cells + divisions: every seed cell also costs a
@@ -580,9 +638,10 @@ def run_per_config(api, synth, torch, dist, dev, local_rank, rank, world, stream
     (config 4: a hundred fast lineages own all the work) - and rank 0 checks the reduced tensor against the same simulation
     unsharded on its own GPU."""
     out = {}
-    plans = [(2, 1, 10, 0), (3, 1, 10, 0), (4, 1, 2, 6 if world > 1 else 0), (5, 1, 4, 0)]
-    for config, n_warm, n_timed, level in plans:
-        w = synth.workload(config)
+    plans = [("config1", synth.workload(1), 3, 50, 0), ("config2", synth.workload(2), 1, 10, 0),
+             ("config2_shape_1e5_cells", synth.workload(2, 0.1), 3, 20, 0), ("config3", synth.workload(3), 1, 10, 0),
+             ("config4", synth.workload(4), 1, 2, 6 if world > 1 else 0), ("config5", synth.workload(5), 1, 4, 0)]
+    for name, w, n_warm, n_timed, level in plans:
         plan = api.Plan(w.values, w.freqs, w.phi)
         n_sets, n_types = w.types.shape[0], w.types.shape[1]
         n_counts = n_sets * plan.n_keys * n_types
@@ -641,7 +700,9 @@ def run_per_config(api, synth, torch, dist, dev, local_rank, rank, world, stream
         barrier()
         eng.close()
         if rank == 0:
-            out["config%d" % config] = rec
+            if name == "config1" and world == 1:
+                rec.update(cli_wall_config1(synth, w))
+            out[name] = rec
         del buf
     return out if rank == 0 else None
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU visit of round 2:  gpurun --timeout 1500 -- 'bash tools/gpu_visit.sh TAG [legs]'
-# legs (default all): tests ref bench ncu
+# legs (default: tests ref bench ncu): tests ref bench bench1 benchref fit ncu ceil san
 #   tests  the whole parity suite (pytest -m gpu) + smoke
 #   ref    tools/ref_probe.py: which reference build simulates config 2 correctly, and how long it takes
 #   bench  bench.py (ours) and bench.py --impl reference
@@ -31,8 +31,26 @@ ref)
 bench)
   timeout 400 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; el bench $?
   cat gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench_$TAG.err
+  ;;
+bench1)   # the one-engine, one-stream figure beside the default (two resident engines alternating)
+  timeout 200 python bench.py --engines 1 --no-cpu-baseline --no-per-config --e2e-steps 2 > gpurun_out/bench_1engine_$TAG.json 2> gpurun_out/bench_1engine_$TAG.err; el bench_1engine $?
+  cut -c1-400 gpurun_out/bench_1engine_$TAG.json
+  ;;
+benchref)
   timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; el bench_ref $?
   cat gpurun_out/bench_ref_$TAG.json; tail -5 gpurun_out/bench_ref_$TAG.err
+  ;;
+fit)
+  timeout 200 python tools/fitness_timing.py > gpurun_out/fitness_timing_$TAG.log 2>&1; el fitness_timing $?
+  cat gpurun_out/fitness_timing_$TAG.log
+  ;;
+ceil)
+  timeout 200 ncu --set full --clock-control none -k regex:k_rng_ceiling -c 6 -f -o gpurun_out/prof_ceilings_$TAG \
+      python -c "import sys; sys.path.insert(0,'.'); from cuda_pro_cell_b200 import api; print(api.rng_ceiling_variants(0, 4096))" > gpurun_out/ncu_ceilings_$TAG.log 2>&1; el ncu_ceilings $?
+  tail -2 gpurun_out/ncu_ceilings_$TAG.log
+  ;;
+san)
+  bash tools/gpu_sanitize.sh $TAG; el sanitize $?
   ;;
 ncu)
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$TAG.csv \
