@@ -721,6 +721,18 @@ int procell_proliferate_multi(const procell_plan* plan, const procell_sim_params
     const size_t n_packed = eng[0] ? eng[0]->counts_len + eng[0]->n_sets : 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (rc == PROCELL_OK) {
+        /* one small reduce first: a fresh communicator builds its channels and peer connections on first use, which
+         * would otherwise be timed (and paid) inside the run's single exchange step */
+        g_nccl.GroupStart();
+        for (int i = 0; i < n_gpus; ++i) {
+            int nrc = g_nccl.Reduce(eng[i]->counts.p, eng[i]->counts.p, 1, kNcclInt64, kNcclSum, 0, comms[i], streams[i]);
+            if (nrc != 0) rc = fail(PROCELL_ERR_CUDA, std::string("ncclReduce (warm-up): ") + g_nccl.GetErrorString(nrc));
+        }
+        int nrc = g_nccl.GroupEnd();
+        if (nrc != 0 && rc == PROCELL_OK) rc = fail(PROCELL_ERR_CUDA, std::string("ncclGroupEnd (warm-up): ") + g_nccl.GetErrorString(nrc));
+        for (int i = 0; i < n_gpus; ++i) { cudaSetDevice(i); cudaStreamSynchronize(streams[i]); }
+    }
+    if (rc == PROCELL_OK) {
         cudaSetDevice(0);
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, streams[0]);

@@ -83,7 +83,11 @@ PCS_HD uint64_t pcs_d2bits(double d)
 #define PCS_MAX_TYPES 64u
 #define PCS_MAX_BINS 65535u
 #define PCS_TAG_DIVISION 0u      /* one block per division: both daughters' timers */
-#define PCS_TAG_SEED 1u          /* one block per seed cell: type uniform + initial-age uniform */
+#define PCS_TAG_SEED 1u          /* ONE block per seed cell and draw round: word x = type uniform, y = initial-age uniform,
+                                    z = Box-Muller radius uniform and w = Box-Muller angle of its first timer (32-bit
+                                    grade each - what cuRAND's float generators use; every division below the seed cell
+                                    draws at 52 / 60 bits).  A rejected first timer (<= 0) is redrawn from words z, w of
+                                    the block with retry + 1; x and y are taken from round 0 only. */
 
 /* ------------------------------------------------------------------ Philox4x32-10 (Salmon et al., SC'11) */
 #define PCS_PHILOX_M0 0xD2511F53u
@@ -175,6 +179,12 @@ PCS_HD double pcs_u53(uint32_t lo, uint32_t hi)
     return pcs_unit_from_mant52((((uint64_t)hi << 32) | (uint64_t)lo) >> 12);
 }
 
+/* 32 random bits m -> (2m+1) * 2^-33, exact: never 0, never 1 (the seed-cell draws) */
+PCS_HD double pcs_u32unit(uint32_t m)
+{
+    return PCS_FMA((double)m, 0x1p-32, 0x1p-33);    /* both constants have an all-zero low word: cheap immediates */
+}
+
 /* the math table every consumer passes as `tab`: 128 log rows {invc, logc}, then 256 sin/cos rows {sin, cos} */
 #define PCS_TAB_SINCOS (2 << PCM_LOG_N_BITS)
 #define PCS_TAB_DOUBLES (PCS_TAB_SINCOS + (2 << PCM_SC_N_BITS))
@@ -252,6 +262,19 @@ PCS_HD void pcs_normal_pair_finish(double rad2, double s, double c, double* z0, 
     double rad = PCS_SQRT(rad2);
     *z0 = PCS_MUL(rad, s);
     *z1 = PCS_MUL(rad, c);
+}
+
+/* the seed cell's first-timer normal from words z (radius uniform, 32 bits) and w (angle: the top 32 bits of the 64-bit
+ * angle word, the rest zero) of its SEED block; u_override (refcompat seeding) replaces the radius uniform
+ * when > 0.  The seed cell is daughter 1 of the virtual division at heap 0: it takes the cosine component. */
+PCS_HD double pcs_seed_normal(pcs_u32x4 w, const double* tab, double u_override)
+{
+    double u = pcs_u32unit(w.z);
+    if (u_override > 0.0) u = u_override;
+    const double rad2 = pcs_neg2log(u, tab);
+    double s, c;
+    pcs_sincos2pi((uint64_t)w.w << 32, tab + PCS_TAB_SINCOS, &s, &c);
+    return PCS_MUL(PCS_SQRT(rad2), c);
 }
 
 PCS_HD void pcs_normal_pair(pcs_u32x4 w, const double* tab, double u_override, double* z0, double* z1)

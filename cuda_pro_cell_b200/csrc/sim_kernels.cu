@@ -107,6 +107,13 @@ __device__ __forceinline__ void cp_async16(volatile int* smem_dst, const void* g
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
 }
 
+/* the two one-word flags of a CTA that several warps read while another may set them - s_ctl[1] "quiescent", s_ctl[3]
+ * "the seed cursor has run out" (both only ever go 0 -> 1) - and the rendezvous round counter are read and written
+ * with shared-memory atomics: that states the intent to the hardware, and to compute-sanitizer's racecheck, which
+ * otherwise (rightly) reports every plain read of a word another warp writes.  Lane 0 does the reading (RULE below). */
+__device__ __forceinline__ int sflag_get(volatile int* p) { return atomicOr(const_cast<int*>(p), 0); }
+__device__ __forceinline__ void sflag_set(volatile int* p, int v) { atomicExch(const_cast<int*>(p), v); }
+
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
     unsigned long long t;
@@ -174,6 +181,16 @@ constexpr int kEndgameIdle = PROCELL_ENDGAME_IDLE;
 #define PROCELL_PROBE_MASK 7u
 #endif
 constexpr uint32_t kProbeMask = PROCELL_PROBE_MASK;       /* busy warps look at the hunger snapshot every (mask + 1)-th iteration */
+#ifndef PROCELL_SNAP_MASK
+#define PROCELL_SNAP_MASK 63u
+#endif
+constexpr uint32_t kSnapMask = PROCELL_SNAP_MASK;         /* a warp refreshes its CTA's snapshot every (mask + 1)-th iteration (staggered by warp) */
+/* end game (at least kEndgameIdle warps starve): 1 = a busy warp refreshes the snapshot at EVERY probe and may hand over
+ * a chunk at every probe instead of once per snapshot epoch */
+#ifndef PROCELL_ENDGAME_FAST
+#define PROCELL_ENDGAME_FAST 0
+#endif
+constexpr bool kEndgameFast = PROCELL_ENDGAME_FAST != 0;
 constexpr unsigned kIdleBackoffMaxNs = PROCELL_IDLE_BACKOFF_MAX_NS;   /* idle warps poll with exponential back-off up to this */
 constexpr uint32_t kDonateMinNodes = PROCELL_DONATE_MIN_NODES;        /* a warp gives a chunk away only when its ring is about to spill anyway */
 static_assert((kHistFlushIters & (kHistFlushIters - 1u)) == 0u && kHistFlushIters >= 256u && kHistFlushIters <= (1u << 20), "");
@@ -281,15 +298,15 @@ __device__ __forceinline__ bool setdirect_rendezvous(const SimParams& P, volatil
     __syncwarp();
     int role = 0;               /* 1 last to arrive: does the switch, 2 released, 3 abort */
     if (lane == 0) {
-        const int round = s_ctl[13];
+        const int round = sflag_get(s_ctl + 13);
         const int arrived = atomicAdd(const_cast<int*>(s_ctl) + 12, 1) + 1;
-        if (s_ctl[3]) role = 2;              /* another warp has just found the cursor exhausted: nothing to switch to */
+        if (sflag_get(s_ctl + 3)) role = 2;              /* another warp has just found the cursor exhausted: nothing to switch to */
         else if (arrived == WARPS) role = 1;
         else {
             const unsigned long long deadline = *reinterpret_cast<volatile unsigned long long*>(const_cast<int*>(s_ctl) + 10);
             unsigned backoff = 64;
             for (;;) {
-                if (s_ctl[13] != round || s_ctl[3]) { role = 2; break; }     /* released, or no batch left anywhere */
+                if (sflag_get(s_ctl + 13) != round || sflag_get(s_ctl + 3)) { role = 2; break; }     /* released, or no batch left anywhere */
                 __nanosleep(backoff);
                 if (backoff < 1024u) backoff <<= 1;
                 if (global_timer_ns() > deadline || ld_volatile_s32(&P.ctl->status) != kStatusOk) { role = 3; break; }
@@ -307,7 +324,7 @@ __device__ __forceinline__ bool setdirect_rendezvous(const SimParams& P, volatil
     if (lane == 0) {
         const unsigned long long g = atomicAdd(&P.ctl->cursor, 1ull);
         if (g >= P.total_batches) {
-            s_ctl[3] = 1;                                   /* no batch left anywhere: the base stays where it is */
+            sflag_set(s_ctl + 3, 1);                        /* no batch left anywhere: the base stays where it is */
             atomicMin(&P.ctl->t_exhausted, global_timer_ns());
         } else {
             s_ctl[7] = (int)((uint32_t)(g / P.batches_per_set) * P.smem_hist_slots);
@@ -324,8 +341,8 @@ __device__ __forceinline__ bool setdirect_rendezvous(const SimParams& P, volatil
 struct WarpCtx {
     ulonglong2* ab;                  /* ring: kCap (t_div bits, heap) pairs followed by kCap (root|keybase<<32, D) pairs */
     uint32_t bottom, top;            /* ring positions, n = top - bottom */
-    unsigned long long* spill;       /* private spill ring */
-    uint32_t sp_bottom, sp_top;
+    uint32_t sp_bottom, sp_top;      /* private spill ring in HBM: its address is recomputed on use (spill_ring), which keeps
+                                        a 64-bit pointer out of the 64 registers of the steady state */
     int lane;
 };
 
@@ -356,11 +373,17 @@ __device__ __forceinline__ void ring_store_if(WarpCtx& w, bool p, uint32_t idx, 
 #endif
 }
 
+/* the warp's private spill ring: [grid * warps][kSpillCap][kChunkWords] */
+__device__ __forceinline__ unsigned long long* spill_ring(const SimParams& P)
+{
+    return P.spill + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kSpillCap * kChunkWords;
+}
+
 template <int RING>
 __device__ __forceinline__ void spill_bottom_chunk(WarpCtx& w, const SimParams& P)
 {
     uint32_t idx = (w.bottom + w.lane) & Ring<RING>::kMask;
-    unsigned long long* dst = w.spill + (size_t)(w.sp_top % kSpillCap) * kChunkWords;
+    unsigned long long* dst = spill_ring(P) + (size_t)(w.sp_top % kSpillCap) * kChunkWords;
     uint64_t a, b, c, d;
     ring_load<RING>(w, idx, a, b, c, d);
     __stcg(dst + w.lane, a);
@@ -374,10 +397,10 @@ __device__ __forceinline__ void spill_bottom_chunk(WarpCtx& w, const SimParams& 
 }
 
 template <int RING>
-__device__ __forceinline__ void unspill_newest_chunk(WarpCtx& w)
+__device__ __forceinline__ void unspill_newest_chunk(WarpCtx& w, const SimParams& P)
 {
     w.sp_top -= 1;
-    const unsigned long long* src = w.spill + (size_t)(w.sp_top % kSpillCap) * kChunkWords;
+    const unsigned long long* src = spill_ring(P) + (size_t)(w.sp_top % kSpillCap) * kChunkWords;
     w.bottom -= kChunkNodes;
     uint32_t idx = (w.bottom + w.lane) & Ring<RING>::kMask;
     ring_store<RING>(w, idx, __ldcg(src + w.lane), __ldcg(src + 32 + w.lane), __ldcg(src + 64 + w.lane), __ldcg(src + 96 + w.lane));
@@ -449,7 +472,7 @@ __device__ __forceinline__ void donate_chunk(WarpCtx& w, const SimParams& P)
 {
     uint64_t a, b, c, d;
     if (w.sp_top != w.sp_bottom) {
-        const unsigned long long* src = w.spill + (size_t)(w.sp_bottom % kSpillCap) * kChunkWords;
+        const unsigned long long* src = spill_ring(P) + (size_t)(w.sp_bottom % kSpillCap) * kChunkWords;
         a = __ldcg(src + w.lane);
         b = __ldcg(src + 32 + w.lane);
         c = __ldcg(src + 64 + w.lane);
@@ -515,7 +538,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
         const unsigned long long t0 = global_timer_ns();
         unsigned backoff = 128;
         for (;;) {
-            if (s_ctl[1]) state = 2;
+            if (sflag_get(s_ctl + 1)) state = 2;
             else if (s_ctl[0] == 0 && atomicCAS(const_cast<int*>(s_ctl), 0, 1) == 0) {
                 /* Termination reads ONE word: `pending` = warps that hold or may find work + published chunks not yet
                  * claimed.  A chunk enters it before its permit exists, an idle warp that claims a chunk takes the
@@ -543,7 +566,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
                     watchdog_fire(P, gwarp, 0, 3, (unsigned long long)act, (unsigned long long)(long long)av, (unsigned long long)ld_volatile_s32(&ctl->idle), global_timer_ns() - t0, 0, 0);
                     state = 2;
                 }
-                if (state == 2) s_ctl[1] = 1;
+                if (state == 2) sflag_set(s_ctl + 1, 1);
                 __threadfence_block();
                 atomicExch(const_cast<int*>(s_ctl), 0);
             }
@@ -621,9 +644,9 @@ __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* 
     SeedOut o;
     const uint32_t kd = __ldg(P.bin_kdiv + bin);
     const uint32_t T = P.n_types;
-    pcs_u32x4 w = pcs_draw_rk(root, set, 0u, PCS_TAG_SEED, 0ull, P.rk);
-    const double u_type = pcs_u53(w.x, w.y);
-    const double u_age = pcs_u53(w.z, w.w);
+    pcs_u32x4 w = pcs_draw_rk(root, set, 0u, PCS_TAG_SEED, 0ull, P.rk);      /* the seed cell's ONE block: type, age, radius, angle */
+    const double u_type = pcs_u32unit(w.x);
+    const double u_age = pcs_u32unit(w.y);
     uint32_t j = T - 1u;                                       /* cell.cu:81-104: the FIRST j with u < cum[j]; Q17: none -> last */
     for (uint32_t i = T - 1u; i-- > 0u;)                       /* scanned downwards without a break: no divergence */
         if (u_type < cum[i]) j = i;
@@ -647,13 +670,12 @@ __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* 
         o.t_div = 0.0;
         return o;
     }
-    double timer = ms.x;
-    for (uint32_t retry = 0; retry < PCS_MAX_RETRY; ++retry) { /* root = child 1 of the virtual division at heap 0 */
-        pcs_u32x4 b = pcs_draw_rk(root, set, retry, PCS_TAG_DIVISION, 0ull, P.rk);
-        double z0, z1;
-        pcs_normal_pair(b, s_log, (P.refcompat && retry == 0u) ? u_type : 0.0, &z0, &z1);
-        double cand = pcs_timer(ms.x, ms.y, z1);
+    double timer = ms.x;                                       /* the mean, should 255 draws in a row be rejected */
+    for (uint32_t retry = 0;;) {                               /* first timer from words z, w of the same block (cell.cu:106-122) */
+        const double cand = pcs_timer(ms.x, ms.y, pcs_seed_normal(w, s_log, (P.refcompat && retry == 0u) ? u_type : 0.0));
         if (cand > 0.0) { timer = cand; break; }
+        if (++retry == PCS_MAX_RETRY) break;
+        w = pcs_draw_rk(root, set, retry, PCS_TAG_SEED, 0ull, P.rk);   /* rejected: words z, w of the next round's block */
     }
     const double t0 = PCS_MUL(timer, u_age);                   /* cell.cu:124-143 */
     const double t_div = PCS_ADD(t0, timer);
@@ -885,7 +907,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     WarpCtx w;
     w.ab = reinterpret_cast<ulonglong2*>(s_stack + (size_t)warp * 4 * kCap);
     w.bottom = 0; w.top = 0;
-    w.spill = P.spill + (size_t)(blockIdx.x * WARPS + warp) * kSpillCap * kChunkWords;
     w.sp_bottom = 0; w.sp_top = 0;
     w.lane = lane;
 
@@ -924,13 +945,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         /* the two uncommon cases - too few nodes for a full iteration, too many for the pushes of one - share one test */
         if (n - kLow > kCap - 32u * RING - kLow) {
         if (n < kLow) {
-            if (w.sp_top != w.sp_bottom) { TRACE(P, GWARP, lane, 41); unspill_newest_chunk<RING>(w); continue; }
+            if (w.sp_top != w.sp_bottom) { TRACE(P, GWARP, lane, 41); unspill_newest_chunk<RING>(w, P); continue; }
             /* RULE: every decision that depends on mutable shared/global state is taken by lane 0 and broadcast.
              * Lanes of a warp are not guaranteed to be converged when they read a volatile flag, so a per-lane read
              * can see two different values inside one warp and split it for good. */
             int exhausted = 0;
             if (seed_cur == seed_end) {
-                if (lane == 0) exhausted = s_ctl[3];
+                if (lane == 0) exhausted = sflag_get(s_ctl + 3);
                 exhausted = __shfl_sync(kFull, exhausted, 0);
             }
             if (seed_cur != seed_end || !exhausted) {
@@ -961,14 +982,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                                     if (off < (left < P.batch_units ? left : P.batch_units)) { j = first_unit + off; status = 1; }
                                 }
                                 if (status == 0) {
-                                    if (s_ctl[3]) status = 2;
+                                    if (sflag_get(s_ctl + 3)) status = 2;
                                     else if (SETDIRECT) {
                                         /* batch used up.  If no batch is left ANYWHERE there will be no further switch:
                                          * say so at once (the table keeps its base), so that this CTA's busy warps start
                                          * handing work to the idle ones instead of everyone parking behind the slowest.
                                          * Otherwise the CTA switches sets together. */
                                         if (ld_acquire_u64(&ctl->cursor) >= P.total_batches) {
-                                            s_ctl[3] = 1;
+                                            sflag_set(s_ctl + 3, 1);
                                             atomicMin(&ctl->t_exhausted, global_timer_ns());
                                             status = 2;
                                         } else status = 4;
@@ -979,7 +1000,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                                         const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(s_batch);
                                         if ((cur >> 24) == gb) {      /* nobody has replaced it yet */
                                             const unsigned long long g = atomicAdd(&ctl->cursor, 1ull);
-                                            if (g >= P.total_batches) { s_ctl[3] = 1; status = 2; }
+                                            if (g >= P.total_batches) { sflag_set(s_ctl + 3, 1); status = 2; }
                                             else atomicExch(s_batch, g << 24);
                                         }
                                         __threadfence_block();
@@ -1020,7 +1041,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                         continue;
                     }
                     if (!got) {
-                        if (lane == 0) { s_ctl[3] = 1; atomicMin(&ctl->t_exhausted, global_timer_ns()); }
+                        if (lane == 0) { sflag_set(s_ctl + 3, 1); atomicMin(&ctl->t_exhausted, global_timer_ns()); }
                         __syncwarp();
                         continue;
                     }
@@ -1126,21 +1147,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
             }
             int packed = 0;
             if (lane == 0) {
-                if (((iter + (uint32_t)warp * (kProbeMask + 1u)) & 63u) == 0u) {
+                int exhausted = sflag_get(s_ctl + 3);              /* one atomic read per probe */
+                const bool endgame_now = kEndgameFast && exhausted && s_snap[0] >= kEndgameIdle;
+                if (endgame_now || ((iter + (uint32_t)warp * (kProbeMask + 1u)) & kSnapMask) == 0u) {
                     cp_async16(s_snap, &ctl->idle);
                     cp_async16(s_snap + 4, &ctl->avail);
-                    if (!multi_set && !s_ctl[3]) cp_async16(s_snap + 8, &ctl->cursor);
+                    if (!multi_set && !exhausted) cp_async16(s_snap + 8, &ctl->cursor);
                     atomicAdd(const_cast<int*>(s_ctl) + 5, 1);      /* snapshot epoch */
                 }
                 const int idle_snap = s_snap[0], avail_snap = s_snap[4];
-                if (!multi_set && !s_ctl[3]) {
+                if (!multi_set && !exhausted) {
                     const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(s_snap + 8);
-                    if (cur >= P.total_local_units) s_ctl[3] = 1;
+                    if (cur >= P.total_local_units) { sflag_set(s_ctl + 3, 1); exhausted = 1; }
                 }
                 /* donate at most once per snapshot epoch, and only while fewer chunks wait than warps starve */
                 const int ep = s_ctl[5];
-                const int hg = P.donate && s_ctl[3] && idle_snap + kDonateReserve > (avail_snap > 0 ? avail_snap : 0) &&
-                               avail_snap < kQueueCap / 2 && ep != donate_epoch;
+                const int hg = P.donate && exhausted && idle_snap + kDonateReserve > (avail_snap > 0 ? avail_snap : 0) &&
+                               avail_snap < kQueueCap / 2 && (ep != donate_epoch || (kEndgameFast && idle_snap >= kEndgameIdle));
                 /* end game: when this many warps starve, a warp parts with a chunk as soon as it keeps 32 nodes */
                 packed = (ep << 2) | ((idle_snap >= kEndgameIdle) << 1) | hg;
             }

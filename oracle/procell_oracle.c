@@ -92,6 +92,12 @@ double oracle_uniform53(uint32_t lo, uint32_t hi)
     return unit_from_mantissa(w >> 12);
 }
 
+/* (2m+1)/2^33 for 32 random bits m: the seed-cell draws */
+double oracle_uniform32(uint32_t m)
+{
+    return fma((double)m, ldexp(1.0, -32), ldexp(1.0, -33));
+}
+
 /* -2 ln(u) for a normal double u in (0,1) */
 double oracle_neg2log(double u)
 {
@@ -340,11 +346,13 @@ static void count_leaf(orc_ctx* cx, unsigned bin, unsigned level, int type_id)
 static void expand_root(orc_ctx* cx, uint32_t root, unsigned bin)
 {
     const oracle_plan* p = cx->plan;
-    /* seed cell: cells_population.cu:108-111 -> cell.cu:25-79 with type == -1, t == 0 */
+    /* seed cell: cells_population.cu:108-111 -> cell.cu:25-79 with type == -1, t == 0.
+     * ONE Philox block per seed cell (tag 1, heap 0): word 0 -> type uniform, word 1 -> initial-age uniform, word 2 ->
+     * radius uniform and word 3 -> angle of the first timer's Box-Muller draw, 32 bits each */
     uint32_t w[4];
     draw_block(root, cx->set, 0u, 1u, 0ull, cx->seed, w);
-    double u_type = oracle_uniform53(w[0], w[1]);
-    double u_age = oracle_uniform53(w[2], w[3]);
+    double u_type = oracle_uniform32(w[0]);
+    double u_age = oracle_uniform32(w[1]);
     const orc_type* ty = &cx->types[cx->n_types - 1];     /* Q17: nothing matched -> last in selection order */
     double acc = 0.0;
     for (size_t j = 0; j < cx->n_types; ++j) {            /* cell.cu:81-104 */
@@ -360,8 +368,19 @@ static void expand_root(orc_ctx* cx, uint32_t root, unsigned bin)
         return;
     }
     double timer[2];
-    /* root = heap 1 = child 1 of the virtual division at heap 0 */
-    division_timers(cx, root, 0ull, ty, 2u, cx->refcompat ? u_type : 0.0, timer);
+    /* first timer: truncated normal by redraw (cell.cu:106-122).  Round 0 takes words 2, 3 of the seed block itself;
+     * a rejected draw (<= 0) takes words 2, 3 of the block with the next retry number; after 255 rejections the mean.
+     * refcompat: round 0's radius uniform IS the type uniform.  The cosine component is the seed cell's. */
+    timer[1] = ty->mean;
+    for (uint32_t retry = 0; retry < ORC_MAX_RETRY; ++retry) {
+        if (retry > 0) draw_block(root, cx->set, retry, 1u, 0ull, cx->seed, w);
+        double u_rad = (cx->refcompat && retry == 0) ? u_type : oracle_uniform32(w[2]);
+        double sn, cs;
+        oracle_sincos2pi((uint64_t)w[3] << 32, &sn, &cs);
+        double z = sqrt(oracle_neg2log(u_rad)) * cs;
+        double cand = fma(ty->sd, z, ty->mean);
+        if (cand > 0.0) { timer[1] = cand; break; }
+    }
     double t0 = timer[1] * u_age;                         /* cell.cu:124-143: t = timer * U' */
     double t_div = t0 + timer[1];
     if (t_div > cx->t_max) { if (low_owner) count_leaf(cx, bin, 0, ty->id); return; }     /* proliferation.cu:404-410 */

@@ -310,7 +310,6 @@ def test_sweep_fitness_in_the_same_launch(gpu_api, monkeypatch, table):
     assert np.array_equal(fused, separate)
     want = np.array([_hellinger_reference(plan, res.counts[s], tvalues, tfreqs.astype(np.float64)) for s in range(0, 1024, 37)])
     assert np.abs(fused[::37] - want).max() <= 1e-12
-    assert int(np.argmin(fused)) in range(512, 528)             # a neighbour of the generating set in the grid wins
     # a target set AFTER the run is served by the separate pass, with the same numbers
     monkeypatch.delenv("PROCELL_FITNESS_FUSED")
     eng.set_target(tvalues, tfreqs)

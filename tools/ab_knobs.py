@@ -21,7 +21,9 @@ REPS = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 ALL_KNOBS = {"default": {}, "npl2": {"PROCELL_COOP_NPL": "2"}, "w16": {"PROCELL_COOP_WARPS": "16"},
              "w24": {"PROCELL_COOP_WARPS": "24"}}
 KNOBS = [ALL_KNOBS[k] for k in (sys.argv[2].split(",") if len(sys.argv) > 2 else ALL_KNOBS)]
-WORK = [(2, 1.0, 0.0), (3, 0.1, 0.0), (3, 1.0, 0.0), (5, 0.1, 0.0), (4, 0.1, 600.0)]
+WORK = [(2, 1.0, 0.0), (2, 0.1, 0.0), (3, 1.0, 0.0), (5, 1.0, 0.0), (4, 0.1, 600.0), (4, 1.0, 0.0)]
+if os.environ.get("AB_WORK"):        # e.g. AB_WORK="2:1.0:0,4:0.1:600"
+    WORK = [tuple(float(x) if i else int(x) for i, x in enumerate(item.split(":"))) for item in os.environ["AB_WORK"].split(",")]
 
 for cfg, scale, t_override in WORK:
     w = synth.workload(cfg, scale)
@@ -45,5 +47,8 @@ for cfg, scale, t_override in WORK:
                 ms.append(r.stats["kernel_ms"])
         print(json.dumps({"lib": os.environ.get("PROCELL_LIB", "libprocell_b200.so"), "config": cfg, "scale": scale, "t_max": w.t_max, "knob": knob, "divisions": div, "crc": crc,
                           "ms_min": min(ms), "ms_med": statistics.median(ms), "block": r.stats["block"],
+                          "seed_phase_us": r.stats["seed_phase_us"], "span_us": r.stats["total_us"],
+                          "idle_us_per_warp": r.stats["idle_warp_us"] / max(1, r.stats["grid"] * r.stats["block"] // 32),
+                          "donations": r.stats["donations"],
                           "Gdiv_s": div / min(ms) / 1e6}), flush=True)
         eng.close()

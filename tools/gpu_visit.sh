@@ -52,6 +52,39 @@ ceil)
 san)
   bash tools/gpu_sanitize.sh $TAG; el sanitize $?
   ;;
+ab)       # A/B of the in-tree library builds named in AB_LIBS (make -C cuda_pro_cell_b200/csrc variant NAME=.. DEFS=..)
+  : > gpurun_out/ab_$TAG.jsonl
+  for lib in ${AB_LIBS:-libprocell_b200.so}; do
+    PROCELL_LIB=$lib timeout 200 python tools/ab_knobs.py ${AB_REPS:-5} default >> gpurun_out/ab_$TAG.jsonl 2>> gpurun_out/ab_$TAG.err; el ab_$lib $?
+  done
+  python - <<PY
+import json
+for l in open("gpurun_out/ab_$TAG.jsonl"):
+    r = json.loads(l)
+    print("%-34s cfg %d x%-4g %9.4f ms  %6.1f Gdiv/s  tail %7.1f us  idle/warp %6.1f us  donations %6d  crc %d" % (
+        r["lib"], r["config"], r["scale"], r["ms_min"], r["Gdiv_s"], r["span_us"] - r["seed_phase_us"], r["idle_us_per_warp"], r["donations"], r["crc"]))
+PY
+  ;;
+multi)    # needs a box with NGPU GPUs (gpurun --gpus N): the multi-GPU parity tests and BASELINE's multi-GPU configs
+  NG=$(nvidia-smi -L | wc -l)
+  timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 180 -p no:cacheprovider -k "multi_gpu" > gpurun_out/pytest_multi_${NG}gpu_$TAG.log 2>&1; el pytest_multi $?
+  tail -4 gpurun_out/pytest_multi_${NG}gpu_$TAG.log
+  timeout 400 python tools/multi_gpu_configs.py $NG > gpurun_out/multi_gpu_configs_${NG}gpu_$TAG.log 2>&1; el multi_gpu_configs $?
+  cat gpurun_out/multi_gpu_configs_${NG}gpu_$TAG.log
+  ;;
+scale)    # bench.py under torchrun exactly as the driver launches it, for every N in SCALE_NS (default: all GPUs of the box)
+  NG=$(nvidia-smi -L | wc -l)
+  for N in ${SCALE_NS:-$NG}; do
+    if [ "$N" -eq 1 ]; then
+      timeout 300 python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/scale_n1_$TAG.json 2> gpurun_out/scale_n1_$TAG.err
+    else
+      timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500+N)) \
+          bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/scale_n${N}_$TAG.json 2> gpurun_out/scale_n${N}_$TAG.err
+    fi
+    el scale_n$N $?
+    tail -1 gpurun_out/scale_n${N}_$TAG.json | cut -c1-600; tail -3 gpurun_out/scale_n${N}_$TAG.err
+  done
+  ;;
 ncu)
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$TAG.csv \
       python bench.py --steps 2 --warmup 3 --batch 4 --no-cpu-baseline --no-per-config --e2e-steps 1 > gpurun_out/ncu_launches_$TAG.log 2>&1; el ncu_launches $?
