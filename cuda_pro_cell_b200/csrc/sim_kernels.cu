@@ -319,7 +319,7 @@ __device__ __forceinline__ bool setdirect_rendezvous(const SimParams& P, volatil
         watchdog_fire(P, gwarp, lane, 4, (unsigned long long)s_ctl[12], (unsigned long long)s_ctl[13], 0, 0, 0, 0);
         return false;
     }
-    hist_drain_at(P, s_hist, lane, (uint32_t)s_ctl[7]);
+    hist_drain_at(P, s_hist, lane, (uint32_t)__shfl_sync(kFull, lane == 0 ? sflag_get(s_ctl + 7) : 0, 0));
     __syncwarp();
     if (lane == 0) {
         const unsigned long long g = atomicAdd(&P.ctl->cursor, 1ull);
@@ -327,7 +327,7 @@ __device__ __forceinline__ bool setdirect_rendezvous(const SimParams& P, volatil
             sflag_set(s_ctl + 3, 1);                        /* no batch left anywhere: the base stays where it is */
             atomicMin(&P.ctl->t_exhausted, global_timer_ns());
         } else {
-            s_ctl[7] = (int)((uint32_t)(g / P.batches_per_set) * P.smem_hist_slots);
+            sflag_set(s_ctl + 7, (int)((uint32_t)(g / P.batches_per_set) * P.smem_hist_slots));
             atomicExch(s_batch, g << 24);
         }
         s_ctl[12] = 0;
@@ -927,6 +927,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     __syncthreads();
     DivCount dc;
     dc.set = 0; dc.cnt = 0;
+    /* MODE 2: this warp's copy of the table base s_ctl[7].  The base changes only inside setdirect_rendezvous while this
+     * warp is parked there, so it is re-read (by lane 0, atomically, then broadcast) exactly when the warp comes back */
+    uint32_t set_base = 0u;
     const bool multi_set = !PLAIN && P.n_sets > 1u;
     uint32_t iter = 0;
     int donate_epoch = -1;
@@ -1038,6 +1041,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                          * warp without any node may wait for the switch */
                         if (n != 0u) goto divide_now;
                         if (!setdirect_rendezvous<WARPS>(P, s_ctl, s_hist, s_batch, lane, GWARP)) break;
+                        set_base = (uint32_t)__shfl_sync(kFull, lane == 0 ? sflag_get(s_ctl + 7) : 0, 0);
                         continue;
                     }
                     if (!got) {
@@ -1084,7 +1088,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 w.top += __popc(live);
                 __syncwarp();
                 if (SETDIRECT) {
-                    count_leaves_setdirect(P, s_hist, so.key, so.kind == 1 ? 1u : 0u, (uint32_t)s_ctl[7]);
+                    count_leaves_setdirect(P, s_hist, so.key, so.kind == 1 ? 1u : 0u, set_base);
                 } else if (PLAIN || P.n_times == 1u) {
                     /* subtree sharding: every GPU builds every seed cell, GPU root % world counts its level-0 leaf */
                     const bool credit = !SUBTREE || root % P.sub_world == P.sub_rank;
@@ -1112,7 +1116,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         ++iter;
         TRACE(P, GWARP, lane, 20);
         const uint32_t take = n < 32u ? n : 32u;
-        const uint32_t hist_base = SETDIRECT ? (uint32_t)s_ctl[7] : 0u;     /* changes only while this warp is parked in the rendezvous */
+        const uint32_t hist_base = SETDIRECT ? set_base : 0u;     /* changes only while this warp is parked in the rendezvous */
         /* PLAIN: one set and at most 64 types, so the (mean, sd) table is always the shared-memory copy (plain LDS) */
         const double2* musd = PLAIN ? s_musd_buf : s_musd;
         if (RING == 2 && n >= 64u) divide_iteration<true, HASHED, PLAIN, RING, RING, MODE>(w, P, s_log, s_hist, musd, 64u, lt_mask, multi_set, dc, hist_base);
