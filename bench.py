@@ -393,7 +393,6 @@ def main():
     ap.add_argument("--e2e-engines", type=int, default=2,
                     help="engines (each with its own stream, count tensor and pinned host buffer) the end-to-end leg keeps in "
                          "flight: with 2 the D2H of simulation i and the H2D of simulation i+2 overlap kernel i+1")
-    ap.add_argument("--engines", type=int, default=2, help="resident engines the device-timed leg alternates between (1 or 2)")
     ap.add_argument("--serial-reduce", action="store_true", help="N > 1: reduce on the compute stream (no overlap with the next simulation)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -427,55 +426,39 @@ def main():
     n_types = w.types.shape[1]
     plan = api.Plan(w.values, w.freqs, w.phi)
     shard = (rank, world, SHARD_UNIT)
-    # two resident engines (own control block, queue, spill rings, count tensor), each on its own stream and used
-    # alternately: the reset kernel and the launch latency of simulation i + 1 hide behind simulation i (its CTAs start as
-    # the CTAs of simulation i retire).  --engines 1 gives the one-engine, one-stream figure of round 1.
-    n_head = max(1, min(2, args.engines))
-    engs_h = [api.Engine(local_rank) for _ in range(n_head)]
-    for e in engs_h:
-        e.load(plan, w.types, w.t_max, w.seed, shard=shard)
-    eng = engs_h[0]
+    # one resident engine on one stream; every simulation of the run writes its OWN result tensor (count tensor + division
+    # counter, 141 KB) in a pool in HBM, so nothing is accumulated or overwritten inside the timed region and the division
+    # total of the timed steps is read from the pool afterwards.  (Alternating two engines on two streams was measured
+    # and changes nothing - 97.58 vs 97.59 G div/s: a persistent kernel's CTAs all retire together - so it is gone.)
+    eng = api.Engine(local_rank)
+    eng.load(plan, w.types, w.t_max, w.seed, shard=shard)
     n_counts = plan.n_keys * n_types
-    bufs = [torch.zeros(n_counts + 1, dtype=torch.int64, device=dev) for _ in range(2)]   # counts + division counter: one reduce
+    n_pool = K * B
+    if n_pool * (n_counts + 1) * 8 > (8 << 30):
+        raise SystemExit("result pool of %d simulations does not fit: lower --steps or --batch" % n_pool)
+    pool = torch.zeros((n_pool, n_counts + 1), dtype=torch.int64, device=dev)
+    warm = torch.zeros((B, n_counts + 1), dtype=torch.int64, device=dev)
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
-    estreams = [torch.cuda.Stream(device=dev) for _ in range(n_head)]
     comm = torch.cuda.Stream(device=dev) if world > 1 and not args.serial_reduce else None
-    div_accs = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(2)]
-    reduced = [None, None]                   # event: the reduce that last read bufs[k] is over
 
-    def simulate(seed, k, accumulate):
-        """one simulation into bufs[k] on engine k % n_head; N > 1: its reduce runs on the communication stream and overlaps the next one"""
-        buf, st, e = bufs[k], estreams[k % n_head], engs_h[k % n_head]
-        if reduced[k] is not None:
-            st.wait_event(reduced[k])
-        e.run(seed, st.cuda_stream, buf.data_ptr(), buf.data_ptr() + 8 * n_counts)
+    def simulate(seed, buf):
+        """one simulation into buf; N > 1: its reduce runs on the communication stream and overlaps the next simulation"""
+        eng.run(seed, stream.cuda_stream, buf.data_ptr(), buf.data_ptr() + 8 * n_counts)
         if world > 1 and comm is not None:
             done = torch.cuda.Event()
-            done.record(st)
+            done.record(stream)
             with torch.cuda.stream(comm):
                 comm.wait_event(done)
                 dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
-                if accumulate:
-                    div_accs[k].add_(buf[n_counts:])
-                ev = torch.cuda.Event()
-                ev.record(comm)
-            reduced[k] = ev
-        else:
-            with torch.cuda.stream(st):
-                if world > 1:
-                    dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
-                if accumulate:
-                    div_accs[k].add_(buf[n_counts:])
-            # buffer k is only ever touched on this stream (one engine: both buffers on the one stream): stream order protects it
+        elif world > 1:
+            dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
 
-    def step(first_seed, accumulate):
-        for st in estreams:
-            st.wait_stream(stream)           # behind the L2 flush and the start event on the main stream
+    def step(first_seed, bufs):
+        if comm is not None:
+            comm.wait_stream(stream)         # the warm-up pool is reused: its last reduce must not overlap a new run into it
         for j in range(B):
-            simulate(first_seed + j, j & 1, accumulate)
-        for st in estreams:
-            stream.wait_stream(st)
+            simulate(first_seed + j, bufs[j])
         if comm is not None:
             stream.wait_stream(comm)         # a step ends when its last reduce has ended
 
@@ -486,10 +469,9 @@ def main():
 
     for i in range(W):
         flush.fill_(i)
-        step(w.seed + 100000 * i, False)
+        step(w.seed + 100000 * i, warm)
     barrier()
-    for e, st in zip(engs_h, estreams):
-        e.finish(st.cuda_stream, fetch=False)        # status word (sticky on the device): no failure during warm-up
+    eng.finish(stream.cuda_stream, fetch=False)      # status word (sticky on the device): no failure during warm-up
 
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
@@ -497,7 +479,7 @@ def main():
     for i in range(K):
         flush.fill_(i & 0xFF)                      # L2 flush (256 MiB > 126 MB L2), outside the event pair
         evs[i][0].record(stream)
-        step(w.seed + 1000 + i * B, True)
+        step(w.seed + 1000 + i * B, pool[i * B:(i + 1) * B])
         evs[i][1].record(stream)
     barrier()
     t_wall1 = time.perf_counter()
@@ -509,24 +491,23 @@ def main():
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     gpu_ms = float(t_ms.item())
     # the device status word is sticky: a pool overflow / watchdog abort in ANY simulation since the last finish is still there
-    for e, st in zip(engs_h, estreams):
-        e.finish(st.cuda_stream, fetch=False)
-    div_timed = int(sum(d.item() for d in div_accs))      # rank 0 holds the reduced totals
+    eng.finish(stream.cuda_stream, fetch=False)
+    div_timed = int(pool[:, n_counts].sum().item())       # rank 0 holds the reduced totals
     div_per_sim = div_timed / (K * B)
     value = div_timed / (gpu_ms * 1e-3) if rank == 0 else 0.0
 
     # ---- N > 1: the reduced tensor of one simulation == the same simulation unsharded on rank 0 (outside any timed region)
     verify = None
     if world > 1:
-        simulate(w.seed + 77, 0, False)
+        simulate(w.seed + 77, warm[0])
         barrier()
         if rank == 0:
             whole = api.Engine(local_rank)
             whole.load(plan, w.types, w.t_max, w.seed, shard=(0, 1, SHARD_UNIT))
-            ref = torch.zeros_like(bufs[0])
+            ref = torch.zeros_like(warm[0])
             whole.run(w.seed + 77, stream.cuda_stream, ref.data_ptr(), ref.data_ptr() + 8 * n_counts)
             whole.finish(stream.cuda_stream, fetch=False)
-            verify = {"reduced_tensor_equals_single_gpu_run": bool(torch.equal(ref, bufs[0])), "divisions": int(ref[n_counts].item()),
+            verify = {"reduced_tensor_equals_single_gpu_run": bool(torch.equal(ref, warm[0])), "divisions": int(ref[n_counts].item()),
                       "what": "count tensor + division counter of one %d-rank simulation after the NCCL reduce vs the same seed "
                               "run unsharded on rank 0" % world}
             whole.close()
@@ -539,7 +520,7 @@ def main():
     host_values, host_freqs = w.values.copy(), w.freqs.copy()
     e2e_div = 0
     n_eng = max(1, args.e2e_engines)
-    engs = (engs_h + [api.Engine(local_rank) for _ in range(n_eng)])[:n_eng]
+    engs = ([eng] + [api.Engine(local_rank) for _ in range(n_eng)])[:n_eng]
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_eng)]
     dbufs = [torch.zeros(n_counts + 1, dtype=torch.int64, device=dev) for _ in range(n_eng)]
     hosts = [torch.zeros(n_counts + 1, dtype=torch.int64).pin_memory() for _ in range(n_eng)]
@@ -583,8 +564,6 @@ def main():
     t_e2e = time.perf_counter() - t0
     for extra in engs:
         extra.close()
-    for e in engs_h:
-        e.close()
     t_e = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
@@ -637,7 +616,7 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD_TEXT, "n_cells": int(plan.n_cells), "simulations_per_step": B,
                            "divisions_per_simulation": div_per_sim, "ms_per_simulation": ms_sim,
-                           "engines": "%d resident engine(s), alternating, each on its own stream" % n_head,
+                           "results": "every simulation of the timed region keeps its own count tensor (pool of %d x %d B in HBM)" % (n_pool, (n_counts + 1) * 8),
                            "sharding": "seed-cell units of %d, rank-strided; one NCCL reduce(sum,int64) per simulation%s"
                                        % (SHARD_UNIT, "" if comm is None else ", on a second stream (overlaps the next simulation)"),
                            "l2": "flushed between steps (256 MiB write), outside the timed events"},

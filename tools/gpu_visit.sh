@@ -32,8 +32,8 @@ bench)
   timeout 400 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; el bench $?
   cat gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench_$TAG.err
   ;;
-bench1)   # the one-engine, one-stream figure beside the default (two resident engines alternating)
-  timeout 200 python bench.py --engines 1 --no-cpu-baseline --no-per-config --e2e-steps 2 > gpurun_out/bench_1engine_$TAG.json 2> gpurun_out/bench_1engine_$TAG.err; el bench_1engine $?
+bench1)   # (retired: the device-timed leg has one engine again)
+  timeout 200 python bench.py --no-cpu-baseline --no-per-config --e2e-steps 2 > gpurun_out/bench_1engine_$TAG.json 2> gpurun_out/bench_1engine_$TAG.err; el bench_1engine $?
   cut -c1-400 gpurun_out/bench_1engine_$TAG.json
   ;;
 benchref)
