@@ -88,12 +88,10 @@ scale)    # bench.py under torchrun exactly as the driver launches it, for every
 ncu)
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$TAG.csv \
       python bench.py --steps 2 --warmup 3 --batch 4 --no-cpu-baseline --no-per-config --e2e-steps 1 > gpurun_out/ncu_launches_$TAG.log 2>&1; el ncu_launches $?
-  for c in 2 3 5 4; do
+  for c in ${NCU_CONFIGS:-2 3 5 4}; do
     timeout 400 ncu --set full --clock-control none -k regex:k_proliferate_coop -s 1 -c 1 -f -o gpurun_out/prof_config${c}_$TAG \
         python tools/prof_one.py $c 1.0 > gpurun_out/ncu_config${c}_$TAG.log 2>&1; el ncu_config$c $?
   done
-  timeout 200 ncu --set full --clock-control none -k regex:k_rng_ceiling -s 1 -c 1 -f -o gpurun_out/prof_ceiling_$TAG \
-      python -c "import sys; sys.path.insert(0,'.'); from cuda_pro_cell_b200 import api; print(api.rng_ceiling(0, 4096))" > gpurun_out/ncu_ceiling_$TAG.log 2>&1; el ncu_ceiling $?
   ls -la gpurun_out/*.ncu-rep
   ;;
 esac
