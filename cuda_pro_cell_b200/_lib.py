@@ -60,6 +60,7 @@ SIGNATURES = {
     "procell_parse_cell_types": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.POINTER(CellType)), C.POINTER(C.c_size_t)]),
     "procell_write_histogram": (C.c_int, [C.c_char_p, C.c_int, C.c_size_t, C.c_size_t, _f64p, _i64p, _i64p]),
     "procell_free": (None, [C.c_void_p]),
+    "procell_type_threshold": (C.c_uint64, [C.c_double]),
     "procell_check_proportions": (C.c_int, [C.POINTER(CellType), C.c_size_t]),
     "procell_plan_create": (C.c_int, [_f64p, _u64p, C.c_size_t, C.c_double, C.POINTER(C.c_void_p)]),
     "procell_plan_destroy": (None, [C.c_void_p]),

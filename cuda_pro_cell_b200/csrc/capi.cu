@@ -202,7 +202,7 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
 
     /* histogram plan + type tables -> HBM: packed into ONE pinned staging buffer and uploaded with one copy.
      * layout (16-byte aligned pieces): bin_start[B+1] u32 | bin_keybase[B] u32 | bin_kdiv[B+1] u8 |
-     *                                  type_cum[S*T] f64 | type_musd[S*T] double2 | type_sel[S*T] u8 */
+     *                                  type_thr[S*T] u32 (+pad) | type_musd[S*T] double2 | type_sel[S*T] u8 */
     auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t off_start = 0;
     const size_t off_keybase = off_start + align16((B + 1) * 4);
@@ -225,7 +225,7 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     uint32_t* h_start = reinterpret_cast<uint32_t*>(st + off_start);
     uint32_t* h_keybase = reinterpret_cast<uint32_t*>(st + off_keybase);
     uint8_t* h_kdiv = st + off_kdiv;
-    double* h_cum = reinterpret_cast<double*>(st + off_cum);
+    uint32_t* h_thr = reinterpret_cast<uint32_t*>(st + off_cum);
     double2* h_musd = reinterpret_cast<double2*>(st + off_musd);
     uint8_t* h_sel = st + off_sel;
     {
@@ -250,7 +250,12 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         double acc = 0.0;
         for (size_t j = 0; j < T; ++j) {
             acc += ty[order[j]].proportion;
-            h_cum[s * T + j] = acc;
+            /* the scan compares the 32-bit type word x with "last x below cum[j]" = threshold - 1 (hostio.cpp:
+             * procell_type_threshold).  The first running sum is the largest proportion, >= (1 - 1e-8) / 64, so no
+             * threshold is 0; a running sum of 1 gives 2^32 - 1, which no x exceeds. */
+            const uint64_t thr = procell_type_threshold(acc);
+            if (thr == 0) return fail(PROCELL_ERR_PROPORTION, "cell-type proportions: a running sum below 2^-33");
+            h_thr[s * T + j] = (uint32_t)(thr - 1);
             h_sel[s * T + j] = (uint8_t)order[j];
             h_musd[s * T + j] = make_double2(ty[j].mean, ty[j].stddev);
         }
@@ -283,7 +288,7 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     P.bin_start = (const uint32_t*)(dt + off_start);
     P.bin_keybase = (const uint32_t*)(dt + off_keybase);
     P.bin_kdiv = (const uint8_t*)(dt + off_kdiv);
-    P.type_cum = (const double*)(dt + off_cum);
+    P.type_thr = (const uint32_t*)(dt + off_cum);
     P.type_sel = (const uint8_t*)(dt + off_sel);
     P.type_musd = (const double2*)(dt + off_musd);
     P.logtab = (const double*)en->logtab.p;

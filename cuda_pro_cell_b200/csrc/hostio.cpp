@@ -120,6 +120,26 @@ const char* procell_version(void) { return "procell-b200 0.1 (sm_100a)"; }
 
 void procell_free(void* p) { free(p); }
 
+/* The seed cell's type uniform is u = (2x + 1) / 2^33 for a 32-bit random word x (procell_spec.h: pcs_u32unit), and its
+ * type is the first j with u < cum[j] (cell.cu:81-104).  For a double c, "u < c" holds exactly for the x below
+ * thr(c) = ceil(c * 2^33) >> 1, computed here in integers from c's mantissa and exponent (no rounding anywhere), so the
+ * kernel compares 32-bit integers instead of doubles.  Returned clamped to [0, 2^32]. */
+uint64_t procell_type_threshold(double cum)
+{
+    if (!(cum > 0.0)) return 0;
+    int e = 0;
+    const double f = frexp(cum, &e);                 /* cum = f * 2^e, f in [0.5, 1) */
+    const uint64_t m = (uint64_t)ldexp(f, 53);       /* 53-bit integer mantissa: cum = m * 2^(e - 53) */
+    const int s = e - 53 + 33;                       /* cum * 2^33 = m * 2^s */
+    if (s >= 11) return 1ull << 32;                  /* cum * 2^33 >= 2^63: far beyond the last x */
+    uint64_t r;                                      /* ceil(m * 2^s) */
+    if (s >= 0) r = m << s;
+    else if (s <= -64) r = 1;
+    else r = (m >> -s) + ((m & ((1ull << -s) - 1ull)) ? 1ull : 0ull);
+    const uint64_t thr = r >> 1;
+    return thr > (1ull << 32) ? (1ull << 32) : thr;
+}
+
 int procell_check_proportions(const procell_cell_type* types, size_t n_types)
 {
     double sum = 0.0;    /* thrust::reduce from 0.0, left to right (parser.cu:52-58) */

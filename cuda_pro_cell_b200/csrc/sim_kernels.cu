@@ -55,7 +55,7 @@ template <int RING> struct Ring {
 };
 constexpr int kSmemMusdEntries = 64;  /* (mean, sd) table cached in shared memory when n_sets * n_types fits */
 /* control words (64 B) + three 16-byte snapshots of the control block, then the type tables of small runs:
- * (mean, sd) 16 B, cumulative proportion 8 B and selection order 1 B per entry */
+ * (mean, sd) 16 B, type threshold 4 B (+ 4 B: the per-warp donation epochs live in that half) and selection order 1 B per entry */
 constexpr int kSmemCtlBytes = 128 + kSmemMusdEntries * (16 + 8 + 1);
 constexpr unsigned kFull = 0xFFFFFFFFu;
 /* kernel MODE: 0 = the kernel as measured in round 1; 1 = subtree sharding compiled in (multi-GPU runs of deep trees);
@@ -639,17 +639,19 @@ __device__ __forceinline__ uint32_t find_bin_warp(const SimParams& P, uint32_t r
  * kind is the number of types of that kind with a smaller file id (a popcount under SimParams::quiet_mask). */
 template <bool SLOT>
 __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* s_log, uint32_t root, uint32_t set,
-                                              uint32_t bin, const double* cum, const uint8_t* sel, const double2* musd)
+                                              uint32_t bin, const uint32_t* thr, const uint8_t* sel, const double2* musd)
 {
     SeedOut o;
     const uint32_t kd = __ldg(P.bin_kdiv + bin);
     const uint32_t T = P.n_types;
     pcs_u32x4 w = pcs_draw_rk(root, set, 0u, PCS_TAG_SEED, 0ull, P.rk);      /* the seed cell's ONE block: type, age, radius, angle */
-    const double u_type = pcs_u32unit(w.x);
     const double u_age = pcs_u32unit(w.y);
-    uint32_t j = T - 1u;                                       /* cell.cu:81-104: the FIRST j with u < cum[j]; Q17: none -> last */
-    for (uint32_t i = T - 1u; i-- > 0u;)                       /* scanned downwards without a break: no divergence */
-        if (u_type < cum[i]) j = i;
+    /* cell.cu:81-104: the FIRST j with u < cum[j]; Q17: none -> the last type.  u = (2x + 1) / 2^33 is below cum[j] exactly
+     * for x <= thr[j] (the host computes thr in integers, hostio.cpp: procell_type_threshold), and the sums ascend, so j
+     * is the number of thresholds x lies above: an integer compare and a predicated add per type, no divergence */
+    uint32_t j = 0u;
+#pragma unroll 1
+    for (uint32_t i = 0u; i + 1u < T; ++i) j += (w.x > thr[i]) ? 1u : 0u;
     const uint32_t type = sel[j];
     const double2 ms = musd[type];
     o.type = type;
@@ -672,7 +674,7 @@ __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* 
     }
     double timer = ms.x;                                       /* the mean, should 255 draws in a row be rejected */
     for (uint32_t retry = 0;;) {                               /* first timer from words z, w of the same block (cell.cu:106-122) */
-        const double cand = pcs_timer(ms.x, ms.y, pcs_seed_normal(w, s_log, (P.refcompat && retry == 0u) ? u_type : 0.0));
+        const double cand = pcs_timer(ms.x, ms.y, pcs_seed_normal(w, s_log, (P.refcompat && retry == 0u) ? pcs_u32unit(w.x) : 0.0));
         if (cand > 0.0) { timer = cand; break; }
         if (++retry == PCS_MAX_RETRY) break;
         w = pcs_draw_rk(root, set, retry, PCS_TAG_SEED, 0ull, P.rk);   /* rejected: words z, w of the next round's block */
@@ -879,15 +881,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 
     double2* s_musd_buf = reinterpret_cast<double2*>(smem_raw + kLogTabDoubles * 8 + 128);
     const bool musd_cached = P.n_sets * P.n_types <= (uint32_t)kSmemMusdEntries;
-    double* s_cum_buf = reinterpret_cast<double*>(smem_raw + kLogTabDoubles * 8 + 128 + kSmemMusdEntries * 16);
+    uint32_t* s_thr_buf = reinterpret_cast<uint32_t*>(smem_raw + kLogTabDoubles * 8 + 128 + kSmemMusdEntries * 16);
     uint8_t* s_sel_buf = reinterpret_cast<uint8_t*>(smem_raw + kLogTabDoubles * 8 + 128 + kSmemMusdEntries * 24);
     if (musd_cached && threadIdx.x < P.n_sets * P.n_types) {
         s_musd_buf[threadIdx.x] = __ldg(P.type_musd + threadIdx.x);
-        s_cum_buf[threadIdx.x] = __ldg(P.type_cum + threadIdx.x);
+        s_thr_buf[threadIdx.x] = __ldg(P.type_thr + threadIdx.x);
         s_sel_buf[threadIdx.x] = __ldg(P.type_sel + threadIdx.x);
     }
     const double2* s_musd = musd_cached ? s_musd_buf : P.type_musd;
-    const double* s_cum = musd_cached ? s_cum_buf : P.type_cum;
+    const uint32_t* s_thr = musd_cached ? s_thr_buf : P.type_thr;
     const uint8_t* s_sel = musd_cached ? s_sel_buf : P.type_sel;
     if (threadIdx.x < 2) s_ctl[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < kLogTabDoubles; i += blockDim.x) s_log[i] = __ldg(P.logtab + i);
@@ -932,7 +934,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     uint32_t set_base = 0u;
     const bool multi_set = !PLAIN && P.n_sets > 1u;
     uint32_t iter = 0;
-    int donate_epoch = -1;
+    /* snapshot epoch of this warp's last donation: one word per warp in shared memory (the upper half of the threshold
+     * buffer, free since the thresholds are 32-bit) - read by lane 0 every probe, written at a donation; as a register it
+     * was the one value ptxas kept spilling at the 64-register cap */
+    volatile int* s_epoch = reinterpret_cast<volatile int*>(s_thr_buf + kSmemMusdEntries) + warp;
+    if (lane == 0) *s_epoch = -1;
+    __syncwarp();
 
     if (lane == 0) {
         atomicAdd(reinterpret_cast<unsigned long long*>(&ctl->pending), 1ull);
@@ -1076,7 +1083,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 #endif
                 if (have) {     /* PLAIN: one set, the tables are always the shared-memory copies */
                     const size_t tab = PLAIN ? 0u : (size_t)seed_set * P.n_types;
-                    so = build_seed<SLOT>(P, s_log, root, seed_set, bin, (PLAIN ? s_cum_buf : s_cum) + tab, (PLAIN ? s_sel_buf : s_sel) + tab,
+                    so = build_seed<SLOT>(P, s_log, root, seed_set, bin, (PLAIN ? s_thr_buf : s_thr) + tab, (PLAIN ? s_sel_buf : s_sel) + tab,
                                     (PLAIN ? s_musd_buf : s_musd) + tab);
                 }
                 const unsigned live = __ballot_sync(kFull, so.kind == 2);
@@ -1167,7 +1174,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 /* donate at most once per snapshot epoch, and only while fewer chunks wait than warps starve */
                 const int ep = s_ctl[5];
                 const int hg = P.donate && exhausted && idle_snap + kDonateReserve > (avail_snap > 0 ? avail_snap : 0) &&
-                               avail_snap < kQueueCap / 2 && (ep != donate_epoch || (kEndgameFast && idle_snap >= kEndgameIdle));
+                               avail_snap < kQueueCap / 2 && (ep != *s_epoch || (kEndgameFast && idle_snap >= kEndgameIdle));
                 /* end game: when this many warps starve, a warp parts with a chunk as soon as it keeps 32 nodes */
                 packed = (ep << 2) | ((idle_snap >= kEndgameIdle) << 1) | hg;
             }
@@ -1175,7 +1182,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
             if ((packed & 1) && (w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= ((packed & 2) ? 64u : kDonateMinNodes * RING)) {
                 /* somebody starves and no seeds are left: give away the shallowest chunk */
                 TRACE(P, GWARP, lane, 50);
-                donate_epoch = packed >> 2;
+                if (lane == 0) *s_epoch = packed >> 2;
                 donate_chunk<RING>(w, P);
             }
         }
@@ -1247,7 +1254,7 @@ __global__ void __launch_bounds__(kSimpleThreads) k_proliferate_simple(const __g
         const uint32_t root = (uint32_t)(gi - (unsigned long long)set * P.n_cells);
         if (P.shard_world > 1u && (root / P.unit) % P.shard_world != P.shard_rank) continue;
         const size_t tab = (size_t)set * P.n_types;
-        SeedOut so = build_seed<false>(P, s_log, root, set, find_bin(P, root), P.type_cum + tab, P.type_sel + tab, P.type_musd + tab);
+        SeedOut so = build_seed<false>(P, s_log, root, set, find_bin(P, root), P.type_thr + tab, P.type_sel + tab, P.type_musd + tab);
         if (so.kind == 1) atomicAdd(counts + so.key, 1ull);
         if (so.kind != 2) continue;
         const double2 ms = __ldg(P.type_musd + (size_t)set * T + so.type);

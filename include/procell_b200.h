@@ -62,6 +62,10 @@ int procell_write_histogram(const char* path, int save_ratio, size_t n_types, si
                             const double* row_value, const int64_t* row_freq, const int64_t* row_ratio);
 void procell_free(void* p);
 int procell_check_proportions(const procell_cell_type* types, size_t n_types);
+/* number of 32-bit words x whose seed-cell type uniform (2x + 1) / 2^33 lies below the cumulative proportion `cum`
+ * (cell.cu:81-104 compares the uniform with the running sums): the integer threshold the kernels scan instead of the
+ * doubles; exact, clamped to [0, 2^32].  Exposed for tests. */
+uint64_t procell_type_threshold(double cum);
 
 /* ---- plan: the result-key precomputation of io::load_fluorescences (src/io/parser.cu:68-154) ---- */
 /* phi == 0 selects the default (smallest value with frequency > 0, parser.cu:80-96). */

@@ -27,4 +27,10 @@ void shim_normal_pair(const uint32_t* w, double u_forced, double* z)
     pcs_normal_pair(b, kRows, u_forced, &z[0], &z[1]);
 }
 double shim_timer(double mean, double sd, double z) { return pcs_timer(mean, sd, z); }
+double shim_u32unit(uint32_t m) { return pcs_u32unit(m); }
+double shim_seed_normal(const uint32_t* w, double u_forced)
+{
+    pcs_u32x4 b; b.x = w[0]; b.y = w[1]; b.z = w[2]; b.w = w[3];
+    return pcs_seed_normal(b, kRows, u_forced);
+}
 }

@@ -26,7 +26,52 @@ def shim():
     S.shim_timer.restype = C.c_double
     S.shim_timer.argtypes = [C.c_double] * 3
     S.shim_draw.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
+    S.shim_u32unit.restype = C.c_double
+    S.shim_u32unit.argtypes = [C.c_uint32]
+    S.shim_seed_normal.restype = C.c_double
+    S.shim_seed_normal.argtypes = [C.POINTER(C.c_uint32), C.c_double]
     return S
+
+
+def test_seed_cell_draws_equal_the_oracle_bitwise(shim, oracle):
+    """the seed cell's ONE block: 32-bit uniforms (type, age, radius) and the first timer's normal from words z, w"""
+    rng = np.random.default_rng(5)
+    L = oracle.lib()
+    L.oracle_uniform32.restype = C.c_double
+    L.oracle_uniform32.argtypes = [C.c_uint32]
+    for m in [0, 1, 2**31, 2**32 - 1] + [int(x) for x in rng.integers(0, 2**32, 5000)]:
+        u = shim.shim_u32unit(m)
+        assert u == L.oracle_uniform32(m) == (2 * m + 1) / 2.0**33 and 0.0 < u < 1.0
+    for _ in range(5000):
+        w = [int(x) for x in rng.integers(0, 2**32, 4)]
+        for forced in (0.0, 0.41):
+            got = shim.shim_seed_normal((C.c_uint32 * 4)(*w), C.c_double(forced))
+            u = forced if forced > 0 else L.oracle_uniform32(w[2])
+            s, c = oracle.sincos2pi(w[3] << 32)
+            assert got == np.sqrt(L.oracle_neg2log(u)) * c
+
+
+def test_integer_type_thresholds_are_exactly_the_double_compare(shim):
+    """The kernels pick the seed cell's type by comparing the 32-bit type word x with integer thresholds
+    (procell_type_threshold) instead of comparing the uniform (2x + 1) / 2^33 with the running proportion sums as
+    cell.cu:81-104 does: "u(x) < cum" must hold for exactly the x below the threshold - checked at the boundary for
+    proportions a user would write, for sums a hair around 1, for tiny and awkward values."""
+    from cuda_pro_cell_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    cums = [0.53, 0.82, 1.0, 1.0 - 1e-9, 1.0 + 1e-9, 0.4, 0.65, 0.17, 1 / 3, 2 / 3, 0.5, 0.25, 2.0**-33, 2.0**-32, 3 * 2.0**-34,
+            2.0**-40, 1e-300, 0.9999999999, float(np.nextafter(1.0, 0.0)), float(np.nextafter(0.5, 1.0))]
+    cums += [float(x) for x in rng.random(3000)] + [float(x) * 2.0**-20 for x in rng.random(200)]
+    cums += [(2 * int(x) + 1) / 2.0**33 for x in rng.integers(0, 2**32, 500)]          # a sum that IS a uniform: strict "<"
+    for c in cums:
+        thr = lib.procell_type_threshold(c)
+        assert 0 <= thr <= 2**32
+        if thr > 0:
+            assert shim.shim_u32unit(thr - 1) < c          # the last x below the sum
+        if thr < 2**32:
+            assert not (shim.shim_u32unit(thr) < c)        # the first x that is not
+    assert lib.procell_type_threshold(0.0) == 0 and lib.procell_type_threshold(-1.0) == 0
+    assert lib.procell_type_threshold(5.0) == 2**32
 
 
 def test_header_equals_oracle_bitwise(shim, oracle):
