@@ -202,13 +202,14 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
 
     /* histogram plan + type tables -> HBM: packed into ONE pinned staging buffer and uploaded with one copy.
      * layout (16-byte aligned pieces): bin_start[B+1] u32 | bin_keybase[B] u32 | bin_kdiv[B+1] u8 |
-     *                                  type_thr[S*T] u32 (+pad) | type_musd[S*T] double2 | type_sel[S*T] u8 */
+     *                                  type_thr[S][T rounded up to 4] u32 | type_musd[S*T] double2 | type_sel[S*T] u8 */
     auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t off_start = 0;
     const size_t off_keybase = off_start + align16((B + 1) * 4);
     const size_t off_kdiv = off_keybase + align16((B + 1) * 4);
     const size_t off_cum = off_kdiv + align16(B + 1);
-    const size_t off_musd = off_cum + align16(S * T * 8);
+    const size_t Tpad = (T + 3) & ~(size_t)3;          /* thresholds are scanned four at a time (one 16-byte load) */
+    const size_t off_musd = off_cum + align16(S * Tpad * 4);
     const size_t off_sel = off_musd + align16(S * T * 16);
     const size_t off_rank = off_sel + align16(S * T);          /* set 0's types by kind: proliferating ids, then quiescent ids */
     const size_t table_bytes = off_rank + align16(T);
@@ -248,6 +249,7 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         for (size_t j = 0; j < T; ++j) order[j] = (int)j;
         std::stable_sort(order, order + T, [&](int a, int b) { return ty[a].proportion > ty[b].proportion; });
         double acc = 0.0;
+        for (size_t j = T; j < Tpad; ++j) h_thr[s * Tpad + j] = 0xFFFFFFFFu;
         for (size_t j = 0; j < T; ++j) {
             acc += ty[order[j]].proportion;
             /* the scan compares the 32-bit type word x with "last x below cum[j]" = threshold - 1 (hostio.cpp:
@@ -255,7 +257,9 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
              * threshold is 0; a running sum of 1 gives 2^32 - 1, which no x exceeds. */
             const uint64_t thr = procell_type_threshold(acc);
             if (thr == 0) return fail(PROCELL_ERR_PROPORTION, "cell-type proportions: a running sum below 2^-33");
-            h_thr[s * T + j] = (uint32_t)(thr - 1);
+            /* the scan counts the thresholds x lies above among the first T - 1; the last type's slot and the padding
+             * up to a multiple of four hold 2^32 - 1, which no x exceeds */
+            h_thr[s * Tpad + j] = j + 1 < T ? (uint32_t)(thr - 1) : 0xFFFFFFFFu;
             h_sel[s * T + j] = (uint8_t)order[j];
             h_musd[s * T + j] = make_double2(ty[j].mean, ty[j].stddev);
         }

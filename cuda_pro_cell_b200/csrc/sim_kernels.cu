@@ -648,10 +648,14 @@ __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* 
     const double u_age = pcs_u32unit(w.y);
     /* cell.cu:81-104: the FIRST j with u < cum[j]; Q17: none -> the last type.  u = (2x + 1) / 2^33 is below cum[j] exactly
      * for x <= thr[j] (the host computes thr in integers, hostio.cpp: procell_type_threshold), and the sums ascend, so j
-     * is the number of thresholds x lies above: an integer compare and a predicated add per type, no divergence */
+     * is the number of thresholds x lies above: an integer compare and an add per type, no divergence */
     uint32_t j = 0u;
+    const uint4* thr4 = reinterpret_cast<const uint4*>(thr);   /* four thresholds per 16-byte load; padding = 2^32 - 1 */
 #pragma unroll 1
-    for (uint32_t i = 0u; i + 1u < T; ++i) j += (w.x > thr[i]) ? 1u : 0u;
+    for (uint32_t i = 0u; i < T; i += 4u) {
+        const uint4 t = thr4[i >> 2];
+        j += (uint32_t)(w.x > t.x) + (uint32_t)(w.x > t.y) + (uint32_t)(w.x > t.z) + (uint32_t)(w.x > t.w);
+    }
     const uint32_t type = sel[j];
     const double2 ms = musd[type];
     o.type = type;
@@ -883,13 +887,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     const bool musd_cached = P.n_sets * P.n_types <= (uint32_t)kSmemMusdEntries;
     uint32_t* s_thr_buf = reinterpret_cast<uint32_t*>(smem_raw + kLogTabDoubles * 8 + 128 + kSmemMusdEntries * 16);
     uint8_t* s_sel_buf = reinterpret_cast<uint8_t*>(smem_raw + kLogTabDoubles * 8 + 128 + kSmemMusdEntries * 24);
+    const uint32_t t_pad = (P.n_types + 3u) & ~3u;       /* row length of the threshold table */
+    const bool thr_cached = musd_cached && P.n_sets * t_pad <= (uint32_t)kSmemMusdEntries;
     if (musd_cached && threadIdx.x < P.n_sets * P.n_types) {
         s_musd_buf[threadIdx.x] = __ldg(P.type_musd + threadIdx.x);
-        s_thr_buf[threadIdx.x] = __ldg(P.type_thr + threadIdx.x);
         s_sel_buf[threadIdx.x] = __ldg(P.type_sel + threadIdx.x);
     }
+    if (thr_cached && threadIdx.x < P.n_sets * t_pad) s_thr_buf[threadIdx.x] = __ldg(P.type_thr + threadIdx.x);
     const double2* s_musd = musd_cached ? s_musd_buf : P.type_musd;
-    const uint32_t* s_thr = musd_cached ? s_thr_buf : P.type_thr;
+    const uint32_t* s_thr = thr_cached ? s_thr_buf : P.type_thr;
     const uint8_t* s_sel = musd_cached ? s_sel_buf : P.type_sel;
     if (threadIdx.x < 2) s_ctl[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < kLogTabDoubles; i += blockDim.x) s_log[i] = __ldg(P.logtab + i);
@@ -1083,7 +1089,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 #endif
                 if (have) {     /* PLAIN: one set, the tables are always the shared-memory copies */
                     const size_t tab = PLAIN ? 0u : (size_t)seed_set * P.n_types;
-                    so = build_seed<SLOT>(P, s_log, root, seed_set, bin, (PLAIN ? s_thr_buf : s_thr) + tab, (PLAIN ? s_sel_buf : s_sel) + tab,
+                    so = build_seed<SLOT>(P, s_log, root, seed_set, bin, (PLAIN ? s_thr_buf : s_thr + (size_t)seed_set * t_pad), (PLAIN ? s_sel_buf : s_sel) + tab,
                                     (PLAIN ? s_musd_buf : s_musd) + tab);
                 }
                 const unsigned live = __ballot_sync(kFull, so.kind == 2);
@@ -1254,7 +1260,8 @@ __global__ void __launch_bounds__(kSimpleThreads) k_proliferate_simple(const __g
         const uint32_t root = (uint32_t)(gi - (unsigned long long)set * P.n_cells);
         if (P.shard_world > 1u && (root / P.unit) % P.shard_world != P.shard_rank) continue;
         const size_t tab = (size_t)set * P.n_types;
-        SeedOut so = build_seed<false>(P, s_log, root, set, find_bin(P, root), P.type_thr + tab, P.type_sel + tab, P.type_musd + tab);
+        SeedOut so = build_seed<false>(P, s_log, root, set, find_bin(P, root), P.type_thr + (size_t)set * ((P.n_types + 3u) & ~3u), P.type_sel + tab,
+                                       P.type_musd + tab);
         if (so.kind == 1) atomicAdd(counts + so.key, 1ull);
         if (so.kind != 2) continue;
         const double2 ms = __ldg(P.type_musd + (size_t)set * T + so.type);

@@ -52,8 +52,9 @@ struct SimParams {
     const uint32_t* bin_keybase;  /* [n_bins]   first key of the bin */
     const uint8_t* bin_kdiv;      /* [n_bins]   halvings allowed (<=63) | 0x80 if level-0 leaves are countable */
     /* type tables, [n_sets][n_types] */
-    const uint32_t* type_thr;     /* selection order (descending proportion): the last 32-bit type word x that lies below
-                                     the running proportion sum, i.e. type j is taken iff x <= type_thr[j] first */
+    const uint32_t* type_thr;     /* [n_sets][n_types rounded up to 4], selection order (descending proportion): the last
+                                     32-bit type word x that lies below the running proportion sum - type j is the first
+                                     with x <= type_thr[j]; the last type's slot and the padding hold 2^32 - 1 */
     const uint8_t* type_sel;      /* file id of the j-th type in selection order */
     const double2* type_musd;     /* (mean, sd) by file id */
     const double* logtab;         /* the math table: 128 x {invc, logc}, then 256 x {sin, cos} */

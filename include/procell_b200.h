@@ -174,12 +174,16 @@ int procell_engine_create(int device, procell_engine** out);
 void procell_engine_destroy(procell_engine* engine);
 /* host -> device upload of the plan and type tables (the H2D leg of an end-to-end step) */
 int procell_engine_load(procell_engine* engine, const procell_plan* plan, const procell_sim_params* params);
-/* Enqueue one simulation on `stream` (a cudaStream_t, NULL = default stream): zero the count tensor, run the
- * kernel.  d_counts / d_divisions are DEVICE pointers ([n_sets][n_keys][n_types] / [n_sets] int64) or NULL to
- * use the engine's own tensors.  Asynchronous. */
+/* Enqueue one simulation on `stream` (a cudaStream_t, NULL = default stream): one launch resets the work pool and
+ * zeroes the count tensor and the division counters, one runs the simulation.  d_counts / d_divisions are DEVICE
+ * pointers ([n_sets][n_keys][n_types] / [n_sets] int64) or NULL to use the engine's own tensors.  Asynchronous; the
+ * tables of the last procell_engine_load are uploaded asynchronously too and the run is ordered behind them. */
 int procell_engine_run(procell_engine* engine, uint64_t seed, void* stream, int64_t* d_counts,
                        int64_t* d_divisions);
-/* wait for the stream, check the device status word, copy the engine's own tensors to host buffers */
+/* wait for the stream, check the device status word, copy the results of the LAST run - from the engine's own tensors
+ * or from the device buffers that run was given - to host buffers (counts / divisions may be NULL).  The status word is
+ * sticky on the device: a failure of any run queued since the previous finish is reported here (PROCELL_ERR_OVERFLOW)
+ * and then cleared. */
 int procell_engine_finish(procell_engine* engine, void* stream, int64_t* counts, int64_t* divisions,
                           procell_run_stats* stats);
 size_t procell_engine_counts_len(const procell_engine* engine); /* n_sets*n_keys*n_types */

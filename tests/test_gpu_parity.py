@@ -483,6 +483,40 @@ def test_config4_full_size_shard_against_the_live_oracle(gpu_api, oracle):
     assert np.array_equal(got.counts, want["counts"]) and np.array_equal(got.divisions, want["divisions"])
 
 
+def test_device_failure_is_sticky_until_finish_and_the_engine_recovers(gpu_api, oracle, monkeypatch):
+    """The device status word is sticky: a run that aborts (here: the watchdog, set to a microsecond) must still be
+    reported by a finish() that comes after FURTHER runs were queued behind it - the reset kernel of those runs does not
+    clear the word - and finish() clears it, so the same engine then simulates correctly again."""
+    import torch
+    v, f = synth.synthetic_histogram(3000)
+    types = np.array([synth.TYPES_CONFIG4])
+    plan, oplan = gpu_api.Plan(v, f, 1e-7), oracle.OraclePlan(v, f, 1e-7)
+    eng = gpu_api.Engine(0)
+    monkeypatch.setenv("PROCELL_WATCHDOG_S", "0.000001")
+    eng.load(plan, types, 400.0, 3)
+    eng.run(3)                               # aborts: every warp trips the deadline at its first check
+    monkeypatch.setenv("PROCELL_WATCHDOG_S", "120")
+    eng.load(plan, types, 100.0, 3)          # short healthy runs queued behind the failed one
+    eng.run(4)
+    eng.run(5)
+    with pytest.raises(gpu_api.ProcellError) as err:
+        eng.finish()
+    assert err.value.code == -5
+    eng.load(plan, types, 300.0, 3)          # the word was cleared by finish(): the engine is usable again
+    eng.run(3)
+    got = eng.finish()
+    want = oracle.simulate(oplan, types, 300.0, 3)
+    assert np.array_equal(got.counts, want["counts"]) and np.array_equal(got.divisions, want["divisions"])
+    # results are read from where the LAST run wrote them: here the caller's device tensor, not the engine's own
+    n = plan.n_keys * types.shape[1]
+    buf = torch.zeros(n + 1, dtype=torch.int64, device="cuda:0")
+    eng.run(3, torch.cuda.current_stream().cuda_stream, buf.data_ptr(), buf.data_ptr() + 8 * n)
+    res = eng.finish(torch.cuda.current_stream().cuda_stream, fetch=True)
+    assert int(res.divisions[0]) == int(buf[n].item()) == int(want["divisions"][0])
+    assert np.array_equal(res.counts.reshape(-1), buf[:n].cpu().numpy()) and np.array_equal(res.counts, want["counts"])
+    eng.close()
+
+
 def test_periodic_drain_bit_exact(gpu_api, oracle, tmp_path):
     """The direct-mode u32 count table is drained into the int64 tensor every 2^20 iterations of a warp (wrap
     protection, sim_kernels.cu hist_drain).  libprocell_b200_drain256.so is the same library with the period set to
