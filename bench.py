@@ -7,22 +7,24 @@ A STEP is one batch of B such simulations (--batch, default 32; each with its ow
 and - at N > 1 - its own NCCL reduce), so that the driver's 20 steps cover ~0.7 s of GPU time instead of 22 ms.
 N > 1 is weak scaling: the histogram holds N x 1e6 cells, seed-cell units are sharded rank-strided, every simulation
 ends with ONE NCCL reduce (sum, int64) of count tensor + division counter to rank 0; the reduce of simulation i runs on
-a second stream and overlaps simulation i + 1 (two count tensors used alternately).
+a second stream and overlaps simulation i + 1.  Every simulation of the timed region keeps its own result tensor (a pool
+in HBM), so nothing is accumulated or overwritten inside the timed region.
 
   value       whole-job divisions/s, tables resident in HBM: CUDA-event time of the K steps (L2 flushed between steps,
               outside the events), max over ranks
   e2e         the same metric through the C ABI with HOST buffers: histogram arrays -> plan -> H2D tables -> kernel ->
               [reduce] -> D2H count tensor -> merged rows, wall clock bracketed by synchronize, two engines in flight
-  per_config  BASELINE configs 2..5 at full size, each with its own ms, divisions/s and roofline fraction; at N > 1
-              config 3 and config 5 are sharded over the ranks by seed-cell units and config 4 by subtrees (strong scaling)
+  per_config  BASELINE configs 1..5 at full size (and the 1e5-cell config-2 shape the reference arm can follow), each with
+              its own ms, divisions/s and roofline fraction - by divisions and by draws; at N > 1 each input is sharded over
+              the ranks, by seed-cell units or - config 4 - by subtrees (strong scaling), and checked against rank 0's own run
   roofline    instruction-issue roofline (FP64/INT-issue bound path, neither HBM nor tensor - DESIGN.md section 5):
               achieved divisions/s over the RNG-only ceiling kernel measured in the same run, with the hardware-unit
               fractions of the committed ncu capture beside it; HBM figures for completeness
   cpu_baseline  the CPU oracle (oracle/, a port with the same Philox streams) on this box's host cores
   verify      N > 1: the reduced tensor of one simulation equals, bit for bit, the same simulation run unsharded on rank 0
 
---impl reference times the reference's own CUDA build (oracle/_ref/, one B200, one process per step) on the SAME input
-file; see run_reference().
+--impl reference times the reference's own CUDA build (oracle/_ref/, one B200) on the SAME 1e6-cell input, run as ten
+processes of 1e5 cells because one reference process cannot simulate more on sm_100; see run_reference().
 """
 import argparse
 import json
