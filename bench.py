@@ -205,7 +205,7 @@ def run_reference(args):
     refdir = ROOT / "oracle" / "_ref"
     w = workload_for(1)
     cfg = {"workload": WORKLOAD_TEXT, "n_cells": int(w.n_cells), "l2": "n/a (separate process per step)"}
-    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": 1, "requested_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg}
     binaries = [b for b in (refdir / "procell_ref_pl", refdir / "procell_ref") if b.exists()]
@@ -218,7 +218,9 @@ def run_reference(args):
         print(json.dumps(line))
         return 0
     tmp = Path(tempfile.mkdtemp(prefix="procell_ref_"))
-    budget_s = 170.0
+    # the arm is the same one-GPU measurement whatever --gpus says (the reference has no multi-GPU path: device 0 is
+    # hard-coded, proliferation.cu:38), so the repeats of a scaling run are kept shorter
+    budget_s = 170.0 if args.gpus <= 1 else 110.0
     t_begin = time.perf_counter()
 
     def measure(binary, wl, label, max_steps):
