@@ -46,13 +46,17 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-/* the math table of procell_spec.h: log rows, then sin/cos rows (bit patterns) */
+/* the math table of procell_spec.h (bit patterns): log rows, sin/cos rows and ziggurat rows - the part the kernels copy
+ * into shared memory - then the ziggurat's wedge rows, which stay in HBM */
 struct MathTable {
     uint64_t log_rows[1 << PCM_LOG_N_BITS][2];
     uint64_t sincos_rows[1 << PCM_SC_N_BITS][2];
+    uint64_t zig_rows[1 << PCM_ZIG_N_BITS][2];
+    uint64_t zig_wedge_rows[1 << PCM_ZIG_N_BITS][2];
 };
-const MathTable kLogRows = { { PCM_LOG_TABLE_ROWS }, { PCM_SINCOS_TABLE_ROWS } };
-static_assert(sizeof(MathTable) == (size_t)kLogTabDoubles * 8, "math table size");
+const MathTable kLogRows = { { PCM_LOG_TABLE_ROWS }, { PCM_SINCOS_TABLE_ROWS }, { PCM_ZIG_TABLE_ROWS }, { PCM_ZIG_WEDGE_ROWS } };
+static_assert(offsetof(MathTable, zig_wedge_rows) == (size_t)kLogTabDoubles * 8, "shared-memory part of the math table");
+static_assert(sizeof(MathTable) == (size_t)kMathTabDoubles * 8, "math table size");
 
 void set_round_keys(SimParams& P, uint64_t seed)
 {
@@ -364,8 +368,9 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
         const int wreq = wenv ? atoi(wenv) : 0;
         en->warps = (wreq == 16 || wreq == 24) ? wreq : 32;
         const char* renv = getenv("PROCELL_COOP_NPL");       /* tuning knob: 2 = 16 warps, two nodes per lane */
-        en->ring = (renv && atoi(renv) == 2) ? 2 : 1;
-        if (en->ring == 2) en->warps = 16;
+        (void)renv;                                          /* the two-nodes-per-lane instance is gone (round 2: the cheap
+                                                                ziggurat draw left it nothing to interleave) */
+        en->ring = 1;
         if (subtree) { en->warps = 32; en->ring = 1; }       /* the subtree-sharding instances exist in the product shape only */
         const size_t fixed = coop_smem_bytes(en->warps, en->ring, 0, 0);
         const size_t room = (size_t)max_smem > fixed ? (size_t)max_smem - fixed : 0;

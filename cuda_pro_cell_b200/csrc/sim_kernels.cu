@@ -37,7 +37,7 @@
 
 namespace procell_b200 {
 
-static_assert(kLogTabDoubles == PCS_TAB_DOUBLES, "math table size");
+static_assert(kLogTabDoubles == PCS_TAB_DOUBLES && kMathTabDoubles == PCS_TAB_ALL_DOUBLES, "math table size");
 
 namespace {
 
@@ -341,10 +341,23 @@ __device__ __forceinline__ bool setdirect_rendezvous(const SimParams& P, volatil
 struct WarpCtx {
     ulonglong2* ab;                  /* ring: kCap (t_div bits, heap) pairs followed by kCap (root|keybase<<32, D) pairs */
     uint32_t bottom, top;            /* ring positions, n = top - bottom */
-    uint32_t sp_bottom, sp_top;      /* private spill ring in HBM: its address is recomputed on use (spill_ring), which keeps
+    uint32_t slow;                   /* the bottom-most `slow` nodes of the ring are retry nodes awaiting a general iteration */
+    uint32_t sp;                     /* private spill ring in HBM, packed into one register: oldest chunk's position in the low
+                                        half (mod 2^16; kSpillCap divides it), number of chunks in the high half.  The ring's
+                                        address is recomputed on use (spill_ring), which keeps
                                         a 64-bit pointer out of the 64 registers of the steady state */
     int lane;
 };
+
+/* nodes in the ring, recomputed where it is needed (cold code) instead of kept from the top of the main loop: the
+ * empty asm keeps the compiler from re-using - and therefore keeping alive, in a register or a spill slot - the hot
+ * loop's copy of the same difference */
+__device__ __forceinline__ uint32_t ring_nodes(const WarpCtx& w)
+{
+    uint32_t t = w.top;
+    asm volatile("" : "+r"(t));
+    return t - w.bottom;
+}
 
 template <int RING>
 __device__ __forceinline__ void ring_load(const WarpCtx& w, uint32_t idx, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d)
@@ -379,31 +392,56 @@ __device__ __forceinline__ unsigned long long* spill_ring(const SimParams& P)
     return P.spill + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kSpillCap * kChunkWords;
 }
 
+/* take the 32 oldest REGULAR nodes out of the ring (spill, donation): they sit above the retry nodes collected at the
+ * bottom, which move up into the gap - a chunk that leaves the warp must not take retry nodes along, or whoever pops it
+ * later pays a general DIVIDE iteration for a few of them.  With a whole warp's worth of retry nodes at the bottom the
+ * chunk is 32 of those instead (it then is expanded by ONE general iteration, every lane busy).  The caller guarantees 32
+ * regular nodes or 32 retry nodes. */
+template <int RING>
+__device__ __forceinline__ void pop_bottom_chunk(WarpCtx& w, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d)
+{
+    constexpr uint32_t kMask = Ring<RING>::kMask;
+    if (w.slow >= (uint32_t)kChunkNodes) {
+        ring_load<RING>(w, (w.bottom + w.lane) & kMask, a, b, c, d);
+        w.slow -= kChunkNodes;
+    } else {
+        ring_load<RING>(w, (w.bottom + w.slow + w.lane) & kMask, a, b, c, d);
+        if (w.slow != 0u) {
+            uint64_t sa = 0, sb = 0, sc = 0, sd = 0;
+            if ((uint32_t)w.lane < w.slow) ring_load<RING>(w, (w.bottom + w.lane) & kMask, sa, sb, sc, sd);
+            __syncwarp();       /* every lane has read its chunk node and its retry node before any slot is overwritten */
+            if ((uint32_t)w.lane < w.slow) ring_store<RING>(w, (w.bottom + kChunkNodes + w.lane) & kMask, sa, sb, sc, sd);
+        }
+    }
+    w.bottom += kChunkNodes;
+    __syncwarp();
+}
+
 template <int RING>
 __device__ __forceinline__ void spill_bottom_chunk(WarpCtx& w, const SimParams& P)
 {
-    uint32_t idx = (w.bottom + w.lane) & Ring<RING>::kMask;
-    unsigned long long* dst = spill_ring(P) + (size_t)(w.sp_top % kSpillCap) * kChunkWords;
+    unsigned long long* dst = spill_ring(P) + (size_t)(((w.sp & 0xFFFFu) + (w.sp >> 16)) % kSpillCap) * kChunkWords;
     uint64_t a, b, c, d;
-    ring_load<RING>(w, idx, a, b, c, d);
+    pop_bottom_chunk<RING>(w, a, b, c, d);
     __stcg(dst + w.lane, a);
     __stcg(dst + 32 + w.lane, b);
     __stcg(dst + 64 + w.lane, c);
     __stcg(dst + 96 + w.lane, d);
-    w.bottom += kChunkNodes;
-    w.sp_top += 1;
-    if (w.sp_top - w.sp_bottom > (uint32_t)kSpillCap && w.lane == 0) atomicExch(&P.ctl->status, kStatusSpillOverflow);
+    w.sp += 0x10000u;
+    if ((w.sp >> 16) > (uint32_t)kSpillCap && w.lane == 0) atomicExch(&P.ctl->status, kStatusSpillOverflow);
     __syncwarp();
 }
 
 template <int RING>
 __device__ __forceinline__ void unspill_newest_chunk(WarpCtx& w, const SimParams& P)
 {
-    w.sp_top -= 1;
-    const unsigned long long* src = spill_ring(P) + (size_t)(w.sp_top % kSpillCap) * kChunkWords;
-    w.bottom -= kChunkNodes;
-    uint32_t idx = (w.bottom + w.lane) & Ring<RING>::kMask;
+    /* the chunk goes on TOP of the ring: the caller holds fewer than 32 regular nodes, so it is expanded next either
+     * way, and the retry nodes collected at the bottom stay where they are */
+    w.sp -= 0x10000u;
+    const unsigned long long* src = spill_ring(P) + (size_t)(((w.sp & 0xFFFFu) + (w.sp >> 16)) % kSpillCap) * kChunkWords;
+    uint32_t idx = (w.top + w.lane) & Ring<RING>::kMask;
     ring_store<RING>(w, idx, __ldcg(src + w.lane), __ldcg(src + 32 + w.lane), __ldcg(src + 64 + w.lane), __ldcg(src + 96 + w.lane));
+    w.top += kChunkNodes;
     __syncwarp();
 }
 
@@ -471,17 +509,15 @@ template <int RING>
 __device__ __forceinline__ void donate_chunk(WarpCtx& w, const SimParams& P)
 {
     uint64_t a, b, c, d;
-    if (w.sp_top != w.sp_bottom) {
-        const unsigned long long* src = spill_ring(P) + (size_t)(w.sp_bottom % kSpillCap) * kChunkWords;
+    if ((w.sp >> 16) != 0u) {
+        const unsigned long long* src = spill_ring(P) + (size_t)((w.sp & 0xFFFFu) % kSpillCap) * kChunkWords;
         a = __ldcg(src + w.lane);
         b = __ldcg(src + 32 + w.lane);
         c = __ldcg(src + 64 + w.lane);
         d = __ldcg(src + 96 + w.lane);
-        w.sp_bottom += 1;
+        w.sp = ((w.sp + 1u) & 0xFFFFu) | ((w.sp & 0xFFFF0000u) - 0x10000u);
     } else {
-        uint32_t idx = (w.bottom + w.lane) & Ring<RING>::kMask;
-        ring_load<RING>(w, idx, a, b, c, d);
-        w.bottom += kChunkNodes;
+        pop_bottom_chunk<RING>(w, a, b, c, d);
     }
     __syncwarp();
     queue_push(P, w.lane, a, b, c, d);
@@ -691,176 +727,228 @@ __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* 
     return o;
 }
 
-/* per-warp division counters: one plain counter for single-set runs, (set, count) with flush-on-change for sweeps */
+/* per-lane division counters.  Sweeps and time series (general instances): divisions of parameter set `set` counted by
+ * this lane and not yet flushed, flushed when the set changes.  PLAIN instances (one set): every DIVIDE iteration counts
+ * as 32 divisions through the warp's iteration counter and `cnt` is this lane's CORRECTION to that (-1 when the lane had
+ * no node or its node was a redraw), so that the common iteration - 32 lanes, 32 first expansions - does not touch it. */
 struct DivCount {
-    uint32_t set, cnt;      /* divisions of parameter set `set` counted by this lane and not yet flushed */
+    uint32_t set, cnt;
 };
 
-/* The node rule for both daughters of one division (proliferation.cu:321-380, :404-410) given their standard normals.
- * FRESH = the node is known to be a first draw with both daughters wanted (retry == 0, mask == 3): the common case,
- * decided for the whole warp by one vote, drops the forced-timer selects and the wanted-daughter masks. */
-template <bool FRESH>
-__device__ __forceinline__ void classify_daughters(const SimParams& P, double2 ms, uint32_t dlo, uint32_t retry, double t_div,
-                                                   double z0, double z1, bool& int0, bool& int1, uint32_t& rej,
-                                                   uint32_t& leaf_inc, double& tc0, double& tc1)
+/* What one lane's popped node came to in a DIVIDE iteration; push_and_count turns it into ring pushes and leaf counts */
+struct DivOut {
+    bool int0, int1;            /* daughter 0 / 1 lives on and will divide */
+    bool got0, got1;            /* daughter 0 / 1 received its timer in THIS iteration (time series) */
+    uint32_t rej;               /* daughters still without a timer (bit c): they go back as a retry node */
+    uint32_t retry_next;        /* retry number of that node */
+    uint32_t leaf_inc, leaf_key, dlo;
+    uint64_t heap, pc;
+    double t_div, tc0, tc1;
+};
+
+__device__ __forceinline__ void divout_clear(DivOut& o)
 {
-    const bool forced = !FRESH && retry >= PCS_MAX_RETRY;      /* 255 redraws failed: the timer is the mean */
-    const double tm0 = forced ? ms.x : pcs_timer(ms.x, ms.y, z0);
-    const double tm1 = forced ? ms.x : pcs_timer(ms.x, ms.y, z1);
-    const bool want0 = FRESH || (dlo & (1u << 28)) != 0u, want1 = FRESH || (dlo & (2u << 28)) != 0u;
-    const bool ok0 = want0 && (tm0 > 0.0 || forced), ok1 = want1 && (tm1 > 0.0 || forced);
-    tc0 = PCS_ADD(t_div, tm0);
-    tc1 = PCS_ADD(t_div, tm1);
-    const bool late0 = tc0 > P.t_max, late1 = tc1 > P.t_max;  /* proliferation.cu:404-410 */
-    const bool deeper = (dlo & (63u << 22)) != 0u;           /* f/2 > phi one level down (:323) */
-    leaf_inc = (uint32_t)(ok0 && late0) + (uint32_t)(ok1 && late1);
-    int0 = ok0 && !late0 && deeper;
-    int1 = ok1 && !late1 && deeper;
-    rej = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
+    o.int0 = false; o.int1 = false; o.got0 = false; o.got1 = false;
+    o.rej = 0; o.retry_next = 0; o.leaf_inc = 0; o.leaf_key = 0; o.dlo = 0;
+    o.heap = 0; o.pc = 0; o.t_div = 0.0; o.tc0 = 0.0; o.tc1 = 0.0;
 }
 
-/* ---- DIVIDE iteration: the lanes below `take` pop one node each (newest first), draw ONE Philox block -> one
- * Box-Muller pair -> both daughters' timers, classify the daughters and push the ones that will divide.
- * FULL = all 32 lanes have a node (the common case): straight-line code.  Otherwise the lanes without a node skip the
- * arithmetic, and every warp collective below is still executed by all 32 lanes with the full mask.
- * NPL = nodes per lane: 1, or 2 in the 16-warp instance with 256-node rings (RING = 2), where lane l expands the
- * nodes top-1-l and top-33-l in one straight-line pass: two independent arithmetic chains for the scheduler to
- * interleave, and the per-iteration overhead (loop control, constant loads, probes) is paid once per 64 divisions. */
-template <bool FULL, bool HASHED, bool PLAIN, int RING, int NPL, int MODE>
-__device__ __forceinline__ void divide_iteration(WarpCtx& w, const SimParams& P, const double* s_log, uint32_t* s_hist,
-                                                 const double2* musd, uint32_t take, unsigned lt_mask, bool multi_set,
-                                                 DivCount& dc, uint32_t hist_base)
+/* bit 30 of a node's D word: the division of this node has been counted already (set on every retry node) */
+constexpr uint32_t kDloCounted = 1u << 30;
+
+/* The node rule for both daughters of one division (proliferation.cu:321-380, :404-410) given which daughters received a
+ * timer (ok) and the timers; fills o.int / o.leaf_inc / o.tc */
+__device__ __forceinline__ void classify_daughters(const SimParams& P, DivOut& o, bool ok0, bool ok1, double tm0, double tm1)
 {
-    constexpr bool SUBTREE = MODE == kModeSubtree, SETDIRECT = MODE == kModeSetDirect;
-    static_assert(NPL == 1 || (FULL && RING >= NPL), "several nodes per lane: full iterations of a wide-ring instance only");
+    o.tc0 = PCS_ADD(o.t_div, tm0);
+    o.tc1 = PCS_ADD(o.t_div, tm1);
+    const bool late0 = o.tc0 > P.t_max, late1 = o.tc1 > P.t_max;  /* proliferation.cu:404-410 */
+    const bool deeper = (o.dlo & (63u << 22)) != 0u;              /* f/2 > phi one level down (:323) */
+    o.leaf_inc = (uint32_t)(ok0 && late0) + (uint32_t)(ok1 && late1);
+    o.int0 = ok0 && !late0 && deeper;
+    o.int1 = ok1 && !late1 && deeper;
+    o.got0 = ok0; o.got1 = ok1;
+}
+
+/* subtree sharding and the division counters: `first` = this iteration is the node's first expansion (a redraw is not
+ * another division) */
+template <int MODE, bool PLAIN>
+__device__ __forceinline__ void credit_division(const SimParams& P, DivOut& o, uint32_t first, uint32_t set, bool multi_set, DivCount& dc)
+{
+    if (MODE == kModeSubtree && o.heap < P.sub_limit) {
+        /* subtree sharding: a node below the shard level is expanded by EVERY GPU (same stream, same outcome);
+         * its division and the leaves among its daughters are credited to GPU root % world only, and of its
+         * daughters AT the shard level this GPU keeps the ones with (root + heap) % world == rank */
+        const uint32_t root = (uint32_t)o.pc;
+        if (root % P.sub_world != P.sub_rank) { o.leaf_inc = 0u; first = 0u; }
+        if (o.heap >= (P.sub_limit >> 1)) {
+            const uint32_t h0 = root + (uint32_t)o.heap * 2u;
+            o.int0 = o.int0 && h0 % P.sub_world == P.sub_rank;
+            o.int1 = o.int1 && (h0 + 1u) % P.sub_world == P.sub_rank;
+        }
+    }
+    if (PLAIN) { dc.cnt += first - 1u; return; }
+    if (multi_set && first && set != dc.set) {
+        if (dc.cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
+        dc.cnt = 0; dc.set = set;
+    }
+    dc.cnt += first;
+}
+
+/* second half of a DIVIDE iteration: `take` nodes have been popped (from the top, or - BOTTOM - from the bottom of the
+ * ring); push the daughters that will divide on top, the retry nodes at the BOTTOM, count the leaves.
+ * Retry nodes - a daughter whose ziggurat trial left the fast path, or whose timer came out <= 0 (cell.cu:114-118) - are
+ * rare (3 % of the divisions) and expensive (a second Philox block, a logarithm), so they are not expanded where they
+ * arise: they collect at the bottom of the ring (w.slow counts them) and are expanded 32 at a time by a general iteration
+ * with every lane busy.  Results do not depend on when a node is expanded: the stream is keyed by (root, path, retry). */
+template <bool FULL, bool HASHED, bool PLAIN, int RING, int MODE>
+__device__ __forceinline__ void push_and_count(WarpCtx& w, const SimParams& P, uint32_t* s_hist, const DivOut& o, uint32_t take,
+                                               bool from_bottom, unsigned lt_mask, uint32_t hist_base)
+{
+    constexpr bool SETDIRECT = MODE == kModeSetDirect;
     constexpr uint32_t kMask = Ring<RING>::kMask;
-    const uint32_t T = P.n_types;
-    /* the key field of a node advances by KS per tree level: n_types, or - PLAIN direct instances, whose table is laid
-     * out by slots - the number of proliferating types */
-    const uint32_t KS = (PLAIN && !HASHED) ? P.kstride : T;
-    bool int0[NPL], int1[NPL];              /* daughter 0 / 1 lives on and will divide */
-    uint32_t rej[NPL], leaf_inc[NPL], leaf_key[NPL], dlo[NPL], retry[NPL];
-    uint64_t heap[NPL], pc[NPL];
-    double t_div[NPL], tc0[NPL], tc1[NPL];
-    /* the arithmetic runs phase by phase over the lane's nodes (pop + Philox, polynomials, square roots, classify):
-     * with NPL = 2 that puts two independent chains side by side in every basic block */
-    pcs_u32x4 blk[NPL];
-    double rad2[NPL], sn[NPL], cs[NPL], z0[NPL], z1[NPL];
-    const bool mine = FULL || (uint32_t)w.lane < take;
-    bool fresh = false;
-#pragma unroll
-    for (int s = 0; s < NPL; ++s) {
-        int0[s] = false; int1[s] = false;
-        rej[s] = 0; leaf_inc[s] = 0; leaf_key[s] = 0; dlo[s] = 0; retry[s] = 0;
-        heap[s] = 0; pc[s] = 0;
-        t_div[s] = 0.0; tc0[s] = 0.0; tc1[s] = 0.0;
-    }
-    if (mine) {
-#pragma unroll
-        for (int s = 0; s < NPL; ++s) {
-            const uint32_t idx = (w.top - 1u - 32u * (uint32_t)s - (uint32_t)w.lane) & kMask;
-            uint64_t a, d;
-            ring_load<RING>(w, idx, a, heap[s], pc[s], d);
-            t_div[s] = pcs_bits2d(a);
-            dlo[s] = (uint32_t)d;
-            retry[s] = (uint32_t)(d >> 32);
-            const uint32_t set = PLAIN ? 0u : (dlo[s] & 0xFFFFu);
-            blk[s] = pcs_draw_rk((uint32_t)pc[s], set, retry[s], PCS_TAG_DIVISION, heap[s], P.rk);
-        }
-#ifndef PROCELL_NO_FRESH_PATH
-        if (FULL) {     /* one vote: are all popped nodes first draws with both daughters wanted? (warp-uniform branch below) */
-            bool f = true;
-#pragma unroll
-            for (int s = 0; s < NPL; ++s) f = f && ((dlo[s] >> 28) | (retry[s] << 4)) == 3u;
-            fresh = __all_sync(kFull, f);
-        }
-#endif
-#pragma unroll
-        for (int s = 0; s < NPL; ++s) pcs_normal_pair_polys(blk[s], s_log, 0.0, &rad2[s], &sn[s], &cs[s]);
-#pragma unroll
-        for (int s = 0; s < NPL; ++s) pcs_normal_pair_finish(rad2[s], sn[s], cs[s], &z0[s], &z1[s]);
-#pragma unroll
-        for (int s = 0; s < NPL; ++s) {
-            const uint32_t set = PLAIN ? 0u : (dlo[s] & 0xFFFFu);
-            const uint32_t type = (dlo[s] >> 16) & 63u;
-            const double2 ms = musd[set * T + type];          /* generic pointer: shared-memory copy or the HBM table */
-            if (fresh) classify_daughters<true>(P, ms, dlo[s], retry[s], t_div[s], z0[s], z1[s], int0[s], int1[s], rej[s], leaf_inc[s], tc0[s], tc1[s]);
-            else classify_daughters<false>(P, ms, dlo[s], retry[s], t_div[s], z0[s], z1[s], int0[s], int1[s], rej[s], leaf_inc[s], tc0[s], tc1[s]);
-            leaf_key[s] = (uint32_t)(pc[s] >> 32) + KS;
-            uint32_t first = (fresh || retry[s] == 0u) ? 1u : 0u;   /* a redraw is not another division */
-            if (SUBTREE && heap[s] < P.sub_limit) {
-                /* subtree sharding: a node below the shard level is expanded by EVERY GPU (same stream, same outcome);
-                 * its division and the leaves among its daughters are credited to GPU root % world only, and of its
-                 * daughters AT the shard level this GPU keeps the ones with (root + heap) % world == rank */
-                const uint32_t root = (uint32_t)pc[s];
-                if (root % P.sub_world != P.sub_rank) { leaf_inc[s] = 0u; first = 0u; }
-                if (heap[s] >= (P.sub_limit >> 1)) {
-                    const uint32_t h0 = root + (uint32_t)heap[s] * 2u;
-                    int0[s] = int0[s] && h0 % P.sub_world == P.sub_rank;
-                    int1[s] = int1[s] && (h0 + 1u) % P.sub_world == P.sub_rank;
-                }
-            }
-            if (multi_set && first && set != dc.set) {
-                if (dc.cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
-                dc.cnt = 0; dc.set = set;
-            }
-            dc.cnt += first;
-        }
-    }
+    const uint32_t KS = (PLAIN && !HASHED) ? P.kstride : P.n_types;
     /* all popped nodes have been read: every lane's loads have returned before it votes below (the predicates depend
-     * on the loaded values of every node it popped) and no lane stores before all have voted on everything, so the
+     * on the loaded values of the node it popped) and no lane stores before all have voted on everything, so the
      * slots may be overwritten.  The partial iteration is divergent above, so it states the ordering explicitly as well. */
     if (!FULL) __syncwarp();
-    w.top -= take;
-    unsigned b0[NPL], b1[NPL], br[NPL];
-#pragma unroll
-    for (int s = 0; s < NPL; ++s) {
-        b0[s] = __ballot_sync(kFull, int0[s]);
-        b1[s] = __ballot_sync(kFull, int1[s]);
-        br[s] = __ballot_sync(kFull, rej[s] != 0u);
-    }
-#pragma unroll
-    for (int s = 0; s < NPL; ++s) {
-        const uint64_t child_c = ((pc[s] >> 32) + KS) << 32 | (pc[s] & 0xFFFFFFFFull);
-        const uint64_t child_d = (uint64_t)((dlo[s] | (3u << 28)) - (1u << 22));
-        const uint32_t i0 = (w.top + __popc(b0[s] & lt_mask)) & kMask;
-        ring_store_if<RING>(w, int0[s], i0, pcs_d2bits(tc0[s]), heap[s] * 2ull, child_c, child_d);
-        w.top += __popc(b0[s]);
-        const uint32_t i1 = (w.top + __popc(b1[s] & lt_mask)) & kMask;
-        ring_store_if<RING>(w, int1[s], i1, pcs_d2bits(tc1[s]), heap[s] * 2ull + 1ull, child_c, child_d);
-        w.top += __popc(b1[s]);
-    }
-#pragma unroll
-    for (int s = 0; s < NPL; ++s) {
-        if (br[s]) {   /* a daughter's timer came out <= 0: redraw it in a later iteration (cell.cu:114-118) */
-            if (rej[s]) {
-                const uint32_t ir = (w.top + __popc(br[s] & lt_mask)) & kMask;
-                ring_store<RING>(w, ir, pcs_d2bits(t_div[s]), heap[s], pc[s],
-                           (uint64_t)((dlo[s] & ~(3u << 28)) | (rej[s] << 28)) | ((uint64_t)(retry[s] + 1u) << 32));
-            }
-            w.top += __popc(br[s]);
+    if (from_bottom) { w.bottom += take; w.slow -= take; } else w.top -= take;
+    const unsigned b0 = __ballot_sync(kFull, o.int0);
+    const unsigned b1 = __ballot_sync(kFull, o.int1);
+    const unsigned br = __ballot_sync(kFull, o.rej != 0u);
+    const uint64_t child_c = ((o.pc >> 32) + KS) << 32 | (o.pc & 0xFFFFFFFFull);
+    const uint64_t child_d = (uint64_t)(((o.dlo & ~kDloCounted) | (3u << 28)) - (1u << 22));
+    const uint32_t i0 = (w.top + __popc(b0 & lt_mask)) & kMask;
+    ring_store_if<RING>(w, o.int0, i0, pcs_d2bits(o.tc0), o.heap * 2ull, child_c, child_d);
+    w.top += __popc(b0);
+    const uint32_t i1 = (w.top + __popc(b1 & lt_mask)) & kMask;
+    ring_store_if<RING>(w, o.int1, i1, pcs_d2bits(o.tc1), o.heap * 2ull + 1ull, child_c, child_d);
+    w.top += __popc(b1);
+    if (br) {
+        if (o.rej) {
+            const uint32_t ir = (w.bottom - 1u - __popc(br & lt_mask)) & kMask;
+            ring_store<RING>(w, ir, pcs_d2bits(o.t_div), o.heap, o.pc,
+                             (uint64_t)((o.dlo & ~(3u << 28)) | (o.rej << 28) | kDloCounted) | ((uint64_t)o.retry_next << 32));
         }
+        w.bottom -= __popc(br);
+        w.slow += __popc(br);
     }
     __syncwarp();
-#pragma unroll
-    for (int s = 0; s < NPL; ++s) {
-        if (SETDIRECT) {
-            count_leaves_setdirect(P, s_hist, leaf_key[s], leaf_inc[s], hist_base);
-        } else if (PLAIN || P.n_times == 1u) {
-            warp_count_leaves<HASHED>(P, s_hist, leaf_key[s], leaf_inc[s]);
-        } else {
-            /* time series: a daughter born at t_div that divides (or would divide) at tc is out of time at every
-             * checkpoint in [t_div, tc) */
-            const bool have0 = (rej[s] & 1u) == 0u && (dlo[s] & (1u << 28)) != 0u;      /* daughter 0 got its timer now */
-            const bool have1 = (rej[s] & 2u) == 0u && (dlo[s] & (2u << 28)) != 0u;
-            for (uint32_t j = 0; j < P.n_times; ++j) {
-                const double tj = P.times[j];
-                const bool born = t_div[s] <= tj;
-                const uint32_t inc = (uint32_t)(have0 && born && tj < tc0[s]) + (uint32_t)(have1 && born && tj < tc1[s]);
-                warp_count_leaves<HASHED>(P, s_hist, leaf_key[s] + j * P.time_stride, inc);
-            }
+    if (SETDIRECT) {
+        count_leaves_setdirect(P, s_hist, o.leaf_key, o.leaf_inc, hist_base);
+    } else if (PLAIN || P.n_times == 1u) {
+        warp_count_leaves<HASHED>(P, s_hist, o.leaf_key, o.leaf_inc);
+    } else {
+        /* time series: a daughter born at t_div that divides (or would divide) at tc is out of time at every
+         * checkpoint in [t_div, tc) */
+        for (uint32_t j = 0; j < P.n_times; ++j) {
+            const double tj = P.times[j];
+            const bool born = o.t_div <= tj;
+            const uint32_t inc = (uint32_t)(o.got0 && born && tj < o.tc0) + (uint32_t)(o.got1 && born && tj < o.tc1);
+            warp_count_leaves<HASHED>(P, s_hist, o.leaf_key + j * P.time_stride, inc);
         }
     }
+}
+
+/* ---- DIVIDE iteration, the common one: the lanes below `take` pop one node each from the top of the ring (newest
+ * first), draw ONE Philox block and make the FAST ziggurat test for both daughters (procell_spec.h: one table row, one
+ * fma, one compare each).  A daughter that passes and whose timer is positive is classified as leaf / dropped / internal;
+ * the others go back as a retry node for the general iteration below.
+ * FULL = all 32 lanes have a node: straight-line code.  Otherwise the lanes without a node skip the arithmetic, and every
+ * warp collective is still executed by all 32 lanes with the full mask.
+ * false (and nothing changed) = one of the popped nodes is a retry node - it reached the top through a spilled or donated
+ * chunk -: the caller runs the general iteration on the same nodes. */
+template <bool FULL, bool HASHED, bool PLAIN, int RING, int MODE>
+__device__ __forceinline__ bool divide_fresh(WarpCtx& w, const SimParams& P, const double* s_tab, uint32_t* s_hist,
+                                             const double2* musd, uint32_t take, unsigned lt_mask, bool multi_set,
+                                             DivCount& dc, uint32_t hist_base)
+{
+    constexpr uint32_t kMask = Ring<RING>::kMask;
+    DivOut o;
+    divout_clear(o);
+    const bool mine = FULL || (uint32_t)w.lane < take;
+    uint32_t retry = 0;
+    pcs_u32x4 blk;
+    blk.x = 0; blk.y = 0; blk.z = 0; blk.w = 0;
+    uint32_t set = 0;
+    if (mine) {
+        const uint32_t idx = (w.top - 1u - (uint32_t)w.lane) & kMask;
+        uint64_t a, d;
+        ring_load<RING>(w, idx, a, o.heap, o.pc, d);
+        o.t_div = pcs_bits2d(a);
+        o.dlo = (uint32_t)d;
+        retry = (uint32_t)(d >> 32);
+        set = PLAIN ? 0u : (o.dlo & 0xFFFFu);
+        blk = pcs_draw_rk((uint32_t)o.pc, set, 0u, PCS_TAG_DIVISION, o.heap, P.rk);
+    }
+    /* one vote: are all popped nodes first draws with both daughters wanted?  (it also tells the compiler that the warp
+     * is converged, so the ballots behind it are plain VOTEs) */
+    if (!__all_sync(kFull, !mine || ((o.dlo >> 28) | (retry << 4)) == 3u)) return false;
+    if (mine) {
+        const uint32_t type = (o.dlo >> 16) & 63u;
+        const double2 ms = musd[set * P.n_types + type];          /* generic pointer: shared-memory copy or the HBM table */
+        double z0, z1;
+        const bool f0 = pcs_zig_fast(blk.x, blk.y, s_tab + PCS_TAB_ZIG, &z0);
+        const bool f1 = pcs_zig_fast(blk.z, blk.w, s_tab + PCS_TAB_ZIG, &z1);
+        const double tm0 = pcs_timer(ms.x, ms.y, z0), tm1 = pcs_timer(ms.x, ms.y, z1);
+        const bool ok0 = f0 && tm0 > 0.0, ok1 = f1 && tm1 > 0.0;
+        classify_daughters(P, o, ok0, ok1, tm0, tm1);
+        o.rej = (uint32_t)!ok0 | ((uint32_t)!ok1 << 1);
+        /* a trial that left the fast path is finished by the general iteration at THIS retry number; if every rejected
+         * daughter passed the fast test (its timer was <= 0), the next thing to do is the redraw */
+        o.retry_next = (f0 && f1) ? 1u : 0u;
+        o.leaf_key = (uint32_t)(o.pc >> 32) + ((PLAIN && !HASHED) ? P.kstride : P.n_types);
+        credit_division<MODE, PLAIN>(P, o, 1u, set, multi_set, dc);
+    }
+    else if (PLAIN) dc.cnt -= 1u;
+    push_and_count<FULL, HASHED, PLAIN, RING, MODE>(w, P, s_hist, o, take, false, lt_mask, hist_base);
+    return true;
+}
+
+/* ---- DIVIDE iteration, the general one: any node - any retry number, either or both daughters wanted.  Each wanted
+ * daughter gets one WHOLE ziggurat trial at the node's retry number (fast test, else wedge test or tail sampler with
+ * further Philox blocks, procell_spec.h: pcs_zig_trial); accepted with a positive timer it is classified, else it stays
+ * wanted and the node goes back with retry + 1; at retry 255 the timer is the mean.  The popped nodes are the `take`
+ * bottom-most of the ring (the collected retry nodes) or - a mixed chunk on top - the newest ones. */
+template <bool HASHED, bool PLAIN, int RING, int MODE>
+__device__ __forceinline__ void divide_general(WarpCtx& w, const SimParams& P, const double* s_tab, uint32_t* s_hist,
+                                               const double2* musd, uint32_t take, bool from_bottom, unsigned lt_mask,
+                                               bool multi_set, DivCount& dc, uint32_t hist_base)
+{
+    constexpr uint32_t kMask = Ring<RING>::kMask;
+    DivOut o;
+    divout_clear(o);
+    if ((uint32_t)w.lane < take) {
+        const uint32_t idx = (from_bottom ? w.bottom + (uint32_t)w.lane : w.top - 1u - (uint32_t)w.lane) & kMask;
+        uint64_t a, d;
+        ring_load<RING>(w, idx, a, o.heap, o.pc, d);
+        o.t_div = pcs_bits2d(a);
+        o.dlo = (uint32_t)d;
+        const uint32_t retry = (uint32_t)(d >> 32);
+        const uint32_t set = PLAIN ? 0u : (o.dlo & 0xFFFFu);
+        const uint32_t type = (o.dlo >> 16) & 63u;
+        const double2 ms = musd[set * P.n_types + type];
+        const bool want0 = (o.dlo & (1u << 28)) != 0u, want1 = (o.dlo & (2u << 28)) != 0u;
+        const bool forced = retry >= PCS_MAX_RETRY;            /* 255 redraws failed: the timer is the mean */
+        bool acc0 = false, acc1 = false;
+        double z0 = 0.0, z1 = 0.0;
+        if (!forced) {
+            const pcs_u32x4 blk = pcs_draw_rk((uint32_t)o.pc, set, retry, PCS_TAG_DIVISION, o.heap, P.rk);
+            const double* wedge = P.logtab + PCS_TAB_WEDGE;
+            if (want0) acc0 = pcs_zig_trial(blk, 0u, &z0, (uint32_t)o.pc, set, retry, o.heap, P.rk, s_tab, wedge);
+            if (want1) acc1 = pcs_zig_trial(blk, 1u, &z1, (uint32_t)o.pc, set, retry, o.heap, P.rk, s_tab, wedge);
+        }
+        const double tm0 = forced ? ms.x : pcs_timer(ms.x, ms.y, z0);
+        const double tm1 = forced ? ms.x : pcs_timer(ms.x, ms.y, z1);
+        const bool ok0 = want0 && (forced || (acc0 && tm0 > 0.0)), ok1 = want1 && (forced || (acc1 && tm1 > 0.0));
+        classify_daughters(P, o, ok0, ok1, tm0, tm1);
+        o.rej = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
+        o.retry_next = retry + 1u;
+        o.leaf_key = (uint32_t)(o.pc >> 32) + ((PLAIN && !HASHED) ? P.kstride : P.n_types);
+        credit_division<MODE, PLAIN>(P, o, (o.dlo & kDloCounted) ? 0u : 1u, set, multi_set, dc);
+    }
+    else if (PLAIN) dc.cnt -= 1u;
+    push_and_count<false, HASHED, PLAIN, RING, MODE>(w, P, s_hist, o, take, from_bottom, lt_mask, hist_base);
 }
 
 }  // namespace
@@ -871,12 +959,11 @@ template <int WARPS, bool HASHED, bool PLAIN, int RING, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid_constant__ SimParams P)
 {
     constexpr bool SUBTREE = MODE == kModeSubtree, SETDIRECT = MODE == kModeSetDirect;
-    static_assert(RING == 1 || RING == 2, "ring of 128 or 256 nodes per warp");
+    static_assert(RING == 1, "128-node ring per warp, one node per lane and iteration");
     static_assert(!SUBTREE || (PLAIN && RING == 1), "subtree sharding: one parameter set, one checkpoint, one node per lane");
     static_assert(!SETDIRECT || (!PLAIN && !HASHED && RING == 1), "set-relative table: sweeps, u32 slots, one node per lane");
     constexpr uint32_t kCap = Ring<RING>::kCap, kMask = Ring<RING>::kMask;
     constexpr bool SLOT = PLAIN && !HASHED;      /* the u32 table is laid out by slots (SimParams::slot_mode is set) */
-    constexpr uint32_t kLow = 32u * RING;        /* below this many nodes a warp looks for seed cells / spilled chunks first */
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_log = reinterpret_cast<double*>(smem_raw);
     volatile int* s_ctl = reinterpret_cast<volatile int*>(smem_raw + kLogTabDoubles * 8);   /* [0] poll lock, [1] quiescent */
@@ -914,8 +1001,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 
     WarpCtx w;
     w.ab = reinterpret_cast<ulonglong2*>(s_stack + (size_t)warp * 4 * kCap);
-    w.bottom = 0; w.top = 0;
-    w.sp_bottom = 0; w.sp_top = 0;
+    w.bottom = 0; w.top = 0; w.slow = 0;
+    w.sp = 0;
     w.lane = lane;
 
     uint32_t seed_cur = 0, seed_end = 0, seed_set = 0;
@@ -957,11 +1044,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     volatile unsigned long long* s_deadline = reinterpret_cast<volatile unsigned long long*>(const_cast<int*>(s_ctl) + 10);
 
     for (;;) {
+        /* the ring holds n nodes: w.slow retry nodes at its bottom, waiting for a general iteration, and above them the
+         * regular ones.  mode 0: full fresh iteration (the common case: 32 regular nodes or more, room for the pushes of
+         * one iteration, fewer than 32 retry nodes), 1: partial fresh iteration, 2: general iteration */
         const uint32_t n = w.top - w.bottom;
-        /* the two uncommon cases - too few nodes for a full iteration, too many for the pushes of one - share one test */
-        if (n - kLow > kCap - 32u * RING - kLow) {
-        if (n < kLow) {
-            if (w.sp_top != w.sp_bottom) { TRACE(P, GWARP, lane, 41); unspill_newest_chunk<RING>(w, P); continue; }
+        const uint32_t nreg = n - w.slow;
+        int mode = 0;
+        uint32_t take = 32u;
+        bool from_bottom = false;
+        if (!(w.slow < 32u && nreg - 32u <= kCap - 64u - w.slow)) {
+        if (n > kCap - 32u) {    /* an iteration pops 32 nodes at most and pushes twice as many: keep that much room in the ring */
+            TRACE(P, GWARP, lane, 40); spill_bottom_chunk<RING>(w, P); continue;
+        }
+        if (w.slow >= 32u) { mode = 2; from_bottom = true; }      /* a warp's worth of retry nodes has collected */
+        else {
+            bool divide_rest = false;      /* MODE 2: expand what is left of the old set before waiting for the switch */
+            if ((w.sp >> 16) != 0u) { TRACE(P, GWARP, lane, 41); unspill_newest_chunk<RING>(w, P); continue; }
             /* RULE: every decision that depends on mutable shared/global state is taken by lane 0 and broadcast.
              * Lanes of a warp are not guaranteed to be converged when they read a volatile flag, so a per-lane read
              * can see two different values inside one warp and split it for good. */
@@ -1052,11 +1150,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                     if (SETDIRECT && wait_switch) {
                         /* the last nodes of the old set are expanded first (partial DIVIDE iterations below); only a
                          * warp without any node may wait for the switch */
-                        if (n != 0u) goto divide_now;
+                        if (ring_nodes(w) != 0u) divide_rest = true;
+                        else {
                         if (!setdirect_rendezvous<WARPS>(P, s_ctl, s_hist, s_batch, lane, GWARP)) break;
                         set_base = (uint32_t)__shfl_sync(kFull, lane == 0 ? sflag_get(s_ctl + 7) : 0, 0);
                         continue;
+                        }
                     }
+                    if (!divide_rest) {
                     if (!got) {
                         if (lane == 0) { sflag_set(s_ctl + 3, 1); atomicMin(&ctl->t_exhausted, global_timer_ns()); }
                         __syncwarp();
@@ -1074,7 +1175,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                     seed_cur = (uint32_t)first; seed_end = (uint32_t)last; seed_set = set;
                     seed_hint = 0xFFFFFFFFu;
                     if (seed_cur >= seed_end) { seed_cur = seed_end; continue; }
+                    }
                 }
+                if (!divide_rest) {
                 /* ---- SEED iteration: one seed cell per lane ---- */
                 TRACE(P, GWARP, lane, 12);
                 const uint32_t root = seed_cur + lane;
@@ -1113,28 +1216,31 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                     }
                 }
                 continue;
+                }
             }
-            if (n == 0u) {
+            const uint32_t left = ring_nodes(w);
+            if (left == 0u) {
                 TRACE(P, GWARP, lane, 30);
                 if (!idle_wait<RING>(w, P, s_ctl, *s_deadline, GWARP)) break;
                 continue;
             }
-        }
-        else {      /* an iteration pops 32 * RING nodes at most and pushes twice as many: keep that much room in the ring */
-            TRACE(P, GWARP, lane, 40); spill_bottom_chunk<RING>(w, P); continue;
+            /* nothing to add: expand what the warp holds - its regular nodes first, then its last retry nodes */
+            if (left != w.slow) { mode = 1; take = left - w.slow; }
+            else { mode = 2; from_bottom = true; take = left; }
         }
         }
 
-    divide_now:
         ++iter;
         TRACE(P, GWARP, lane, 20);
-        const uint32_t take = n < 32u ? n : 32u;
         const uint32_t hist_base = SETDIRECT ? set_base : 0u;     /* changes only while this warp is parked in the rendezvous */
         /* PLAIN: one set and at most 64 types, so the (mean, sd) table is always the shared-memory copy (plain LDS) */
         const double2* musd = PLAIN ? s_musd_buf : s_musd;
-        if (RING == 2 && n >= 64u) divide_iteration<true, HASHED, PLAIN, RING, RING, MODE>(w, P, s_log, s_hist, musd, 64u, lt_mask, multi_set, dc, hist_base);
-        else if (take == 32u) divide_iteration<true, HASHED, PLAIN, RING, 1, MODE>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc, hist_base);
-        else divide_iteration<false, HASHED, PLAIN, RING, 1, MODE>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc, hist_base);
+        if (mode == 0) {
+            if (!divide_fresh<true, HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, 32u, lt_mask, multi_set, dc, hist_base)) mode = 2;
+        } else if (mode == 1) {
+            if (!divide_fresh<false, HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc, hist_base)) mode = 2;
+        }
+        if (mode == 2) divide_general<HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, take, from_bottom, lt_mask, multi_set, dc, hist_base);
 
         /* hunger probe, every 8th iteration (every 4th costs 1.8 % on config 2).  The CTA keeps a snapshot of "how many warps are starving", "how many
          * donated chunks are waiting" and "where is the seed cursor" in shared memory.  Every 64th iteration
@@ -1144,7 +1250,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         if ((iter & kProbeMask) == 0u) {
             if ((iter & 255u) == 0u) {       /* every 256 iterations: flush the 32-bit division counters, check the watchdog */
                 if (!multi_set) {
-                    const uint32_t tot = __reduce_add_sync(kFull, dc.cnt);
+                    const uint32_t tot = (PLAIN ? 32u * 256u : 0u) + __reduce_add_sync(kFull, dc.cnt);
                     if (lane == 0 && tot) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions), (unsigned long long)tot);
                     dc.cnt = 0;
                 } else if (dc.cnt > (1u << 30)) {
@@ -1158,7 +1264,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 int late = 0;
                 if (lane == 0) late = global_timer_ns() > *s_deadline;
                 if (__shfl_sync(kFull, late, 0)) {
-                    watchdog_fire(P, GWARP, lane, 1, n, w.sp_top - w.sp_bottom, seed_cur, seed_end, iter, 0);
+                    watchdog_fire(P, GWARP, lane, 1, ring_nodes(w), w.sp >> 16, seed_cur, seed_end, iter, 0);
                     break;
                 }
             }
@@ -1185,7 +1291,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 packed = (ep << 2) | ((idle_snap >= kEndgameIdle) << 1) | hg;
             }
             packed = __shfl_sync(kFull, packed, 0);
-            if ((packed & 1) && (w.top - w.bottom + 32u * (w.sp_top - w.sp_bottom)) >= ((packed & 2) ? 64u : kDonateMinNodes * RING)) {
+            if ((packed & 1) && (w.top - w.bottom + 32u * (w.sp >> 16)) >= ((packed & 2) ? 64u : kDonateMinNodes * RING)) {
                 /* somebody starves and no seeds are left: give away the shallowest chunk */
                 TRACE(P, GWARP, lane, 50);
                 if (lane == 0) *s_epoch = packed >> 2;
@@ -1200,7 +1306,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     if (multi_set) {
         if (dc.cnt) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions) + dc.set, (unsigned long long)dc.cnt);
     } else {
-        const uint32_t tot = __reduce_add_sync(kFull, dc.cnt);     /* < 32 * 256 since the last periodic flush */
+        const uint32_t tot = (PLAIN ? 32u * (iter & 255u) : 0u) + __reduce_add_sync(kFull, dc.cnt);     /* <= 32 * 256 since the last periodic flush */
         if (lane == 0 && tot) atomicAdd(reinterpret_cast<unsigned long long*>(P.divisions), (unsigned long long)tot);
     }
     __syncthreads();
@@ -1276,17 +1382,17 @@ __global__ void __launch_bounds__(kSimpleThreads) k_proliferate_simple(const __g
             const uint32_t retry = st_m[sp] >> 8;
             const uint32_t level = 63u - (uint32_t)__clzll((long long)heap);
             const bool forced = retry >= PCS_MAX_RETRY;
-            double z[2] = { 0.0, 0.0 };
-            if (!forced) {
-                pcs_u32x4 blk = pcs_draw_rk(root, set, retry, PCS_TAG_DIVISION, heap, P.rk);
-                pcs_normal_pair(blk, s_log, 0.0, &z[0], &z[1]);
-            }
+            pcs_u32x4 blk;
+            blk.x = 0; blk.y = 0; blk.z = 0; blk.w = 0;
+            if (!forced) blk = pcs_draw_rk(root, set, retry, PCS_TAG_DIVISION, heap, P.rk);
             if (retry == 0u) ++ndiv;
-#pragma unroll
+#pragma unroll 1
             for (uint32_t c = 0; c < 2u; ++c) {
                 if (!(mask & (1u << c))) continue;
-                const double timer = forced ? ms.x : pcs_timer(ms.x, ms.y, z[c]);
-                if (timer > 0.0 || forced) {
+                double z = 0.0;
+                const bool acc = forced || pcs_zig_trial(blk, c, &z, root, set, retry, heap, P.rk, s_log, P.logtab + PCS_TAB_WEDGE);
+                const double timer = forced ? ms.x : pcs_timer(ms.x, ms.y, z);
+                if (acc && (timer > 0.0 || forced)) {
                     mask &= ~(1u << c);
                     const double tc = PCS_ADD(t_div, timer);
                     if (tc > P.t_max) atomicAdd(counts + so.key + (level + 1u) * T, 1ull);
@@ -1318,8 +1424,8 @@ __global__ void __launch_bounds__(256) k_queue_init(unsigned long long* q_seq, C
     for (size_t k = i; k < n_divisions; k += stride) divisions[k] = 0ull;
 }
 
-/* RNG-only ceiling: the per-division arithmetic (one Philox block, one Box-Muller pair, two timers, two time
- * updates, four compares) with no tree, no stack and no atomics.  Three shapes of the same loop are built, and the
+/* RNG-only ceiling: the per-division arithmetic of the common case (one Philox block, two fast ziggurat tests, two timers,
+ * two time updates, four compares) with no tree, no stack and no atomics.  Three shapes of the same loop are built, and the
  * roofline is quoted against the FASTEST of them measured live (a ceiling that could be raised by reshaping the loop
  * would flatter the product kernel):
  *   variant 0: one chain per thread, 256-thread CTAs, 6 CTAs per SM (48 warps; the shape measured in round 1)
@@ -1345,10 +1451,11 @@ __device__ __forceinline__ void rng_ceiling_body(int iters, const double* logtab
         for (int c = 0; c < CHAINS; ++c) {
             pcs_u32x4 blk = pcs_draw_rk(tid, (uint32_t)c, 0u, PCS_TAG_DIVISION, heap[c], K.rk);
             double z0, z1;
-            pcs_normal_pair(blk, s_log, 0.0, &z0, &z1);
+            const bool f0 = pcs_zig_fast(blk.x, blk.y, s_log + PCS_TAB_ZIG, &z0);
+            const bool f1 = pcs_zig_fast(blk.z, blk.w, s_log + PCS_TAB_ZIG, &z1);
             const double a = pcs_timer(mean, sd, z0), b = pcs_timer(mean, sd, z1);
             const double ta = PCS_ADD(t[c], a), tb = PCS_ADD(t[c], b);
-            acc += (a > 0.0) + (b > 0.0) + (ta > t_max) + (tb > t_max);
+            acc += (f0 && a > 0.0) + (f1 && b > 0.0) + (ta > t_max) + (tb > t_max);
             t[c] = (ta > t_max) ? 0.0 : ta;
             heap[c] = heap[c] * 2ull + (blk.x & 1u);
             if (heap[c] >> 62) heap[c] = 1;
@@ -1396,25 +1503,22 @@ static cudaError_t coop_max_grid_t(int device, size_t smem_bytes, int* grid_out)
     return cudaSuccess;
 }
 
-/* the 16 instances without the subtree-sharding rule: CTA shape (32 / 24 / 16 warps with 128-node rings, 16 warps with 256-node rings and two nodes
- * per lane) x histogram mode x PLAIN */
+/* the 12 instances without the subtree-sharding rule: CTA shape (32 / 24 / 16 warps) x histogram mode x PLAIN */
 #define COOP_DISPATCH(warps, ring, hashed, plain, X)                                                  \
     do {                                                                                             \
-        switch (((ring) == 2 ? 12 : (warps) == 32 ? 0 : (warps) == 24 ? 4 : 8) + ((hashed) ? 2 : 0) + ((plain) ? 1 : 0)) { \
+        switch (((warps) == 32 ? 0 : (warps) == 24 ? 4 : 8) + ((hashed) ? 2 : 0) + ((plain) ? 1 : 0)) { \
         case 0: X(32, false, false, 1); break;  case 1: X(32, false, true, 1); break;                \
         case 2: X(32, true, false, 1); break;   case 3: X(32, true, true, 1); break;                 \
         case 4: X(24, false, false, 1); break;  case 5: X(24, false, true, 1); break;                \
         case 6: X(24, true, false, 1); break;   case 7: X(24, true, true, 1); break;                 \
         case 8: X(16, false, false, 1); break;  case 9: X(16, false, true, 1); break;                \
-        case 10: X(16, true, false, 1); break;  case 11: X(16, true, true, 1); break;                \
-        case 12: X(16, false, false, 2); break; case 13: X(16, false, true, 2); break;               \
-        case 14: X(16, true, false, 2); break;  default: X(16, true, true, 2); break;                \
+        case 10: X(16, true, false, 1); break;  default: X(16, true, true, 1); break;                \
         }                                                                                            \
     } while (0)
 
 cudaError_t coop_max_grid(int device, int warps, int ring, int hashed, int plain, size_t smem_bytes, int* grid_out)
 {
-    if (ring == 2 && warps != 16) return cudaErrorInvalidValue;
+    if (ring != 1) return cudaErrorInvalidValue;
 #define X(W, H, PL, R) return coop_max_grid_t<W, H, PL, R>(device, smem_bytes, grid_out)
     COOP_DISPATCH(warps, ring, hashed, plain, X);
 #undef X
@@ -1451,7 +1555,7 @@ cudaError_t coop_max_grid_setdirect(int device, size_t smem_bytes, int* grid_out
 
 cudaError_t launch_coop(const SimParams& p, int warps, int ring, int grid, cudaStream_t stream)
 {
-    if (ring == 2 && warps != 16) return cudaErrorInvalidValue;
+    if (ring != 1) return cudaErrorInvalidValue;
     const size_t smem = coop_smem_bytes(warps, ring, p.smem_hist_slots, p.hist_hashed);
     const bool plain = coop_is_plain(p);
     if (p.hist_setdirect) {

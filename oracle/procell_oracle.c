@@ -14,9 +14,9 @@
  * What is NOT the reference's: the random stream.  The reference re-seeds a cuRAND XORWOW state from
  * wall-clock-derived integers for every draw (src/utils/util.cu:143-169), which is neither reproducible
  * nor shardable.  The north-star spec replaces it with Philox4x32-10 (Salmon et al., SC'11; the published
- * algorithm, restated below) keyed by (root cell, tree path), one block per division, and a Box-Muller
- * transform built from a fixed sequence of correctly-rounded IEEE-754 operations so that GPU and CPU
- * agree bit for bit.  oracle/xorwow_ref.c restates the reference's own stream for the distributional check.
+ * algorithm, restated below) keyed by (root cell, tree path), one block per division, whose two normals are drawn by
+ * the ziggurat method (division timers) or a Box-Muller transform (the seed cell's first timer), both built from a fixed
+ * sequence of correctly-rounded IEEE-754 operations so that GPU and CPU agree bit for bit.  oracle/xorwow_ref.c restates the reference's own stream for the distributional check.
  *
  * PARITY PINNING: the reference ships no tests, golden vectors or fixtures for this path, so the
  * pin is the reference itself: tests/golden/ref_*.json hold outputs of the UNMODIFIED reference binary run on a
@@ -314,9 +314,73 @@ typedef struct {
     uint32_t sub_level, sub_world, sub_rank;
 } orc_ctx;
 
-/* truncated-normal timers for the children in `want` (bit c = child c) of the division at `heap` */
+/* ------------------------------------------------------------------------------------------------
+ * Standard normal for a division timer: the ziggurat method (Marsaglia & Tsang, "The Ziggurat Method for Generating
+ * Random Variables", J. Stat. Softw. 5(8), 2000 - the published algorithm, restated).  256 layers of equal area under
+ * f(x) = exp(-x^2/2); zig_rows[i] = { x_i, x_(i+1) } with x_0 = V/f(r), x_1 = r, x_256 = 0.
+ *   64 random bits (lo, hi): layer = hi >> 24, sign = bit 23 of hi, and 1.m with m = (hi & 0xFFFFF):lo a double in [1, 2).
+ *   x = (1.m - 1) * x_layer (one fma).  x < x_(layer+1): under the curve for sure, accept.
+ *   layer 0 otherwise: the tail beyond r, by a = -ln(U1)/r until -2 ln(U2) > a^2, x = r + a.
+ *   layer >= 1 otherwise: the wedge; y uniform between f(x_layer) and f(x_(layer+1)), accept iff y < f(x), i.e.
+ *   -2 ln y > x^2.  A rejected trial counts as a rejected draw (the division redraws with the next retry number).
+ * The extra uniforms come from further Philox blocks of the same (root, heap, retry) with tag 2 (+ attempt number in
+ * the tail); daughter c reads half c of a block, as for the first one.
+ * ---------------------------------------------------------------------------------------------- */
+static const uint64_t zig_rows[1 << PCM_ZIG_N_BITS][2] = { PCM_ZIG_TABLE_ROWS };
+static const uint64_t zig_wedge[1 << PCM_ZIG_N_BITS][2] = { PCM_ZIG_WEDGE_ROWS };
+#define ORC_ZIG_TAIL_TRIES 200
+
+/* 1 = accepted (normal in *z), 0 = rejected.  words[4] = the division's block of this retry */
+int oracle_zig_trial(const uint32_t words[4], unsigned c, uint32_t root, uint32_t set, uint32_t retry, uint64_t heap,
+                     uint64_t seed, double* z)
+{
+    const uint32_t lo = words[2 * c], hi = words[2 * c + 1];
+    const unsigned layer = hi >> (32 - PCM_ZIG_N_BITS);
+    const int negative = (hi >> (31 - PCM_ZIG_N_BITS)) & 1;
+    const double one_to_two = as_f64(0x3FF0000000000000ull | ((uint64_t)(hi & 0xFFFFFu) << 32) | lo);
+    const double edge = as_f64(zig_rows[layer][0]);
+    double x = fma(one_to_two, edge, -edge);
+    if (!(x < as_f64(zig_rows[layer][1]))) {
+        uint32_t e[4];
+        if (layer == 0) {
+            double beyond = 0.0;
+            for (uint32_t attempt = 0; attempt < ORC_ZIG_TAIL_TRIES; ++attempt) {
+                draw_block(root, set, retry, 2u + attempt, heap, seed, e);
+                double a = oracle_neg2log(oracle_uniform32(e[2 * c])) * as_f64(PCM_BITS_ZIG_INV2R);
+                if (oracle_neg2log(oracle_uniform32(e[2 * c + 1])) > a * a) { beyond = a; break; }
+            }
+            x = as_f64(PCM_BITS_ZIG_R) + beyond;
+        } else {
+            draw_block(root, set, retry, 2u, heap, seed, e);
+            double height = fma(oracle_uniform53(e[2 * c], e[2 * c + 1]), as_f64(zig_wedge[layer][1]), as_f64(zig_wedge[layer][0]));
+            if (!(oracle_neg2log(height) > x * x)) return 0;
+        }
+    }
+    *z = negative ? -x : x;
+    return 1;
+}
+
+/* n standard normals exactly as a division's daughter 0 / 1 would receive them (root = sample index / 2, heap 1, redraw on
+ * rejection): for the law tests of the sampler.  trials (optional) receives the total number of trials made. */
+void oracle_zig_fill(uint64_t seed, uint64_t n, double* out, uint64_t* trials)
+{
+    uint64_t made = 0;
+    for (uint64_t k = 0; k < n; ++k) {
+        out[k] = 0.0;
+        for (uint32_t retry = 0; retry < ORC_MAX_RETRY; ++retry) {
+            uint32_t w[4];
+            draw_block((uint32_t)(k >> 1), 0u, retry, 0u, 1ull, seed, w);
+            ++made;
+            if (oracle_zig_trial(w, (unsigned)(k & 1), (uint32_t)(k >> 1), 0u, retry, 1ull, seed, &out[k])) break;
+        }
+    }
+    if (trials) *trials = made;
+}
+
+/* truncated-normal timers for the children in `want` (bit c = child c) of the division at `heap`: child c is tried at
+ * retry 0, 1, 2, ... until a trial is accepted AND the timer is positive (cell.cu:106-122: redraw while <= 0) */
 static void division_timers(const orc_ctx* cx, uint32_t root, uint64_t heap, const orc_type* ty,
-                            unsigned want, double u_first, double timer[2])
+                            unsigned want, double timer[2])
 {
     for (uint32_t retry = 0; want; ++retry) {
         if (retry == ORC_MAX_RETRY) {            /* 255 rejections in a row: fall back to the mean */
@@ -325,12 +389,12 @@ static void division_timers(const orc_ctx* cx, uint32_t root, uint64_t heap, con
             break;
         }
         uint32_t w[4];
-        double z[2];
         draw_block(root, cx->set, retry, 0u, heap, cx->seed, w);
-        oracle_normal_pair(w, retry == 0 ? u_first : 0.0, z);
         for (unsigned c = 0; c < 2; ++c) {
+            double z;
             if (!(want & (1u << c))) continue;
-            double cand = fma(ty->sd, z[c], ty->mean);
+            if (!oracle_zig_trial(w, c, root, cx->set, retry, heap, cx->seed, &z)) continue;
+            double cand = fma(ty->sd, z, ty->mean);
             if (cand > 0.0) { timer[c] = cand; want &= ~(1u << c); }
         }
     }
@@ -396,7 +460,7 @@ static void expand_root(orc_ctx* cx, uint32_t root, unsigned bin)
          * exists on one rank only */
         const int credit = !sub || level >= cx->sub_level || low_owner;
         if (credit) cx->divisions += 1;
-        division_timers(cx, root, nd.heap, ty, 3u, 0.0, timer);
+        division_timers(cx, root, nd.heap, ty, 3u, timer);
         for (unsigned c = 0; c < 2; ++c) {
             double t_child = nd.t_div + timer[c];         /* child.t = parent.t + parent.timer; + own timer */
             if (t_child > cx->t_max) { if (credit) count_leaf(cx, bin, level + 1, ty->id); }

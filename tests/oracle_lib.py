@@ -40,6 +40,9 @@ def lib():
         L.oracle_neg2log.restype = C.c_double
         L.oracle_sincos2pi.argtypes = [C.c_uint64, _f64p, _f64p]
         L.oracle_normal_pair.argtypes = [_u32p, C.c_double, _f64p]
+        L.oracle_zig_trial.argtypes = [_u32p, C.c_uint, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, _f64p]
+        L.oracle_zig_trial.restype = C.c_int
+        L.oracle_zig_fill.argtypes = [C.c_uint64, C.c_uint64, _f64p, _u64p]
         L.oracle_plan_create.argtypes = [_f64p, _u64p, C.c_size_t, C.c_double]
         L.oracle_plan_create.restype = C.c_void_p
         L.oracle_plan_free.argtypes = [C.c_void_p]
@@ -79,6 +82,22 @@ def normal_pair(words, u_forced=0.0):
     z = (C.c_double * 2)()
     lib().oracle_normal_pair(w, u_forced, z)
     return z[0], z[1]
+
+
+def zig_trial(words, c, root=0, set_=0, retry=0, heap=1, seed=0):
+    """one whole ziggurat trial for daughter c: (accepted, z)"""
+    w = (C.c_uint32 * 4)(*words)
+    z = C.c_double(0.0)
+    ok = lib().oracle_zig_trial(w, c, root, set_, retry, C.c_uint64(heap), C.c_uint64(seed), C.byref(z))
+    return bool(ok), z.value
+
+
+def zig_fill(seed: int, n: int):
+    """n standard normals as divisions draw them (redraw on rejection) and the number of trials made"""
+    out = np.zeros(n, dtype=np.float64)
+    trials = (C.c_uint64 * 1)()
+    lib().oracle_zig_fill(C.c_uint64(seed), C.c_uint64(n), out.ctypes.data_as(_f64p), trials)
+    return out, int(trials[0])
 
 
 class OraclePlan:

@@ -3,8 +3,13 @@
  * the header the kernels include states the same operation sequence as the oracle (bit-for-bit). */
 #include "../cuda_pro_cell_b200/csrc/procell_spec.h"
 
-static const struct { uint64_t log_rows[1 << PCM_LOG_N_BITS][2]; uint64_t sincos_rows[1 << PCM_SC_N_BITS][2]; } kTab =
-    { { PCM_LOG_TABLE_ROWS }, { PCM_SINCOS_TABLE_ROWS } };
+static const struct {
+    uint64_t log_rows[1 << PCM_LOG_N_BITS][2];
+    uint64_t sincos_rows[1 << PCM_SC_N_BITS][2];
+    uint64_t zig_rows[1 << PCM_ZIG_N_BITS][2];
+    uint64_t zig_wedge_rows[1 << PCM_ZIG_N_BITS][2];
+} kTab = { { PCM_LOG_TABLE_ROWS }, { PCM_SINCOS_TABLE_ROWS }, { PCM_ZIG_TABLE_ROWS }, { PCM_ZIG_WEDGE_ROWS } };
+static_assert(sizeof(kTab) == PCS_TAB_ALL_DOUBLES * 8, "math table layout");
 static const double* const kRows = reinterpret_cast<const double*>(&kTab);
 
 extern "C" {
@@ -26,6 +31,16 @@ void shim_normal_pair(const uint32_t* w, double u_forced, double* z)
     pcs_u32x4 b; b.x = w[0]; b.y = w[1]; b.z = w[2]; b.w = w[3];
     pcs_normal_pair(b, kRows, u_forced, &z[0], &z[1]);
 }
+/* one whole ziggurat trial for daughter c of the division whose block (tag 0, this retry) is w: 1 = accepted */
+int shim_zig_trial(const uint32_t* w, uint32_t c, uint32_t root, uint32_t set, uint32_t retry, uint64_t heap, uint64_t seed, double* z)
+{
+    uint32_t rk[20];
+    pcs_round_keys((uint32_t)seed, (uint32_t)(seed >> 32), rk);
+    pcs_u32x4 b; b.x = w[0]; b.y = w[1]; b.z = w[2]; b.w = w[3];
+    return pcs_zig_trial(b, c, z, root, set, retry, heap, rk, kRows, kRows + PCS_TAB_WEDGE) ? 1 : 0;
+}
+/* the fast test alone (what the common DIVIDE iteration evaluates): 1 = accepted; *z is set either way */
+int shim_zig_fast(uint32_t lo, uint32_t hi, double* z) { return pcs_zig_fast(lo, hi, kRows + PCS_TAB_ZIG, z) ? 1 : 0; }
 double shim_timer(double mean, double sd, double z) { return pcs_timer(mean, sd, z); }
 double shim_u32unit(uint32_t m) { return pcs_u32unit(m); }
 double shim_seed_normal(const uint32_t* w, double u_forced)

@@ -30,6 +30,11 @@ def shim():
     S.shim_u32unit.argtypes = [C.c_uint32]
     S.shim_seed_normal.restype = C.c_double
     S.shim_seed_normal.argtypes = [C.POINTER(C.c_uint32), C.c_double]
+    S.shim_zig_trial.restype = C.c_int
+    S.shim_zig_trial.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64,
+                                 C.POINTER(C.c_double)]
+    S.shim_zig_fast.restype = C.c_int
+    S.shim_zig_fast.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
     return S
 
 
@@ -88,6 +93,50 @@ def test_header_equals_oracle_bitwise(shim, oracle):
         zf = (C.c_double * 2)()
         shim.shim_normal_pair((C.c_uint32 * 4)(*w), C.c_double(0.37), zf)
         assert (zf[0], zf[1]) == oracle.normal_pair(w, 0.37)
+
+
+def test_ziggurat_trials_equal_the_oracle_bitwise(shim, oracle):
+    """Division timers: the header's ziggurat trial (fast test, wedge test, tail sampler) against the oracle's independent
+    restatement, bit for bit - on random blocks (98.5 % fast), on blocks forced onto the edge of a layer (wedge tests,
+    both outcomes), on the base strip beyond r (the tail sampler) and on the top layer (always a wedge test)."""
+    rng = np.random.default_rng(9)
+    seen = {"fast": 0, "wedge_acc": 0, "wedge_rej": 0, "tail": 0}
+
+    def check(w, c, root, st, retry, heap, seed):
+        z = C.c_double(0.0)
+        got = shim.shim_zig_trial((C.c_uint32 * 4)(*w), c, root, st, retry, C.c_uint64(heap), C.c_uint64(seed), C.byref(z))
+        ok, want = oracle.zig_trial(w, c, root, st, retry, heap, seed)
+        assert bool(got) == ok
+        if ok:
+            assert z.value == want and np.isfinite(want)
+        zf = C.c_double(0.0)
+        fast = shim.shim_zig_fast(w[2 * c], w[2 * c + 1], C.byref(zf))
+        layer = w[2 * c + 1] >> 24
+        if fast:
+            assert ok and zf.value == want
+            seen["fast"] += 1
+        elif layer == 0:
+            assert ok and abs(want) >= 3.6541528853610088          # the tail sampler always accepts, beyond r
+            assert (want < 0) == bool((w[2 * c + 1] >> 23) & 1)
+            seen["tail"] += 1
+        else:
+            if ok:
+                assert want == zf.value                            # a wedge test does not move the point
+            seen["wedge_acc" if ok else "wedge_rej"] += 1
+
+    for _ in range(20000):
+        w = [int(x) for x in rng.integers(0, 2**32, 4)]
+        check(w, int(rng.integers(0, 2)), int(rng.integers(0, 2**32)), int(rng.integers(0, 65536)), int(rng.integers(0, 255)),
+              int(rng.integers(1, 2**62)), int(rng.integers(0, 2**63)))
+    for _ in range(20000):          # mantissa close to 1: the point is near the outer edge of its layer
+        w = [int(x) for x in rng.integers(0, 2**32, 4)]
+        c = int(rng.integers(0, 2))
+        layer = int(rng.choice([0, 0, 1, 2, 127, 254, 255, int(rng.integers(0, 256))]))
+        frac = 0xFFFFF - int(rng.integers(0, 0x30000))
+        w[2 * c + 1] = (layer << 24) | (int(rng.integers(0, 2)) << 23) | (int(rng.integers(0, 8)) << 20) | frac
+        check(w, c, int(rng.integers(0, 2**32)), int(rng.integers(0, 65536)), int(rng.integers(0, 255)),
+              int(rng.integers(1, 2**62)), int(rng.integers(0, 2**63)))
+    assert seen["fast"] > 19000 and seen["wedge_acc"] > 1000 and seen["wedge_rej"] > 1000 and seen["tail"] > 1000, seen
 
 
 def test_header_counter_layout(shim, oracle):

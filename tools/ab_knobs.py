@@ -3,7 +3,7 @@
 load the engine (the knobs are read at load time), run REPS times, report min / median kernel_ms and a checksum of
 the count tensor (all settings must agree: results do not depend on scheduling).
 
-  python tools/ab_knobs.py [REPS] [default,npl2,w16,w24]     # prints one JSON line per (knob, workload)
+  python tools/ab_knobs.py [REPS] [default,w16,w24]     # prints one JSON line per (knob, workload)
   PROCELL_LIB=libprocell_b200_x.so python tools/ab_knobs.py 5 default       # another in-tree build of the library
 """
 import json
@@ -18,7 +18,7 @@ sys.path.insert(0, str(ROOT))
 from cuda_pro_cell_b200 import api, synth  # noqa: E402
 
 REPS = int(sys.argv[1]) if len(sys.argv) > 1 else 5
-ALL_KNOBS = {"default": {}, "npl2": {"PROCELL_COOP_NPL": "2"}, "w16": {"PROCELL_COOP_WARPS": "16"},
+ALL_KNOBS = {"default": {}, "w16": {"PROCELL_COOP_WARPS": "16"},
              "w24": {"PROCELL_COOP_WARPS": "24"}}
 KNOBS = [ALL_KNOBS[k] for k in (sys.argv[2].split(",") if len(sys.argv) > 2 else ALL_KNOBS)]
 WORK = [(2, 1.0, 0.0), (2, 0.1, 0.0), (3, 1.0, 0.0), (5, 1.0, 0.0), (4, 0.1, 600.0), (4, 1.0, 0.0)]
