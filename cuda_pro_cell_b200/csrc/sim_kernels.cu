@@ -432,17 +432,32 @@ __device__ __forceinline__ void spill_bottom_chunk(WarpCtx& w, const SimParams& 
     __syncwarp();
 }
 
+/* a chunk of 32 nodes enters the ring (from the spill ring or the donation queue).  INVARIANT of the ring: above the
+ * `slow` retry nodes at its bottom every node is a FRESH one (first draw, both daughters wanted) - that is what lets the
+ * common DIVIDE iteration pop 32 nodes without looking at them.  Chunks are all-fresh or all-retry by construction
+ * (pop_bottom_chunk); one with ANY retry node in it goes to the bottom as a whole, where the general iteration - which
+ * takes any node - expands it; a fresh one goes on top: the caller holds fewer than 32 regular nodes, so it is expanded
+ * next either way. */
+template <int RING>
+__device__ __forceinline__ void accept_chunk(WarpCtx& w, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
+{
+    if (__any_sync(kFull, (d >> 28) != 3ull)) {          /* mask != 3, or counted, or retry > 0 */
+        w.bottom -= kChunkNodes;
+        ring_store<RING>(w, (w.bottom + w.lane) & Ring<RING>::kMask, a, b, c, d);
+        w.slow += kChunkNodes;
+    } else {
+        ring_store<RING>(w, (w.top + w.lane) & Ring<RING>::kMask, a, b, c, d);
+        w.top += kChunkNodes;
+    }
+    __syncwarp();
+}
+
 template <int RING>
 __device__ __forceinline__ void unspill_newest_chunk(WarpCtx& w, const SimParams& P)
 {
-    /* the chunk goes on TOP of the ring: the caller holds fewer than 32 regular nodes, so it is expanded next either
-     * way, and the retry nodes collected at the bottom stay where they are */
     w.sp -= 0x10000u;
     const unsigned long long* src = spill_ring(P) + (size_t)(((w.sp & 0xFFFFu) + (w.sp >> 16)) % kSpillCap) * kChunkWords;
-    uint32_t idx = (w.top + w.lane) & Ring<RING>::kMask;
-    ring_store<RING>(w, idx, __ldcg(src + w.lane), __ldcg(src + 32 + w.lane), __ldcg(src + 64 + w.lane), __ldcg(src + 96 + w.lane));
-    w.top += kChunkNodes;
-    __syncwarp();
+    accept_chunk<RING>(w, __ldcg(src + w.lane), __ldcg(src + 32 + w.lane), __ldcg(src + 64 + w.lane), __ldcg(src + 96 + w.lane));
 }
 
 /* bounded MPMC queue of chunks (Vyukov): slot s is writable by ticket p when seq[s]==p, readable when seq[s]==p+1 */
@@ -551,10 +566,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
             ticket = __shfl_sync(kFull, ticket, 0);
             uint64_t a, b, c, d;
             if (!queue_read_ticket(P, w.lane, ticket, a, b, c, d)) return false;     /* watchdog abort */
-            uint32_t idx = (w.top + w.lane) & Ring<RING>::kMask;
-            ring_store<RING>(w, idx, a, b, c, d);
-            w.top += kChunkNodes;
-            __syncwarp();
+            accept_chunk<RING>(w, a, b, c, d);
             return true;
         }
     }
@@ -619,10 +631,7 @@ __device__ __forceinline__ bool idle_wait(WarpCtx& w, const SimParams& P, volati
     ticket = __shfl_sync(kFull, ticket, 0);
     uint64_t a, b, c, d;
     if (!queue_read_ticket(P, w.lane, ticket, a, b, c, d)) return false;     /* watchdog abort */
-    uint32_t idx = (w.top + w.lane) & Ring<RING>::kMask;
-    ring_store<RING>(w, idx, a, b, c, d);
-    w.top += kChunkNodes;
-    __syncwarp();
+    accept_chunk<RING>(w, a, b, c, d);
     return true;
 }
 
@@ -856,10 +865,9 @@ __device__ __forceinline__ void push_and_count(WarpCtx& w, const SimParams& P, u
  * the others go back as a retry node for the general iteration below.
  * FULL = all 32 lanes have a node: straight-line code.  Otherwise the lanes without a node skip the arithmetic, and every
  * warp collective is still executed by all 32 lanes with the full mask.
- * false (and nothing changed) = one of the popped nodes is a retry node - it reached the top through a spilled or donated
- * chunk -: the caller runs the general iteration on the same nodes. */
+ * The popped nodes are fresh by the ring's invariant (accept_chunk): nothing is checked here. */
 template <bool FULL, bool HASHED, bool PLAIN, int RING, int MODE>
-__device__ __forceinline__ bool divide_fresh(WarpCtx& w, const SimParams& P, const double* s_tab, uint32_t* s_hist,
+__device__ __forceinline__ void divide_fresh(WarpCtx& w, const SimParams& P, const double* s_tab, uint32_t* s_hist,
                                              const double2* musd, uint32_t take, unsigned lt_mask, bool multi_set,
                                              DivCount& dc, uint32_t hist_base)
 {
@@ -867,7 +875,6 @@ __device__ __forceinline__ bool divide_fresh(WarpCtx& w, const SimParams& P, con
     DivOut o;
     divout_clear(o);
     const bool mine = FULL || (uint32_t)w.lane < take;
-    uint32_t retry = 0;
     pcs_u32x4 blk;
     blk.x = 0; blk.y = 0; blk.z = 0; blk.w = 0;
     uint32_t set = 0;
@@ -877,14 +884,8 @@ __device__ __forceinline__ bool divide_fresh(WarpCtx& w, const SimParams& P, con
         ring_load<RING>(w, idx, a, o.heap, o.pc, d);
         o.t_div = pcs_bits2d(a);
         o.dlo = (uint32_t)d;
-        retry = (uint32_t)(d >> 32);
         set = PLAIN ? 0u : (o.dlo & 0xFFFFu);
         blk = pcs_draw_rk((uint32_t)o.pc, set, 0u, PCS_TAG_DIVISION, o.heap, P.rk);
-    }
-    /* one vote: are all popped nodes first draws with both daughters wanted?  (it also tells the compiler that the warp
-     * is converged, so the ballots behind it are plain VOTEs) */
-    if (!__all_sync(kFull, !mine || ((o.dlo >> 28) | (retry << 4)) == 3u)) return false;
-    if (mine) {
         const uint32_t type = (o.dlo >> 16) & 63u;
         const double2 ms = musd[set * P.n_types + type];          /* generic pointer: shared-memory copy or the HBM table */
         double z0, z1;
@@ -902,7 +903,6 @@ __device__ __forceinline__ bool divide_fresh(WarpCtx& w, const SimParams& P, con
     }
     else if (PLAIN) dc.cnt -= 1u;
     push_and_count<FULL, HASHED, PLAIN, RING, MODE>(w, P, s_hist, o, take, false, lt_mask, hist_base);
-    return true;
 }
 
 /* ---- DIVIDE iteration, the general one: any node - any retry number, either or both daughters wanted.  Each wanted
@@ -918,29 +918,50 @@ __device__ __forceinline__ void divide_general(WarpCtx& w, const SimParams& P, c
     constexpr uint32_t kMask = Ring<RING>::kMask;
     DivOut o;
     divout_clear(o);
-    if ((uint32_t)w.lane < take) {
+    const bool mine = (uint32_t)w.lane < take;
+    uint32_t retry = 0u, set = 0u, want = 0u;
+    double2 ms = make_double2(0.0, 0.0);
+    pcs_u32x4 blk;
+    blk.x = 0; blk.y = 0; blk.z = 0; blk.w = 0;
+    if (mine) {
         const uint32_t idx = (from_bottom ? w.bottom + (uint32_t)w.lane : w.top - 1u - (uint32_t)w.lane) & kMask;
         uint64_t a, d;
         ring_load<RING>(w, idx, a, o.heap, o.pc, d);
         o.t_div = pcs_bits2d(a);
         o.dlo = (uint32_t)d;
-        const uint32_t retry = (uint32_t)(d >> 32);
-        const uint32_t set = PLAIN ? 0u : (o.dlo & 0xFFFFu);
-        const uint32_t type = (o.dlo >> 16) & 63u;
-        const double2 ms = musd[set * P.n_types + type];
-        const bool want0 = (o.dlo & (1u << 28)) != 0u, want1 = (o.dlo & (2u << 28)) != 0u;
-        const bool forced = retry >= PCS_MAX_RETRY;            /* 255 redraws failed: the timer is the mean */
-        bool acc0 = false, acc1 = false;
-        double z0 = 0.0, z1 = 0.0;
-        if (!forced) {
-            const pcs_u32x4 blk = pcs_draw_rk((uint32_t)o.pc, set, retry, PCS_TAG_DIVISION, o.heap, P.rk);
-            const double* wedge = P.logtab + PCS_TAB_WEDGE;
-            if (want0) acc0 = pcs_zig_trial(blk, 0u, &z0, (uint32_t)o.pc, set, retry, o.heap, P.rk, s_tab, wedge);
-            if (want1) acc1 = pcs_zig_trial(blk, 1u, &z1, (uint32_t)o.pc, set, retry, o.heap, P.rk, s_tab, wedge);
+        retry = (uint32_t)(d >> 32);
+        set = PLAIN ? 0u : (o.dlo & 0xFFFFu);
+        ms = musd[set * P.n_types + ((o.dlo >> 16) & 63u)];
+        want = (o.dlo >> 28) & 3u;
+        blk = pcs_draw_rk((uint32_t)o.pc, set, retry, PCS_TAG_DIVISION, o.heap, P.rk);
+    }
+    const bool forced = retry >= PCS_MAX_RETRY;                /* 255 redraws failed: the timer is the mean */
+    /* The trials run in two passes of warp-uniform shape: pass 0 gives every lane's FIRST wanted daughter its trial (most
+     * retry nodes want one daughter only), pass 1 - skipped by the whole warp when no node wants both - the second one.
+     * Within a pass the slow part (second Philox block, wedge test or tail sampler) is entered by the lanes whose fast test
+     * failed, and skipped by the warp when there is none: a node that is here for a non-positive timer redraws with a
+     * fresh block and passes the fast test like any other. */
+    double zc[2] = { 0.0, 0.0 };
+    bool accc[2] = { false, false };
+#pragma unroll
+    for (uint32_t pass = 0; pass < 2u; ++pass) {
+        const bool act = mine && !forced && (pass == 0u ? want != 0u : want == 3u);
+        if (!__any_sync(kFull, act)) continue;
+        const uint32_t c = pass == 0u ? ((want & 1u) ? 0u : 1u) : 1u;            /* which daughter this lane tries now */
+        const uint32_t lo = c ? blk.z : blk.x, hi = c ? blk.w : blk.y;
+        double z;
+        bool acc = pcs_zig_fast(lo, hi, s_tab + PCS_TAB_ZIG, &z);
+        if (act && !acc) acc = pcs_zig_slow(hi, c, &z, (uint32_t)o.pc, set, retry, o.heap, P.rk, s_tab, P.logtab + PCS_TAB_WEDGE);
+        __syncwarp();
+        if (act) {
+            if (c) { zc[1] = z; accc[1] = acc; } else { zc[0] = z; accc[0] = acc; }
         }
-        const double tm0 = forced ? ms.x : pcs_timer(ms.x, ms.y, z0);
-        const double tm1 = forced ? ms.x : pcs_timer(ms.x, ms.y, z1);
-        const bool ok0 = want0 && (forced || (acc0 && tm0 > 0.0)), ok1 = want1 && (forced || (acc1 && tm1 > 0.0));
+    }
+    if (mine) {
+        const bool want0 = (want & 1u) != 0u, want1 = (want & 2u) != 0u;
+        const double tm0 = forced ? ms.x : pcs_timer(ms.x, ms.y, zc[0]);
+        const double tm1 = forced ? ms.x : pcs_timer(ms.x, ms.y, zc[1]);
+        const bool ok0 = want0 && (forced || (accc[0] && tm0 > 0.0)), ok1 = want1 && (forced || (accc[1] && tm1 > 0.0));
         classify_daughters(P, o, ok0, ok1, tm0, tm1);
         o.rej = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
         o.retry_next = retry + 1u;
@@ -1235,12 +1256,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         const uint32_t hist_base = SETDIRECT ? set_base : 0u;     /* changes only while this warp is parked in the rendezvous */
         /* PLAIN: one set and at most 64 types, so the (mean, sd) table is always the shared-memory copy (plain LDS) */
         const double2* musd = PLAIN ? s_musd_buf : s_musd;
-        if (mode == 0) {
-            if (!divide_fresh<true, HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, 32u, lt_mask, multi_set, dc, hist_base)) mode = 2;
-        } else if (mode == 1) {
-            if (!divide_fresh<false, HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc, hist_base)) mode = 2;
-        }
-        if (mode == 2) divide_general<HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, take, from_bottom, lt_mask, multi_set, dc, hist_base);
+        if (mode == 0) divide_fresh<true, HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, 32u, lt_mask, multi_set, dc, hist_base);
+        else if (mode == 1) divide_fresh<false, HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc, hist_base);
+        else divide_general<HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, take, from_bottom, lt_mask, multi_set, dc, hist_base);
 
         /* hunger probe, every 8th iteration (every 4th costs 1.8 % on config 2).  The CTA keeps a snapshot of "how many warps are starving", "how many
          * donated chunks are waiting" and "where is the seed cursor" in shared memory.  Every 64th iteration
