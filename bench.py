@@ -17,7 +17,7 @@ in HBM), so nothing is accumulated or overwritten inside the timed region.
   per_config  BASELINE configs 1..5 at full size (and the 1e5-cell config-2 shape the reference arm can follow), each with
               its own ms, divisions/s and roofline fraction - by divisions and by draws; at N > 1 each input is sharded over
               the ranks, by seed-cell units or - config 4 - by subtrees (strong scaling), and checked against rank 0's own run
-  roofline    instruction-issue roofline (FP64/INT-issue bound path, neither HBM nor tensor - DESIGN.md section 5):
+  roofline    instruction-issue / shared-memory roofline (neither HBM nor tensor bound - DESIGN.md section 5):
               achieved divisions/s over the RNG-only ceiling kernel measured in the same run, with the hardware-unit
               fractions of the committed ncu capture beside it; HBM figures for completeness
   cpu_baseline  the CPU oracle (oracle/, a port with the same Philox streams) on this box's host cores
@@ -599,11 +599,14 @@ def main():
         ms_sim = gpu_ms / (K * B)
         hw = hw_fractions()
         roofline = {"bound": "issue",
-                    "bound_detail": "FP64 + INT instruction issue; neither HBM nor tensor bound (DESIGN.md section 5)",
+                    "bound_detail": "instruction issue (0.77 of the issue slots) and shared-memory wavefronts (0.89 of the LSU data pipe) "
+                                    "together; neither HBM nor tensor bound (DESIGN.md section 5, roofline.hardware)",
                     "achieved": per_gpu / 1e9, "peak": ceiling / 1e9, "unit": "Gdivisions/s per GPU",
                     "frac": per_gpu / ceiling,
-                    "peak_source": "k_rng_ceiling measured live: one Philox4x32-10 block + Box-Muller pair + 2 timers per division, no "
-                                   "tree/atomics; the fastest of three shapes of that loop",
+                    "peak_source": "k_rng_ceiling measured live: the arithmetic of the common DIVIDE iteration alone - one Philox4x32-10 block, "
+                                   "two fast ziggurat tests, 2 timers, 2 time updates, the compares - with no tree, ring or atomics; "
+                                   "the fastest of three shapes of that loop.  The ceiling rose from 175 (Box-Muller, first half of "
+                                   "round 2) to ~250 G/s when the draw became a ziggurat: frac fell although the kernel got faster",
                     "peak_variants_Gdiv_s": ceiling_variants,
                     "traffic": None,
                     "hbm": {"achieved": alg_bytes / (ms_sim * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -672,7 +675,7 @@ def cli_wall_config1(synth, w):
 def run_per_config(api, synth, torch, dist, dev, local_rank, rank, world, stream, barrier, ceiling):
     """BASELINE configs 2..5 at full size, one record each: ms per simulation (CUDA events, max over ranks), divisions/s,
     fraction of the live RNG ceiling - by divisions, and by DRAWS (seed cells + divisions: every seed cell also costs a
-    Philox block and a Box-Muller timer, and configs 3 and 5 are seed-heavy).  N > 1 is STRONG scaling here: the one input
+    Philox block and a timer draw, and configs 3 and 5 are seed-heavy).  N > 1 is STRONG scaling here: the one input
     is sharded over the ranks - seed-cell units (configs 2, 3, 5; unit chosen by the library) or subtrees at tree level 6
     (config 4: a hundred fast lineages own all the work) - and rank 0 checks the reduced tensor against the same simulation
     unsharded on its own GPU."""

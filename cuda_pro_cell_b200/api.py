@@ -317,7 +317,7 @@ def simulate(values, freqs, types, t_max, phi=0.0, seed=0x5EED0000, track_ratio=
 
 
 def rng_ceiling(device: int = 0, iters: int = 2048):
-    """(ms, pairs): time of the RNG-only micro-kernel and the number of Philox+Box-Muller pairs it drew."""
+    """(ms, pairs): time of the RNG-only micro-kernel and the number of divisions' worth of draws (one Philox block + two fast ziggurat tests each) it made."""
     ms, pairs = C.c_double(), C.c_double()
     check(_lib.load().procell_rng_ceiling(int(device), int(iters), C.byref(ms), C.byref(pairs)))
     return ms.value, pairs.value

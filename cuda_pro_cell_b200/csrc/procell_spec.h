@@ -1,8 +1,8 @@
 /* procell_spec.h - the arithmetic specification of the B200 proliferation simulator.
  *
  * Everything that decides WHICH histogram comes out lives here: the Philox4x32-10 stream
- * layout, the bits->uniform maps, the fixed-operation-sequence FP64 log / sincos used by the
- * Box-Muller transform, and the node rule.  The sm_100a kernels (sim_kernels.cu) include this
+ * layout, the bits->uniform maps, the ziggurat sampler of the division timers, the fixed-operation-sequence
+ * FP64 log / sincos behind it and behind the seed cell's Box-Muller transform, and the node rule.  The sm_100a kernels (sim_kernels.cu) include this
  * header; the CPU oracle (oracle/procell_oracle.c) restates it independently in plain C.
  *
  * Replaces, in the reference (ericniso/cuda-pro-cell):
@@ -10,7 +10,7 @@
  *                                 a fresh curand_init per draw) -> counter-based Philox keyed by
  *                                 (root cell, tree path), one block per DIVISION (both daughters).
  *                                 The standard normal behind a division timer is drawn with the ziggurat
- *                                 method (Marsaglia & Tsang 2000; exact in law): 98.5 % of the draws are one
+ *                                 method (Marsaglia & Tsang 2000; exact in law): 99.2 % of the draws are one
  *                                 table row, one fma and one compare; the seed cell's first timer keeps the
  *                                 Box-Muller transform (the refcompat coupling of SURVEY Q1 is defined on it).
  *   src/simulation/cell.cu:106-143 determine_cell_timer / determine_cell_initial_t
@@ -89,7 +89,7 @@ PCS_HD uint64_t pcs_d2bits(double d)
 #define PCS_TAG_DIVISION 0u      /* one block per division: both daughters' timers */
 #define PCS_TAG_ZIGX 2u          /* extra uniforms of a ziggurat trial that left the fast path: wedge test, or attempt k of
                                     the tail sampler with tag 2 + k */
-#define PCS_ZIG_TAIL_TRIES 200u  /* tags 2 .. 201; the tail sampler accepts 93.5 % of its attempts */
+#define PCS_ZIG_TAIL_TRIES 200u  /* tags 2 .. 201; the tail sampler accepts 94 % of its attempts */
 #define PCS_TAG_SEED 1u          /* ONE block per seed cell and draw round: word x = type uniform, y = initial-age uniform,
                                     z = Box-Muller radius uniform and w = Box-Muller angle of its first timer (32-bit
                                     grade each - what cuRAND's float generators use; every division below the seed cell
@@ -192,8 +192,8 @@ PCS_HD double pcs_u32unit(uint32_t m)
     return PCS_FMA((double)m, 0x1p-32, 0x1p-33);    /* both constants have an all-zero low word: cheap immediates */
 }
 
-/* the math table every consumer passes as `tab`: 128 log rows {invc, logc}, then 256 sin/cos rows {sin, cos}, then 256
- * ziggurat rows {x_i, x_i+1} (the kernels keep these three in shared memory), then 256 wedge rows {f(x_i), f(x_i+1) - f(x_i)}
+/* the math table every consumer passes as `tab`: 128 log rows {invc, logc}, then 256 sin/cos rows {sin, cos}, then 512
+ * ziggurat rows {x_i, x_i+1} (the kernels keep these three in shared memory), then 512 wedge rows {f(x_i), f(x_i+1) - f(x_i)}
  * that only the rare wedge test reads (global memory on the device) */
 #define PCS_TAB_SINCOS (2 << PCM_LOG_N_BITS)
 #define PCS_TAB_ZIG (PCS_TAB_SINCOS + (2 << PCM_SC_N_BITS))
@@ -297,23 +297,26 @@ PCS_HD void pcs_normal_pair(pcs_u32x4 w, const double* tab, double u_override, d
 }
 
 /* ------------------------------------------------------------------ one standard normal by the ziggurat method
- * (Marsaglia & Tsang 2000) from 64 random bits (lo, hi): layer i = top 8 bits of hi, sign = the next bit, and the 52
- * bits (hi & 0xFFFFF):lo are the mantissa of d in [1, 2).  x = fma(d, x_i, -x_i) = (d - 1) * x_i rounded once.
- * FAST: x < x_{i+1}: the point lies under the curve whatever its height - accept (98.5 % of the draws).
+ * (Marsaglia & Tsang 2000; 512 layers) from 64 random bits (lo, hi): sign = the top bit of hi, layer i = the 9 bits below
+ * it, and the 53 bits M = (hi & 0x1FFFFF):lo the uniform M * 2^-53 in [0, 1).  x = M * 2^-53 * x_i, rounded once: the 64-bit
+ * word M IS the double M * 2^-1074 (exponent fields 0 and 1 both read that way), and the table holds x_i * 2^1021, so
+ * that is ONE multiplication and no integer-to-double conversion (FP64 subnormals run at full speed on the device).
+ * FAST: x < x_{i+1}: the point lies under the curve whatever its height - accept (99.2 % of the draws).
  * Otherwise the trial goes on in pcs_zig_slow with further uniforms from the blocks tagged PCS_TAG_ZIGX:
  *   layer 0 (x >= r): Marsaglia's tail sampler, a = -ln(U1)/r until -2 ln(U2) > a^2, x = r + a  (always accepts);
  *   layer i >= 1: the wedge - height y = f(x_i) + U (f(x_{i+1}) - f(x_i)), accept iff y < f(x), tested as
  *   -2 ln(y) > x^2 with the same fixed-sequence logarithm as everywhere else; a rejected trial is a rejected DRAW:
  *   the caller redraws with retry + 1 exactly as for a timer <= 0.
- * tab_zig: 256 rows {x_i, x_{i+1}} (shared memory on the device). */
+ * tab_zig: 512 rows {x_i * 2^1021, x_{i+1}} (shared memory on the device). */
+#define PCS_ZIG_LAYER(hi) (((hi) >> (31 - PCM_ZIG_N_BITS)) & ((1u << PCM_ZIG_N_BITS) - 1u))
 PCS_HD bool pcs_zig_fast(uint32_t lo, uint32_t hi, const double* tab_zig, double* z_out)
 {
-    const uint32_t i = hi >> (32 - PCM_ZIG_N_BITS);
-    const double xi = tab_zig[2 * i];
+    const uint32_t i = PCS_ZIG_LAYER(hi);
+    const double xs = tab_zig[2 * i];
     const double xn = tab_zig[2 * i + 1];
-    const double d = pcs_bits2d(((uint64_t)((hi & 0x000FFFFFu) | 0x3FF00000u) << 32) | (uint64_t)lo);
-    const double x = PCS_FMA(d, xi, -xi);
-    *z_out = pcs_bits2d(pcs_d2bits(x) ^ ((uint64_t)((hi << PCM_ZIG_N_BITS) & 0x80000000u) << 32));
+    const double m = pcs_bits2d(((uint64_t)(hi & 0x001FFFFFu) << 32) | (uint64_t)lo);     /* M * 2^-1074 */
+    const double x = PCS_MUL(m, xs);
+    *z_out = pcs_bits2d(pcs_d2bits(x) | ((uint64_t)(hi & 0x80000000u) << 32));
     return x < xn;
 }
 
@@ -322,7 +325,7 @@ PCS_HD bool pcs_zig_fast(uint32_t lo, uint32_t hi, const double* tab_zig, double
 PCS_HD bool pcs_zig_slow(uint32_t hi, uint32_t c, double* z_io, uint32_t root, uint32_t set, uint32_t retry, uint64_t heap,
                          const uint32_t* rk, const double* tab, const double* wedge)
 {
-    const uint32_t i = hi >> (32 - PCM_ZIG_N_BITS);
+    const uint32_t i = PCS_ZIG_LAYER(hi);
     const uint64_t sign = pcs_d2bits(*z_io) & 0x8000000000000000ULL;
     const double x = pcs_bits2d(pcs_d2bits(*z_io) & 0x7FFFFFFFFFFFFFFFULL);
     if (i != 0u) {
@@ -331,7 +334,7 @@ PCS_HD bool pcs_zig_slow(uint32_t hi, uint32_t c, double* z_io, uint32_t root, u
         const double y = PCS_FMA(uu, wedge[2 * i + 1], wedge[2 * i]);
         return pcs_neg2log(y, tab) > PCS_MUL(x, x);
     }
-    double a = 0.0;                                 /* should every attempt fail (probability 1e-237): x = r */
+    double a = 0.0;                                 /* should every attempt fail (probability 1e-240): x = r */
     for (uint32_t k = 0; k < PCS_ZIG_TAIL_TRIES; ++k) {
         const pcs_u32x4 e = pcs_draw_rk(root, set, retry, PCS_TAG_ZIGX + k, heap, rk);
         const double u1 = pcs_u32unit(c ? e.z : e.x);

@@ -10,8 +10,11 @@
  * k_proliferate_coop - persistent, one CTA per SM, 32 warps (16 / 24 as tuning shapes).  Each warp owns a 128-node
  *   ring in shared memory.  An iteration is warp-uniform: either SEED (32 lanes build 32 seed cells: bin, type,
  *   first timer, initial age; living roots are pushed) or DIVIDE (32 lanes pop the 32 newest = deepest nodes, each
- *   draws ONE Philox block -> one Box-Muller pair -> both daughters' timers, classifies the daughters as leaf /
- *   dropped / internal and pushes the internal ones with predicated 16-byte stores).  While a warp holds fewer than
+ *   draws ONE Philox block and makes the fast test of the ziggurat method for both daughters' normals - a table row, a
+ *   multiplication and a compare each -, classifies the daughters as leaf / dropped / internal and pushes the internal
+ *   ones with predicated 16-byte stores; a daughter whose draw needs more - the ziggurat's wedge or tail, a redraw after
+ *   a non-positive timer: 2-3 % of the divisions - goes to the BOTTOM of the ring as a retry node, and 32 of those are
+ *   expanded together by a general iteration).  While a warp holds fewer than
  *   32 nodes every node is expanded each iteration (the breadth-first warm-up); from 32 on, expansion is depth-first,
  *   and the ring overflows in 32-node chunks into a private spill ring in HBM.  Starving warps are fed through a
  *   bounded MPMC queue of chunks that busy warps fill from the BOTTOM of their stacks (the shallowest nodes = the
@@ -22,8 +25,7 @@
  *
  *   Two further compile-time modes of the same kernel: MODE 1 = subtree sharding for multi-GPU runs of deep trees,
  *   MODE 2 = sweeps with a direct table of the CTA's current parameter set and a CTA-wide rendezvous at batch switches
- *   (config 5: 70.4 -> 60.7 ms).  Both are bit-exact against the oracle on a B200 (profiles/r1i_*); the MODE 0
- *   instances are byte-identical to the build the round-1 measurements were made with.
+ *   (config 5: 70.4 -> 60.7 ms in round 1).  Every instance is bit-exact against the oracle on a B200 (tests/test_gpu_parity.py).
  *
  * k_proliferate_simple - one thread per lineage with a local-memory stack and global atomics: the bring-up
  *   kernel, kept as an independent device-side cross-check of the cooperative one.
@@ -178,7 +180,7 @@ constexpr bool coop_is_plain(const SimParams& p) { return p.n_sets == 1u && p.n_
 #endif
 constexpr int kEndgameIdle = PROCELL_ENDGAME_IDLE;
 #ifndef PROCELL_PROBE_MASK
-#define PROCELL_PROBE_MASK 7u
+#define PROCELL_PROBE_MASK 15u
 #endif
 constexpr uint32_t kProbeMask = PROCELL_PROBE_MASK;       /* busy warps look at the hunger snapshot every (mask + 1)-th iteration */
 #ifndef PROCELL_SNAP_MASK
@@ -807,7 +809,7 @@ __device__ __forceinline__ void credit_division(const SimParams& P, DivOut& o, u
 /* second half of a DIVIDE iteration: `take` nodes have been popped (from the top, or - BOTTOM - from the bottom of the
  * ring); push the daughters that will divide on top, the retry nodes at the BOTTOM, count the leaves.
  * Retry nodes - a daughter whose ziggurat trial left the fast path, or whose timer came out <= 0 (cell.cu:114-118) - are
- * rare (3 % of the divisions) and expensive (a second Philox block, a logarithm), so they are not expanded where they
+ * rare (2-3 % of the divisions) and expensive (a second Philox block, a logarithm), so they are not expanded where they
  * arise: they collect at the bottom of the ring (w.slow counts them) and are expanded 32 at a time by a general iteration
  * with every lane busy.  Results do not depend on when a node is expanded: the stream is keyed by (root, path, retry). */
 template <bool FULL, bool HASHED, bool PLAIN, int RING, int MODE>
@@ -1260,7 +1262,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         else if (mode == 1) divide_fresh<false, HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc, hist_base);
         else divide_general<HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, take, from_bottom, lt_mask, multi_set, dc, hist_base);
 
-        /* hunger probe, every 8th iteration (every 4th costs 1.8 % on config 2).  The CTA keeps a snapshot of "how many warps are starving", "how many
+        /* hunger probe, every 16th iteration (every 8th costs 1 %, every 4th 3 % on config 2).  The CTA keeps a snapshot of "how many warps are starving", "how many
          * donated chunks are waiting" and "where is the seed cursor" in shared memory.  Every 64th iteration
          * (staggered by warp) one lane refreshes it with three 16-byte cp.async.cg copies straight from the control
          * block in HBM/L2 into shared memory: no registers, no waiting, the values simply turn up a little later.

@@ -14,8 +14,8 @@ constexpr int kChunkNodes = 32;                /* spill / donation granule: one 
 constexpr int kChunkWords = 4 * kChunkNodes;   /* 4 x u64 fields per node, field-major */
 constexpr int kSpillCap = 128;                 /* private spill ring, chunks per warp */
 constexpr int kQueueCap = 8192;                /* shared donation queue, chunks (power of two) */
-constexpr int kLogTabDoubles = 1280;          /* math table in shared memory: 128 log rows {invc, logc} + 256 sin/cos rows + 256 ziggurat rows (procell_spec.h) */
-constexpr int kMathTabDoubles = 1792;         /* the table in HBM: the same, then 256 wedge rows that only the rare wedge test reads */
+constexpr int kLogTabDoubles = 1792;          /* math table in shared memory: 128 log rows {invc, logc} + 256 sin/cos rows + 512 ziggurat rows (procell_spec.h) */
+constexpr int kMathTabDoubles = 2816;         /* the table in HBM: the same, then 512 wedge rows that only the rare wedge test reads */
 constexpr int kSimpleThreads = 128;
 constexpr int kSimpleStack = 136;              /* >= 2*63 + slack entries per thread */
 
@@ -58,7 +58,7 @@ struct SimParams {
                                      with x <= type_thr[j]; the last type's slot and the padding hold 2^32 - 1 */
     const uint8_t* type_sel;      /* file id of the j-th type in selection order */
     const double2* type_musd;     /* (mean, sd) by file id */
-    const double* logtab;         /* the math table: 128 x {invc, logc}, 256 x {sin, cos}, 256 x {x_i, x_i+1}, 256 x wedge rows */
+    const double* logtab;         /* the math table: 128 x {invc, logc}, 256 x {sin, cos}, 512 x {x_i, x_i+1}, 512 x wedge rows */
     /* outputs */
     long long* counts;            /* [n_sets][n_keys][n_types] */
     long long* divisions;         /* [n_sets] */

@@ -202,7 +202,7 @@ int procell_engine_fitness(procell_engine* engine, void* stream, const int64_t* 
  * procell_engine_fitness call was served that way, 0 if it ran the separate kernel (PROCELL_FITNESS_FUSED=0 forces 0). */
 int procell_engine_fitness_in_launch(const procell_engine* engine);
 
-/* RNG-only micro-kernel: per thread `iters` Philox blocks + Box-Muller pairs + timers into a register
+/* RNG-only micro-kernel: per thread `iters` Philox blocks + two fast ziggurat tests + timers into a register
  * accumulator (the instruction-issue ceiling the roofline fraction is quoted against).  Returns ms. */
 int procell_rng_ceiling(int device, int iters, double* ms_out, double* pairs_out);
 /* The loop exists in three shapes (48 warps per SM; 64 warps per SM at 32 registers; two independent chains per thread):

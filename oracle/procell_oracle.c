@@ -316,10 +316,11 @@ typedef struct {
 
 /* ------------------------------------------------------------------------------------------------
  * Standard normal for a division timer: the ziggurat method (Marsaglia & Tsang, "The Ziggurat Method for Generating
- * Random Variables", J. Stat. Softw. 5(8), 2000 - the published algorithm, restated).  256 layers of equal area under
- * f(x) = exp(-x^2/2); zig_rows[i] = { x_i, x_(i+1) } with x_0 = V/f(r), x_1 = r, x_256 = 0.
- *   64 random bits (lo, hi): layer = hi >> 24, sign = bit 23 of hi, and 1.m with m = (hi & 0xFFFFF):lo a double in [1, 2).
- *   x = (1.m - 1) * x_layer (one fma).  x < x_(layer+1): under the curve for sure, accept.
+ * Random Variables", J. Stat. Softw. 5(8), 2000 - the published algorithm, restated).  512 layers of equal area under
+ * f(x) = exp(-x^2/2); zig_rows[i] = { x_i, x_(i+1) } with x_0 = V/f(r), x_1 = r, x_512 = 0.
+ *   64 random bits (lo, hi): sign = bit 31 of hi, layer = the 9 bits below it, and the 53-bit integer M = (hi & 0x1FFFFF):lo
+ *   gives the uniform M / 2^53.  x = (M / 2^53) * x_layer (one rounding).  x < x_(layer+1): under the curve for sure, accept.
+ *   (The table row holds x_layer * 2^1021 - the kernels multiply it with M read as a subnormal double - and is unscaled here.)
  *   layer 0 otherwise: the tail beyond r, by a = -ln(U1)/r until -2 ln(U2) > a^2, x = r + a.
  *   layer >= 1 otherwise: the wedge; y uniform between f(x_layer) and f(x_(layer+1)), accept iff y < f(x), i.e.
  *   -2 ln y > x^2.  A rejected trial counts as a rejected draw (the division redraws with the next retry number).
@@ -335,11 +336,12 @@ int oracle_zig_trial(const uint32_t words[4], unsigned c, uint32_t root, uint32_
                      uint64_t seed, double* z)
 {
     const uint32_t lo = words[2 * c], hi = words[2 * c + 1];
-    const unsigned layer = hi >> (32 - PCM_ZIG_N_BITS);
-    const int negative = (hi >> (31 - PCM_ZIG_N_BITS)) & 1;
-    const double one_to_two = as_f64(0x3FF0000000000000ull | ((uint64_t)(hi & 0xFFFFFu) << 32) | lo);
-    const double edge = as_f64(zig_rows[layer][0]);
-    double x = fma(one_to_two, edge, -edge);
+    const unsigned layer = (hi >> (31 - PCM_ZIG_N_BITS)) & ((1u << PCM_ZIG_N_BITS) - 1u);
+    const int negative = (int)(hi >> 31);
+    const uint64_t mant53 = ((uint64_t)(hi & 0x1FFFFFu) << 32) | lo;
+    const double uniform = ldexp((double)mant53, -53);             /* exact: 53 bits */
+    const double edge = ldexp(as_f64(zig_rows[layer][0]), -1021);   /* exact */
+    double x = uniform * edge;
     if (!(x < as_f64(zig_rows[layer][1]))) {
         uint32_t e[4];
         if (layer == 0) {

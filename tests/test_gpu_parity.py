@@ -430,14 +430,14 @@ def test_config5_full_size_bit_exact_on_the_set_relative_instance(gpu_api, oracl
     """BASELINE config 5 at FULL size: 1024 parameter sets x 1e6 cells in ONE launch (3.8e9 divisions).  At this size
     procell_engine_load selects the sweep instance with the set-relative direct table (kernel MODE 2) by itself - no
     environment knob - and that is asserted from the launch's shared-memory size: math table + control words + 32 rings
-    (coop_smem_bytes with 0 slots = 143 040 B) plus ONE set's keys x types x 4 B, not the hashed cache's power of two."""
+    (coop_smem_bytes with 0 slots = 147 136 B) plus ONE set's keys x types x 4 B, not the hashed cache's power of two."""
     w = synth.workload(5)
     assert w.types.shape[0] == 1024 and w.n_cells == 1_000_000
     plan = gpu_api.Plan(w.values, w.freqs, w.phi)
     oplan = oracle.OraclePlan(w.values, w.freqs, w.phi)
     got = gpu_api.proliferate(plan, w.types, w.t_max, w.seed)
     n_types = w.types.shape[1]
-    assert got.stats["smem_bytes"] == 143040 + plan.n_keys * n_types * 4, "the set-relative instance was not selected"
+    assert got.stats["smem_bytes"] == 147136 + plan.n_keys * n_types * 4, "the set-relative instance was not selected"
     want = oracle.simulate(oplan, w.types, w.t_max, w.seed)
     assert np.array_equal(got.divisions, want["divisions"])
     assert np.array_equal(got.counts, want["counts"])
@@ -662,7 +662,7 @@ def test_periodic_drain_of_the_set_relative_table(gpu_api, oracle, tmp_path):
         "plan = api.Plan(v, f, 0.5)\n"
         "types = np.array(%r)\n"
         "r = api.proliferate(plan, types, 240.0, 11)\n"
-        "assert r.stats['smem_bytes'] == 143040 + 4 * plan.n_keys * 4, 'the set-relative instance was not selected'\n"
+        "assert r.stats['smem_bytes'] == 147136 + 4 * plan.n_keys * 4, 'the set-relative instance was not selected'\n"
         "np.savez(%r, counts=r.counts, divisions=r.divisions)\n" % (str(root), types.tolist(), str(out)))
     env = dict(os.environ, PROCELL_LIB=lib.name, PROCELL_SWEEP_DIRECT="1", PROCELL_WATCHDOG_S="30")
     subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=150)

@@ -1,6 +1,8 @@
 """The arithmetic header the kernels include (cuda_pro_cell_b200/csrc/procell_spec.h), built for the HOST by a
 test-only shim, must agree bit-for-bit with the oracle's independent restatement.  Catches a spec typo without a GPU."""
 import ctypes as C
+import re
+import struct
 import subprocess
 from pathlib import Path
 
@@ -8,6 +10,10 @@ import numpy as np
 import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
+_INC = (ROOT / "cuda_pro_cell_b200" / "csrc" / "procell_math_tables.inc").read_text()
+ZIG_BITS = int(re.search(r"#define PCM_ZIG_N_BITS\s+(\d+)", _INC).group(1))        # layers of the ziggurat = 2^ZIG_BITS
+ZIG_N = 1 << ZIG_BITS
+ZIG_R = struct.unpack("<d", struct.pack("<Q", int(re.search(r"#define PCM_BITS_ZIG_R\s+0x([0-9A-F]+)ULL", _INC).group(1), 16)))[0]
 
 
 @pytest.fixture(scope="module")
@@ -97,7 +103,7 @@ def test_header_equals_oracle_bitwise(shim, oracle):
 
 def test_ziggurat_trials_equal_the_oracle_bitwise(shim, oracle):
     """Division timers: the header's ziggurat trial (fast test, wedge test, tail sampler) against the oracle's independent
-    restatement, bit for bit - on random blocks (98.5 % fast), on blocks forced onto the edge of a layer (wedge tests,
+    restatement, bit for bit - on random blocks (99 % fast), on blocks forced onto the edge of a layer (wedge tests,
     both outcomes), on the base strip beyond r (the tail sampler) and on the top layer (always a wedge test)."""
     rng = np.random.default_rng(9)
     seen = {"fast": 0, "wedge_acc": 0, "wedge_rej": 0, "tail": 0}
@@ -111,13 +117,13 @@ def test_ziggurat_trials_equal_the_oracle_bitwise(shim, oracle):
             assert z.value == want and np.isfinite(want)
         zf = C.c_double(0.0)
         fast = shim.shim_zig_fast(w[2 * c], w[2 * c + 1], C.byref(zf))
-        layer = w[2 * c + 1] >> 24
+        layer = (w[2 * c + 1] >> (31 - ZIG_BITS)) & (ZIG_N - 1)
         if fast:
             assert ok and zf.value == want
             seen["fast"] += 1
         elif layer == 0:
-            assert ok and abs(want) >= 3.6541528853610088          # the tail sampler always accepts, beyond r
-            assert (want < 0) == bool((w[2 * c + 1] >> 23) & 1)
+            assert ok and abs(want) >= ZIG_R          # the tail sampler always accepts, beyond r
+            assert (want < 0) == bool(w[2 * c + 1] >> 31)
             seen["tail"] += 1
         else:
             if ok:
@@ -131,9 +137,9 @@ def test_ziggurat_trials_equal_the_oracle_bitwise(shim, oracle):
     for _ in range(20000):          # mantissa close to 1: the point is near the outer edge of its layer
         w = [int(x) for x in rng.integers(0, 2**32, 4)]
         c = int(rng.integers(0, 2))
-        layer = int(rng.choice([0, 0, 1, 2, 127, 254, 255, int(rng.integers(0, 256))]))
-        frac = 0xFFFFF - int(rng.integers(0, 0x30000))
-        w[2 * c + 1] = (layer << 24) | (int(rng.integers(0, 2)) << 23) | (int(rng.integers(0, 8)) << 20) | frac
+        layer = int(rng.choice([0, 0, 1, 2, ZIG_N // 2 - 1, ZIG_N - 2, ZIG_N - 1, int(rng.integers(0, ZIG_N))]))
+        frac = 0x1FFFFF - int(rng.integers(0, 0x60000))
+        w[2 * c + 1] = (int(rng.integers(0, 2)) << 31) | (layer << (31 - ZIG_BITS)) | (int(rng.integers(0, 1 << (10 - ZIG_BITS))) << 21) | frac
         check(w, c, int(rng.integers(0, 2**32)), int(rng.integers(0, 65536)), int(rng.integers(0, 255)),
               int(rng.integers(1, 2**62)), int(rng.integers(0, 2**63)))
     assert seen["fast"] > 19000 and seen["wedge_acc"] > 1000 and seen["wedge_rej"] > 1000 and seen["tail"] > 1000, seen

@@ -5,7 +5,7 @@
 
 Extracts the sm_100a cubin (cuobjdump -xelf), disassembles it with inlining information (nvdisasm -gi) and counts
 SASS instructions per source line.  `--by outer` attributes every instruction to the line of the KERNEL body it
-was inlined into (so "Philox + Box-Muller of the DIVIDE iteration" is one row), `--by inner` to the innermost
+was inlined into (so "Philox + ziggurat of the DIVIDE iteration" is one row), `--by inner` to the innermost
 line, `--by chain` to the whole inline chain.  The kernels of this repo are issue-bound, so
 instruction counts of the straight-line DIVIDE / SEED iterations are the first-order cost model used when tuning
 without a GPU at hand."""
