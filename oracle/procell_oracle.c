@@ -339,8 +339,8 @@ int oracle_zig_trial(const uint32_t words[4], unsigned c, uint32_t root, uint32_
     const unsigned layer = (hi >> (31 - PCM_ZIG_N_BITS)) & ((1u << PCM_ZIG_N_BITS) - 1u);
     const int negative = (int)(hi >> 31);
     const uint64_t mant53 = ((uint64_t)(hi & 0x1FFFFFu) << 32) | lo;
-    const double uniform = ldexp((double)mant53, -53);             /* exact: 53 bits */
-    const double edge = ldexp(as_f64(zig_rows[layer][0]), -1021);   /* exact */
+    const double uniform = (double)mant53 * 0x1p-53;               /* exact: 53 bits, a power of two */
+    const double edge = as_f64(zig_rows[layer][0]) * 0x1p-1021;     /* exact: undoes the table's scaling */
     double x = uniform * edge;
     if (!(x < as_f64(zig_rows[layer][1]))) {
         uint32_t e[4];

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Hardware-unit fractions of profiled launches, as JSON for bench.py's `roofline.hardware`.
 
-  python tools/hw_fractions.py OUT.json NAME=REPORT.ncu-rep[:divisions[:draws]] ...
+  python tools/hw_fractions.py OUT.json NAME=REPORT.ncu-rep[#k][:divisions[:draws]] ...
 
 Every REPORT is one kernel launch captured with `ncu --set full --clock-control none`.  Per launch: duration, executed
 warp instructions, issue-slot fraction (instructions / SMSP cycles elapsed: one issue slot per SMSP and cycle), FP64 /
@@ -16,9 +16,14 @@ import sys
 
 
 def raw(rep):
+    """REPORT or REPORT#k: the k-th profiled launch of a report that holds several (0 = first)"""
+    k = 0
+    if "#" in rep:
+        rep, k = rep.rsplit("#", 1)
+        k = int(k)
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units, vals = rows[0], rows[1], rows[2 + k]
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}
     m = {}
     for h, u, v in zip(hdr, units, vals):
@@ -26,7 +31,7 @@ def raw(rep):
             m[h] = float(v.replace(",", "")) * (scale.get(u, 1.0) if (h.startswith("dram__bytes") or h == "gpu__time_duration.sum") else 1.0)
         except ValueError:
             pass
-    m["__kernel"] = rows[2][hdr.index("Kernel Name")] if "Kernel Name" in hdr else ""
+    m["__kernel"] = rows[2 + k][hdr.index("Kernel Name")] if "Kernel Name" in hdr else ""
     return m
 
 
