@@ -90,11 +90,13 @@ PCS_HD uint64_t pcs_d2bits(double d)
 #define PCS_TAG_ZIGX 2u          /* extra uniforms of a ziggurat trial that left the fast path: wedge test, or attempt k of
                                     the tail sampler with tag 2 + k */
 #define PCS_ZIG_TAIL_TRIES 200u  /* tags 2 .. 201; the tail sampler accepts 94 % of its attempts */
-#define PCS_TAG_SEED 1u          /* ONE block per seed cell and draw round: word x = type uniform, y = initial-age uniform,
-                                    z = Box-Muller radius uniform and w = Box-Muller angle of its first timer (32-bit
-                                    grade each - what cuRAND's float generators use; every division below the seed cell
-                                    draws at 52 / 60 bits).  A rejected first timer (<= 0) is redrawn from words z, w of
-                                    the block with retry + 1; x and y are taken from round 0 only. */
+#define PCS_TAG_SEED 1u          /* ONE block per seed cell and draw round: word x = type uniform, y = initial-age uniform
+                                    (32-bit grade each - what cuRAND's float generators use), words z, w = the normal of
+                                    its first timer: ideal seeding makes one ziggurat trial on the 64 bits, as daughter 1
+                                    of a division at tree path 0 would (extra uniforms: blocks tagged 2.. of (root, path 0,
+                                    retry)); refcompat seeding a Box-Muller draw with z the radius uniform and w the angle.
+                                    A rejected first timer (trial rejected, or <= 0) is redrawn from words z, w of the
+                                    block with retry + 1; x and y are taken from round 0 only. */
 
 /* ------------------------------------------------------------------ Philox4x32-10 (Salmon et al., SC'11) */
 #define PCS_PHILOX_M0 0xD2511F53u

@@ -341,7 +341,10 @@ __device__ __forceinline__ bool setdirect_rendezvous(const SimParams& P, volatil
 }
 
 struct WarpCtx {
-    ulonglong2* ab;                  /* ring: kCap (t_div bits, heap) pairs followed by kCap (root|keybase<<32, D) pairs */
+    uint32_t ab;                     /* ring: shared-memory address of kCap (t_div bits, heap) pairs followed by kCap
+                                        (root|keybase<<32, D) pairs.  The ring starts on a 2 KB boundary of the shared-memory
+                                        window, so the address of slot idx is ab | ((idx << 4) & 0x7F0): a shift and ONE
+                                        logic instruction, no add (the kernel checks the alignment when it starts) */
     uint32_t bottom, top;            /* ring positions, n = top - bottom */
     uint32_t slow;                   /* the bottom-most `slow` nodes of the ring are retry nodes awaiting a general iteration */
     uint32_t sp;                     /* private spill ring in HBM, packed into one register: oldest chunk's position in the low
@@ -364,15 +367,17 @@ __device__ __forceinline__ uint32_t ring_nodes(const WarpCtx& w)
 template <int RING>
 __device__ __forceinline__ void ring_load(const WarpCtx& w, uint32_t idx, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d)
 {
-    const ulonglong2 x = w.ab[idx], y = w.ab[Ring<RING>::kCap + idx];    /* the second half: a constant offset */
-    a = x.x; b = x.y; c = y.x; d = y.y;
+    const unsigned sab = w.ab | ((idx << 4) & (Ring<RING>::kMask << 4));
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%4];\n\tld.shared.v2.u64 {%2, %3}, [%4+%5];"
+                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "r"(sab), "n"(Ring<RING>::kCap * 16u) : "memory");
 }
 
 template <int RING>
 __device__ __forceinline__ void ring_store(WarpCtx& w, uint32_t idx, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
 {
-    w.ab[idx] = make_ulonglong2(a, b);
-    w.ab[Ring<RING>::kCap + idx] = make_ulonglong2(c, d);
+    const unsigned sab = w.ab | ((idx << 4) & (Ring<RING>::kMask << 4));
+    asm volatile("st.shared.v2.u64 [%0], {%1, %2};\n\tst.shared.v2.u64 [%0+%5], {%3, %4};"
+                 :: "r"(sab), "l"(a), "l"(b), "l"(c), "l"(d), "n"(Ring<RING>::kCap * 16u) : "memory");
 }
 
 /* the same under a predicate, as two predicated STS.128 instead of a branch around four stores */
@@ -382,7 +387,7 @@ __device__ __forceinline__ void ring_store_if(WarpCtx& w, bool p, uint32_t idx, 
 #ifdef PROCELL_BRANCHY_PUSH
     if (p) ring_store<RING>(w, idx, a, b, c, d);
 #else
-    const unsigned sab = (unsigned)__cvta_generic_to_shared(w.ab + idx);
+    const unsigned sab = w.ab | ((idx << 4) & (Ring<RING>::kMask << 4));
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.v2.u64 [%1], {%2, %3};\n\t@q st.shared.v2.u64 [%1+%6], {%4, %5};\n\t}"
                  :: "r"((unsigned)p), "r"(sab), "l"(a), "l"(b), "l"(c), "l"(d), "n"(Ring<RING>::kCap * 16u) : "memory");
 #endif
@@ -725,8 +730,15 @@ __device__ __forceinline__ SeedOut build_seed(const SimParams& P, const double* 
     }
     double timer = ms.x;                                       /* the mean, should 255 draws in a row be rejected */
     for (uint32_t retry = 0;;) {                               /* first timer from words z, w of the same block (cell.cu:106-122) */
-        const double cand = pcs_timer(ms.x, ms.y, pcs_seed_normal(w, s_log, (P.refcompat && retry == 0u) ? pcs_u32unit(w.x) : 0.0));
-        if (cand > 0.0) { timer = cand; break; }
+        /* ideal seeding: one ziggurat trial on the 64 bits (z, w), as for daughter 1 of a division at heap 0 (extra uniforms
+         * from the blocks tagged 2.. of (root, heap 0, retry)); refcompat seeding: the Box-Muller draw whose radius uniform
+         * is the type uniform - the coupling is defined on that transform */
+        double zn;
+        bool acc = true;
+        if (P.refcompat) zn = pcs_seed_normal(w, s_log, retry == 0u ? pcs_u32unit(w.x) : 0.0);
+        else acc = pcs_zig_trial(w, 1u, &zn, root, set, retry, 0ull, P.rk, s_log, P.logtab + PCS_TAB_WEDGE);
+        const double cand = pcs_timer(ms.x, ms.y, zn);
+        if (acc && cand > 0.0) { timer = cand; break; }
         if (++retry == PCS_MAX_RETRY) break;
         w = pcs_draw_rk(root, set, retry, PCS_TAG_SEED, 0ull, P.rk);   /* rejected: words z, w of the next round's block */
     }
@@ -821,8 +833,9 @@ __device__ __forceinline__ void push_and_count(WarpCtx& w, const SimParams& P, u
     const uint32_t KS = (PLAIN && !HASHED) ? P.kstride : P.n_types;
     /* all popped nodes have been read: every lane's loads have returned before it votes below (the predicates depend
      * on the loaded values of the node it popped) and no lane stores before all have voted on everything, so the
-     * slots may be overwritten.  The partial iteration is divergent above, so it states the ordering explicitly as well. */
-    if (!FULL) __syncwarp();
+     * slots may be overwritten.  The barrier states that ordering formally (racecheck reports the pops and pushes of one
+     * iteration as a hazard without it); on a converged warp it is one WARPSYNC. */
+    __syncwarp();
     if (from_bottom) { w.bottom += take; w.slow -= take; } else w.top -= take;
     const unsigned b0 = __ballot_sync(kFull, o.int0);
     const unsigned b1 = __ballot_sync(kFull, o.int1);
@@ -988,15 +1001,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     constexpr uint32_t kCap = Ring<RING>::kCap, kMask = Ring<RING>::kMask;
     constexpr bool SLOT = PLAIN && !HASHED;      /* the u32 table is laid out by slots (SimParams::slot_mode is set) */
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_log = reinterpret_cast<double*>(smem_raw);
-    volatile int* s_ctl = reinterpret_cast<volatile int*>(smem_raw + kLogTabDoubles * 8);   /* [0] poll lock, [1] quiescent */
-    uint64_t* s_stack = reinterpret_cast<uint64_t*>(smem_raw + kLogTabDoubles * 8 + kSmemCtlBytes);
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + kLogTabDoubles * 8 + kSmemCtlBytes + (size_t)WARPS * 4 * kCap * 8);
+    /* layout: (mean, sd) table 1 KB | rings | math tables | control words + threshold / epoch / selection tables | count table.
+     * Dynamic shared memory starts 1 KB into the shared-memory window on sm_100, so the rings start on a 2 KB boundary and
+     * a ring slot's address is one OR (WarpCtx::ab); nothing is padded.  Checked below: a different window offset traps. */
+    constexpr size_t kRingsOff = (size_t)kSmemMusdEntries * 16, kRingsBytes = (size_t)WARPS * 4 * kCap * 8;
+    constexpr size_t kTabOff = kRingsOff + kRingsBytes, kCtlOff = kTabOff + (size_t)kLogTabDoubles * 8;
+    static_assert(kSmemMusdEntries * 16 == 1024, "the (mean, sd) table is the 1 KB in front of the rings");
+    double* s_log = reinterpret_cast<double*>(smem_raw + kTabOff);
+    volatile int* s_ctl = reinterpret_cast<volatile int*>(smem_raw + kCtlOff);   /* [0] poll lock, [1] quiescent */
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + kCtlOff + (kSmemCtlBytes - kSmemMusdEntries * 16));
 
-    double2* s_musd_buf = reinterpret_cast<double2*>(smem_raw + kLogTabDoubles * 8 + 128);
+    double2* s_musd_buf = reinterpret_cast<double2*>(smem_raw);
     const bool musd_cached = P.n_sets * P.n_types <= (uint32_t)kSmemMusdEntries;
-    uint32_t* s_thr_buf = reinterpret_cast<uint32_t*>(smem_raw + kLogTabDoubles * 8 + 128 + kSmemMusdEntries * 16);
-    uint8_t* s_sel_buf = reinterpret_cast<uint8_t*>(smem_raw + kLogTabDoubles * 8 + 128 + kSmemMusdEntries * 24);
+    uint32_t* s_thr_buf = reinterpret_cast<uint32_t*>(smem_raw + kCtlOff + 128);
+    uint8_t* s_sel_buf = reinterpret_cast<uint8_t*>(smem_raw + kCtlOff + 128 + kSmemMusdEntries * 8);
     const uint32_t t_pad = (P.n_types + 3u) & ~3u;       /* row length of the threshold table */
     const bool thr_cached = musd_cached && P.n_sets * t_pad <= (uint32_t)kSmemMusdEntries;
     if (musd_cached && threadIdx.x < P.n_sets * P.n_types) {
@@ -1023,7 +1041,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     ControlBlock* ctl = P.ctl;
 
     WarpCtx w;
-    w.ab = reinterpret_cast<ulonglong2*>(s_stack + (size_t)warp * 4 * kCap);
+    w.ab = (uint32_t)__cvta_generic_to_shared(smem_raw + kRingsOff) + (uint32_t)warp * (4u * kCap * 8u);
+    if ((w.ab & (kCap * 16u - 1u)) != 0u) __trap();          /* the ring is not on a 2 KB boundary: ring_load's OR would be wrong */
     w.bottom = 0; w.top = 0; w.slow = 0;
     w.sp = 0;
     w.lane = lane;

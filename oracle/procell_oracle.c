@@ -413,8 +413,9 @@ static void expand_root(orc_ctx* cx, uint32_t root, unsigned bin)
 {
     const oracle_plan* p = cx->plan;
     /* seed cell: cells_population.cu:108-111 -> cell.cu:25-79 with type == -1, t == 0.
-     * ONE Philox block per seed cell (tag 1, heap 0): word 0 -> type uniform, word 1 -> initial-age uniform, word 2 ->
-     * radius uniform and word 3 -> angle of the first timer's Box-Muller draw, 32 bits each */
+     * ONE Philox block per seed cell (tag 1, heap 0): word 0 -> type uniform, word 1 -> initial-age uniform (32 bits each),
+     * words 2, 3 -> the first timer's normal: 64 bits for a ziggurat trial (ideal seeding), or radius uniform and angle of a
+     * Box-Muller draw at 32 bits each (refcompat seeding) */
     uint32_t w[4];
     draw_block(root, cx->set, 0u, 1u, 0ull, cx->seed, w);
     double u_type = oracle_uniform32(w[0]);
@@ -435,15 +436,22 @@ static void expand_root(orc_ctx* cx, uint32_t root, unsigned bin)
     }
     double timer[2];
     /* first timer: truncated normal by redraw (cell.cu:106-122).  Round 0 takes words 2, 3 of the seed block itself;
-     * a rejected draw (<= 0) takes words 2, 3 of the block with the next retry number; after 255 rejections the mean.
-     * refcompat: round 0's radius uniform IS the type uniform.  The cosine component is the seed cell's. */
+     * a rejected draw (trial rejected, or timer <= 0) takes words 2, 3 of the block with the next retry number; after 255
+     * rejections the mean. */
     timer[1] = ty->mean;
     for (uint32_t retry = 0; retry < ORC_MAX_RETRY; ++retry) {
         if (retry > 0) draw_block(root, cx->set, retry, 1u, 0ull, cx->seed, w);
-        double u_rad = (cx->refcompat && retry == 0) ? u_type : oracle_uniform32(w[2]);
-        double sn, cs;
-        oracle_sincos2pi((uint64_t)w[3] << 32, &sn, &cs);
-        double z = sqrt(oracle_neg2log(u_rad)) * cs;
+        double z;
+        if (cx->refcompat) {
+            /* the reference's coupling is defined on a Box-Muller draw: round 0's radius uniform IS the type uniform */
+            double u_rad = retry == 0 ? u_type : oracle_uniform32(w[2]);
+            double sn, cs;
+            oracle_sincos2pi((uint64_t)w[3] << 32, &sn, &cs);
+            z = sqrt(oracle_neg2log(u_rad)) * cs;
+        } else {
+            /* ideal seeding: one ziggurat trial on words 2, 3, exactly as daughter 1 of a division at tree path 0 would make it */
+            if (!oracle_zig_trial(w, 1u, root, cx->set, retry, 0ull, cx->seed, &z)) continue;
+        }
         double cand = fma(ty->sd, z, ty->mean);
         if (cand > 0.0) { timer[1] = cand; break; }
     }
