@@ -60,10 +60,52 @@ constexpr int kSmemMusdEntries = 64;  /* (mean, sd) table cached in shared memor
  * (mean, sd) 16 B, type threshold 4 B (+ 4 B: the per-warp donation epochs live in that half) and selection order 1 B per entry */
 constexpr int kSmemCtlBytes = 128 + kSmemMusdEntries * (16 + 8 + 1);
 constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr uint32_t kDynSmemWindow = 0x400u;      /* where dynamic shared memory starts in the shared-memory window on sm_100 */
 /* kernel MODE: 0 = the kernel as measured in round 1; 1 = subtree sharding compiled in (multi-GPU runs of deep trees);
  * 2 = sweeps with a set-relative direct histogram table and a CTA-wide rendezvous at batch switches */
 constexpr int kModeBase = 0, kModeSubtree = 1, kModeSetDirect = 2;
 
+/* Shared memory of k_proliferate_coop: (mean, sd) table 1 KB | rings | math tables | control words + threshold / epoch /
+ * selection tables | count table.  The *Addr members are addresses in the shared-memory WINDOW (what ld.shared takes):
+ * compile-time constants, so the table accesses of the hot loop are `LDS [register + immediate]` - see the window check at
+ * the top of the kernel. */
+template <int WARPS, int RING> struct SmemLayout {
+    static constexpr uint32_t kRingsOff = (uint32_t)kSmemMusdEntries * 16u;
+    static constexpr uint32_t kRingsBytes = (uint32_t)WARPS * 4u * Ring<RING>::kCap * 8u;
+    static constexpr uint32_t kTabOff = kRingsOff + kRingsBytes;
+    static constexpr uint32_t kCtlOff = kTabOff + (uint32_t)kLogTabDoubles * 8u;
+    static constexpr uint32_t kMusdAddr = kDynSmemWindow;
+    static constexpr uint32_t kZigAddr = kDynSmemWindow + kTabOff + (uint32_t)PCS_TAB_ZIG * 8u;
+};
+
+/* pcs_zig_fast (procell_spec.h) with the table row read from the shared-memory window address ZIG_ADDR + 16 * layer (the
+ * asm keeps the row offset a register and the table base an immediate of the load), and with the sign put on the
+ * multiplicand instead of OR-ed onto the product: (-M) * xs = -(M * xs) bit for bit (round-to-nearest is symmetric, a signed
+ * zero included), so *z_out is the same double as pcs_zig_fast's, the test is |x| < x_next, and the draw's high word is not
+ * needed again after the multiplication (tests: every GPU parity test compares against the oracle's pcs_zig_fast). */
+template <uint32_t ZIG_ADDR>
+__device__ __forceinline__ bool zig_fast_smem(uint32_t lo, uint32_t hi, double* z_out)
+{
+    static_assert(31 - PCM_ZIG_N_BITS >= 4, "layer field sits high enough to become a byte offset by one shift");
+    const uint32_t off = (hi >> (31 - PCM_ZIG_N_BITS - 4)) & (((1u << PCM_ZIG_N_BITS) - 1u) << 4);      /* 16 * PCS_ZIG_LAYER(hi) */
+    double xs, xn;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(xs), "=d"(xn) : "r"(off), "n"(ZIG_ADDR));
+    const double m = pcs_bits2d(((uint64_t)(hi & 0x801FFFFFu) << 32) | (uint64_t)lo);     /* +-M * 2^-1074 */
+    const double x = PCS_MUL(m, xs);
+    *z_out = x;
+    return fabs(x) < xn;
+}
+
+/* (mean, sd) of type `type` of the ONE parameter set of a PLAIN instance, from the table at the start of shared memory;
+ * dlo = the node's D word (type in bits 16..21) */
+template <uint32_t MUSD_ADDR>
+__device__ __forceinline__ double2 musd_smem(uint32_t dlo)
+{
+    const uint32_t off = (dlo >> 12) & (63u << 4);
+    double2 ms;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(ms.x), "=d"(ms.y) : "r"(off), "n"(MUSD_ADDR));
+    return ms;
+}
 /* A node = a cell that WILL divide: 4 x u64, kept in the ring as two 16-byte pairs (A,B) and (C,D) so that a pop is
  * two LDS.128 and a push two STS.128; chunks in HBM (spill rings, donation queue) are field-major
  *   A  t_div   time of its division = birth time of its daughters (double bits)
@@ -274,7 +316,14 @@ __device__ __forceinline__ void warp_count_leaves(const SimParams& P, uint32_t* 
 }
 
 /* watchdog: record where this warp is and abort the launch */
-__device__ __noinline__ void watchdog_fire(const SimParams& P, uint32_t gwarp, int lane, unsigned long long code,
+/* inlined at its five (cold) call sites: as a real call its argument registers - P.ctl, P.dbg, a zero - were set up at the
+ * head of the main loop, five instructions in EVERY iteration */
+#ifdef PROCELL_WD_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+void watchdog_fire(const SimParams& P, uint32_t gwarp, int lane, unsigned long long code,
                                            unsigned long long a, unsigned long long b, unsigned long long c,
                                            unsigned long long d, unsigned long long e, unsigned long long f)
 {
@@ -391,6 +440,50 @@ __device__ __forceinline__ void ring_store_if(WarpCtx& w, bool p, uint32_t idx, 
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.v2.u64 [%1], {%2, %3};\n\t@q st.shared.v2.u64 [%1+%6], {%4, %5};\n\t}"
                  :: "r"((unsigned)p), "r"(sab), "l"(a), "l"(b), "l"(c), "l"(d), "n"(Ring<RING>::kCap * 16u) : "memory");
 #endif
+}
+
+/* A pop as the DIVIDE iterations want it: the (C, D) pair as four 32-bit words - root, key, D's low word, retry number -
+ * so that nothing downstream masks or shifts a 64-bit register pair (the compiler otherwise multiplies Philox's first
+ * round as a 64 x 64-bit product of a masked pair and adds a 64-bit constant to C to step the key). */
+template <int RING>
+__device__ __forceinline__ void ring_load_node(const WarpCtx& w, uint32_t idx, uint64_t& a, uint64_t& heap, uint32_t& root,
+                                               uint32_t& key, uint32_t& dlo, uint32_t& retry)
+{
+    const unsigned sab = w.ab | ((idx << 4) & (Ring<RING>::kMask << 4));
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%6];\n\tld.shared.v4.u32 {%2, %3, %4, %5}, [%6+%7];"
+                 : "=l"(a), "=l"(heap), "=r"(root), "=r"(key), "=r"(dlo), "=r"(retry) : "r"(sab), "n"(Ring<RING>::kCap * 16u) : "memory");
+}
+
+/* the two pushes of a DIVIDE iteration, each under its predicate, in ONE statement: daughter c goes to slot idx_c as
+ * (t_div bits, heap) and (root, key, D's low word, D's high word); the second pair is the same four registers for both
+ * daughters, so the compiler builds it once (as two statements it built it twice). */
+template <int RING>
+__device__ __forceinline__ void ring_store_daughters_if(WarpCtx& w, bool p0, uint32_t idx0, uint64_t a0, uint64_t heap0,
+                                                        bool p1, uint32_t idx1, uint64_t a1, uint64_t heap1,
+                                                        uint32_t root, uint32_t key, uint32_t dlo, uint32_t dhi)
+{
+    const unsigned s0 = w.ab | ((idx0 << 4) & (Ring<RING>::kMask << 4));
+    const unsigned s1 = w.ab | ((idx1 << 4) & (Ring<RING>::kMask << 4));
+    uint64_t c, d;             /* packed here, as register pairs: both stores then name the same two 64-bit registers */
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "r"(root), "r"(key));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(dlo), "r"(dhi));
+    asm volatile("{\n\t.reg .pred q0, q1;\n\tsetp.ne.u32 q0, %0, 0;\n\tsetp.ne.u32 q1, %1, 0;\n\t"
+                 "@q0 st.shared.v2.u64 [%2], {%4, %5};\n\t"
+                 "@q0 st.shared.v2.u64 [%2+%10], {%8, %9};\n\t"
+                 "@q1 st.shared.v2.u64 [%3], {%6, %7};\n\t"
+                 "@q1 st.shared.v2.u64 [%3+%10], {%8, %9};\n\t}"
+                 :: "r"((unsigned)p0), "r"((unsigned)p1), "r"(s0), "r"(s1), "l"(a0), "l"(heap0), "l"(a1), "l"(heap1),
+                    "l"(c), "l"(d), "n"(Ring<RING>::kCap * 16u) : "memory");
+}
+
+/* Philox block of (root, set, retry, tag, heap).  The empty asm statements pin the two 32-bit counter words that come out
+ * of 64-bit values, so that the first round's products are 32 x 32 -> 64 (one IMAD.WIDE each) like the other nine: left
+ * to itself the compiler sees zext(trunc(x)) = x & 0xFFFFFFFF and emits a 64-bit multiply (two more instructions each). */
+__device__ __forceinline__ pcs_u32x4 draw_block(uint32_t root, uint32_t set, uint32_t retry, uint32_t tag, uint64_t heap, const uint32_t* rk)
+{
+    uint32_t h_lo = (uint32_t)heap, h_hi = (uint32_t)(heap >> 32);
+    asm("" : "+r"(root), "+r"(h_lo));
+    return pcs_philox4x32_10_rk(root, set | (retry << 16) | (tag << 24), h_lo, h_hi, rk);
 }
 
 /* the warp's private spill ring: [grid * warps][kSpillCap][kChunkWords] */
@@ -765,7 +858,10 @@ struct DivOut {
     uint32_t rej;               /* daughters still without a timer (bit c): they go back as a retry node */
     uint32_t retry_next;        /* retry number of that node */
     uint32_t leaf_inc, leaf_key, dlo;
-    uint64_t heap, pc;
+    uint32_t root, key;         /* the node's C word: root cell id, count-tensor index (or table slot) of the node itself */
+    uint32_t child_dhi;         /* high word of a daughter's D word: 0 (retry 0).  The common iteration passes the popped node's
+                                   own high word, which is 0 by the ring's invariant - a register that is there already */
+    uint64_t heap;
     double t_div, tc0, tc1;
 };
 
@@ -773,7 +869,7 @@ __device__ __forceinline__ void divout_clear(DivOut& o)
 {
     o.int0 = false; o.int1 = false; o.got0 = false; o.got1 = false;
     o.rej = 0; o.retry_next = 0; o.leaf_inc = 0; o.leaf_key = 0; o.dlo = 0;
-    o.heap = 0; o.pc = 0; o.t_div = 0.0; o.tc0 = 0.0; o.tc1 = 0.0;
+    o.heap = 0; o.root = 0; o.key = 0; o.child_dhi = 0; o.t_div = 0.0; o.tc0 = 0.0; o.tc1 = 0.0;
 }
 
 /* bit 30 of a node's D word: the division of this node has been counted already (set on every retry node) */
@@ -802,7 +898,7 @@ __device__ __forceinline__ void credit_division(const SimParams& P, DivOut& o, u
         /* subtree sharding: a node below the shard level is expanded by EVERY GPU (same stream, same outcome);
          * its division and the leaves among its daughters are credited to GPU root % world only, and of its
          * daughters AT the shard level this GPU keeps the ones with (root + heap) % world == rank */
-        const uint32_t root = (uint32_t)o.pc;
+        const uint32_t root = o.root;
         if (root % P.sub_world != P.sub_rank) { o.leaf_inc = 0u; first = 0u; }
         if (o.heap >= (P.sub_limit >> 1)) {
             const uint32_t h0 = root + (uint32_t)o.heap * 2u;
@@ -840,18 +936,18 @@ __device__ __forceinline__ void push_and_count(WarpCtx& w, const SimParams& P, u
     const unsigned b0 = __ballot_sync(kFull, o.int0);
     const unsigned b1 = __ballot_sync(kFull, o.int1);
     const unsigned br = __ballot_sync(kFull, o.rej != 0u);
-    const uint64_t child_c = ((o.pc >> 32) + KS) << 32 | (o.pc & 0xFFFFFFFFull);
-    const uint64_t child_d = (uint64_t)(((o.dlo & ~kDloCounted) | (3u << 28)) - (1u << 22));
+    const uint32_t child_key = o.key + KS;                 /* one tree level down (= o.leaf_key) */
+    const uint32_t child_dlo = ((o.dlo & ~kDloCounted) | (3u << 28)) - (1u << 22);
     const uint32_t i0 = (w.top + __popc(b0 & lt_mask)) & kMask;
-    ring_store_if<RING>(w, o.int0, i0, pcs_d2bits(o.tc0), o.heap * 2ull, child_c, child_d);
     w.top += __popc(b0);
     const uint32_t i1 = (w.top + __popc(b1 & lt_mask)) & kMask;
-    ring_store_if<RING>(w, o.int1, i1, pcs_d2bits(o.tc1), o.heap * 2ull + 1ull, child_c, child_d);
     w.top += __popc(b1);
+    ring_store_daughters_if<RING>(w, o.int0, i0, pcs_d2bits(o.tc0), o.heap * 2ull, o.int1, i1, pcs_d2bits(o.tc1), o.heap * 2ull + 1ull,
+                                  o.root, child_key, child_dlo, o.child_dhi);
     if (br) {
         if (o.rej) {
             const uint32_t ir = (w.bottom - 1u - __popc(br & lt_mask)) & kMask;
-            ring_store<RING>(w, ir, pcs_d2bits(o.t_div), o.heap, o.pc,
+            ring_store<RING>(w, ir, pcs_d2bits(o.t_div), o.heap, (uint64_t)o.root | ((uint64_t)o.key << 32),
                              (uint64_t)((o.dlo & ~(3u << 28)) | (o.rej << 28) | kDloCounted) | ((uint64_t)o.retry_next << 32));
         }
         w.bottom -= __popc(br);
@@ -881,7 +977,7 @@ __device__ __forceinline__ void push_and_count(WarpCtx& w, const SimParams& P, u
  * FULL = all 32 lanes have a node: straight-line code.  Otherwise the lanes without a node skip the arithmetic, and every
  * warp collective is still executed by all 32 lanes with the full mask.
  * The popped nodes are fresh by the ring's invariant (accept_chunk): nothing is checked here. */
-template <bool FULL, bool HASHED, bool PLAIN, int RING, int MODE>
+template <int WARPS, bool FULL, bool HASHED, bool PLAIN, int RING, int MODE>
 __device__ __forceinline__ void divide_fresh(WarpCtx& w, const SimParams& P, const double* s_tab, uint32_t* s_hist,
                                              const double2* musd, uint32_t take, unsigned lt_mask, bool multi_set,
                                              DivCount& dc, uint32_t hist_base)
@@ -895,17 +991,17 @@ __device__ __forceinline__ void divide_fresh(WarpCtx& w, const SimParams& P, con
     uint32_t set = 0;
     if (mine) {
         const uint32_t idx = (w.top - 1u - (uint32_t)w.lane) & kMask;
-        uint64_t a, d;
-        ring_load<RING>(w, idx, a, o.heap, o.pc, d);
+        uint64_t a;
+        ring_load_node<RING>(w, idx, a, o.heap, o.root, o.key, o.dlo, o.child_dhi);      /* high word of D: 0, the node is fresh */
         o.t_div = pcs_bits2d(a);
-        o.dlo = (uint32_t)d;
         set = PLAIN ? 0u : (o.dlo & 0xFFFFu);
-        blk = pcs_draw_rk((uint32_t)o.pc, set, 0u, PCS_TAG_DIVISION, o.heap, P.rk);
-        const uint32_t type = (o.dlo >> 16) & 63u;
-        const double2 ms = musd[set * P.n_types + type];          /* generic pointer: shared-memory copy or the HBM table */
+        blk = draw_block(o.root, set, 0u, PCS_TAG_DIVISION, o.heap, P.rk);
+        using L = SmemLayout<WARPS, RING>;
+        /* PLAIN: one set, the (mean, sd) table is the shared-memory copy; else a generic pointer - that copy or the HBM table */
+        const double2 ms = PLAIN ? musd_smem<L::kMusdAddr>(o.dlo) : musd[set * P.n_types + ((o.dlo >> 16) & 63u)];
         double z0, z1;
-        const bool f0 = pcs_zig_fast(blk.x, blk.y, s_tab + PCS_TAB_ZIG, &z0);
-        const bool f1 = pcs_zig_fast(blk.z, blk.w, s_tab + PCS_TAB_ZIG, &z1);
+        const bool f0 = zig_fast_smem<L::kZigAddr>(blk.x, blk.y, &z0);
+        const bool f1 = zig_fast_smem<L::kZigAddr>(blk.z, blk.w, &z1);
         const double tm0 = pcs_timer(ms.x, ms.y, z0), tm1 = pcs_timer(ms.x, ms.y, z1);
         const bool ok0 = f0 && tm0 > 0.0, ok1 = f1 && tm1 > 0.0;
         classify_daughters(P, o, ok0, ok1, tm0, tm1);
@@ -913,7 +1009,7 @@ __device__ __forceinline__ void divide_fresh(WarpCtx& w, const SimParams& P, con
         /* a trial that left the fast path is finished by the general iteration at THIS retry number; if every rejected
          * daughter passed the fast test (its timer was <= 0), the next thing to do is the redraw */
         o.retry_next = (f0 && f1) ? 1u : 0u;
-        o.leaf_key = (uint32_t)(o.pc >> 32) + ((PLAIN && !HASHED) ? P.kstride : P.n_types);
+        o.leaf_key = o.key + ((PLAIN && !HASHED) ? P.kstride : P.n_types);
         credit_division<MODE, PLAIN>(P, o, 1u, set, multi_set, dc);
     }
     else if (PLAIN) dc.cnt -= 1u;
@@ -940,15 +1036,13 @@ __device__ __forceinline__ void divide_general(WarpCtx& w, const SimParams& P, c
     blk.x = 0; blk.y = 0; blk.z = 0; blk.w = 0;
     if (mine) {
         const uint32_t idx = (from_bottom ? w.bottom + (uint32_t)w.lane : w.top - 1u - (uint32_t)w.lane) & kMask;
-        uint64_t a, d;
-        ring_load<RING>(w, idx, a, o.heap, o.pc, d);
+        uint64_t a;
+        ring_load_node<RING>(w, idx, a, o.heap, o.root, o.key, o.dlo, retry);
         o.t_div = pcs_bits2d(a);
-        o.dlo = (uint32_t)d;
-        retry = (uint32_t)(d >> 32);
         set = PLAIN ? 0u : (o.dlo & 0xFFFFu);
         ms = musd[set * P.n_types + ((o.dlo >> 16) & 63u)];
         want = (o.dlo >> 28) & 3u;
-        blk = pcs_draw_rk((uint32_t)o.pc, set, retry, PCS_TAG_DIVISION, o.heap, P.rk);
+        blk = draw_block(o.root, set, retry, PCS_TAG_DIVISION, o.heap, P.rk);
     }
     const bool forced = retry >= PCS_MAX_RETRY;                /* 255 redraws failed: the timer is the mean */
     /* The trials run in two passes of warp-uniform shape: pass 0 gives every lane's FIRST wanted daughter its trial (most
@@ -966,7 +1060,7 @@ __device__ __forceinline__ void divide_general(WarpCtx& w, const SimParams& P, c
         const uint32_t lo = c ? blk.z : blk.x, hi = c ? blk.w : blk.y;
         double z;
         bool acc = pcs_zig_fast(lo, hi, s_tab + PCS_TAB_ZIG, &z);
-        if (act && !acc) acc = pcs_zig_slow(hi, c, &z, (uint32_t)o.pc, set, retry, o.heap, P.rk, s_tab, P.logtab + PCS_TAB_WEDGE);
+        if (act && !acc) acc = pcs_zig_slow(hi, c, &z, o.root, set, retry, o.heap, P.rk, s_tab, P.logtab + PCS_TAB_WEDGE);
         __syncwarp();
         if (act) {
             if (c) { zc[1] = z; accc[1] = acc; } else { zc[0] = z; accc[0] = acc; }
@@ -980,7 +1074,7 @@ __device__ __forceinline__ void divide_general(WarpCtx& w, const SimParams& P, c
         classify_daughters(P, o, ok0, ok1, tm0, tm1);
         o.rej = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
         o.retry_next = retry + 1u;
-        o.leaf_key = (uint32_t)(o.pc >> 32) + ((PLAIN && !HASHED) ? P.kstride : P.n_types);
+        o.leaf_key = o.key + ((PLAIN && !HASHED) ? P.kstride : P.n_types);
         credit_division<MODE, PLAIN>(P, o, (o.dlo & kDloCounted) ? 0u : 1u, set, multi_set, dc);
     }
     else if (PLAIN) dc.cnt -= 1u;
@@ -1000,13 +1094,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     static_assert(!SETDIRECT || (!PLAIN && !HASHED && RING == 1), "set-relative table: sweeps, u32 slots, one node per lane");
     constexpr uint32_t kCap = Ring<RING>::kCap, kMask = Ring<RING>::kMask;
     constexpr bool SLOT = PLAIN && !HASHED;      /* the u32 table is laid out by slots (SimParams::slot_mode is set) */
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    /* layout: (mean, sd) table 1 KB | rings | math tables | control words + threshold / epoch / selection tables | count table.
-     * Dynamic shared memory starts 1 KB into the shared-memory window on sm_100, so the rings start on a 2 KB boundary and
-     * a ring slot's address is one OR (WarpCtx::ab); nothing is padded.  Checked below: a different window offset traps. */
-    constexpr size_t kRingsOff = (size_t)kSmemMusdEntries * 16, kRingsBytes = (size_t)WARPS * 4 * kCap * 8;
-    constexpr size_t kTabOff = kRingsOff + kRingsBytes, kCtlOff = kTabOff + (size_t)kLogTabDoubles * 8;
-    static_assert(kSmemMusdEntries * 16 == 1024, "the (mean, sd) table is the 1 KB in front of the rings");
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    /* Dynamic shared memory starts kDynSmemWindow bytes into the CTA's shared-memory window (sm_100: the first 1 KB is the
+     * system's), so the rings start on a 2 KB boundary - a ring slot's address is one OR (WarpCtx::ab) - and, with the
+     * window offset a compile-time constant, every table address of the hot loop is an immediate (no window base to
+     * rematerialise: S2R + MOV + LEA, and an add per access).  A launch that finds another offset stops with
+     * kStatusSmemWindow before it touches anything (capi.cu reports it as a failed run). */
+    using L = SmemLayout<WARPS, RING>;
+    unsigned char* const smem_raw = reinterpret_cast<unsigned char*>(__cvta_shared_to_generic(kDynSmemWindow));
+    if ((uint32_t)__cvta_generic_to_shared(smem_dyn) != kDynSmemWindow) {
+        if (threadIdx.x == 0) atomicExch(&P.ctl->status, kStatusSmemWindow);
+        return;
+    }
+    constexpr size_t kRingsOff = L::kRingsOff, kTabOff = L::kTabOff, kCtlOff = L::kCtlOff;
+    static_assert(kSmemMusdEntries * 16 == 1024 && ((kDynSmemWindow + L::kRingsOff) & (kCap * 16u - 1u)) == 0u,
+                  "the (mean, sd) table is the 1 KB in front of the rings, which start on a 2 KB boundary of the window");
     double* s_log = reinterpret_cast<double*>(smem_raw + kTabOff);
     volatile int* s_ctl = reinterpret_cast<volatile int*>(smem_raw + kCtlOff);   /* [0] poll lock, [1] quiescent */
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + kCtlOff + (kSmemCtlBytes - kSmemMusdEntries * 16));
@@ -1037,12 +1139,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    /* lanes below this one, from the special register: the compiler keeps it in a register through the loop, where it
+     * rebuilt (1 << lane) - 1 in every iteration (-4 instructions per DIVIDE iteration) */
+#ifdef PROCELL_LTMASK_SHIFT
     const unsigned lt_mask = (1u << lane) - 1u;
+#else
+    unsigned lt_mask;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+#endif
     ControlBlock* ctl = P.ctl;
 
     WarpCtx w;
-    w.ab = (uint32_t)__cvta_generic_to_shared(smem_raw + kRingsOff) + (uint32_t)warp * (4u * kCap * 8u);
-    if ((w.ab & (kCap * 16u - 1u)) != 0u) __trap();          /* the ring is not on a 2 KB boundary: ring_load's OR would be wrong */
+    w.ab = kDynSmemWindow + (uint32_t)kRingsOff + (uint32_t)warp * (4u * kCap * 8u);     /* on a 2 KB boundary (static_assert above) */
     w.bottom = 0; w.top = 0; w.slow = 0;
     w.sp = 0;
     w.lane = lane;
@@ -1277,8 +1385,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         const uint32_t hist_base = SETDIRECT ? set_base : 0u;     /* changes only while this warp is parked in the rendezvous */
         /* PLAIN: one set and at most 64 types, so the (mean, sd) table is always the shared-memory copy (plain LDS) */
         const double2* musd = PLAIN ? s_musd_buf : s_musd;
-        if (mode == 0) divide_fresh<true, HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, 32u, lt_mask, multi_set, dc, hist_base);
-        else if (mode == 1) divide_fresh<false, HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc, hist_base);
+        if (mode == 0) divide_fresh<WARPS, true, HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, 32u, lt_mask, multi_set, dc, hist_base);
+        else if (mode == 1) divide_fresh<WARPS, false, HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, take, lt_mask, multi_set, dc, hist_base);
         else divide_general<HASHED, PLAIN, RING, MODE>(w, P, s_log, s_hist, musd, take, from_bottom, lt_mask, multi_set, dc, hist_base);
 
         /* hunger probe, every 16th iteration (every 8th costs 1 %, every 4th 3 % on config 2).  The CTA keeps a snapshot of "how many warps are starving", "how many

@@ -25,6 +25,7 @@ constexpr int kStatusSpillOverflow = 1;
 constexpr int kStatusQueueTimeout = 2;
 constexpr int kStatusIdleTimeout = 3;
 constexpr int kStatusWatchdog = 4;
+constexpr int kStatusSmemWindow = 5;           /* dynamic shared memory does not start where the kernel was compiled for */
 constexpr int kDbgWords = 8;                   /* per-warp debug record written when the watchdog fires */
 
 /* control block in global memory; every hot word on its own 128-byte line */
