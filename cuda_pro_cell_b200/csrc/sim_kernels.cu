@@ -60,6 +60,7 @@ constexpr int kSmemMusdEntries = 64;  /* (mean, sd) table cached in shared memor
  * (mean, sd) 16 B, type threshold 4 B (+ 4 B: the per-warp donation epochs live in that half) and selection order 1 B per entry */
 constexpr int kSmemCtlBytes = 128 + kSmemMusdEntries * (16 + 8 + 1);
 constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr uint32_t kSlot = 16u;                  /* ring positions count bytes of the (A, B) half: 16 per node (WarpCtx) */
 constexpr uint32_t kDynSmemWindow = 0x400u;      /* where dynamic shared memory starts in the shared-memory window on sm_100 */
 /* kernel MODE: 0 = the kernel as measured in round 1; 1 = subtree sharding compiled in (multi-GPU runs of deep trees);
  * 2 = sweeps with a set-relative direct histogram table and a CTA-wide rendezvous at batch switches */
@@ -394,8 +395,10 @@ struct WarpCtx {
                                         (root|keybase<<32, D) pairs.  The ring starts on a 2 KB boundary of the shared-memory
                                         window, so the address of slot idx is ab | ((idx << 4) & 0x7F0): a shift and ONE
                                         logic instruction, no add (the kernel checks the alignment when it starts) */
-    uint32_t bottom, top;            /* ring positions, n = top - bottom */
-    uint32_t slow;                   /* the bottom-most `slow` nodes of the ring are retry nodes awaiting a general iteration */
+    uint32_t bottom, top;            /* ring positions IN BYTES of the (A, B) half - kSlot = 16 per node -, n = (top - bottom) / 16: a
+                                        slot's address is ab | (position & 0x7F0) with no shift, and position + 16 * count is one IMAD */
+    uint32_t slow;                   /* the bottom-most slow / 16 nodes of the ring are retry nodes awaiting a general iteration (bytes too) */
+    uint32_t nl16;                   /* -16 * (lane + 1): the newest node this lane pops sits at top + nl16 */
     uint32_t sp;                     /* private spill ring in HBM, packed into one register: oldest chunk's position in the low
                                         half (mod 2^16; kSpillCap divides it), number of chunks in the high half.  The ring's
                                         address is recomputed on use (spill_ring), which keeps
@@ -410,33 +413,33 @@ __device__ __forceinline__ uint32_t ring_nodes(const WarpCtx& w)
 {
     uint32_t t = w.top;
     asm volatile("" : "+r"(t));
-    return t - w.bottom;
+    return (t - w.bottom) >> 4;
 }
 
 template <int RING>
-__device__ __forceinline__ void ring_load(const WarpCtx& w, uint32_t idx, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d)
+__device__ __forceinline__ void ring_load(const WarpCtx& w, uint32_t pos, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d)
 {
-    const unsigned sab = w.ab | ((idx << 4) & (Ring<RING>::kMask << 4));
+    const unsigned sab = w.ab | (pos & (Ring<RING>::kMask << 4));
     asm volatile("ld.shared.v2.u64 {%0, %1}, [%4];\n\tld.shared.v2.u64 {%2, %3}, [%4+%5];"
                  : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "r"(sab), "n"(Ring<RING>::kCap * 16u) : "memory");
 }
 
 template <int RING>
-__device__ __forceinline__ void ring_store(WarpCtx& w, uint32_t idx, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
+__device__ __forceinline__ void ring_store(WarpCtx& w, uint32_t pos, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
 {
-    const unsigned sab = w.ab | ((idx << 4) & (Ring<RING>::kMask << 4));
+    const unsigned sab = w.ab | (pos & (Ring<RING>::kMask << 4));
     asm volatile("st.shared.v2.u64 [%0], {%1, %2};\n\tst.shared.v2.u64 [%0+%5], {%3, %4};"
                  :: "r"(sab), "l"(a), "l"(b), "l"(c), "l"(d), "n"(Ring<RING>::kCap * 16u) : "memory");
 }
 
 /* the same under a predicate, as two predicated STS.128 instead of a branch around four stores */
 template <int RING>
-__device__ __forceinline__ void ring_store_if(WarpCtx& w, bool p, uint32_t idx, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
+__device__ __forceinline__ void ring_store_if(WarpCtx& w, bool p, uint32_t pos, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
 {
 #ifdef PROCELL_BRANCHY_PUSH
-    if (p) ring_store<RING>(w, idx, a, b, c, d);
+    if (p) ring_store<RING>(w, pos, a, b, c, d);
 #else
-    const unsigned sab = w.ab | ((idx << 4) & (Ring<RING>::kMask << 4));
+    const unsigned sab = w.ab | (pos & (Ring<RING>::kMask << 4));
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.v2.u64 [%1], {%2, %3};\n\t@q st.shared.v2.u64 [%1+%6], {%4, %5};\n\t}"
                  :: "r"((unsigned)p), "r"(sab), "l"(a), "l"(b), "l"(c), "l"(d), "n"(Ring<RING>::kCap * 16u) : "memory");
 #endif
@@ -446,10 +449,10 @@ __device__ __forceinline__ void ring_store_if(WarpCtx& w, bool p, uint32_t idx, 
  * so that nothing downstream masks or shifts a 64-bit register pair (the compiler otherwise multiplies Philox's first
  * round as a 64 x 64-bit product of a masked pair and adds a 64-bit constant to C to step the key). */
 template <int RING>
-__device__ __forceinline__ void ring_load_node(const WarpCtx& w, uint32_t idx, uint64_t& a, uint64_t& heap, uint32_t& root,
+__device__ __forceinline__ void ring_load_node(const WarpCtx& w, uint32_t pos, uint64_t& a, uint64_t& heap, uint32_t& root,
                                                uint32_t& key, uint32_t& dlo, uint32_t& retry)
 {
-    const unsigned sab = w.ab | ((idx << 4) & (Ring<RING>::kMask << 4));
+    const unsigned sab = w.ab | (pos & (Ring<RING>::kMask << 4));
     asm volatile("ld.shared.v2.u64 {%0, %1}, [%6];\n\tld.shared.v4.u32 {%2, %3, %4, %5}, [%6+%7];"
                  : "=l"(a), "=l"(heap), "=r"(root), "=r"(key), "=r"(dlo), "=r"(retry) : "r"(sab), "n"(Ring<RING>::kCap * 16u) : "memory");
 }
@@ -458,12 +461,12 @@ __device__ __forceinline__ void ring_load_node(const WarpCtx& w, uint32_t idx, u
  * (t_div bits, heap) and (root, key, D's low word, D's high word); the second pair is the same four registers for both
  * daughters, so the compiler builds it once (as two statements it built it twice). */
 template <int RING>
-__device__ __forceinline__ void ring_store_daughters_if(WarpCtx& w, bool p0, uint32_t idx0, uint64_t a0, uint64_t heap0,
-                                                        bool p1, uint32_t idx1, uint64_t a1, uint64_t heap1,
+__device__ __forceinline__ void ring_store_daughters_if(WarpCtx& w, bool p0, uint32_t pos0, uint64_t a0, uint64_t heap0,
+                                                        bool p1, uint32_t pos1, uint64_t a1, uint64_t heap1,
                                                         uint32_t root, uint32_t key, uint32_t dlo, uint32_t dhi)
 {
-    const unsigned s0 = w.ab | ((idx0 << 4) & (Ring<RING>::kMask << 4));
-    const unsigned s1 = w.ab | ((idx1 << 4) & (Ring<RING>::kMask << 4));
+    const unsigned s0 = w.ab | (pos0 & (Ring<RING>::kMask << 4));
+    const unsigned s1 = w.ab | (pos1 & (Ring<RING>::kMask << 4));
     uint64_t c, d;             /* packed here, as register pairs: both stores then name the same two 64-bit registers */
     asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "r"(root), "r"(key));
     asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(dlo), "r"(dhi));
@@ -500,20 +503,21 @@ __device__ __forceinline__ unsigned long long* spill_ring(const SimParams& P)
 template <int RING>
 __device__ __forceinline__ void pop_bottom_chunk(WarpCtx& w, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d)
 {
-    constexpr uint32_t kMask = Ring<RING>::kMask;
-    if (w.slow >= (uint32_t)kChunkNodes) {
-        ring_load<RING>(w, (w.bottom + w.lane) & kMask, a, b, c, d);
-        w.slow -= kChunkNodes;
+    constexpr uint32_t kChunk = (uint32_t)kChunkNodes * kSlot;
+    const uint32_t lane_pos = (uint32_t)w.lane * kSlot;
+    if (w.slow >= kChunk) {
+        ring_load<RING>(w, w.bottom + lane_pos, a, b, c, d);
+        w.slow -= kChunk;
     } else {
-        ring_load<RING>(w, (w.bottom + w.slow + w.lane) & kMask, a, b, c, d);
+        ring_load<RING>(w, w.bottom + w.slow + lane_pos, a, b, c, d);
         if (w.slow != 0u) {
             uint64_t sa = 0, sb = 0, sc = 0, sd = 0;
-            if ((uint32_t)w.lane < w.slow) ring_load<RING>(w, (w.bottom + w.lane) & kMask, sa, sb, sc, sd);
+            if (lane_pos < w.slow) ring_load<RING>(w, w.bottom + lane_pos, sa, sb, sc, sd);
             __syncwarp();       /* every lane has read its chunk node and its retry node before any slot is overwritten */
-            if ((uint32_t)w.lane < w.slow) ring_store<RING>(w, (w.bottom + kChunkNodes + w.lane) & kMask, sa, sb, sc, sd);
+            if (lane_pos < w.slow) ring_store<RING>(w, w.bottom + kChunk + lane_pos, sa, sb, sc, sd);
         }
     }
-    w.bottom += kChunkNodes;
+    w.bottom += kChunk;
     __syncwarp();
 }
 
@@ -542,12 +546,12 @@ template <int RING>
 __device__ __forceinline__ void accept_chunk(WarpCtx& w, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
 {
     if (__any_sync(kFull, (d >> 28) != 3ull)) {          /* mask != 3, or counted, or retry > 0 */
-        w.bottom -= kChunkNodes;
-        ring_store<RING>(w, (w.bottom + w.lane) & Ring<RING>::kMask, a, b, c, d);
-        w.slow += kChunkNodes;
+        w.bottom -= (uint32_t)kChunkNodes * kSlot;
+        ring_store<RING>(w, w.bottom + (uint32_t)w.lane * kSlot, a, b, c, d);
+        w.slow += (uint32_t)kChunkNodes * kSlot;
     } else {
-        ring_store<RING>(w, (w.top + w.lane) & Ring<RING>::kMask, a, b, c, d);
-        w.top += kChunkNodes;
+        ring_store<RING>(w, w.top + (uint32_t)w.lane * kSlot, a, b, c, d);
+        w.top += (uint32_t)kChunkNodes * kSlot;
     }
     __syncwarp();
 }
@@ -855,7 +859,7 @@ struct DivCount {
 struct DivOut {
     bool int0, int1;            /* daughter 0 / 1 lives on and will divide */
     bool got0, got1;            /* daughter 0 / 1 received its timer in THIS iteration (time series) */
-    uint32_t rej;               /* daughters still without a timer (bit c): they go back as a retry node */
+    bool rej0, rej1;            /* daughter 0 / 1 is still without a timer: the node goes back as a retry node */
     uint32_t retry_next;        /* retry number of that node */
     uint32_t leaf_inc, leaf_key, dlo;
     uint32_t root, key;         /* the node's C word: root cell id, count-tensor index (or table slot) of the node itself */
@@ -868,7 +872,7 @@ struct DivOut {
 __device__ __forceinline__ void divout_clear(DivOut& o)
 {
     o.int0 = false; o.int1 = false; o.got0 = false; o.got1 = false;
-    o.rej = 0; o.retry_next = 0; o.leaf_inc = 0; o.leaf_key = 0; o.dlo = 0;
+    o.rej0 = false; o.rej1 = false; o.retry_next = 0; o.leaf_inc = 0; o.leaf_key = 0; o.dlo = 0;
     o.heap = 0; o.root = 0; o.key = 0; o.child_dhi = 0; o.t_div = 0.0; o.tc0 = 0.0; o.tc1 = 0.0;
 }
 
@@ -883,7 +887,9 @@ __device__ __forceinline__ void classify_daughters(const SimParams& P, DivOut& o
     o.tc1 = PCS_ADD(o.t_div, tm1);
     const bool late0 = o.tc0 > P.t_max, late1 = o.tc1 > P.t_max;  /* proliferation.cu:404-410 */
     const bool deeper = (o.dlo & (63u << 22)) != 0u;              /* f/2 > phi one level down (:323) */
-    o.leaf_inc = (uint32_t)(ok0 && late0) + (uint32_t)(ok1 && late1);
+    /* (ok0 && late0) + (ok1 && late1) as select + predicated add: two instructions where the compiler's own form took four */
+    asm("{\n\t.reg .pred pa, pb;\n\tsetp.ne.u32 pa, %1, 0;\n\tsetp.ne.u32 pb, %2, 0;\n\tselp.u32 %0, 1, 0, pa;\n\t@pb add.u32 %0, %0, 1;\n\t}"
+        : "=r"(o.leaf_inc) : "r"((uint32_t)(ok0 && late0)), "r"((uint32_t)(ok1 && late1)));
     o.int0 = ok0 && !late0 && deeper;
     o.int1 = ok1 && !late1 && deeper;
     o.got0 = ok0; o.got1 = ok1;
@@ -925,33 +931,33 @@ __device__ __forceinline__ void push_and_count(WarpCtx& w, const SimParams& P, u
                                                bool from_bottom, unsigned lt_mask, uint32_t hist_base)
 {
     constexpr bool SETDIRECT = MODE == kModeSetDirect;
-    constexpr uint32_t kMask = Ring<RING>::kMask;
     const uint32_t KS = (PLAIN && !HASHED) ? P.kstride : P.n_types;
     /* all popped nodes have been read: every lane's loads have returned before it votes below (the predicates depend
      * on the loaded values of the node it popped) and no lane stores before all have voted on everything, so the
      * slots may be overwritten.  The barrier states that ordering formally (racecheck reports the pops and pushes of one
      * iteration as a hazard without it); on a converged warp it is one WARPSYNC. */
     __syncwarp();
-    if (from_bottom) { w.bottom += take; w.slow -= take; } else w.top -= take;
+    if (from_bottom) { w.bottom += take * kSlot; w.slow -= take * kSlot; } else w.top -= take * kSlot;
     const unsigned b0 = __ballot_sync(kFull, o.int0);
     const unsigned b1 = __ballot_sync(kFull, o.int1);
-    const unsigned br = __ballot_sync(kFull, o.rej != 0u);
+    const unsigned br = __ballot_sync(kFull, o.rej0 || o.rej1);
     const uint32_t child_key = o.key + KS;                 /* one tree level down (= o.leaf_key) */
     const uint32_t child_dlo = ((o.dlo & ~kDloCounted) | (3u << 28)) - (1u << 22);
-    const uint32_t i0 = (w.top + __popc(b0 & lt_mask)) & kMask;
-    w.top += __popc(b0);
-    const uint32_t i1 = (w.top + __popc(b1 & lt_mask)) & kMask;
-    w.top += __popc(b1);
+    const uint32_t i0 = w.top + kSlot * __popc(b0 & lt_mask);
+    w.top += kSlot * __popc(b0);
+    const uint32_t i1 = w.top + kSlot * __popc(b1 & lt_mask);
+    w.top += kSlot * __popc(b1);
     ring_store_daughters_if<RING>(w, o.int0, i0, pcs_d2bits(o.tc0), o.heap * 2ull, o.int1, i1, pcs_d2bits(o.tc1), o.heap * 2ull + 1ull,
                                   o.root, child_key, child_dlo, o.child_dhi);
     if (br) {
-        if (o.rej) {
-            const uint32_t ir = (w.bottom - 1u - __popc(br & lt_mask)) & kMask;
+        if (o.rej0 || o.rej1) {
+            const uint32_t rej = (uint32_t)o.rej0 | ((uint32_t)o.rej1 << 1);
+            const uint32_t ir = w.bottom - kSlot - kSlot * __popc(br & lt_mask);
             ring_store<RING>(w, ir, pcs_d2bits(o.t_div), o.heap, (uint64_t)o.root | ((uint64_t)o.key << 32),
-                             (uint64_t)((o.dlo & ~(3u << 28)) | (o.rej << 28) | kDloCounted) | ((uint64_t)o.retry_next << 32));
+                             (uint64_t)((o.dlo & ~(3u << 28)) | (rej << 28) | kDloCounted) | ((uint64_t)o.retry_next << 32));
         }
-        w.bottom -= __popc(br);
-        w.slow += __popc(br);
+        w.bottom -= kSlot * __popc(br);
+        w.slow += kSlot * __popc(br);
     }
     __syncwarp();
     if (SETDIRECT) {
@@ -982,7 +988,6 @@ __device__ __forceinline__ void divide_fresh(WarpCtx& w, const SimParams& P, con
                                              const double2* musd, uint32_t take, unsigned lt_mask, bool multi_set,
                                              DivCount& dc, uint32_t hist_base)
 {
-    constexpr uint32_t kMask = Ring<RING>::kMask;
     DivOut o;
     divout_clear(o);
     const bool mine = FULL || (uint32_t)w.lane < take;
@@ -990,9 +995,8 @@ __device__ __forceinline__ void divide_fresh(WarpCtx& w, const SimParams& P, con
     blk.x = 0; blk.y = 0; blk.z = 0; blk.w = 0;
     uint32_t set = 0;
     if (mine) {
-        const uint32_t idx = (w.top - 1u - (uint32_t)w.lane) & kMask;
         uint64_t a;
-        ring_load_node<RING>(w, idx, a, o.heap, o.root, o.key, o.dlo, o.child_dhi);      /* high word of D: 0, the node is fresh */
+        ring_load_node<RING>(w, w.top + w.nl16, a, o.heap, o.root, o.key, o.dlo, o.child_dhi);      /* high word of D: 0, the node is fresh */
         o.t_div = pcs_bits2d(a);
         set = PLAIN ? 0u : (o.dlo & 0xFFFFu);
         blk = draw_block(o.root, set, 0u, PCS_TAG_DIVISION, o.heap, P.rk);
@@ -1005,7 +1009,7 @@ __device__ __forceinline__ void divide_fresh(WarpCtx& w, const SimParams& P, con
         const double tm0 = pcs_timer(ms.x, ms.y, z0), tm1 = pcs_timer(ms.x, ms.y, z1);
         const bool ok0 = f0 && tm0 > 0.0, ok1 = f1 && tm1 > 0.0;
         classify_daughters(P, o, ok0, ok1, tm0, tm1);
-        o.rej = (uint32_t)!ok0 | ((uint32_t)!ok1 << 1);
+        o.rej0 = !ok0; o.rej1 = !ok1;
         /* a trial that left the fast path is finished by the general iteration at THIS retry number; if every rejected
          * daughter passed the fast test (its timer was <= 0), the next thing to do is the redraw */
         o.retry_next = (f0 && f1) ? 1u : 0u;
@@ -1026,7 +1030,6 @@ __device__ __forceinline__ void divide_general(WarpCtx& w, const SimParams& P, c
                                                const double2* musd, uint32_t take, bool from_bottom, unsigned lt_mask,
                                                bool multi_set, DivCount& dc, uint32_t hist_base)
 {
-    constexpr uint32_t kMask = Ring<RING>::kMask;
     DivOut o;
     divout_clear(o);
     const bool mine = (uint32_t)w.lane < take;
@@ -1035,9 +1038,9 @@ __device__ __forceinline__ void divide_general(WarpCtx& w, const SimParams& P, c
     pcs_u32x4 blk;
     blk.x = 0; blk.y = 0; blk.z = 0; blk.w = 0;
     if (mine) {
-        const uint32_t idx = (from_bottom ? w.bottom + (uint32_t)w.lane : w.top - 1u - (uint32_t)w.lane) & kMask;
+        const uint32_t pos = from_bottom ? w.bottom + (uint32_t)w.lane * kSlot : w.top + w.nl16;
         uint64_t a;
-        ring_load_node<RING>(w, idx, a, o.heap, o.root, o.key, o.dlo, retry);
+        ring_load_node<RING>(w, pos, a, o.heap, o.root, o.key, o.dlo, retry);
         o.t_div = pcs_bits2d(a);
         set = PLAIN ? 0u : (o.dlo & 0xFFFFu);
         ms = musd[set * P.n_types + ((o.dlo >> 16) & 63u)];
@@ -1072,7 +1075,7 @@ __device__ __forceinline__ void divide_general(WarpCtx& w, const SimParams& P, c
         const double tm1 = forced ? ms.x : pcs_timer(ms.x, ms.y, zc[1]);
         const bool ok0 = want0 && (forced || (accc[0] && tm0 > 0.0)), ok1 = want1 && (forced || (accc[1] && tm1 > 0.0));
         classify_daughters(P, o, ok0, ok1, tm0, tm1);
-        o.rej = (uint32_t)(want0 && !ok0) | ((uint32_t)(want1 && !ok1) << 1);
+        o.rej0 = want0 && !ok0; o.rej1 = want1 && !ok1;
         o.retry_next = retry + 1u;
         o.leaf_key = o.key + ((PLAIN && !HASHED) ? P.kstride : P.n_types);
         credit_division<MODE, PLAIN>(P, o, (o.dlo & kDloCounted) ? 0u : 1u, set, multi_set, dc);
@@ -1092,7 +1095,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     static_assert(RING == 1, "128-node ring per warp, one node per lane and iteration");
     static_assert(!SUBTREE || (PLAIN && RING == 1), "subtree sharding: one parameter set, one checkpoint, one node per lane");
     static_assert(!SETDIRECT || (!PLAIN && !HASHED && RING == 1), "set-relative table: sweeps, u32 slots, one node per lane");
-    constexpr uint32_t kCap = Ring<RING>::kCap, kMask = Ring<RING>::kMask;
+    constexpr uint32_t kCap = Ring<RING>::kCap;
     constexpr bool SLOT = PLAIN && !HASHED;      /* the u32 table is laid out by slots (SimParams::slot_mode is set) */
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     /* Dynamic shared memory starts kDynSmemWindow bytes into the CTA's shared-memory window (sm_100: the first 1 KB is the
@@ -1152,6 +1155,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     WarpCtx w;
     w.ab = kDynSmemWindow + (uint32_t)kRingsOff + (uint32_t)warp * (4u * kCap * 8u);     /* on a 2 KB boundary (static_assert above) */
     w.bottom = 0; w.top = 0; w.slow = 0;
+    w.nl16 = ~(uint32_t)lane * kSlot;
+    asm volatile("" : "+r"(w.nl16));       /* a value of its own: kept in a register, not rebuilt from the lane id in every iteration */
     w.sp = 0;
     w.lane = lane;
 
@@ -1197,16 +1202,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
         /* the ring holds n nodes: w.slow retry nodes at its bottom, waiting for a general iteration, and above them the
          * regular ones.  mode 0: full fresh iteration (the common case: 32 regular nodes or more, room for the pushes of
          * one iteration, fewer than 32 retry nodes), 1: partial fresh iteration, 2: general iteration */
-        const uint32_t n = w.top - w.bottom;
+        const uint32_t n = w.top - w.bottom;                 /* bytes, like every ring position: kSlot per node */
         const uint32_t nreg = n - w.slow;
         int mode = 0;
         uint32_t take = 32u;
         bool from_bottom = false;
-        if (!(w.slow < 32u && nreg - 32u <= kCap - 64u - w.slow)) {
-        if (n > kCap - 32u) {    /* an iteration pops 32 nodes at most and pushes twice as many: keep that much room in the ring */
+        if (!(w.slow < 32u * kSlot && nreg - 32u * kSlot <= (kCap - 64u) * kSlot - w.slow)) {
+        if (n > (kCap - 32u) * kSlot) {    /* an iteration pops 32 nodes at most and pushes twice as many: keep that much room in the ring */
             TRACE(P, GWARP, lane, 40); spill_bottom_chunk<RING>(w, P); continue;
         }
-        if (w.slow >= 32u) { mode = 2; from_bottom = true; }      /* a warp's worth of retry nodes has collected */
+        if (w.slow >= 32u * kSlot) { mode = 2; from_bottom = true; }      /* a warp's worth of retry nodes has collected */
         else {
             bool divide_rest = false;      /* MODE 2: expand what is left of the old set before waiting for the switch */
             if ((w.sp >> 16) != 0u) { TRACE(P, GWARP, lane, 41); unspill_newest_chunk<RING>(w, P); continue; }
@@ -1347,11 +1352,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 }
                 const unsigned live = __ballot_sync(kFull, so.kind == 2);
                 if (so.kind == 2) {
-                    uint32_t idx = (w.top + __popc(live & lt_mask)) & kMask;
-                    ring_store<RING>(w, idx, pcs_d2bits(so.t_div), 1ull, (uint64_t)root | ((uint64_t)so.key << 32),
+                    const uint32_t pos = w.top + kSlot * __popc(live & lt_mask);
+                    ring_store<RING>(w, pos, pcs_d2bits(so.t_div), 1ull, (uint64_t)root | ((uint64_t)so.key << 32),
                                (uint64_t)pack_dlo(seed_set, so.type, so.kdiv - 1u, 3u));
                 }
-                w.top += __popc(live);
+                w.top += kSlot * __popc(live);
                 __syncwarp();
                 if (SETDIRECT) {
                     count_leaves_setdirect(P, s_hist, so.key, so.kind == 1 ? 1u : 0u, set_base);
@@ -1375,7 +1380,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 continue;
             }
             /* nothing to add: expand what the warp holds - its regular nodes first, then its last retry nodes */
-            if (left != w.slow) { mode = 1; take = left - w.slow; }
+            if (left != w.slow / kSlot) { mode = 1; take = left - w.slow / kSlot; }
             else { mode = 2; from_bottom = true; take = left; }
         }
         }
@@ -1438,7 +1443,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
                 packed = (ep << 2) | ((idle_snap >= kEndgameIdle) << 1) | hg;
             }
             packed = __shfl_sync(kFull, packed, 0);
-            if ((packed & 1) && (w.top - w.bottom + 32u * (w.sp >> 16)) >= ((packed & 2) ? 64u : kDonateMinNodes * RING)) {
+            if ((packed & 1) && ((w.top - w.bottom) / kSlot + 32u * (w.sp >> 16)) >= ((packed & 2) ? 64u : kDonateMinNodes * RING)) {
                 /* somebody starves and no seeds are left: give away the shallowest chunk */
                 TRACE(P, GWARP, lane, 50);
                 if (lane == 0) *s_epoch = packed >> 2;
