@@ -97,6 +97,15 @@ __device__ __forceinline__ bool zig_fast_smem(uint32_t lo, uint32_t hi, double* 
     return fabs(x) < xn;
 }
 
+/* the same with the table behind an ordinary pointer (the ceiling kernels' own static shared-memory copy) */
+__device__ __forceinline__ bool zig_fast_signed(uint32_t lo, uint32_t hi, const double* tab_zig, double* z_out)
+{
+    const double2 row = *reinterpret_cast<const double2*>(tab_zig + 2u * PCS_ZIG_LAYER(hi));
+    const double x = PCS_MUL(pcs_bits2d(((uint64_t)(hi & 0x801FFFFFu) << 32) | (uint64_t)lo), row.x);
+    *z_out = x;
+    return fabs(x) < row.y;
+}
+
 /* (mean, sd) of type `type` of the ONE parameter set of a PLAIN instance, from the table at the start of shared memory;
  * dlo = the node's D word (type in bits 16..21) */
 template <uint32_t MUSD_ADDR>
@@ -222,6 +231,9 @@ constexpr bool coop_is_plain(const SimParams& p) { return p.n_sets == 1u && p.n_
 #define PROCELL_ENDGAME_IDLE 512
 #endif
 constexpr int kEndgameIdle = PROCELL_ENDGAME_IDLE;
+#ifndef PROCELL_LEAF_MERGE
+#define PROCELL_LEAF_MERGE 0
+#endif
 #ifndef PROCELL_PROBE_MASK
 #define PROCELL_PROBE_MASK 15u
 #endif
@@ -236,6 +248,10 @@ constexpr uint32_t kSnapMask = PROCELL_SNAP_MASK;         /* a warp refreshes it
 #define PROCELL_ENDGAME_FAST 0
 #endif
 constexpr bool kEndgameFast = PROCELL_ENDGAME_FAST != 0;
+#ifndef PROCELL_PARK_BACKOFF_MAX_NS
+#define PROCELL_PARK_BACKOFF_MAX_NS 1024u
+#endif
+constexpr unsigned kParkBackoffMaxNs = PROCELL_PARK_BACKOFF_MAX_NS;   /* warps parked at a set switch (MODE 2) poll with back-off up to this */
 constexpr unsigned kIdleBackoffMaxNs = PROCELL_IDLE_BACKOFF_MAX_NS;   /* idle warps poll with exponential back-off up to this */
 constexpr uint32_t kDonateMinNodes = PROCELL_DONATE_MIN_NODES;        /* a warp gives a chunk away only when its ring is about to spill anyway */
 static_assert((kHistFlushIters & (kHistFlushIters - 1u)) == 0u && kHistFlushIters >= 256u && kHistFlushIters <= (1u << 20), "");
@@ -360,7 +376,7 @@ __device__ __forceinline__ bool setdirect_rendezvous(const SimParams& P, volatil
             for (;;) {
                 if (sflag_get(s_ctl + 13) != round || sflag_get(s_ctl + 3)) { role = 2; break; }     /* released, or no batch left anywhere */
                 __nanosleep(backoff);
-                if (backoff < 1024u) backoff <<= 1;
+                if (backoff < kParkBackoffMaxNs) backoff <<= 1;
                 if (global_timer_ns() > deadline || ld_volatile_s32(&P.ctl->status) != kStatusOk) { role = 3; break; }
             }
         }
@@ -963,6 +979,29 @@ __device__ __forceinline__ void push_and_count(WarpCtx& w, const SimParams& P, u
     if (SETDIRECT) {
         count_leaves_setdirect(P, s_hist, o.leaf_key, o.leaf_inc, hist_base);
     } else if (PLAIN || P.n_times == 1u) {
+#if PROCELL_LEAF_MERGE == 1
+        if (PLAIN && !HASHED) {
+            /* the 32 newest nodes of a depth-first front mostly belong to one lineage and one or two tree levels, so most lanes
+             * count into the SAME slot and the shared-memory atomic unit serialises them (11 wavefronts per iteration for 17
+             * lanes, ncu).  The lanes whose key is lane 0's add their leaves up in one REDUX and lane 0 issues one atomic
+             * for all of them; a lane with another key issues its own, as before. */
+            const uint32_t k0 = __shfl_sync(kFull, o.leaf_key, 0);
+            const bool same = o.leaf_key == k0;
+            const uint32_t total = __reduce_add_sync(kFull, same ? o.leaf_inc : 0u);
+            uint32_t val = same ? 0u : o.leaf_inc;
+            if (w.lane == 0) val = total;
+            if (val > 0u) atomicAdd(&s_hist[o.leaf_key], val);
+        } else
+#elif PROCELL_LEAF_MERGE == 2
+        if (PLAIN && !HASHED) {
+            /* full merge: MATCH.ANY groups the lanes by key, the group's total is two population counts, its lowest lane adds */
+            const unsigned b1 = __ballot_sync(kFull, o.leaf_inc == 1u);
+            const unsigned b2 = __ballot_sync(kFull, o.leaf_inc == 2u);
+            const unsigned grp = __match_any_sync(kFull, o.leaf_key);
+            const uint32_t total = (uint32_t)__popc(grp & b1) + 2u * (uint32_t)__popc(grp & b2);
+            if ((grp & lt_mask) == 0u && total > 0u) atomicAdd(&s_hist[o.leaf_key], total);
+        } else
+#endif
         warp_count_leaves<HASHED>(P, s_hist, o.leaf_key, o.leaf_inc);
     } else {
         /* time series: a daughter born at t_div that divides (or would divide) at tc is out of time at every
@@ -1601,10 +1640,12 @@ __device__ __forceinline__ void rng_ceiling_body(int iters, const double* logtab
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int c = 0; c < CHAINS; ++c) {
-            pcs_u32x4 blk = pcs_draw_rk(tid, (uint32_t)c, 0u, PCS_TAG_DIVISION, heap[c], K.rk);
+            /* the product kernel's forms of the block and of the fast test (draw_block, zig_fast_signed): the ceiling is the
+             * best arithmetic we know, so whatever makes the product's arithmetic cheaper goes in here too */
+            pcs_u32x4 blk = draw_block(tid, (uint32_t)c, 0u, PCS_TAG_DIVISION, heap[c], K.rk);
             double z0, z1;
-            const bool f0 = pcs_zig_fast(blk.x, blk.y, s_log + PCS_TAB_ZIG, &z0);
-            const bool f1 = pcs_zig_fast(blk.z, blk.w, s_log + PCS_TAB_ZIG, &z1);
+            const bool f0 = zig_fast_signed(blk.x, blk.y, s_log + PCS_TAB_ZIG, &z0);
+            const bool f1 = zig_fast_signed(blk.z, blk.w, s_log + PCS_TAB_ZIG, &z1);
             const double a = pcs_timer(mean, sd, z0), b = pcs_timer(mean, sd, z1);
             const double ta = PCS_ADD(t[c], a), tb = PCS_ADD(t[c], b);
             acc += (f0 && a > 0.0) + (f1 && b > 0.0) + (ta > t_max) + (tb > t_max);
