@@ -598,15 +598,23 @@ def main():
         alg_bytes = float(h2d + d2h)          # tables read once + count tensor written once per launch
         ms_sim = gpu_ms / (K * B)
         hw = hw_fractions()
-        roofline = {"bound": "issue",
-                    "bound_detail": "instruction issue (0.77 of the issue slots) and shared-memory wavefronts (0.89 of the LSU data pipe) "
-                                    "together; neither HBM nor tensor bound (DESIGN.md section 5, roofline.hardware)",
+        c2 = (hw[1].get("config2") or {}) if hw is not None else {}
+        c4 = (hw[1].get("config4") or {}) if hw is not None else {}
+        roofline = {"bound": "shared-memory wavefronts",
+                    "bound_detail": "shared-memory wavefronts (LSU data pipe: %.2f of its peak on this workload, %.2f on config 4) with "
+                                    "instruction issue behind them (%.2f / %.2f of the issue slots); neither HBM nor tensor bound "
+                                    "(DESIGN.md section 5, roofline.hardware)"
+                                    % (c2.get("shared_wavefront_frac", float("nan")), c4.get("shared_wavefront_frac", float("nan")),
+                                       c2.get("issue_slot_frac", float("nan")), c4.get("issue_slot_frac", float("nan"))),
+                    "binding_unit": {"name": "l1tex data pipe, shared-memory wavefronts", "frac": c2.get("shared_wavefront_frac"),
+                                     "issue_slot_frac": c2.get("issue_slot_frac"), "from": "committed ncu capture of this build"},
                     "achieved": per_gpu / 1e9, "peak": ceiling / 1e9, "unit": "Gdivisions/s per GPU",
                     "frac": per_gpu / ceiling,
                     "peak_source": "k_rng_ceiling measured live: the arithmetic of the common DIVIDE iteration alone - one Philox4x32-10 block, "
                                    "two fast ziggurat tests, 2 timers, 2 time updates, the compares - with no tree, ring or atomics; "
-                                   "the fastest of three shapes of that loop.  The ceiling rose from 175 (Box-Muller, first half of "
-                                   "round 2) to ~250 G/s when the draw became a ziggurat: frac fell although the kernel got faster",
+                                   "the fastest of three shapes of that loop, with every arithmetic shortcut of the product kernel.  "
+                                   "The ceiling rose from 175 (Box-Muller, first half of round 2) to ~270 G/s with the ziggurat draw "
+                                   "and the cheaper block / fast-test forms: frac fell although the kernel got faster",
                     "peak_variants_Gdiv_s": ceiling_variants,
                     "traffic": None,
                     "hbm": {"achieved": alg_bytes / (ms_sim * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

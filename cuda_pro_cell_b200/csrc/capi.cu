@@ -533,7 +533,10 @@ int procell_engine_finish(procell_engine* en, void* stream_v, int64_t* counts, i
         /* the word is sticky on the device (any run since the last finish may have set it): clear it now that it is
          * being reported, so that the engine can be used again */
         cudaMemset(reinterpret_cast<unsigned char*>(en->ctl.p) + offsetof(ControlBlock, status), 0, sizeof(int));
+        static const char* const kStatusText[] = { "ok", "spill ring overflow", "donation queue timeout", "idle-wait timeout",
+                                                   "watchdog", "dynamic shared memory does not start where the kernel was compiled for (sm_100: 0x400)" };
         std::string msg = "device work pool failure, status " + std::to_string(status);
+        if (status > 0 && status < (int)(sizeof(kStatusText) / sizeof(kStatusText[0]))) msg += std::string(" (") + kStatusText[status] + ")";
         if (status == kStatusWatchdog && en->dbg.p) {      /* where were the warps when the watchdog fired */
             const size_t nw = (size_t)en->grid * en->warps;
             std::vector<unsigned long long> rec(nw * kDbgWords);
