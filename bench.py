@@ -600,9 +600,9 @@ def main():
         hw = hw_fractions()
         c2 = (hw[1].get("config2") or {}) if hw is not None else {}
         c4 = (hw[1].get("config4") or {}) if hw is not None else {}
-        roofline = {"bound": "shared-memory wavefronts",
-                    "bound_detail": "shared-memory wavefronts (LSU data pipe: %.2f of its peak on this workload, %.2f on config 4) with "
-                                    "instruction issue behind them (%.2f / %.2f of the issue slots); neither HBM nor tensor bound "
+        roofline = {"bound": "shared-memory wavefronts + instruction issue",
+                    "bound_detail": "shared-memory wavefronts (LSU data pipe: %.2f of its peak on this workload, %.2f on config 4) and "
+                                    "instruction issue (%.2f / %.2f of the issue slots) together; neither HBM nor tensor bound "
                                     "(DESIGN.md section 5, roofline.hardware)"
                                     % (c2.get("shared_wavefront_frac", float("nan")), c4.get("shared_wavefront_frac", float("nan")),
                                        c2.get("issue_slot_frac", float("nan")), c4.get("issue_slot_frac", float("nan"))),

@@ -85,6 +85,7 @@ SIGNATURES = {
     "procell_engine_set_target": (C.c_int, [C.c_void_p, _f64p, _u64p, C.c_size_t]),
     "procell_engine_fitness": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _f64p]),
     "procell_engine_fitness_in_launch": (C.c_int, [C.c_void_p]),
+    "procell_engine_kernel_mode": (C.c_int, [C.c_void_p]),
     "procell_rng_ceiling_variants": (C.c_int, [C.c_int, C.c_int, _f64p, _f64p]),
     "procell_rng_ceiling": (C.c_int, [C.c_int, C.c_int, _f64p, _f64p]),
     "procell_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),

@@ -275,6 +275,11 @@ class Engine:
         """True if the last fitness() was computed by the simulation launch itself (target set before run())."""
         return bool(_lib.load().procell_engine_fitness_in_launch(self.h))
 
+    def kernel_mode(self) -> int:
+        """Instance of the simulation kernel the loaded simulation runs on (0 base, 1 subtree sharding, 2 set-relative
+        sweep table, 3 deep trees with merged leaf counts, -1 bring-up kernel): procell_engine_kernel_mode."""
+        return int(_lib.load().procell_engine_kernel_mode(self.h))
+
     def close(self):
         if getattr(self, "h", None):
             _lib.load().procell_engine_destroy(self.h)

@@ -352,6 +352,7 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
     P.donate = !(denv && atoi(denv) == 1);
     en->kernel = sp->kernel;
     P.hist_setdirect = 0;
+    P.leaf_merge = 0;
     P.slot_mode = 0;
     P.kstride = (uint32_t)T;
     if (en->kernel == PROCELL_KERNEL_SIMPLE) {
@@ -415,9 +416,28 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
             P.hist_hashed = 1;
             P.smem_hist_slots = slots;
         }
+        if (plain && !P.hist_hashed && !subtree && en->warps == 32 && en->ring == 1) {
+            /* Deep lineage trees -> the instance that merges equal leaf keys before the shared-memory atomic (sim_kernels.cu,
+             * kModeMerge): it pays where DIVIDE iterations are nearly all of the work and the shared-memory pipe is the bound,
+             * and costs 3 % where seed cells are a third of the draws.  Expected depth of a lineage = the smaller of the
+             * generations t_max leaves room for (fastest type) and the halvings phi allows (mean over the seed cells). */
+            double fastest = 0.0;
+            for (size_t j = 0; j < T; ++j) if (sp->types[j].mean > 0.0 && (fastest == 0.0 || sp->types[j].mean < fastest)) fastest = sp->types[j].mean;
+            double halvings = 0.0;
+            for (size_t b = 0; b < B; ++b) halvings += (double)(plan->bin_kdiv[b] & 63u) * (double)(plan->bin_start[b + 1] - plan->bin_start[b]);
+            halvings = plan->n_cells ? halvings / (double)plan->n_cells : 0.0;
+            const double generations = fastest > 0.0 ? P.t_max / fastest : 0.0;
+            const double depth = generations < halvings ? generations : halvings;
+            /* ... and only where there is work for every warp for a while: a run that is mostly its tail (1e5 cells of
+             * config 2's shape: 0.2 ms) is bound by latency, and the merge adds to it (measured: -3.6 %) */
+            P.leaf_merge = depth >= 6.0 && (double)plan->n_cells * std::exp2(depth < 30.0 ? depth : 30.0) >= 5e8;
+            const char* lm = getenv("PROCELL_LEAF_MERGE");       /* 0 / 1 forces the choice (tests, A/B) */
+            if (lm) P.leaf_merge = atoi(lm) != 0;
+        }
         en->smem = coop_smem_bytes(en->warps, en->ring, P.smem_hist_slots, P.hist_hashed);
         int grid = 0;
         if (P.hist_setdirect) CU(coop_max_grid_setdirect(en->device, en->smem, &grid), "occupancy query");
+        else if (P.leaf_merge) CU(coop_max_grid_merge(en->device, en->smem, &grid), "occupancy query");
         else if (subtree) CU(coop_max_grid_subtree(en->device, P.hist_hashed, en->smem, &grid), "occupancy query");
         else CU(coop_max_grid(en->device, en->warps, en->ring, P.hist_hashed, (P.n_sets == 1u && P.n_times == 1u) ? 1 : 0, en->smem, &grid), "occupancy query");
         if (grid <= 0) return fail(PROCELL_ERR_CUDA, "cooperative kernel does not fit on this device");
@@ -656,6 +676,16 @@ int procell_engine_fitness(procell_engine* en, void* stream_v, const int64_t* d_
 }
 
 int procell_engine_fitness_in_launch(const procell_engine* en) { return en && en->fit_last_from_launch ? 1 : 0; }
+
+/* which instance of the cooperative kernel the loaded simulation runs on: 0 base, 1 subtree sharding, 2 sweep with a
+ * set-relative table, 3 deep trees with merged leaf counts; -1: not the cooperative kernel / nothing loaded */
+int procell_engine_kernel_mode(const procell_engine* en)
+{
+    if (!en || en->kernel == PROCELL_KERNEL_SIMPLE) return -1;
+    if (en->P.hist_setdirect) return 2;
+    if (en->P.sub_world > 1u) return 1;
+    return en->P.leaf_merge ? 3 : 0;
+}
 
 /* ---- single-process multi-GPU: seed-cell units sharded over the GPUs of one box, ONE ncclReduce(sum, int64) ---- */
 namespace {

@@ -63,8 +63,9 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint32_t kSlot = 16u;                  /* ring positions count bytes of the (A, B) half: 16 per node (WarpCtx) */
 constexpr uint32_t kDynSmemWindow = 0x400u;      /* where dynamic shared memory starts in the shared-memory window on sm_100 */
 /* kernel MODE: 0 = the kernel as measured in round 1; 1 = subtree sharding compiled in (multi-GPU runs of deep trees);
- * 2 = sweeps with a set-relative direct histogram table and a CTA-wide rendezvous at batch switches */
-constexpr int kModeBase = 0, kModeSubtree = 1, kModeSetDirect = 2;
+ * 2 = sweeps with a set-relative direct histogram table and a CTA-wide rendezvous at batch switches; 3 = deep trees on one
+ * parameter set: equal leaf keys of a DIVIDE iteration are merged before the shared-memory atomic */
+constexpr int kModeBase = 0, kModeSubtree = 1, kModeSetDirect = 2, kModeMerge = 3;
 
 /* Shared memory of k_proliferate_coop: (mean, sd) table 1 KB | rings | math tables | control words + threshold / epoch /
  * selection tables | count table.  The *Addr members are addresses in the shared-memory WINDOW (what ld.shared takes):
@@ -231,9 +232,6 @@ constexpr bool coop_is_plain(const SimParams& p) { return p.n_sets == 1u && p.n_
 #define PROCELL_ENDGAME_IDLE 512
 #endif
 constexpr int kEndgameIdle = PROCELL_ENDGAME_IDLE;
-#ifndef PROCELL_LEAF_MERGE
-#define PROCELL_LEAF_MERGE 0
-#endif
 #ifndef PROCELL_PROBE_MASK
 #define PROCELL_PROBE_MASK 15u
 #endif
@@ -979,29 +977,19 @@ __device__ __forceinline__ void push_and_count(WarpCtx& w, const SimParams& P, u
     if (SETDIRECT) {
         count_leaves_setdirect(P, s_hist, o.leaf_key, o.leaf_inc, hist_base);
     } else if (PLAIN || P.n_times == 1u) {
-#if PROCELL_LEAF_MERGE == 1
-        if (PLAIN && !HASHED) {
-            /* the 32 newest nodes of a depth-first front mostly belong to one lineage and one or two tree levels, so most lanes
-             * count into the SAME slot and the shared-memory atomic unit serialises them (11 wavefronts per iteration for 17
-             * lanes, ncu).  The lanes whose key is lane 0's add their leaves up in one REDUX and lane 0 issues one atomic
-             * for all of them; a lane with another key issues its own, as before. */
-            const uint32_t k0 = __shfl_sync(kFull, o.leaf_key, 0);
-            const bool same = o.leaf_key == k0;
-            const uint32_t total = __reduce_add_sync(kFull, same ? o.leaf_inc : 0u);
-            uint32_t val = same ? 0u : o.leaf_inc;
-            if (w.lane == 0) val = total;
-            if (val > 0u) atomicAdd(&s_hist[o.leaf_key], val);
-        } else
-#elif PROCELL_LEAF_MERGE == 2
-        if (PLAIN && !HASHED) {
-            /* full merge: MATCH.ANY groups the lanes by key, the group's total is two population counts, its lowest lane adds */
+        if (MODE == kModeMerge) {
+            /* The 32 newest nodes of a depth-first front mostly belong to one lineage and one or two tree levels, so most lanes
+             * count into the SAME slot and the shared-memory atomic unit serialises them: 10.5 wavefronts per iteration for 17
+             * lanes (ncu), a sixth of the shared-memory traffic of a kernel that is bound by it on deep trees.  MATCH.ANY groups
+             * the lanes by key, a group's total is two population counts over the ballots "one leaf" / "two leaves", and its
+             * lowest lane adds: 8 wavefronts less for 11 instructions more - config 4 -2.4 %, config 2 -1.3 %, but +3.5 % on
+             * config 3, where a DIVIDE iteration is half the work and issue is the bound: hence an instance of its own. */
             const unsigned b1 = __ballot_sync(kFull, o.leaf_inc == 1u);
             const unsigned b2 = __ballot_sync(kFull, o.leaf_inc == 2u);
             const unsigned grp = __match_any_sync(kFull, o.leaf_key);
             const uint32_t total = (uint32_t)__popc(grp & b1) + 2u * (uint32_t)__popc(grp & b2);
             if ((grp & lt_mask) == 0u && total > 0u) atomicAdd(&s_hist[o.leaf_key], total);
         } else
-#endif
         warp_count_leaves<HASHED>(P, s_hist, o.leaf_key, o.leaf_inc);
     } else {
         /* time series: a daughter born at t_div that divides (or would divide) at tc is out of time at every
@@ -1134,6 +1122,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_proliferate_coop(const __grid
     static_assert(RING == 1, "128-node ring per warp, one node per lane and iteration");
     static_assert(!SUBTREE || (PLAIN && RING == 1), "subtree sharding: one parameter set, one checkpoint, one node per lane");
     static_assert(!SETDIRECT || (!PLAIN && !HASHED && RING == 1), "set-relative table: sweeps, u32 slots, one node per lane");
+    static_assert(MODE != kModeMerge || (PLAIN && !HASHED && RING == 1), "merged leaf counts: one parameter set, direct u32 table");
     constexpr uint32_t kCap = Ring<RING>::kCap;
     constexpr bool SLOT = PLAIN && !HASHED;      /* the u32 table is laid out by slots (SimParams::slot_mode is set) */
     extern __shared__ __align__(16) unsigned char smem_dyn[];
@@ -1746,6 +1735,19 @@ cudaError_t coop_max_grid_setdirect(int device, size_t smem_bytes, int* grid_out
     return cudaSuccess;
 }
 
+cudaError_t coop_max_grid_merge(int device, size_t smem_bytes, int* grid_out)
+{
+    int per_sm = 0, sms = 0;
+    cudaError_t e = cudaFuncSetAttribute(k_proliferate_coop<32, false, true, 1, kModeMerge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proliferate_coop<32, false, true, 1, kModeMerge>, 1024, smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    *grid_out = per_sm * sms;
+    return cudaSuccess;
+}
+
 cudaError_t launch_coop(const SimParams& p, int warps, int ring, int grid, cudaStream_t stream)
 {
     if (ring != 1) return cudaErrorInvalidValue;
@@ -1760,6 +1762,11 @@ cudaError_t launch_coop(const SimParams& p, int warps, int ring, int grid, cudaS
         if (warps != 32 || ring != 1 || !plain) return cudaErrorInvalidValue;
         if (p.hist_hashed) k_proliferate_coop<32, true, true, 1, kModeSubtree><<<grid, 1024, smem, stream>>>(p);
         else k_proliferate_coop<32, false, true, 1, kModeSubtree><<<grid, 1024, smem, stream>>>(p);
+        return cudaGetLastError();
+    }
+    if (p.leaf_merge) {
+        if (warps != 32 || ring != 1 || !plain || p.hist_hashed) return cudaErrorInvalidValue;
+        k_proliferate_coop<32, false, true, 1, kModeMerge><<<grid, 1024, smem, stream>>>(p);
         return cudaGetLastError();
     }
 #define X(W, H, PL, R) k_proliferate_coop<W, H, PL, R, kModeBase><<<grid, W * 32, smem, stream>>>(p)

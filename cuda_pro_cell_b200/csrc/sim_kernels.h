@@ -125,6 +125,10 @@ struct SimParams {
     const uint32_t* fit_key_channel;   /* [n_keys] key -> target channel, 0xFFFFFFFF = not an output row */
     const double* fit_target;          /* [fit_channels] target shares */
     double* fit_out;                   /* [n_sets] */
+    /* 1: deep lineage trees (capi.cu: expected depth from t_max and the halvings phi allows) - the PLAIN direct instance that
+     * merges equal leaf keys of a DIVIDE iteration before the shared-memory atomic (kernel MODE kModeMerge).  Host-side
+     * choice of the instance only; last in the block so that the other instances' parameter offsets stay where they were */
+    int leaf_merge;
 };
 
 /* ring = 1: 128-node ring per warp, one node per lane and iteration (warps = 32, 24 or 16);
@@ -137,6 +141,8 @@ cudaError_t coop_max_grid(int device, int warps, int ring, int hashed, int plain
 cudaError_t coop_max_grid_subtree(int device, int hashed, size_t smem_bytes, int* grid_out);
 /* the sweep instance with a set-relative direct table (p.hist_setdirect): 32 warps, 128-node rings */
 cudaError_t coop_max_grid_setdirect(int device, size_t smem_bytes, int* grid_out);
+/* the PLAIN direct instance with merged leaf counts (p.leaf_merge): 32 warps, 128-node rings */
+cudaError_t coop_max_grid_merge(int device, size_t smem_bytes, int* grid_out);
 cudaError_t launch_simple(const SimParams& p, int grid, cudaStream_t stream);
 /* resets the queue and the control block (the status word excepted: it is sticky until the host has read it) and
  * zeroes the count tensor and the division counters of the run - one launch instead of a kernel and two memsets */

@@ -201,6 +201,11 @@ int procell_engine_fitness(procell_engine* engine, void* stream, const int64_t* 
  * 8 bytes per set.  Same arithmetic, same bits as the separate pass (csrc/fitness_device.h).  Returns 1 if the last
  * procell_engine_fitness call was served that way, 0 if it ran the separate kernel (PROCELL_FITNESS_FUSED=0 forces 0). */
 int procell_engine_fitness_in_launch(const procell_engine* engine);
+/* Which instance of the simulation kernel the loaded simulation runs on (diagnostic; results do not depend on it):
+ * 0 base, 1 subtree sharding, 2 sweep with a set-relative count table, 3 deep lineage trees - equal leaf keys of an
+ * iteration merged before the shared-memory atomic (chosen at load time from t_max / fastest mean and the halvings phi
+ * allows; PROCELL_LEAF_MERGE=0/1 forces it) -, -1 the bring-up kernel or nothing loaded. */
+int procell_engine_kernel_mode(const procell_engine* engine);
 
 /* RNG-only micro-kernel: per thread `iters` Philox blocks + two fast ziggurat tests + timers into a register
  * accumulator (the instruction-issue ceiling the roofline fraction is quoted against).  Returns ms. */

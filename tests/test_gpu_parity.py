@@ -152,6 +152,60 @@ def test_deep_tree_imbalance(gpu_api, oracle):
     assert np.array_equal(simple.counts, got.counts)
 
 
+@pytest.mark.parametrize("shape", ["config2_tenth", "deep", "shallow"])
+def test_merged_leaf_counts_instance_bit_exact(gpu_api, oracle, monkeypatch, shape):
+    """Kernel MODE 3 (deep lineage trees, one parameter set: equal leaf keys of a DIVIDE iteration are merged before the
+    shared-memory atomic) gives the oracle's tensor, forced on and forced off.  Left alone the host picks it only for
+    deep trees with work for every warp (config 2 and config 4 at full size: checked at load time below, and their
+    full-size parity tests then run on it), not for these small inputs."""
+    if shape == "config2_tenth":
+        w = synth.workload(2, 0.1)
+        values, freqs, types, t_max, phi = w.values, w.freqs, w.types, w.t_max, w.phi
+    elif shape == "deep":
+        values, freqs = np.array([1000.0, 2000.0, 4000.0]), np.array([3, 2, 2], dtype=np.uint64)
+        types, t_max, phi = np.array([[(0.5, 24.0, 4.0), (0.3, 40.0, 9.0), (0.2, -1.0, -1.0)]]), 400.0, 1e-7
+    else:
+        values, freqs = synth.synthetic_histogram(20000)
+        types, t_max, phi = np.array([synth.TYPES_CONFIG2]), 336.0, 0.0          # default phi: a lineage halves 0-5 times
+    plan, oplan = gpu_api.Plan(values, freqs, phi), oracle.OraclePlan(values, freqs, phi)
+    want = oracle.simulate(oplan, types, t_max, 0x5EED0033)
+    modes = {}
+    for force in (None, "0", "1"):
+        if force is None:
+            monkeypatch.delenv("PROCELL_LEAF_MERGE", raising=False)
+        else:
+            monkeypatch.setenv("PROCELL_LEAF_MERGE", force)
+        eng = gpu_api.Engine(0)
+        try:
+            eng.load(plan, types, t_max, 0x5EED0033)
+            modes[force] = eng.kernel_mode()
+            eng.run()
+            got = eng.finish()
+        finally:
+            eng.close()
+        assert np.array_equal(got.counts, want["counts"]) and np.array_equal(got.divisions, want["divisions"]), force
+    assert modes["0"] == 0 and modes["1"] == 3 and modes[None] == 0, modes
+
+
+def test_kernel_instance_chosen_per_workload(gpu_api, monkeypatch):
+    """procell_engine_kernel_mode at load time for BASELINE's configs at full size: deep trees with work for every warp
+    (configs 2 and 4) get the merged-leaf-count instance, the seed-heavy config 3 and config 1 the base one, the large
+    sweep (config 5) the set-relative one."""
+    for k in ("PROCELL_LEAF_MERGE", "PROCELL_SWEEP_DIRECT"):
+        monkeypatch.delenv(k, raising=False)
+    want = {1: 0, 2: 3, 3: 0, 4: 3, 5: 2}
+    got = {}
+    for cfg in want:
+        w = synth.workload(cfg)
+        eng = gpu_api.Engine(0)
+        try:
+            eng.load(gpu_api.Plan(w.values, w.freqs, w.phi), w.types, w.t_max, w.seed)
+            got[cfg] = eng.kernel_mode()
+        finally:
+            eng.close()
+    assert got == want
+
+
 def test_full_size_properties(gpu_api):
     """BASELINE config 2 at FULL size (1e6 cells, ~1e8 divisions): size-independent properties."""
     w = synth.workload(2)

@@ -19,8 +19,9 @@ from cuda_pro_cell_b200 import api, synth  # noqa: E402
 
 REPS = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 ALL_KNOBS = {"default": {}, "w16": {"PROCELL_COOP_WARPS": "16"},
-             "w24": {"PROCELL_COOP_WARPS": "24"}}
-KNOBS = [ALL_KNOBS[k] for k in (sys.argv[2].split(",") if len(sys.argv) > 2 else ALL_KNOBS)]
+             "w24": {"PROCELL_COOP_WARPS": "24"},
+             "nomerge": {"PROCELL_LEAF_MERGE": "0"}, "merge": {"PROCELL_LEAF_MERGE": "1"}}   # kernel MODE 3 forced off / on
+KNOBS = [ALL_KNOBS[k] for k in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("default", "w16", "w24"))]
 WORK = [(2, 1.0, 0.0), (2, 0.1, 0.0), (3, 1.0, 0.0), (5, 1.0, 0.0), (4, 0.1, 600.0), (4, 1.0, 0.0)]
 if os.environ.get("AB_WORK"):        # e.g. AB_WORK="2:1.0:0,4:0.1:600"
     WORK = [tuple(float(x) if i else int(x) for i, x in enumerate(item.split(":"))) for item in os.environ["AB_WORK"].split(",")]
@@ -31,7 +32,7 @@ for cfg, scale, t_override in WORK:
         w.t_max = t_override
     plan = api.Plan(w.values, w.freqs, w.phi)
     for knob in KNOBS:
-        for k in ("PROCELL_COOP_NPL", "PROCELL_COOP_WARPS"):
+        for k in ("PROCELL_COOP_NPL", "PROCELL_COOP_WARPS", "PROCELL_LEAF_MERGE"):
             os.environ.pop(k, None)
         os.environ.update(knob)
         eng = api.Engine(0)

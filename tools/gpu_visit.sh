@@ -55,14 +55,14 @@ san)
 ab)       # A/B of the in-tree library builds named in AB_LIBS (make -C cuda_pro_cell_b200/csrc variant NAME=.. DEFS=..)
   : > gpurun_out/ab_$TAG.jsonl
   for lib in ${AB_LIBS:-libprocell_b200.so}; do
-    PROCELL_LIB=$lib timeout 200 python tools/ab_knobs.py ${AB_REPS:-5} default >> gpurun_out/ab_$TAG.jsonl 2>> gpurun_out/ab_$TAG.err; el ab_$lib $?
+    PROCELL_LIB=$lib timeout 200 python tools/ab_knobs.py ${AB_REPS:-5} ${AB_KNOBS:-default} >> gpurun_out/ab_$TAG.jsonl 2>> gpurun_out/ab_$TAG.err; el ab_$lib $?
   done
   python - <<PY
 import json
 for l in open("gpurun_out/ab_$TAG.jsonl"):
     r = json.loads(l)
     print("%-34s cfg %d x%-4g %9.4f ms  %6.1f Gdiv/s  tail %7.1f us  idle/warp %6.1f us  donations %6d  crc %d" % (
-        r["lib"], r["config"], r["scale"], r["ms_min"], r["Gdiv_s"], r["span_us"] - r["seed_phase_us"], r["idle_us_per_warp"], r["donations"], r["crc"]))
+        r["lib"] + "".join(" %s=%s" % kv for kv in r["knob"].items()), r["config"], r["scale"], r["ms_min"], r["Gdiv_s"], r["span_us"] - r["seed_phase_us"], r["idle_us_per_warp"], r["donations"], r["crc"]))
 PY
   ;;
 multi)    # needs a box with NGPU GPUs (gpurun --gpus N): the multi-GPU parity tests and BASELINE's multi-GPU configs
