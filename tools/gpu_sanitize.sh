@@ -2,7 +2,8 @@
 # compute-sanitizer (memcheck, racecheck, initcheck) on small runs that cover every kernel mode:
 #   gpurun --timeout 600 -- 'bash tools/gpu_sanitize.sh TAG'      -> gpurun_out/sanitizer_{memcheck,racecheck,initcheck}_TAG.log
 # direct table in slot layout (PLAIN), hashed cache + batches, spill + donation, time series, the 16-warp shape,
-# subtree sharding (MODE 1), set-relative sweep table with rendezvous (MODE 2), sweep fitness in the launch
+# subtree sharding (MODE 1), set-relative sweep table with rendezvous (MODE 2), sweep fitness in the launch,
+# merged leaf counts (MODE 3)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TAG=${1:-r2}
@@ -22,6 +23,10 @@ eng=api.Engine(0); types=synth.sweep_types(1024)[::128]
 eng.load(plan,types,80.0,4); eng.set_target(plan.row_value[::3].copy(), np.arange(1,len(plan.row_value[::3])+1,dtype=np.uint64))
 eng.run(); r7=eng.finish(); fit=eng.fitness(); fused=eng.fitness_in_launch(); eng.close()   # MODE 2 + fitness in the launch
 del os.environ["PROCELL_SWEEP_DIRECT"]
+os.environ["PROCELL_LEAF_MERGE"]="1"
+r8=api.proliferate(plan,[synth.TYPES_CONFIG2],100.0,3)                 # merged leaf counts (MODE 3), forced on this small input
+del os.environ["PROCELL_LEAF_MERGE"]
+assert np.array_equal(r8.counts,r.counts)
 os.environ["PROCELL_COOP_WARPS"]="16"
 r5=api.proliferate(plan,[synth.TYPES_CONFIG2],100.0,3)
 print("ok",int(r.divisions.sum()),int(r2.divisions.sum()),int(r3.divisions.sum()),r3.stats['donations'],int(r4.counts.sum()),
