@@ -977,7 +977,7 @@ __device__ __forceinline__ void push_and_count(WarpCtx& w, const SimParams& P, u
     if (SETDIRECT) {
         count_leaves_setdirect(P, s_hist, o.leaf_key, o.leaf_inc, hist_base);
     } else if (PLAIN || P.n_times == 1u) {
-        if (MODE == kModeMerge) {
+        if (MODE == kModeMerge) {        /* (the subtree-sharding instance does not gain from it: 77.9 -> 78.6 ms for one rank of eight of config 4) */
             /* The 32 newest nodes of a depth-first front mostly belong to one lineage and one or two tree levels, so most lanes
              * count into the SAME slot and the shared-memory atomic unit serialises them: 10.5 wavefronts per iteration for 17
              * lanes (ncu), a sixth of the shared-memory traffic of a kernel that is bound by it on deep trees.  MATCH.ANY groups
