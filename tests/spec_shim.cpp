@@ -41,6 +41,43 @@ int shim_zig_trial(const uint32_t* w, uint32_t c, uint32_t root, uint32_t set, u
 }
 /* the fast test alone (what the common DIVIDE iteration evaluates): 1 = accepted; *z is set either way */
 int shim_zig_fast(uint32_t lo, uint32_t hi, double* z) { return pcs_zig_fast(lo, hi, kRows + PCS_TAB_ZIG, z) ? 1 : 0; }
+/* The form the KERNELS evaluate (sim_kernels.cu: zig_fast_smem / zig_fast_signed): the sign goes on the multiplicand
+ * instead of being OR-ed onto the product, the test is |x| < x_next.  Restated here operation for operation so that the
+ * CPU suite can show it is pcs_zig_fast bit for bit - value (a signed zero included) and verdict - on every layer. */
+static int zig_fast_kernel_form(uint32_t lo, uint32_t hi, double* z)
+{
+    const double* row = kRows + PCS_TAB_ZIG + 2u * PCS_ZIG_LAYER(hi);
+    const double x = PCS_MUL(pcs_bits2d(((uint64_t)(hi & 0x801FFFFFu) << 32) | (uint64_t)lo), row[0]);
+    *z = x;
+    return (x < 0.0 ? -x : x) < row[1] ? 1 : 0;
+}
+int shim_zig_fast_kernel_form(uint32_t lo, uint32_t hi, double* z) { return zig_fast_kernel_form(lo, hi, z); }
+/* n pseudo-random draws (xorshift64*, every layer and both signs come up) + the edge mantissas of every layer: number of
+ * draws on which the two forms differ in verdict or in the BITS of z */
+uint64_t shim_zig_fast_forms_differ(uint64_t n, uint64_t state)
+{
+    uint64_t bad = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        state ^= state >> 12; state ^= state << 25; state ^= state >> 27;
+        const uint64_t r = state * 0x2545F4914F6CDD1DULL;
+        double a, b;
+        const int fa = pcs_zig_fast((uint32_t)r, (uint32_t)(r >> 32), kRows + PCS_TAB_ZIG, &a) ? 1 : 0;
+        const int fb = zig_fast_kernel_form((uint32_t)r, (uint32_t)(r >> 32), &b);
+        bad += (fa != fb) || pcs_d2bits(a) != pcs_d2bits(b);
+    }
+    static const uint64_t edge[] = { 0, 1, 2, 0xFFFFFFFFull, 0x100000000ull, 0x000FFFFFFFFFFFFFull, 0x0010000000000000ull,
+                                     0x001FFFFFFFFFFFFEull, 0x001FFFFFFFFFFFFFull };
+    for (uint32_t layer = 0; layer < (1u << PCM_ZIG_N_BITS); ++layer)
+        for (uint32_t sign = 0; sign < 2; ++sign)
+            for (uint64_t m : edge) {
+                const uint32_t hi = (sign << 31) | (layer << (31 - PCM_ZIG_N_BITS)) | (uint32_t)(m >> 32), lo = (uint32_t)m;
+                double a, b;
+                const int fa = pcs_zig_fast(lo, hi, kRows + PCS_TAB_ZIG, &a) ? 1 : 0;
+                const int fb = zig_fast_kernel_form(lo, hi, &b);
+                bad += (fa != fb) || pcs_d2bits(a) != pcs_d2bits(b);
+            }
+    return bad;
+}
 double shim_timer(double mean, double sd, double z) { return pcs_timer(mean, sd, z); }
 double shim_u32unit(uint32_t m) { return pcs_u32unit(m); }
 double shim_seed_normal(const uint32_t* w, double u_forced)

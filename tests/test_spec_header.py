@@ -41,7 +41,23 @@ def shim():
                                  C.POINTER(C.c_double)]
     S.shim_zig_fast.restype = C.c_int
     S.shim_zig_fast.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
+    S.shim_zig_fast_kernel_form.restype = C.c_int
+    S.shim_zig_fast_kernel_form.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
+    S.shim_zig_fast_forms_differ.restype = C.c_uint64
+    S.shim_zig_fast_forms_differ.argtypes = [C.c_uint64, C.c_uint64]
     return S
+
+
+def test_kernel_form_of_the_fast_ziggurat_test_is_the_spec_bitwise(shim):
+    """The kernels put the draw's sign on the multiplicand and test |x| < x_next (sim_kernels.cu: zig_fast_smem) where
+    the spec ORs the sign onto the product (procell_spec.h: pcs_zig_fast).  (-M) * x_i = -(M * x_i) exactly, so both the
+    verdict and the bits of z - a signed zero included - must agree: 2e7 random draws and the edge mantissas (0, 1, the
+    subnormal / normal boundary, all ones) of every layer with either sign."""
+    assert shim.shim_zig_fast_forms_differ(20_000_000, 0x9E3779B97F4A7C15) == 0
+    z, zk = C.c_double(1.0), C.c_double(1.0)
+    hi = 1 << 31                                              # layer 0, mantissa 0, negative: z = -0.0 in both forms
+    assert shim.shim_zig_fast(0, hi, C.byref(z)) == shim.shim_zig_fast_kernel_form(0, hi, C.byref(zk)) == 1
+    assert struct.pack("<d", z.value) == struct.pack("<d", zk.value) == struct.pack("<d", -0.0)
 
 
 def test_seed_cell_draws_equal_the_oracle_bitwise(shim, oracle):
