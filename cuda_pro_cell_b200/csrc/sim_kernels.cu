@@ -408,9 +408,9 @@ __device__ __forceinline__ bool setdirect_rendezvous(const SimParams& P, volatil
 
 struct WarpCtx {
     uint32_t ab;                     /* ring: shared-memory address of kCap (t_div bits, heap) pairs followed by kCap
-                                        (root|keybase<<32, D) pairs.  The ring starts on a 2 KB boundary of the shared-memory
-                                        window, so the address of slot idx is ab | ((idx << 4) & 0x7F0): a shift and ONE
-                                        logic instruction, no add (the kernel checks the alignment when it starts) */
+                                        (root|key<<32, D) pairs.  The ring starts on a 2 KB boundary of the shared-memory
+                                        window (SmemLayout; static_assert in the kernel), so the address of the slot at byte
+                                        position p is ab | (p & 0x7F0): ONE logic instruction, no shift, no add */
     uint32_t bottom, top;            /* ring positions IN BYTES of the (A, B) half - kSlot = 16 per node -, n = (top - bottom) / 16: a
                                         slot's address is ab | (position & 0x7F0) with no shift, and position + 16 * count is one IMAD */
     uint32_t slow;                   /* the bottom-most slow / 16 nodes of the ring are retry nodes awaiting a general iteration (bytes too) */
@@ -446,19 +446,6 @@ __device__ __forceinline__ void ring_store(WarpCtx& w, uint32_t pos, uint64_t a,
     const unsigned sab = w.ab | (pos & (Ring<RING>::kMask << 4));
     asm volatile("st.shared.v2.u64 [%0], {%1, %2};\n\tst.shared.v2.u64 [%0+%5], {%3, %4};"
                  :: "r"(sab), "l"(a), "l"(b), "l"(c), "l"(d), "n"(Ring<RING>::kCap * 16u) : "memory");
-}
-
-/* the same under a predicate, as two predicated STS.128 instead of a branch around four stores */
-template <int RING>
-__device__ __forceinline__ void ring_store_if(WarpCtx& w, bool p, uint32_t pos, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
-{
-#ifdef PROCELL_BRANCHY_PUSH
-    if (p) ring_store<RING>(w, pos, a, b, c, d);
-#else
-    const unsigned sab = w.ab | (pos & (Ring<RING>::kMask << 4));
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.v2.u64 [%1], {%2, %3};\n\t@q st.shared.v2.u64 [%1+%6], {%4, %5};\n\t}"
-                 :: "r"((unsigned)p), "r"(sab), "l"(a), "l"(b), "l"(c), "l"(d), "n"(Ring<RING>::kCap * 16u) : "memory");
-#endif
 }
 
 /* A pop as the DIVIDE iterations want it: the (C, D) pair as four 32-bit words - root, key, D's low word, retry number -
