@@ -70,6 +70,7 @@ SIGNATURES = {
     "procell_plan_n_cells": (C.c_uint64, [C.c_void_p]),
     "procell_plan_phi": (C.c_double, [C.c_void_p]),
     "procell_plan_depth_capped": (C.c_int, [C.c_void_p]),
+    "procell_plan_lineage_depth": (C.c_double, [C.c_void_p, _f64p, C.c_size_t, C.c_double]),
     "procell_plan_export": (C.c_int, [C.c_void_p, _f64p, _u32p, _u32p, _u8p]),
     "procell_merge_rows": (C.c_int, [C.c_void_p, _i64p, C.c_size_t, _i64p, _i64p]),
     "procell_proliferate": (C.c_int, [C.c_void_p, C.POINTER(SimParams), C.c_int, _i64p, _i64p, C.POINTER(RunStats)]),

@@ -130,6 +130,12 @@ class Plan:
         v, f = read_histogram(path)
         return cls(v, f, phi)
 
+    def lineage_depth(self, types, t_max: float) -> float:
+        """Expected depth of a lineage tree for one parameter set: min(t_max / fastest mean, mean halvings phi allows)
+        (procell_plan_lineage_depth; the library picks the deep-tree kernel instance from it)."""
+        t = _types_array(types)[0]
+        return float(_lib.load().procell_plan_lineage_depth(self.h, t.ctypes.data_as(_f64p), len(t), float(t_max)))
+
     def merge_rows(self, counts_one_set: np.ndarray):
         """counts [n_keys][n_types] -> (row_freq [n_rows], row_ratio [n_rows][n_types])."""
         c = np.ascontiguousarray(counts_one_set, dtype=np.int64)

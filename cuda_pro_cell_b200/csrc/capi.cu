@@ -421,13 +421,7 @@ int procell_engine_load(procell_engine* en, const procell_plan* plan, const proc
              * kModeMerge): it pays where DIVIDE iterations are nearly all of the work and the shared-memory pipe is the bound,
              * and costs 3 % where seed cells are a third of the draws.  Expected depth of a lineage = the smaller of the
              * generations t_max leaves room for (fastest type) and the halvings phi allows (mean over the seed cells). */
-            double fastest = 0.0;
-            for (size_t j = 0; j < T; ++j) if (sp->types[j].mean > 0.0 && (fastest == 0.0 || sp->types[j].mean < fastest)) fastest = sp->types[j].mean;
-            double halvings = 0.0;
-            for (size_t b = 0; b < B; ++b) halvings += (double)(plan->bin_kdiv[b] & 63u) * (double)(plan->bin_start[b + 1] - plan->bin_start[b]);
-            halvings = plan->n_cells ? halvings / (double)plan->n_cells : 0.0;
-            const double generations = fastest > 0.0 ? P.t_max / fastest : 0.0;
-            const double depth = generations < halvings ? generations : halvings;
+            const double depth = procell_plan_lineage_depth(plan, sp->types, T, P.t_max);
             /* ... and only where there is work for every warp for a while: a run that is mostly its tail (1e5 cells of
              * config 2's shape: 0.2 ms) is bound by latency, and the merge adds to it (measured: -3.6 %) */
             P.leaf_merge = depth >= 6.0 && (double)plan->n_cells * std::exp2(depth < 30.0 ? depth : 30.0) >= 5e8;

@@ -201,6 +201,21 @@ int procell_plan_create(const double* value, const uint64_t* freq, size_t n_line
 void procell_plan_destroy(procell_plan* plan) { delete plan; }
 size_t procell_plan_n_bins(const procell_plan* plan) { return plan ? plan->bin_value.size() : 0; }
 size_t procell_plan_n_keys(const procell_plan* plan) { return plan ? plan->n_keys : 0; }
+
+double procell_plan_lineage_depth(const procell_plan* plan, const procell_cell_type* types, size_t n_types, double t_max)
+{
+    if (!plan || !types || plan->n_cells == 0) return 0.0;
+    double fastest = 0.0;
+    for (size_t j = 0; j < n_types; ++j)
+        if (types[j].mean > 0.0 && (fastest == 0.0 || types[j].mean < fastest)) fastest = types[j].mean;
+    if (!(fastest > 0.0) || !(t_max > 0.0)) return 0.0;
+    double halvings = 0.0;
+    for (size_t b = 0; b + 1 < plan->bin_start.size(); ++b)
+        halvings += (double)(plan->bin_kdiv[b] & 63u) * (double)(plan->bin_start[b + 1] - plan->bin_start[b]);
+    halvings /= (double)plan->n_cells;
+    const double generations = t_max / fastest;
+    return generations < halvings ? generations : halvings;
+}
 size_t procell_plan_n_rows(const procell_plan* plan) { return plan ? plan->row_value.size() : 0; }
 uint64_t procell_plan_n_cells(const procell_plan* plan) { return plan ? plan->n_cells : 0; }
 double procell_plan_phi(const procell_plan* plan) { return plan ? plan->phi : 0.0; }

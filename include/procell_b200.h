@@ -78,6 +78,10 @@ size_t procell_plan_n_rows(const procell_plan* plan);   /* distinct values value
 uint64_t procell_plan_n_cells(const procell_plan* plan);
 double procell_plan_phi(const procell_plan* plan);
 int procell_plan_depth_capped(const procell_plan* plan);
+/* Expected depth of a lineage tree (diagnostic; no GPU needed): the smaller of the generations t_max leaves room for -
+ * t_max / the smallest positive mean among `types` - and the halvings phi allows, averaged over the seed cells.  The
+ * library uses it to choose the kernel instance for deep trees (procell_engine_kernel_mode). */
+double procell_plan_lineage_depth(const procell_plan* plan, const procell_cell_type* types, size_t n_types, double t_max);
 /* any pointer may be NULL; sizes: row_value[n_rows], key_row[n_keys], bin_keybase[n_bins], bin_kdiv[n_bins] */
 int procell_plan_export(const procell_plan* plan, double* row_value, uint32_t* key_row,
                         uint32_t* bin_keybase, uint8_t* bin_kdiv);

@@ -131,6 +131,29 @@ def _cli(*args):
     return subprocess.run([str(_lib.CLI_PATH), *args], capture_output=True, text=True, timeout=60)
 
 
+def test_lineage_depth_of_the_five_configs():
+    """procell_plan_lineage_depth (no GPU needed): min(t_max / fastest mean, mean halvings phi allows) - what the library
+    chooses the deep-tree kernel instance from (>= 6 and cells x 2^depth >= 5e8: configs 2 and 4; the choice itself is
+    checked on the GPU, test_kernel_instance_chosen_per_workload)."""
+    want = {1: (168.0 / 48.33, None), 2: (10.0, 10.0), 3: (None, None), 4: (30.0, 30.0)}
+    got = {}
+    for cfg in (1, 2, 3, 4):
+        w = synth.workload(cfg, 1.0 if cfg != 3 else 0.01)
+        plan = api.Plan(w.values, w.freqs, w.phi)
+        got[cfg] = plan.lineage_depth(w.types, w.t_max)
+        # independent restatement from the exported plan
+        weights = np.diff(np.concatenate([[0], np.cumsum(w.freqs[w.freqs > 0])])).astype(np.float64)
+        halvings = float(((plan.bin_kdiv & 63) * weights).sum() / weights.sum())
+        fastest = min(m for _, m, _ in w.types[0] if m > 0)
+        assert got[cfg] == pytest.approx(min(w.t_max / fastest, halvings), rel=1e-12)
+    assert got[2] == want[2][0] and got[4] == want[4][0]            # time-bound: 240 / 24 and 720 / 24 generations
+    assert 1.0 < got[1] < 2.0 and 1.5 < got[3] < 2.5                 # phi-bound: a lineage halves once or twice
+    plan = api.Plan(np.array([8.0, 16.0]), np.array([3, 1], dtype=np.uint64), 0.5)
+    assert plan.lineage_depth([(1.0, -1.0, -1.0)], 100.0) == 0.0     # nothing proliferates
+    assert plan.lineage_depth([(1.0, 10.0, 1.0)], 0.0) == 0.0        # no time
+    assert plan.lineage_depth([(0.5, 10.0, 1.0), (0.5, 5.0, 1.0)], 1e6) == pytest.approx((3 * 3 + 4 * 1) / 4.0)   # 8 / 2^(k+1) > 0.5: k = 0..2; 16: k = 0..3
+
+
 def test_cli_messages_match_the_reference(tmp_path):
     """stdout + exit status 1, same strings as cmdargs.cpp:41-45,48-75,97-106 (README spellings accepted too)"""
     r = _cli("--bogus")
